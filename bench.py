@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""bench.py -- LF evaluations/second on the north-star workload (200 taxa x 2000 codons, MG94xREV, 4 omega classes).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    N>1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+A "step" is ONE full likelihood-function evaluation: every one of the B*C rate matrices handed over, exponentiated,
+the whole tree pruned for all patterns and classes, root reduction, one fp64 lnL back.
+  value : evaluations/s with the inputs already resident in HBM (device time, CUDA events on the engine's stream,
+          K steps, max over ranks).
+  e2e   : the same through the public C-ABI call sequence a host makes (hb2_set_matrices_packed + hb2_evaluate_classes)
+          with HOST buffers: the H2D copy of that step's matrices and the D2H read of lnL are inside the timed region.
+Multi-GPU: patterns are sharded across ranks (strong scaling of one alignment); one fp64 ncclAllReduce per evaluation.
+The oracle / reference binary under oracle/ is used only for cpu_baseline and --impl reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(taxa=200, codons=2000, classes=4)
+NAME = "MG94xREV 200 taxa x 2000 codons, 4 omega classes (synthetic, seed 20260924)"
+METRIC = "LF evals/sec, 200-taxon x 2000-codon MG94xREV 4 omega-cats"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.path = tempfile.mktemp(prefix="hb2clk_", suffix=".csv")
+        self.proc = None
+        self.device = device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_work(w, S):
+    """SURVEY.md §8(d) per-evaluation algorithmic work for S patterns (all classes)."""
+    L, I, D, C = w.tree.n_leaves, w.tree.n_internal, w.D, w.C
+    B = L + I - 1
+    flops = C * ((I - 1) * S * 2 * D * D + (L + B) * S * D + 2 * S * D)
+    byts = C * ((2 * I - 1) * S * D * 8 + B * D * D * 8 + L * S)
+    expm_flops = C * B * 7 * 2 * D ** 3          # this engine: 6 products + ~1 squaring per matrix
+    return flops, byts, expm_flops
+
+
+def cpu_baseline_sample(steps, warmup, threads):
+    """Reference HYPHYMP (oracle/_ref/hyphy) on a bounded sample: same tree/model/classes, 1/8 of the codons.
+    Pruning + per-pattern work scale linearly in patterns, expm does not: full-size evals/s are reported as
+    sample evals/s * (S_sample/S_full), which flatters the CPU slightly (its expm share is counted 1/8)."""
+    from hyphy_b200 import synth
+    from oracle import ref_harness as rh, port
+    frac = 8
+    ws = synth.codon_workload(WORKLOAD["taxa"], WORKLOAD["codons"] // frac, WORKLOAD["classes"])
+    S_full = None
+    if rh.have_reference():
+        r = rh.run_reference(ws, n_evals=steps, threads=threads, per_site=False, n_warm=warmup)
+        rate_sample = steps / r["loop_seconds"]
+        kind, cores = "reference", threads
+        lnl = r["lnL"]
+    else:
+        port.lnl(ws)
+        t0 = time.perf_counter()
+        for _ in range(max(1, steps // 4)):
+            lnl, _ = port.lnl(ws)
+        rate_sample = max(1, steps // 4) / (time.perf_counter() - t0)
+        kind, cores = "port", 1
+    return dict(kind=kind, cores=cores, rate_sample=rate_sample, S_sample=ws.S, lnl_sample=lnl,
+                sample=f"{WORKLOAD['taxa']} taxa x {WORKLOAD['codons'] // frac} codons x {WORKLOAD['classes']} classes "
+                       f"(1/{frac} of the codons, S={ws.S} patterns), {steps} full evaluations after {warmup} warm-up; "
+                       f"value = sample evals/s x S_sample/S_full")
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    from hyphy_b200 import synth
+    threads = os.cpu_count() or 1
+    w_full_S = synth.codon_workload(WORKLOAD["taxa"], WORKLOAD["codons"], WORKLOAD["classes"]).S
+    t0 = time.time()
+    cb = cpu_baseline_sample(args.steps, args.warmup, threads)
+    value = cb["rate_sample"] * cb["S_sample"] / w_full_S
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": NAME, "patterns": w_full_S, "l2": "inputs larger than L2 (n/a on CPU)"},
+            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]},
+            "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.time() - t0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+
+    import torch
+    from hyphy_b200 import synth, LikelihoodFunction, Partition
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    w = synth.codon_workload(WORKLOAD["taxa"], WORKLOAD["codons"], WORKLOAD["classes"])
+    S = w.S
+    # contiguous pattern shards, balanced by count
+    lo, hi = rank * S // world, (rank + 1) * S // world
+    lf = LikelihoodFunction(w, device=local_rank, pattern_slice=slice(lo, hi) if world > 1 else None)
+    if world > 1:
+        uid = [Partition.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        lf.part.comm_init(world, rank, uid[0])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # per-step host inputs: one global parameter moved => every matrix changes (SURVEY §8d evaluation stream)
+    n_variants = 4
+    Qts = [np.ascontiguousarray(w.Qt(perturb=1e-4 * k)) for k in range(n_variants)]
+    pinned = []
+    for q in Qts:                                   # the host's matrices live in pinned memory
+        t = torch.from_numpy(q).pin_memory()
+        pinned.append(t)
+    Qts = [t.numpy() for t in pinned]
+
+    def e2e_step(k):
+        q = Qts[k % n_variants]
+        for c in range(w.C):
+            lf.part.set_matrices(c, lf.all_nodes, q[c])
+        return lf.compute()
+
+    lnl0 = e2e_step(0)                              # also the first (whole-tree) evaluation
+    for k in range(args.warmup):
+        e2e_step(k)
+    # ---- e2e: public API with host buffers ---------------------------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        e2e_step(k)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    # ---- resident: device time by CUDA events on the engine's stream ---------------------------------
+    lf.part.set_matrices(0, lf.all_nodes, Qts[0][0])
+    for c in range(1, w.C):
+        lf.part.set_matrices(c, lf.all_nodes, Qts[0][c])
+    lf.part.time_resident(w.class_weights, w.pi, iters=args.warmup)
+    launches0 = lf.part.launch_count
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ms, stage, lnl_res = lf.part.time_resident(w.class_weights, w.pi, iters=args.steps)
+    barrier()
+    clocks = sampler.stop()
+    launches = lf.part.launch_count - launches0
+    ms = max_over_ranks(ms)
+    stage = [max_over_ranks(float(s)) for s in stage]
+    lf.close()
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        flops, byts, expm_flops = algorithmic_work(w, S)
+        # dominant kernel: the fused pruning update (one launch per tree level); per-launch = per-evaluation / levels
+        prune_launches = (launches // args.steps) - 3        # minus expm, combine, final_sum
+        prune_ms = stage[1]
+        achieved_gbs = (byts / world) / (prune_ms * 1e-3) / 1e9
+        roofline = {"kernel": "prune64_kernel (fp64 fused pruning update, all tree levels)", "bound": "hbm",
+                    "achieved": achieved_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / pk["hbm_gbs"],
+                    "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({pk_kind})",
+                    "launches_per_eval": prune_launches, "avg_launch_ms": prune_ms / max(prune_launches, 1),
+                    "algorithmic_bytes_per_eval": byts, "algorithmic_flops_per_eval": flops,
+                    "fp64_tflops_pruning": (flops / world) / (prune_ms * 1e-3) / 1e12,
+                    "fp64_tflops_expm": expm_flops / (stage[0] * 1e-3) / 1e12 if stage[0] > 0 else None,
+                    "stage_ms": {"expm": stage[0], "pruning": stage[1], "root": stage[2]}}
+        h2d = int(w.C * w.tree.n_branches * w.D * w.D * 8 + w.C * w.tree.n_branches * 4 + (64 + w.C) * 8)
+        line = {"metric": METRIC, "value": 1000.0 / ms, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": NAME, "patterns": S, "branches": w.tree.n_branches, "states": w.D, "classes": w.C,
+                           "sharding": f"patterns/{world}", "l2": "inputs larger than L2 (830 MB of conditionals per evaluation)"},
+                "e2e": {"value": 1000.0 / e2e_ms, "unit": "evals/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "lnL": lnl0, "lnL_resident": lnl_res}
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                threads = os.cpu_count() or 1
+                cb = cpu_baseline_sample(6, 1, threads)
+                v = cb["rate_sample"] * cb["S_sample"] / S
+                line["cpu_baseline"] = {"value": v, "unit": "evals/s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}
+            except Exception as e:                   # the baseline is a report, never a reason to lose the bench line
+                line["cpu_baseline"] = {"value": None, "unit": "evals/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,632 @@
+// hb2_engine.cu -- C++ host side of libhyphy_b200.so: the C ABI of include/hyphy_b200.h over the CUDA kernels.
+//
+// Mirrors, for one partition, what the reference does inside _LikelihoodFunction::ComputeBlock
+// (likefunc.cpp:10783-11289): keep the per-node caches resident (here: in HBM), take the changed matrices,
+// re-exponentiate them, re-prune the dirty part of the tree, reduce at the root, hand back one double.
+// No CPU fallback exists on this path: every failure is an error code (fatal for the host).
+#include "../../include/hyphy_b200.h"
+#include "hb2_kernels_fp64.cuh"
+
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include <nccl.h>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+
+#define CU(x)                                                                                         \
+    do {                                                                                              \
+        cudaError_t e_ = (x);                                                                         \
+        if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ---- NCCL through dlopen: single-GPU users never need the library -------------------------------
+struct NcclApi {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool load() {
+        if (h) return true;
+        const char *names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (h) break;
+        }
+        if (!h) return false;
+        GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
+        AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+        CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && AllReduce && CommDestroy && GetErrorString;
+    }
+} g_nccl;
+
+int pad_states(int64_t D) {
+    if (D <= 4) return 4;
+    if (D <= 8) return 8;
+    if (D <= 16) return 16;
+    if (D <= 24) return 24;
+    if (D <= 32) return 32;
+    if (D <= 64) return 64;
+    return -1;
+}
+
+}  // namespace
+
+struct hb2_partition {
+    int device = 0, flags = 0;
+    cudaStream_t stream = nullptr;
+    int64_t S = 0, D = 0, L = 0, I = 0, C = 0, B = 0, nAmb = 0;
+    int Dp = 0;
+    int64_t Sp = 0;
+    std::vector<int64_t> parents;
+    std::vector<std::vector<int>> children;   // per internal node, flat ids
+    std::vector<int> height;                  // per internal node: 0 = only leaf children
+    int max_height = 0;
+    // device
+    int *d_leaf = nullptr, *d_scal = nullptr, *d_rootE = nullptr, *d_child_start = nullptr, *d_child_ids = nullptr;
+    int *d_jobs = nullptr, *d_dst = nullptr, *d_flag = nullptr, *d_mix_first = nullptr;
+    double *d_ambig = nullptr, *d_freq = nullptr, *d_cond = nullptr, *d_PT = nullptr, *d_Q = nullptr, *d_pi = nullptr;
+    double *d_rootL = nullptr, *d_weights = nullptr, *d_partial = nullptr, *d_lnL = nullptr, *d_siteL = nullptr, *d_mix_w = nullptr;
+    long long *d_siteScale = nullptr;
+    // pinned host staging
+    double *h_Q = nullptr, *h_small = nullptr;   // h_small: pi (Dp) + weights (C) + lnL (1)
+    int *h_jobs = nullptr, *h_dst = nullptr;
+    // pending matrices: entries [0, n_pending) of h_Q / h_dst, with kinds
+    int64_t n_pending = 0;
+    std::vector<int> pending_kind;
+    int64_t q_capacity = 0;                   // in matrices
+    std::vector<char> have_matrix;            // [C*B]
+    std::vector<char> is_rate;                // [C*B] slot holds a rate matrix resident in d_Qres (for hb2_time_resident)
+    double *d_Qres = nullptr;                 // [C][B][D*D] last rate matrices, resident copy
+    bool first_eval_done = false;
+    std::vector<char> evaluated_cat;          // [C] whole tree pruned at least once
+    int64_t launches = 0;
+    ncclComm_t comm = nullptr;
+    int n_ranks = 1;
+    int n_partial_blocks = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_staging = nullptr;
+    bool staging_busy = false;
+};
+
+namespace {
+
+int launch_expm(hb2_partition *p, const double *dQ, const int *d_dst, int n, int is_trans, const double *mix_w,
+                const int *mix_first, double *qres) {
+    if (n <= 0) return 0;
+    hb2::ExpmArgs a{dQ, d_dst, mix_w, mix_first, p->d_PT, qres, (int)p->D, is_trans};
+    switch (p->Dp) {
+        case 64: hb2::expm64_kernel<<<n, 256, 5 * 64 * hb2::LD64 * sizeof(double), p->stream>>>(a); break;
+        case 4: hb2::expm_small_kernel<4><<<n, 128, hb2::expm_small_smem_bytes(4), p->stream>>>(a); break;
+        case 8: hb2::expm_small_kernel<8><<<n, 128, hb2::expm_small_smem_bytes(8), p->stream>>>(a); break;
+        case 16: hb2::expm_small_kernel<16><<<n, 128, hb2::expm_small_smem_bytes(16), p->stream>>>(a); break;
+        case 24: hb2::expm_small_kernel<24><<<n, 128, hb2::expm_small_smem_bytes(24), p->stream>>>(a); break;
+        case 32: hb2::expm_small_kernel<32><<<n, 128, hb2::expm_small_smem_bytes(32), p->stream>>>(a); break;
+        default: return fail("unsupported padded state count %d", p->Dp);
+    }
+    p->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int launch_prune(hb2_partition *p, const hb2::PruneArgs &a, const int *d_jobs, int njobs, int ncls) {
+    if (njobs <= 0) return 0;
+    if (p->Dp == 64) {
+        dim3 grid((unsigned)(p->Sp / hb2::TILE_P), (unsigned)njobs, (unsigned)ncls);
+        hb2::prune64_kernel<<<grid, 256, 2 * 64 * hb2::LD64 * sizeof(double), p->stream>>>(a, d_jobs);
+    } else {
+        dim3 grid((unsigned)(p->Sp / 128), (unsigned)njobs, (unsigned)ncls);
+        switch (p->Dp) {
+            case 4: hb2::prune_small_kernel<4><<<grid, 128, 0, p->stream>>>(a, d_jobs); break;
+            case 8: hb2::prune_small_kernel<8><<<grid, 128, 0, p->stream>>>(a, d_jobs); break;
+            case 16: hb2::prune_small_kernel<16><<<grid, 128, 0, p->stream>>>(a, d_jobs); break;
+            case 24: hb2::prune_small_kernel<24><<<grid, 128, 0, p->stream>>>(a, d_jobs); break;
+            case 32: hb2::prune_small_kernel<32><<<grid, 128, 0, p->stream>>>(a, d_jobs); break;
+            default: return fail("unsupported padded state count %d", p->Dp);
+        }
+    }
+    p->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// Flush matrices handed over since the last evaluation: one H2D copy + one (or two) expm launches.
+int flush_matrices(hb2_partition *p) {
+    const int64_t n = p->n_pending;
+    if (n == 0) return 0;
+    const size_t dd = (size_t)p->D * p->D;
+    CU(cudaMemcpyAsync(p->d_Q, p->h_Q, n * dd * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CU(cudaMemcpyAsync(p->d_dst, p->h_dst, n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    // the pinned staging buffers are reused by the next hb2_set_matrices: it waits on this event (copies only)
+    CU(cudaEventRecord(p->ev_staging, p->stream));
+    p->staging_busy = true;
+    // pending entries are grouped by kind in runs; one launch per run.  Rate matrices also leave a resident copy
+    // in d_Qres (written by the kernel while it loads them) so a whole evaluation can be replayed on device.
+    int64_t i = 0;
+    while (i < n) {
+        int64_t j = i;
+        while (j < n && p->pending_kind[j] == p->pending_kind[i]) j++;
+        const int is_trans = p->pending_kind[i] == HB2_MATRIX_TRANS;
+        if (launch_expm(p, p->d_Q + i * dd, p->d_dst + i, (int)(j - i), is_trans, nullptr, nullptr, is_trans ? nullptr : p->d_Qres)) return 1;
+        i = j;
+    }
+    for (int64_t k = 0; k < n; k++) p->is_rate[p->h_dst[k]] = (p->pending_kind[k] == HB2_MATRIX_RATE);
+    p->n_pending = 0;
+    p->pending_kind.clear();
+    return 0;
+}
+
+int stage_matrix(hb2_partition *p, int64_t cat, int64_t node, const double *M, int kind) {
+    if (cat < 0) cat = 0;
+    if (cat >= p->C) return fail("rate class %lld out of range (C=%lld)", (long long)cat, (long long)p->C);
+    if (node < 0 || node >= p->B) return fail("node id %lld has no branch (valid 0..%lld)", (long long)node, (long long)p->B - 1);
+    if (kind != HB2_MATRIX_RATE && kind != HB2_MATRIX_TRANS) return fail("unknown matrix kind %d", kind);
+    if (p->n_pending == p->q_capacity) {
+        cudaSetDevice(p->device);
+        if (flush_matrices(p)) return 1;
+    }
+    if (p->staging_busy) {                    // previous flush's H2D copies must have left the pinned buffers
+        CU(cudaEventSynchronize(p->ev_staging));
+        p->staging_busy = false;
+    }
+    const size_t dd = (size_t)p->D * p->D;
+    memcpy(p->h_Q + p->n_pending * dd, M, dd * sizeof(double));
+    p->h_dst[p->n_pending] = (int)(cat * p->B + node);
+    p->pending_kind.push_back(kind);
+    p->have_matrix[cat * p->B + node] = 1;
+    p->n_pending++;
+    return 0;
+}
+
+// Build the per-level job lists for a set of dirty nodes (closure: parents of dirty nodes and all their ancestors).
+// update == nullptr => whole tree.  Returns levels[h] = internal indices at height h to recompute.
+int plan_levels(hb2_partition *p, int64_t nUpdate, const int64_t *update, std::vector<std::vector<int>> &levels) {
+    levels.assign(p->max_height + 1, {});
+    std::vector<char> dirty(p->I, 0);
+    if (update == nullptr || nUpdate < 0) {
+        std::fill(dirty.begin(), dirty.end(), 1);
+    } else {
+        for (int64_t k = 0; k < nUpdate; k++) {
+            int64_t n = update[k];
+            if (n < 0 || n >= p->L + p->I) return fail("updateNodes[%lld]=%lld out of range", (long long)k, (long long)n);
+            int64_t par = p->parents[n];
+            while (par >= 0 && !dirty[par]) {
+                dirty[par] = 1;
+                par = p->parents[p->L + par];
+            }
+        }
+    }
+    for (int64_t i = 0; i < p->I; i++)
+        if (dirty[i]) levels[p->height[i]].push_back((int)i);
+    return 0;
+}
+
+hb2::PruneArgs prune_args(hb2_partition *p, int cat0) {
+    hb2::PruneArgs a;
+    a.PT = p->d_PT; a.cond = p->d_cond; a.scal = p->d_scal; a.leaf = p->d_leaf; a.ambig = p->d_ambig; a.pi = p->d_pi;
+    a.rootL = p->d_rootL; a.rootE = p->d_rootE;
+    a.tree.child_start = p->d_child_start; a.tree.child_ids = p->d_child_ids;
+    a.L = (int)p->L; a.I = (int)p->I; a.B = (int)p->B; a.D = (int)p->D; a.Sp = (int)p->Sp; a.cat0 = cat0;
+    return a;
+}
+
+int run_pruning(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector<int>> &levels) {
+    // upload all job lists in one copy
+    int total = 0;
+    for (auto &lv : levels) total += (int)lv.size();
+    if (total == 0) return 0;
+    int off = 0;
+    for (auto &lv : levels) { std::copy(lv.begin(), lv.end(), p->h_jobs + off); off += (int)lv.size(); }
+    CU(cudaMemcpyAsync(p->d_jobs, p->h_jobs, total * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    hb2::PruneArgs a = prune_args(p, cat0);
+    off = 0;
+    for (auto &lv : levels) {
+        if (launch_prune(p, a, p->d_jobs + off, (int)lv.size(), ncls)) return 1;
+        off += (int)lv.size();
+    }
+    return 0;
+}
+
+int run_root(hb2_partition *p, int c0, int nc, bool use_weights, bool want_sites) {
+    CU(cudaMemsetAsync(p->d_flag, 0, sizeof(int), p->stream));
+    hb2::CombineArgs c;
+    c.rootL = p->d_rootL; c.rootE = p->d_rootE; c.weights = use_weights ? p->d_weights : nullptr; c.freq = p->d_freq;
+    c.partial = p->d_partial; c.flag = p->d_flag; c.siteL = want_sites ? p->d_siteL : nullptr;
+    c.siteScale = want_sites ? p->d_siteScale : nullptr;
+    c.Sp = (int)p->Sp; c.S = (int)p->S; c.c0 = c0; c.nc = nc;
+    hb2::combine_kernel<<<p->n_partial_blocks, 256, 0, p->stream>>>(c);
+    hb2::final_sum_kernel<<<1, 256, 0, p->stream>>>(p->d_partial, p->n_partial_blocks, p->d_flag, p->d_lnL);
+    p->launches += 2;
+    CU(cudaGetLastError());
+    if (p->comm) {
+        ncclResult_t r = g_nccl.AllReduce(p->d_lnL, p->d_lnL, 1, ncclDouble, ncclSum, p->comm, p->stream);
+        if (r != ncclSuccess) return fail("ncclAllReduce: %s", g_nccl.GetErrorString(r));
+    }
+    return 0;
+}
+
+int check_ready(hb2_partition *p, int c0, int nc) {
+    for (int c = c0; c < c0 + nc; c++)
+        for (int64_t b = 0; b < p->B; b++)
+            if (!p->have_matrix[c * p->B + b])
+                return fail("no matrix was ever set for rate class %d, node %lld", c, (long long)b);
+    return 0;
+}
+
+int evaluate_impl(hb2_partition *p, int c0, int nc, const double *weights, int64_t nUpdate, const int64_t *updateNodes,
+                  const double *rootFreqs, double *lnL, double *siteL, int64_t *siteScale) {
+    if (!p) return fail("null partition");
+    if (!rootFreqs || !lnL) return fail("rootFreqs and lnL must not be null");
+    CU(cudaSetDevice(p->device));
+    if (check_ready(p, c0, nc)) return 1;
+    if (flush_matrices(p)) return 1;
+    // small inputs: pi (padded) and class weights
+    double *hs = p->h_small;
+    for (int k = 0; k < p->Dp; k++) hs[k] = k < p->D ? rootFreqs[k] : 0.0;
+    if (weights) for (int c = 0; c < nc; c++) hs[p->Dp + c] = weights[c];
+    CU(cudaMemcpyAsync(p->d_pi, hs, p->Dp * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    if (weights) CU(cudaMemcpyAsync(p->d_weights, hs + p->Dp, nc * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    // classes never pruned before need the whole tree regardless of updateNodes (likefunc.cpp:10965-10967)
+    bool all = (updateNodes == nullptr || nUpdate < 0);
+    for (int c = c0; c < c0 + nc; c++) if (!p->evaluated_cat[c]) all = true;
+    std::vector<std::vector<int>> levels;
+    if (plan_levels(p, all ? -1 : nUpdate, all ? nullptr : updateNodes, levels)) return 1;
+    // the root must always be recomputed when anything changed; if nothing is dirty (only pi/weights changed)
+    // the root tile products are still valid but rootL depends on pi -> recompute the root node
+    bool any = false;
+    for (auto &lv : levels) any = any || !lv.empty();
+    if (!any) levels[p->height[p->I - 1]].push_back((int)p->I - 1);
+    if (run_pruning(p, c0, nc, levels)) return 1;
+    const bool want_sites = siteL != nullptr || siteScale != nullptr;
+    if (run_root(p, c0, nc, weights != nullptr, want_sites)) return 1;
+    CU(cudaMemcpyAsync(hs + p->Dp + p->C, p->d_lnL, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (siteL) CU(cudaMemcpyAsync(siteL, p->d_siteL, p->S * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (siteScale) CU(cudaMemcpyAsync(siteScale, p->d_siteScale, p->S * sizeof(long long), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    *lnL = hs[p->Dp + p->C];
+    for (int c = c0; c < c0 + nc; c++) p->evaluated_cat[c] = 1;
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int hb2_abi_version(void) { return HB2_ABI_VERSION; }
+const char *hb2_last_error(void) { return g_err.c_str(); }
+
+int hb2_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, int64_t C, const int64_t *flatParents,
+               const int64_t *leafState, const double *ambig, int64_t nAmb, const int64_t *patternFreq, int device,
+               int flags) {
+    if (!out) return fail("out is null");
+    *out = nullptr;
+    if (S <= 0 || D < 2 || L < 2 || I < 1 || C < 1) return fail("bad sizes S=%lld D=%lld L=%lld I=%lld C=%lld", (long long)S, (long long)D, (long long)L, (long long)I, (long long)C);
+    if (!flatParents || !leafState || !patternFreq) return fail("null input array");
+    if (nAmb > 0 && !ambig) return fail("nAmb > 0 but ambig is null");
+    const int Dp = pad_states(D);
+    if (Dp < 0) return fail("state count %lld not supported (max 64)", (long long)D);
+    int ndev = hb2_device_count();
+    if (ndev <= 0) return fail("no CUDA device visible: the B200 engine has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail("device %d out of range (%d visible)", device, ndev);
+    CU(cudaSetDevice(device));
+
+    hb2_partition *p = new hb2_partition();
+    p->device = device; p->flags = flags; p->S = S; p->D = D; p->L = L; p->I = I; p->C = C; p->B = L + I - 1; p->nAmb = nAmb;
+    p->Dp = Dp;
+    const int64_t tile = (Dp == 64) ? hb2::TILE_P : 128;
+    p->Sp = (S + tile - 1) / tile * tile;
+    p->parents.assign(flatParents, flatParents + L + I);
+    p->children.assign(I, {});
+    int roots = 0;
+    for (int64_t n = 0; n < L + I; n++) {
+        int64_t par = flatParents[n];
+        if (par == -1) { roots++; if (n != L + I - 1) { delete p; return fail("root must be the last node (found -1 parent at %lld)", (long long)n); } continue; }
+        if (par < 0 || par >= I) { delete p; return fail("flatParents[%lld]=%lld out of range", (long long)n, (long long)par); }
+        if (n >= L && par <= n - L) { delete p; return fail("internal nodes must be in post-order (node %lld has parent %lld)", (long long)n, (long long)par); }
+        p->children[par].push_back((int)n);
+    }
+    if (roots != 1) { delete p; return fail("tree must have exactly one root"); }
+    p->height.assign(I, 0);
+    for (int64_t i = 0; i < I; i++) {
+        if (p->children[i].empty()) { delete p; return fail("internal node %lld has no children", (long long)i); }
+        int h = 0;
+        for (int ch : p->children[i]) if (ch >= L) h = std::max(h, p->height[ch - L] + 1);
+        p->height[i] = h;
+        p->max_height = std::max(p->max_height, h);
+    }
+    for (int64_t k = 0; k < L * S; k++) {
+        int64_t c = leafState[k];
+        if (c >= D || c < -nAmb) { delete p; return fail("leafState[%lld]=%lld out of range", (long long)k, (long long)c); }
+    }
+#define CUP(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fail("%s failed: %s", #x, cudaGetErrorString(e_)); hb2_destroy(p); return 1; } } while (0)
+    CUP(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    for (auto &e : p->ev) CUP(cudaEventCreate(&e));
+    CUP(cudaEventCreateWithFlags(&p->ev_staging, cudaEventDisableTiming));
+    const size_t Sp = p->Sp, dpdp = (size_t)Dp * Dp, dd = (size_t)D * D;
+    CUP(cudaMalloc(&p->d_leaf, L * Sp * sizeof(int)));
+    CUP(cudaMalloc(&p->d_ambig, std::max<int64_t>(nAmb, 1) * Dp * sizeof(double)));
+    CUP(cudaMalloc(&p->d_freq, Sp * sizeof(double)));
+    CUP(cudaMalloc(&p->d_cond, (size_t)C * I * Sp * Dp * sizeof(double)));
+    CUP(cudaMalloc(&p->d_scal, (size_t)C * I * Sp * sizeof(int)));
+    CUP(cudaMalloc(&p->d_PT, (size_t)C * p->B * dpdp * sizeof(double)));
+    CUP(cudaMalloc(&p->d_Qres, (size_t)C * p->B * dd * sizeof(double)));
+    p->q_capacity = C * p->B;
+    CUP(cudaMalloc(&p->d_Q, (size_t)p->q_capacity * dd * sizeof(double)));
+    CUP(cudaMalloc(&p->d_dst, p->q_capacity * sizeof(int)));
+    CUP(cudaMalloc(&p->d_mix_w, p->q_capacity * sizeof(double)));
+    CUP(cudaMalloc(&p->d_mix_first, p->q_capacity * sizeof(int)));
+    CUP(cudaMalloc(&p->d_pi, Dp * sizeof(double)));
+    CUP(cudaMalloc(&p->d_rootL, (size_t)C * Sp * sizeof(double)));
+    CUP(cudaMalloc(&p->d_rootE, (size_t)C * Sp * sizeof(int)));
+    CUP(cudaMalloc(&p->d_weights, C * sizeof(double)));
+    p->n_partial_blocks = (int)((S + 255) / 256);
+    CUP(cudaMalloc(&p->d_partial, p->n_partial_blocks * sizeof(double)));
+    CUP(cudaMalloc(&p->d_lnL, sizeof(double)));
+    CUP(cudaMalloc(&p->d_flag, sizeof(int)));
+    CUP(cudaMalloc(&p->d_siteL, Sp * sizeof(double)));
+    CUP(cudaMalloc(&p->d_siteScale, Sp * sizeof(long long)));
+    CUP(cudaMalloc(&p->d_jobs, I * sizeof(int)));
+    CUP(cudaMalloc(&p->d_child_start, (I + 1) * sizeof(int)));
+    CUP(cudaMalloc(&p->d_child_ids, (L + I) * sizeof(int)));
+    CUP(cudaMallocHost(&p->h_Q, (size_t)p->q_capacity * dd * sizeof(double)));
+    CUP(cudaMallocHost(&p->h_dst, p->q_capacity * sizeof(int)));
+    CUP(cudaMallocHost(&p->h_small, (Dp + C + 8) * sizeof(double)));
+    CUP(cudaMallocHost(&p->h_jobs, I * sizeof(int)));
+    CUP(cudaMemsetAsync(p->d_cond, 0, (size_t)C * I * Sp * Dp * sizeof(double), p->stream));
+    CUP(cudaMemsetAsync(p->d_scal, 0, (size_t)C * I * Sp * sizeof(int), p->stream));
+    CUP(cudaMemsetAsync(p->d_PT, 0, (size_t)C * p->B * dpdp * sizeof(double), p->stream));
+    CUP(cudaMemsetAsync(p->d_rootL, 0, (size_t)C * Sp * sizeof(double), p->stream));
+    CUP(cudaMemsetAsync(p->d_rootE, 0, (size_t)C * Sp * sizeof(int), p->stream));
+    {   // static uploads (pageable host vectors: synchronous copies are fine at setup time)
+        std::vector<int> leaf((size_t)L * Sp, 0);          // padding patterns: state 0 everywhere, frequency 0
+        for (int64_t l = 0; l < L; l++)
+            for (int64_t s = 0; s < S; s++) leaf[l * Sp + s] = (int)leafState[l * S + s];
+        std::vector<double> amb((size_t)std::max<int64_t>(nAmb, 1) * Dp, 0.0);
+        for (int64_t a = 0; a < nAmb; a++)
+            for (int64_t k = 0; k < D; k++) amb[a * Dp + k] = ambig[a * D + k];
+        std::vector<double> fr(Sp, 0.0);
+        for (int64_t s = 0; s < S; s++) fr[s] = (double)patternFreq[s];
+        std::vector<int> cs(I + 1, 0), ci;
+        for (int64_t i = 0; i < I; i++) { cs[i] = (int)ci.size(); for (int ch : p->children[i]) ci.push_back(ch); }
+        cs[I] = (int)ci.size();
+        CUP(cudaStreamSynchronize(p->stream));
+        CUP(cudaMemcpy(p->d_leaf, leaf.data(), leaf.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CUP(cudaMemcpy(p->d_ambig, amb.data(), amb.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CUP(cudaMemcpy(p->d_freq, fr.data(), fr.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CUP(cudaMemcpy(p->d_child_start, cs.data(), cs.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CUP(cudaMemcpy(p->d_child_ids, ci.data(), ci.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (Dp == 32) CUP(cudaFuncSetAttribute(hb2::expm_small_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hb2::expm_small_smem_bytes(32)));
+    if (Dp == 64) {
+        CUP(cudaFuncSetAttribute(hb2::expm64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(5 * 64 * hb2::LD64 * sizeof(double))));
+        CUP(cudaFuncSetAttribute(hb2::prune64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 64 * hb2::LD64 * sizeof(double))));
+    }
+#undef CUP
+    p->have_matrix.assign(C * p->B, 0);
+    p->is_rate.assign(C * p->B, 0);
+    p->evaluated_cat.assign(C, 0);
+    *out = p;
+    return 0;
+}
+
+int hb2_set_matrices(hb2_partition *p, int64_t cat, int64_t n, const int64_t *nodeIds, const double *const *M, int kind) {
+    if (!p) return fail("null partition");
+    if (n < 0 || (n > 0 && (!nodeIds || !M))) return fail("bad matrix list");
+    for (int64_t k = 0; k < n; k++) {
+        if (!M[k]) return fail("matrix %lld is null", (long long)k);
+        if (stage_matrix(p, cat, nodeIds[k], M[k], kind)) return 1;
+    }
+    return 0;
+}
+
+int hb2_set_matrices_packed(hb2_partition *p, int64_t cat, int64_t n, const int64_t *nodeIds, const double *M, int kind) {
+    if (!p) return fail("null partition");
+    if (n < 0 || (n > 0 && (!nodeIds || !M))) return fail("bad matrix list");
+    const size_t dd = (size_t)p->D * p->D;
+    for (int64_t k = 0; k < n; k++)
+        if (stage_matrix(p, cat, nodeIds[k], M + k * dd, kind)) return 1;
+    return 0;
+}
+
+int hb2_set_mixture_matrices(hb2_partition *p, int64_t cat, int64_t n, const int64_t *nodeIds, int64_t K, const double *M,
+                             const double *w) {
+    if (!p) return fail("null partition");
+    if (n < 0 || K < 1 || (n > 0 && (!nodeIds || !M || !w))) return fail("bad mixture arguments");
+    if (cat < 0) cat = 0;
+    if (cat >= p->C) return fail("rate class %lld out of range", (long long)cat);
+    if (n > p->q_capacity) return fail("too many nodes");
+    CU(cudaSetDevice(p->device));
+    if (flush_matrices(p)) return 1;         // keep ordering with plain matrices staged earlier
+    const size_t dd = (size_t)p->D * p->D;
+    std::vector<double> hw(n);
+    std::vector<int> hf(n);
+    for (int64_t k = 0; k < K; k++) {        // one launch per component: components of a node accumulate in order
+        for (int64_t i = 0; i < n; i++) {
+            if (nodeIds[i] < 0 || nodeIds[i] >= p->B) return fail("node id %lld has no branch", (long long)nodeIds[i]);
+            memcpy(p->h_Q + i * dd, M + (i * K + k) * dd, dd * sizeof(double));
+            p->h_dst[i] = (int)(cat * p->B + nodeIds[i]);
+            hw[i] = w[i * K + k];
+            hf[i] = (k == 0);
+        }
+        CU(cudaMemcpyAsync(p->d_Q, p->h_Q, n * dd * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        CU(cudaMemcpyAsync(p->d_dst, p->h_dst, n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+        CU(cudaMemcpyAsync(p->d_mix_w, hw.data(), n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        CU(cudaMemcpyAsync(p->d_mix_first, hf.data(), n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+        if (launch_expm(p, p->d_Q, p->d_dst, (int)n, 0, p->d_mix_w, p->d_mix_first, nullptr)) return 1;
+        CU(cudaStreamSynchronize(p->stream));
+    }
+    for (int64_t i = 0; i < n; i++) { p->have_matrix[cat * p->B + nodeIds[i]] = 1; p->is_rate[cat * p->B + nodeIds[i]] = 0; }
+    return 0;
+}
+
+int hb2_evaluate(hb2_partition *p, int64_t cat, int64_t nUpdate, const int64_t *updateNodes, const double *rootFreqs,
+                 double *lnL, double *siteL, int64_t *siteScale) {
+    if (!p) return fail("null partition");
+    if (cat < 0) cat = 0;
+    if (cat >= p->C) return fail("rate class %lld out of range", (long long)cat);
+    return evaluate_impl(p, (int)cat, 1, nullptr, nUpdate, updateNodes, rootFreqs, lnL, siteL, siteScale);
+}
+
+int hb2_evaluate_classes(hb2_partition *p, const double *weights, int64_t nUpdate, const int64_t *updateNodes,
+                         const double *rootFreqs, double *lnL, double *siteL, int64_t *siteScale) {
+    if (!p) return fail("null partition");
+    if (!weights) return fail("weights must not be null");
+    return evaluate_impl(p, 0, (int)p->C, weights, nUpdate, updateNodes, rootFreqs, lnL, siteL, siteScale);
+}
+
+int hb2_read_conditionals(hb2_partition *p, int64_t cat, int64_t inode, double *cond, int32_t *exp2) {
+    if (!p || !cond || !exp2) return fail("null argument");
+    if (cat < 0) cat = 0;
+    if (cat >= p->C || inode < 0 || inode >= p->I) return fail("index out of range");
+    CU(cudaSetDevice(p->device));
+    std::vector<double> tmp((size_t)p->Sp * p->Dp);
+    std::vector<int> te(p->Sp);
+    CU(cudaStreamSynchronize(p->stream));
+    CU(cudaMemcpy(tmp.data(), p->d_cond + ((size_t)cat * p->I + inode) * p->Sp * p->Dp, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(te.data(), p->d_scal + ((size_t)cat * p->I + inode) * p->Sp, te.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int64_t s = 0; s < p->S; s++) {
+        for (int64_t k = 0; k < p->D; k++) cond[s * p->D + k] = tmp[s * p->Dp + k];
+        exp2[s] = te[s];
+    }
+    return 0;
+}
+
+int hb2_read_transition(hb2_partition *p, int64_t cat, int64_t node, double *P) {
+    if (!p || !P) return fail("null argument");
+    if (cat < 0) cat = 0;
+    if (cat >= p->C || node < 0 || node >= p->B) return fail("index out of range");
+    CU(cudaSetDevice(p->device));
+    if (flush_matrices(p)) return 1;
+    std::vector<double> tmp((size_t)p->Dp * p->Dp);
+    CU(cudaStreamSynchronize(p->stream));
+    CU(cudaMemcpy(tmp.data(), p->d_PT + ((size_t)cat * p->B + node) * p->Dp * p->Dp, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < p->D; i++)
+        for (int64_t j = 0; j < p->D; j++) P[i * p->D + j] = tmp[j * p->Dp + i];   // stored transposed
+    return 0;
+}
+
+int hb2_comm_unique_id(void *uniqueId128) {
+    if (!uniqueId128) return fail("null id buffer");
+    if (!g_nccl.load()) return fail("cannot load libnccl.so.2: %s", dlerror());
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail("ncclGetUniqueId: %s", g_nccl.GetErrorString(r));
+    memcpy(uniqueId128, &id, 128);
+    return 0;
+}
+
+int hb2_comm_init(hb2_partition *p, int nRanks, int rank, const void *uniqueId128) {
+    if (!p || !uniqueId128) return fail("null argument");
+    if (nRanks < 1 || rank < 0 || rank >= nRanks) return fail("bad rank %d of %d", rank, nRanks);
+    if (!g_nccl.load()) return fail("cannot load libnccl.so.2: %s", dlerror());
+    CU(cudaSetDevice(p->device));
+    ncclUniqueId id;
+    memcpy(&id, uniqueId128, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&p->comm, nRanks, id, rank);
+    if (r != ncclSuccess) { p->comm = nullptr; return fail("ncclCommInitRank: %s", g_nccl.GetErrorString(r)); }
+    p->n_ranks = nRanks;
+    return 0;
+}
+
+void hb2_destroy(hb2_partition *p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    if (p->comm) g_nccl.CommDestroy(p->comm);
+    void *dev[] = {p->d_leaf, p->d_scal, p->d_rootE, p->d_child_start, p->d_child_ids, p->d_jobs, p->d_dst, p->d_flag,
+                   p->d_mix_first, p->d_ambig, p->d_freq, p->d_cond, p->d_PT, p->d_Q, p->d_pi, p->d_rootL, p->d_weights,
+                   p->d_partial, p->d_lnL, p->d_siteL, p->d_mix_w, p->d_siteScale, p->d_Qres};
+    for (void *d : dev) if (d) cudaFree(d);
+    if (p->h_Q) cudaFreeHost(p->h_Q);
+    if (p->h_small) cudaFreeHost(p->h_small);
+    if (p->h_jobs) cudaFreeHost(p->h_jobs);
+    if (p->h_dst) cudaFreeHost(p->h_dst);
+    for (auto &e : p->ev) if (e) cudaEventDestroy(e);
+    if (p->ev_staging) cudaEventDestroy(p->ev_staging);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+int64_t hb2_launch_count(const hb2_partition *p) { return p ? p->launches : 0; }
+
+int hb2_time_resident(hb2_partition *p, const double *weights, const double *rootFreqs, int iters, double *msPerEval,
+                      double *stageMs, double *lnL) {
+    if (!p || !weights || !rootFreqs || !msPerEval) return fail("null argument");
+    if (iters < 1) return fail("iters must be >= 1");
+    CU(cudaSetDevice(p->device));
+    if (check_ready(p, 0, (int)p->C)) return 1;
+    if (flush_matrices(p)) return 1;
+    // every slot must hold a resident rate matrix so that the expm stage can be replayed
+    std::vector<int> dst;
+    for (int64_t k = 0; k < p->C * p->B; k++) {
+        if (!p->is_rate[k]) return fail("hb2_time_resident needs HB2_MATRIX_RATE matrices in every slot");
+        dst.push_back((int)k);
+    }
+    memcpy(p->h_dst, dst.data(), dst.size() * sizeof(int));
+    CU(cudaMemcpyAsync(p->d_dst, p->h_dst, dst.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    double *hs = p->h_small;
+    for (int k = 0; k < p->Dp; k++) hs[k] = k < p->D ? rootFreqs[k] : 0.0;
+    for (int c = 0; c < p->C; c++) hs[p->Dp + c] = weights[c];
+    CU(cudaMemcpyAsync(p->d_pi, hs, p->Dp * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CU(cudaMemcpyAsync(p->d_weights, hs + p->Dp, p->C * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    std::vector<std::vector<int>> levels;
+    if (plan_levels(p, -1, nullptr, levels)) return 1;
+    double tot = 0, st[3] = {0, 0, 0};
+    for (int it = 0; it < iters; it++) {
+        CU(cudaEventRecord(p->ev[0], p->stream));
+        if (launch_expm(p, p->d_Qres, p->d_dst, (int)dst.size(), 0, nullptr, nullptr, nullptr)) return 1;
+        CU(cudaEventRecord(p->ev[1], p->stream));
+        if (run_pruning(p, 0, (int)p->C, levels)) return 1;
+        CU(cudaEventRecord(p->ev[2], p->stream));
+        if (run_root(p, 0, (int)p->C, true, false)) return 1;
+        CU(cudaEventRecord(p->ev[3], p->stream));
+        CU(cudaEventSynchronize(p->ev[3]));
+        float a = 0, b = 0, c = 0;
+        CU(cudaEventElapsedTime(&a, p->ev[0], p->ev[1]));
+        CU(cudaEventElapsedTime(&b, p->ev[1], p->ev[2]));
+        CU(cudaEventElapsedTime(&c, p->ev[2], p->ev[3]));
+        st[0] += a; st[1] += b; st[2] += c; tot += a + b + c;
+    }
+    *msPerEval = tot / iters;
+    if (stageMs) for (int k = 0; k < 3; k++) stageMs[k] = st[k] / iters;
+    if (lnL) {
+        CU(cudaMemcpy(lnL, p->d_lnL, sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    for (int c = 0; c < p->C; c++) p->evaluated_cat[c] = 1;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,603 @@
+// hb2_kernels_fp64.cuh -- fp64 CUDA kernels of the likelihood hot path (sm_100a).
+//
+//   expm64_kernel / expm_small_kernel   P = exp(Q t) per (branch, rate class), one CTA per matrix
+//                                       (replaces _Matrix::Exponentiate, reference matrix.cpp:5537-5951)
+//   prune64_kernel / prune_small_kernel fused Felsenstein update of one internal node for a tile of patterns:
+//                                       all children folded (leaf column gather, ambiguity mat-vec, internal
+//                                       contraction), per-pattern renormalisation, root pi-dot
+//                                       (replaces ComputeTreeBlockByBranch, reference tree_evaluator.cpp:3556-4171)
+//   combine_kernel / final_sum_kernel   rate-class mixture, log, pattern-frequency weighting, deterministic sum
+//                                       (replaces likefunc2.cpp:828-859,1446-1506 and tree_evaluator.cpp:4093-4149)
+//
+// Device data layout (Dp = padded state count, Sp = pattern count padded to 64):
+//   PT    [C][B][Dp][Dp]   TRANSPOSED transition matrices: PT[j][k] = P(parent k -> child j); padding = 0
+//   cond  [C][I][Sp][Dp]   conditionals of internal nodes, renormalised per (node, pattern) so max_k = [0.5,1)
+//   scal  [C][I][Sp]       int32 binary exponent: true conditional = cond * 2^scal
+//   leaf  [L][Sp]          int32 state code (>=0) or -(ambiguity row + 1)
+//   ambig [nAmb][Dp]       0/1 rows
+// Underflow handling is the engine's own (exact power-of-two renormalisation at every node) and is converted to the
+// reference's 2^64-count convention only at the boundary (last bullet).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace hb2 {
+
+constexpr int TILE_P = 64;          // patterns per CTA in the 64-state kernel
+constexpr int LD64 = 66;            // smem leading dimension (doubles) for 64x64 operands: conflict-free row pairs
+
+struct TreeDev {
+    const int *child_start;         // [I+1]
+    const int *child_ids;           // flat node ids of the children of each internal node
+};
+
+struct PruneArgs {
+    const double *PT;               // [C][B][Dp*Dp]
+    double *cond;                   // [C][I][Sp][Dp]
+    int *scal;                      // [C][I][Sp]
+    const int *leaf;                // [L][Sp]
+    const double *ambig;            // [nAmb][Dp]
+    const double *pi;               // [Dp] root frequencies (padding 0)
+    double *rootL;                  // [C][Sp]
+    int *rootE;                     // [C][Sp]
+    TreeDev tree;
+    int L, I, B, D, Sp, cat0;
+};
+
+__device__ __forceinline__ double exp2i(int e) {   // exact 2^e for |e| < 1022
+    return __longlong_as_double((long long)(e + 1023) << 52);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 64x64x64 fp64 tile product, 256 threads, each thread owns a 4x4 block of C:
+//   acc[i][j] += sum_k A[(4*ty+i)*LD64 + k] * B[k*LD64 + 4*tx + j]
+// A rows are read as broadcasts (two distinct rows per warp, 16 banks apart thanks to LD64), B as 32-byte vectors.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_mm64(const double *__restrict__ A, const double *__restrict__ Bm,
+                                          int tx, int ty, double (&acc)[4][4]) {
+    const double *a0 = A + (4 * ty) * LD64;
+    const double *b0 = Bm + 4 * tx;
+#pragma unroll 4
+    for (int k = 0; k < 64; k += 2) {
+        double2 a[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const double2 *>(a0 + i * LD64 + k);
+        double2 b00 = *reinterpret_cast<const double2 *>(b0 + k * LD64);
+        double2 b01 = *reinterpret_cast<const double2 *>(b0 + k * LD64 + 2);
+        double2 b10 = *reinterpret_cast<const double2 *>(b0 + (k + 1) * LD64);
+        double2 b11 = *reinterpret_cast<const double2 *>(b0 + (k + 1) * LD64 + 2);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            acc[i][0] = fma(a[i].x, b00.x, acc[i][0]);
+            acc[i][1] = fma(a[i].x, b00.y, acc[i][1]);
+            acc[i][2] = fma(a[i].x, b01.x, acc[i][2]);
+            acc[i][3] = fma(a[i].x, b01.y, acc[i][3]);
+            acc[i][0] = fma(a[i].y, b10.x, acc[i][0]);
+            acc[i][1] = fma(a[i].y, b10.y, acc[i][1]);
+            acc[i][2] = fma(a[i].y, b11.x, acc[i][2]);
+            acc[i][3] = fma(a[i].y, b11.y, acc[i][3]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Matrix exponential, 64-padded states.  One CTA (256 threads) per matrix.
+//   in : Q [n][D*D] row-major rate matrices (Q*t, diagonal = -rowsum), dst[n] = slot index into PT
+//   out: PT[slot] = exp(Q)^T with padding rows/cols zeroed, negatives clamped, columns repaired to sum to 1
+// Algorithm (engine's own, same result as the reference's Taylor+squaring to ~1e-15): scale by 2^-s so that
+// ||A||_inf <= 1, degree-15 Taylor polynomial by Paterson-Stockmeyer with A^2,A^3,A^4 (6 products), s squarings.
+// mix_w != nullptr: PT[slot] (+)= w * result, used for explicit-form mixtures (sum_k w_k Exp(Q_k)).
+// ------------------------------------------------------------------------------------------------
+struct ExpmArgs {
+    const double *Q;        // [n][D*D]
+    const int *dst;         // [n]
+    const double *mix_w;    // nullable [n]
+    const int *mix_first;   // nullable [n]: 1 => overwrite, 0 => accumulate
+    double *PT;
+    double *Qres;           // nullable [slots][D*D]: resident copy of the rate matrices, written while loading
+    int D;
+    int is_trans;           // 1: input already a transition matrix -> just transpose/pad
+};
+
+__device__ __forceinline__ double taylor_c(int k) {
+    const double c[16] = {1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
+                          1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0, 1.0 / 87178291200.0,
+                          1.0 / 1307674368000.0};
+    return c[k];
+}
+
+__global__ void __launch_bounds__(256, 1) expm64_kernel(ExpmArgs a) {
+    extern __shared__ __align__(16) double sm[];
+    double *A1 = sm, *A2 = A1 + 64 * LD64, *A3 = A2 + 64 * LD64, *A4 = A3 + 64 * LD64, *R = A4 + 64 * LD64;
+    __shared__ double red[64];
+    __shared__ int s_shift;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int D = a.D;
+    const double *Q = a.Q + (size_t)blockIdx.x * D * D;
+    double *out = a.PT + (size_t)a.dst[blockIdx.x] * 4096;
+
+    // load transposed + zero padded: A1[j][i] = Q[i][j]
+    for (int idx = tid; idx < 64 * 64; idx += 256) {
+        int i = idx >> 6, j = idx & 63;
+        double v = (i < D && j < D) ? Q[(size_t)i * D + j] : 0.0;
+        A1[j * LD64 + i] = v;
+        if (a.Qres && i < D && j < D) a.Qres[(size_t)a.dst[blockIdx.x] * D * D + (size_t)i * D + j] = v;
+    }
+    __syncthreads();
+    if (a.is_trans) {
+        for (int idx = tid; idx < 4096; idx += 256) out[idx] = A1[(idx >> 6) * LD64 + (idx & 63)];
+        return;
+    }
+    // ||A||_1 of A^T == ||Q||_inf: max over columns i of sum_j |A1[j][i]|
+    if (tid < 64) {
+        double s = 0.0;
+        for (int j = 0; j < 64; j++) s += fabs(A1[j * LD64 + tid]);
+        red[tid] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double m = 0.0;
+        bool bad = false;
+        for (int i = 0; i < 64; i++) { if (!(red[i] == red[i]) || isinf(red[i])) bad = true; m = fmax(m, red[i]); }
+        int e = 0;
+        if (m > 0.0) frexp(m, &e);
+        s_shift = bad ? -1 : max(e, 0);
+    }
+    __syncthreads();
+    const int shift = s_shift;
+    if (shift < 0 || shift > 900) {           // NaN/inf or absurd rates: propagate NaN (host sees NaN lnL)
+        for (int idx = tid; idx < 4096; idx += 256) out[idx] = __longlong_as_double(0x7ff8000000000000LL);
+        return;
+    }
+    if (shift > 0) {
+        const double sc = exp2i(-shift);
+        for (int idx = tid; idx < 64 * 64; idx += 256) A1[(idx >> 6) * LD64 + (idx & 63)] *= sc;
+        __syncthreads();
+    }
+    double acc[4][4];
+    auto zero = [&]() {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+    };
+    auto store = [&](double *M) {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j += 2)
+                *reinterpret_cast<double2 *>(M + (4 * ty + i) * LD64 + 4 * tx + j) = make_double2(acc[i][j], acc[i][j + 1]);
+    };
+    zero(); tile_mm64(A1, A1, tx, ty, acc); store(A2);
+    __syncthreads();
+    zero(); tile_mm64(A2, A1, tx, ty, acc); store(A3);
+    zero(); tile_mm64(A2, A2, tx, ty, acc); store(A4);
+    // R = B3 = c12 I + c13 A + c14 A2 + c15 A3
+    auto poly_block = [&](int q, int i, int j) -> double {
+        int r = 4 * ty + i, c = 4 * tx + j, o = r * LD64 + c;
+        double v = taylor_c(4 * q + 1) * A1[o] + taylor_c(4 * q + 2) * A2[o];
+        if (r == c) v += taylor_c(4 * q);
+        return v;   // the A3 term is added by the caller after the barrier that publishes A3
+    };
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int o = (4 * ty + i) * LD64 + 4 * tx + j;
+            R[o] = poly_block(3, i, j) + taylor_c(15) * A3[o];
+        }
+    __syncthreads();
+    for (int q = 2; q >= 0; q--) {               // R = R*A4 + B_q   (all matrices are polynomials in A: they commute)
+        zero(); tile_mm64(R, A4, tx, ty, acc);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int o = (4 * ty + i) * LD64 + 4 * tx + j;
+                R[o] = acc[i][j] + poly_block(q, i, j) + taylor_c(4 * q + 3) * A3[o];
+            }
+        __syncthreads();
+    }
+    for (int s = 0; s < shift; s++) {            // squarings
+        zero(); tile_mm64(R, R, tx, ty, acc);
+        __syncthreads();
+        store(R);
+        __syncthreads();
+    }
+    // clamp negatives, zero the padding, repair: column k of PT (= row k of P) must sum to 1
+    for (int idx = tid; idx < 64 * 64; idx += 256) {
+        int j = idx >> 6, k = idx & 63;
+        double v = R[j * LD64 + k];
+        if (j >= D || k >= D) v = 0.0; else if (v < 0.0) v = 0.0;
+        R[j * LD64 + k] = v;
+    }
+    __syncthreads();
+    if (tid < 64) {
+        double s = 0.0;
+        for (int j = 0; j < 64; j++) if (j != tid) s += R[j * LD64 + tid];
+        if (tid < D) R[tid * LD64 + tid] = fmax(1.0 - s, 0.0);
+    }
+    __syncthreads();
+    if (a.mix_w) {
+        const double w = a.mix_w[blockIdx.x];
+        const bool first = a.mix_first[blockIdx.x] != 0;
+        for (int idx = tid; idx < 4096; idx += 256) {
+            double v = w * R[(idx >> 6) * LD64 + (idx & 63)];
+            out[idx] = first ? v : out[idx] + v;
+        }
+    } else {
+        for (int idx = tid; idx < 4096; idx += 256) out[idx] = R[(idx >> 6) * LD64 + (idx & 63)];
+    }
+}
+
+// Small state spaces (Dp <= 32): one CTA of 128 threads per matrix, plain shared-memory products.
+constexpr size_t expm_small_smem_bytes(int DP) { return (size_t)6 * DP * (DP + 1) * sizeof(double); }
+template <int DP>
+__global__ void __launch_bounds__(128) expm_small_kernel(ExpmArgs a) {
+    constexpr int LD = DP + 1;
+    extern __shared__ __align__(16) double sm[];          // 6 matrices of DP*LD doubles (expm_small_smem_bytes)
+    double *A1 = sm, *A2 = A1 + DP * LD, *A3 = A2 + DP * LD, *A4 = A3 + DP * LD, *R = A4 + DP * LD, *T = R + DP * LD;
+    __shared__ double red[DP];
+    __shared__ int s_shift;
+    const int tid = threadIdx.x, D = a.D;
+    const double *Q = a.Q + (size_t)blockIdx.x * D * D;
+    double *out = a.PT + (size_t)a.dst[blockIdx.x] * DP * DP;
+    for (int idx = tid; idx < DP * DP; idx += 128) {
+        int i = idx / DP, j = idx % DP;
+        const double v = (i < D && j < D) ? Q[(size_t)i * D + j] : 0.0;
+        A1[j * LD + i] = v;
+        if (a.Qres && i < D && j < D) a.Qres[(size_t)a.dst[blockIdx.x] * D * D + (size_t)i * D + j] = v;
+    }
+    __syncthreads();
+    if (a.is_trans) {
+        for (int idx = tid; idx < DP * DP; idx += 128) out[idx] = A1[(idx / DP) * LD + idx % DP];
+        return;
+    }
+    if (tid < DP) {
+        double s = 0.0;
+        for (int j = 0; j < DP; j++) s += fabs(A1[j * LD + tid]);
+        red[tid] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double m = 0.0; bool bad = false;
+        for (int i = 0; i < DP; i++) { if (!(red[i] == red[i]) || isinf(red[i])) bad = true; m = fmax(m, red[i]); }
+        int e = 0;
+        if (m > 0.0) frexp(m, &e);
+        s_shift = bad ? -1 : max(e, 0);
+    }
+    __syncthreads();
+    const int shift = s_shift;
+    if (shift < 0 || shift > 900) {
+        for (int idx = tid; idx < DP * DP; idx += 128) out[idx] = __longlong_as_double(0x7ff8000000000000LL);
+        return;
+    }
+    if (shift > 0) {
+        const double sc = exp2i(-shift);
+        for (int idx = tid; idx < DP * DP; idx += 128) A1[(idx / DP) * LD + idx % DP] *= sc;
+        __syncthreads();
+    }
+    auto mm = [&](double *Cm, const double *X, const double *Y) {      // Cm = X*Y (Cm distinct from X,Y)
+        for (int idx = tid; idx < DP * DP; idx += 128) {
+            int r = idx / DP, c = idx % DP;
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < DP; k++) s = fma(X[r * LD + k], Y[k * LD + c], s);
+            Cm[r * LD + c] = s;
+        }
+        __syncthreads();
+    };
+    mm(A2, A1, A1); mm(A3, A2, A1); mm(A4, A2, A2);
+    auto poly = [&](int q, int r, int c) -> double {
+        int o = r * LD + c;
+        double v = taylor_c(4 * q + 1) * A1[o] + taylor_c(4 * q + 2) * A2[o] + taylor_c(4 * q + 3) * A3[o];
+        if (r == c) v += taylor_c(4 * q);
+        return v;
+    };
+    for (int idx = tid; idx < DP * DP; idx += 128) R[(idx / DP) * LD + idx % DP] = poly(3, idx / DP, idx % DP);
+    __syncthreads();
+    for (int q = 2; q >= 0; q--) {
+        mm(T, R, A4);
+        for (int idx = tid; idx < DP * DP; idx += 128) { int r = idx / DP, c = idx % DP; R[r * LD + c] = T[r * LD + c] + poly(q, r, c); }
+        __syncthreads();
+    }
+    for (int s = 0; s < shift; s++) {
+        mm(T, R, R);
+        for (int idx = tid; idx < DP * DP; idx += 128) { int o = (idx / DP) * LD + idx % DP; R[o] = T[o]; }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < DP * DP; idx += 128) {
+        int j = idx / DP, k = idx % DP;
+        double v = R[j * LD + k];
+        if (j >= D || k >= D) v = 0.0; else if (v < 0.0) v = 0.0;
+        R[j * LD + k] = v;
+    }
+    __syncthreads();
+    if (tid < DP) {
+        double s = 0.0;
+        for (int j = 0; j < DP; j++) if (j != tid) s += R[j * LD + tid];
+        if (tid < D) R[tid * LD + tid] = fmax(1.0 - s, 0.0);
+    }
+    __syncthreads();
+    if (a.mix_w) {
+        const double w = a.mix_w[blockIdx.x];
+        const bool first = a.mix_first[blockIdx.x] != 0;
+        for (int idx = tid; idx < DP * DP; idx += 128) {
+            double v = w * R[(idx / DP) * LD + idx % DP];
+            out[idx] = first ? v : out[idx] + v;
+        }
+    } else {
+        for (int idx = tid; idx < DP * DP; idx += 128) out[idx] = R[(idx / DP) * LD + idx % DP];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused pruning update, 33..64 states (codon models), fp64.
+// grid = (Sp/64, jobs, classes); block = 256 threads as a 16x16 grid, thread (tx,ty) owns patterns 4ty..4ty+3
+// and parent states 4tx..4tx+3 of the tile.  jobs[blockIdx.y] = internal index of the parent to (re)compute.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2) prune64_kernel(PruneArgs a, const int *__restrict__ jobs) {
+    extern __shared__ __align__(16) double sm[];
+    double *Xs = sm;                    // [64][LD64] child conditionals (pattern-major)
+    double *Ps = sm + 64 * LD64;        // [64][LD64] PT of the child's branch
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int par = jobs[blockIdx.y];
+    const int cat = a.cat0 + blockIdx.z;
+    const int s0 = blockIdx.x * TILE_P;
+    const size_t Sp = a.Sp;
+    double v[4][4];
+    int ex[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        ex[i] = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[i][j] = 1.0;
+    }
+    const int c_begin = a.tree.child_start[par], c_end = a.tree.child_start[par + 1];
+    for (int ci = c_begin; ci < c_end; ci++) {
+        const int child = a.tree.child_ids[ci];
+        const double *PT = a.PT + ((size_t)cat * a.B + child) * 4096;
+        if (child < a.L) {
+            // leaf: column gather PT[state][k]; ambiguous: sum_j amb[j] PT[j][k]
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int code = a.leaf[(size_t)child * Sp + s0 + 4 * ty + i];
+                double m0, m1, m2, m3;
+                if (code >= 0) {
+                    const double2 *p = reinterpret_cast<const double2 *>(PT + (size_t)code * 64 + 4 * tx);
+                    double2 q0 = __ldg(p), q1 = __ldg(p + 1);
+                    m0 = q0.x; m1 = q0.y; m2 = q1.x; m3 = q1.y;
+                } else {
+                    const double *amb = a.ambig + (size_t)(-code - 1) * 64;
+                    m0 = m1 = m2 = m3 = 0.0;
+                    for (int j = 0; j < a.D; j++) {
+                        const double w = __ldg(amb + j);
+                        if (w != 0.0) {
+                            const double2 *p = reinterpret_cast<const double2 *>(PT + (size_t)j * 64 + 4 * tx);
+                            double2 q0 = __ldg(p), q1 = __ldg(p + 1);
+                            m0 = fma(w, q0.x, m0); m1 = fma(w, q0.y, m1); m2 = fma(w, q1.x, m2); m3 = fma(w, q1.y, m3);
+                        }
+                    }
+                }
+                v[i][0] *= m0; v[i][1] *= m1; v[i][2] *= m2; v[i][3] *= m3;
+            }
+        } else {
+            const int cin = child - a.L;
+            const double *X = a.cond + (((size_t)cat * a.I + cin) * Sp + s0) * 64;
+            __syncthreads();            // previous child's tiles fully consumed
+            for (int idx = tid; idx < 2048; idx += 256) {       // 4096 doubles as double2, coalesced
+                const int r = idx >> 5, c2 = (idx & 31) * 2;
+                *reinterpret_cast<double2 *>(Xs + r * LD64 + c2) = *reinterpret_cast<const double2 *>(X + r * 64 + c2);
+                *reinterpret_cast<double2 *>(Ps + r * LD64 + c2) = __ldg(reinterpret_cast<const double2 *>(PT + r * 64 + c2));
+            }
+            __syncthreads();
+            double acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+            tile_mm64(Xs, Ps, tx, ty, acc);
+            const int *sc = a.scal + ((size_t)cat * a.I + cin) * Sp + s0 + 4 * ty;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                ex[i] += sc[i];
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[i][j] *= acc[i][j];
+            }
+        }
+    }
+    // per-pattern renormalisation: exact power of two so that max_k lands in [0.5, 1)
+    const bool is_root = (par == a.I - 1);
+    double *outp = a.cond + (((size_t)cat * a.I + par) * Sp + s0) * 64;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        double m = fmax(fmax(v[i][0], v[i][1]), fmax(v[i][2], v[i][3]));
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        int e = 0;
+        if (m > 0.0 && m < INFINITY) {
+            e = ilogb(m) + 1;
+            const double s1 = exp2i(-(e / 2)), s2 = exp2i(-(e - e / 2));   // two steps: |e| may exceed 1022
+#pragma unroll
+            for (int j = 0; j < 4; j++) v[i][j] = v[i][j] * s1 * s2;
+        }
+        ex[i] += e;
+        const int row = 4 * ty + i;
+        *reinterpret_cast<double2 *>(outp + (size_t)row * 64 + 4 * tx) = make_double2(v[i][0], v[i][1]);
+        *reinterpret_cast<double2 *>(outp + (size_t)row * 64 + 4 * tx + 2) = make_double2(v[i][2], v[i][3]);
+        if (tx == 0) a.scal[((size_t)cat * a.I + par) * Sp + s0 + row] = ex[i];
+        if (is_root) {
+            double r = v[i][0] * a.pi[4 * tx] + v[i][1] * a.pi[4 * tx + 1] + v[i][2] * a.pi[4 * tx + 2] + v[i][3] * a.pi[4 * tx + 3];
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+            if (tx == 0) {
+                a.rootL[(size_t)cat * Sp + s0 + row] = r;
+                a.rootE[(size_t)cat * Sp + s0 + row] = ex[i];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused pruning update for small state spaces (Dp in {4,8,16,24,32}): one thread per pattern.
+// grid = (Sp/128, jobs, classes), block = 128.  PT of each child is staged in shared memory (broadcast reads).
+// ------------------------------------------------------------------------------------------------
+template <int DP>
+__global__ void __launch_bounds__(128) prune_small_kernel(PruneArgs a, const int *__restrict__ jobs) {
+    __shared__ double Ps[DP * DP];
+    const int tid = threadIdx.x;
+    const int par = jobs[blockIdx.y];
+    const int cat = a.cat0 + blockIdx.z;
+    const size_t Sp = a.Sp;
+    const size_t s = (size_t)blockIdx.x * 128 + tid;       // Sp is a multiple of 128 for the small kernels
+    double v[DP];
+#pragma unroll
+    for (int k = 0; k < DP; k++) v[k] = 1.0;
+    int ex = 0;
+    const int c_begin = a.tree.child_start[par], c_end = a.tree.child_start[par + 1];
+    for (int ci = c_begin; ci < c_end; ci++) {
+        const int child = a.tree.child_ids[ci];
+        const double *PT = a.PT + ((size_t)cat * a.B + child) * DP * DP;
+        __syncthreads();
+        for (int idx = tid; idx < DP * DP; idx += 128) Ps[idx] = __ldg(PT + idx);
+        __syncthreads();
+        if (child < a.L) {
+            const int code = a.leaf[(size_t)child * Sp + s];
+            if (code >= 0) {
+#pragma unroll
+                for (int k = 0; k < DP; k++) v[k] *= Ps[code * DP + k];
+            } else {
+                const double *amb = a.ambig + (size_t)(-code - 1) * DP;
+                double acc[DP];
+#pragma unroll
+                for (int k = 0; k < DP; k++) acc[k] = 0.0;
+                for (int j = 0; j < a.D; j++) {
+                    const double w = __ldg(amb + j);
+#pragma unroll
+                    for (int k = 0; k < DP; k++) acc[k] = fma(w, Ps[j * DP + k], acc[k]);
+                }
+#pragma unroll
+                for (int k = 0; k < DP; k++) v[k] *= acc[k];
+            }
+        } else {
+            const int cin = child - a.L;
+            const double *X = a.cond + (((size_t)cat * a.I + cin) * Sp + s) * DP;
+            double acc[DP];
+#pragma unroll
+            for (int k = 0; k < DP; k++) acc[k] = 0.0;
+#pragma unroll
+            for (int j = 0; j < DP; j += 2) {
+                const double2 x = *reinterpret_cast<const double2 *>(X + j);
+#pragma unroll
+                for (int k = 0; k < DP; k++) acc[k] = fma(x.x, Ps[j * DP + k], acc[k]);
+#pragma unroll
+                for (int k = 0; k < DP; k++) acc[k] = fma(x.y, Ps[(j + 1) * DP + k], acc[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < DP; k++) v[k] *= acc[k];
+            ex += a.scal[((size_t)cat * a.I + cin) * Sp + s];
+        }
+    }
+    double m = 0.0;
+#pragma unroll
+    for (int k = 0; k < DP; k++) m = fmax(m, v[k]);
+    if (m > 0.0 && m < INFINITY) {
+        const int e = ilogb(m) + 1;
+        const double s1 = exp2i(-(e / 2)), s2 = exp2i(-(e - e / 2));
+#pragma unroll
+        for (int k = 0; k < DP; k++) v[k] = v[k] * s1 * s2;
+        ex += e;
+    }
+    double *outp = a.cond + (((size_t)cat * a.I + par) * Sp + s) * DP;
+#pragma unroll
+    for (int k = 0; k < DP; k += 2) *reinterpret_cast<double2 *>(outp + k) = make_double2(v[k], v[k + 1]);
+    a.scal[((size_t)cat * a.I + par) * Sp + s] = ex;
+    if (par == a.I - 1) {
+        double r = 0.0;
+#pragma unroll
+        for (int k = 0; k < DP; k++) r = fma(v[k], a.pi[k], r);
+        a.rootL[(size_t)cat * Sp + s] = r;
+        a.rootE[(size_t)cat * Sp + s] = ex;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Root reduction: rate-class mixture + log + pattern frequency + block partial sums.
+//   L_s = sum_c w_c * rootL[c][s] * 2^(rootE[c][s]);  lnL_s = log(sum_c w_c rootL 2^(e_c-emax)) + emax ln2
+// Optional per-pattern outputs in the reference's convention: siteL * 2^(-64*siteScale).
+// partial[block] = sum over the block's patterns of freq*lnL_s (tree reduction, deterministic);
+// flag[0] |= 1 if any pattern with freq>0 has L <= 0.
+// ------------------------------------------------------------------------------------------------
+struct CombineArgs {
+    const double *rootL; const int *rootE; const double *weights; const double *freq;
+    double *partial; int *flag; double *siteL; long long *siteScale;
+    int Sp, S, c0, nc;
+};
+
+__global__ void __launch_bounds__(256) combine_kernel(CombineArgs a) {
+    __shared__ double red[256];
+    const int s = blockIdx.x * 256 + threadIdx.x;
+    double term = 0.0;
+    if (s < a.S) {
+        int emax = INT_MIN;
+        for (int c = 0; c < a.nc; c++) {
+            const double l = a.rootL[(size_t)(a.c0 + c) * a.Sp + s];
+            if (l > 0.0) emax = max(emax, a.rootE[(size_t)(a.c0 + c) * a.Sp + s]);
+        }
+        double sum = 0.0;
+        bool nan_seen = false;
+        for (int c = 0; c < a.nc; c++) {
+            const double l = a.rootL[(size_t)(a.c0 + c) * a.Sp + s];
+            const double w = a.weights ? a.weights[c] : 1.0;
+            if (l != l) nan_seen = true;
+            if (l > 0.0) {
+                const int de = a.rootE[(size_t)(a.c0 + c) * a.Sp + s] - emax;       // <= 0
+                sum += w * l * (de < -1000 ? 0.0 : exp2i(de));
+            }
+        }
+        if (nan_seen) sum = __longlong_as_double(0x7ff8000000000000LL);
+        if (emax == INT_MIN) emax = 0;
+        const double f = a.freq[s];
+        double lnl;
+        if (sum > 0.0) lnl = log(sum) + (double)emax * 0.693147180559945309417232121458;
+        else if (sum != sum) lnl = sum;
+        else { lnl = -INFINITY; if (f > 0.0) atomicOr(a.flag, 1); }
+        term = (f > 0.0) ? f * lnl : 0.0;
+        if (a.siteL) {
+            // reference convention: L_true = siteL * 2^(-64*count); keep siteL in (2^-64, 1]
+            long long cnt = 0; double outL = sum;
+            if (sum > 0.0) {
+                int e2 = emax;                       // L_true = sum * 2^e2
+                cnt = (e2 < 0) ? (long long)((-e2) / 64) : -(long long)((e2 + 63) / 64);
+                const int rem = e2 + (int)(64 * cnt);    // in (-64, 0]
+                outL = sum * exp2i(rem);
+            }
+            a.siteL[s] = outL; a.siteScale[s] = cnt;
+        }
+    }
+    red[threadIdx.x] = term;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) a.partial[blockIdx.x] = red[0];
+}
+
+__global__ void __launch_bounds__(256) final_sum_kernel(const double *partial, int n, const int *flag, double *out) {
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s += partial[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = (*flag) ? -INFINITY : red[0];
+}
+
+}  // namespace hb2

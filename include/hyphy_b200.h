@@ -1,0 +1,118 @@
+/*
+ * hyphy_b200.h -- C ABI of the B200-native phylogenetic-likelihood engine (libhyphy_b200.so).
+ *
+ * This is the drop-in boundary behind the reference's `_LikelihoodFunction::ComputeBlock`
+ * (veg/hyphy src/core/likefunc.cpp:10783-11289).  The reference has no plugin interface for its evaluator; the
+ * only precedent is the dormant `#ifdef MDSOCL` trio (construct in SetupLFCaches likefunc.cpp:4182-4184, init
+ * :4313-4316, destroy :10546-10551).  The entry points below are what a maintainer binds at those three places
+ * (INTEGRATION.md shows the patch).  Plain pointers and sizes only; no C++/torch types cross this line.
+ *
+ * Conventions (all follow the reference so host arrays can be passed unmodified):
+ *   - nodes: 0..L-1 leaves in post-order, L..L+I-1 internal nodes in post-order, root = L+I-1;
+ *     flatParents[node] = parent's INTERNAL index (0..I-1), root = -1        (tree.cpp:722-766, tree.h:336)
+ *   - leafState[l*S + s]: original pattern order; >=0 state index, <0 -> ambiguity row -(code+1)
+ *                                                                            (likefunc.cpp:4265-4308)
+ *   - matrices: D*D row-major doubles, row = parent(from) state, column = child(to) state
+ *                                                                            (tree_evaluator.cpp:232,3674)
+ *   - per-pattern results use the reference's scaler convention L_true = L * 2^(-64*count)
+ *                                                                            (likefunc2.cpp:828-859,1484-1506)
+ *   - errors: every call returns 0 on success, nonzero on failure (hb2_last_error() has the text).  There is NO
+ *     CPU fallback: a missing GPU makes hb2_create fail and the host must treat that as fatal
+ *     (HandleApplicationError, global_things.cpp:787).  Numerical failures are value-encoded exactly like
+ *     tree_evaluator.cpp:4094-4148: lnL = -inf when a pattern has likelihood <= 0, NaN is propagated.
+ *   - threading: one host thread per partition handle at a time (ComputeBlock is entered from the single
+ *     interpreter thread; OpenMP lives inside it).  Calls block until the result is on the host.
+ */
+#ifndef HYPHY_B200_H
+#define HYPHY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB2_ABI_VERSION 1
+
+typedef struct hb2_partition hb2_partition;   /* opaque: one per (likelihood function, partition) */
+
+/* hb2_create flags */
+#define HB2_FLAG_DEFAULT        0
+#define HB2_FLAG_FORCE_FP64     1   /* always use the fp64 pruning kernels (parity reference), never the tensor path */
+
+/* matrix kinds for hb2_set_matrices */
+#define HB2_MATRIX_RATE   0   /* numeric rate matrix Q*t after MultByFreqs: engine exponentiates on device
+                                 (replaces _Matrix::Exponentiate matrix.cpp:5537 / ExponentiateMatrices tree.cpp:2932) */
+#define HB2_MATRIX_TRANS  1   /* transition matrix P already exponentiated by the host (GetCompExp()->theData) */
+
+int         hb2_abi_version(void);
+const char *hb2_last_error(void);              /* thread-local text of the last failure */
+int         hb2_device_count(void);            /* number of visible CUDA devices (0 => hb2_create will fail) */
+
+/* Replaces the allocation half of _LikelihoodFunction::SetupLFCaches (likefunc.cpp:4163-4319) for one partition.
+ * S patterns, D states, L leaves, I internal nodes, C rate classes (categoryCount, >=1).
+ * ambig: nAmb*D doubles of 0/1 (dataset_filter.cpp:1594-1632); patternFreq: theFilter->theFrequencies.
+ * All host arrays are copied; the caller keeps ownership.  device = CUDA ordinal. */
+int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, int64_t C,
+               const int64_t *flatParents, const int64_t *leafState, const double *ambig, int64_t nAmb,
+               const int64_t *patternFreq, int device, int flags);
+
+/* Replaces ExponentiateMatrices (tree.cpp:2932-3113) + _CalcNode::SetCompExp (calcnode.cpp:714): hands the engine
+ * the matrices of the nodes in `*matrices` (DetermineNodesForUpdate, tree.cpp:3117) for rate class `cat`
+ * (0..C-1; -1 is accepted as 0 for partitions without category variables, likefunc.cpp:10843).
+ * nodeIds[k] in 0..L+I-2; M[k] -> D*D doubles.  kind = HB2_MATRIX_RATE | HB2_MATRIX_TRANS. */
+int hb2_set_matrices(hb2_partition *p, int64_t cat, int64_t n, const int64_t *nodeIds,
+                     const double *const *M, int kind);
+/* same, matrices packed back to back (n*D*D doubles) */
+int hb2_set_matrices_packed(hb2_partition *p, int64_t cat, int64_t n, const int64_t *nodeIds,
+                            const double *M, int kind);
+
+/* Explicit-form mixtures P = sum_k w_k Exp(Q_k) per branch (BS-REL; tree.cpp:3047-3089):
+ * K components for each listed node, M packed [n][K][D*D], w packed [n][K]. */
+int hb2_set_mixture_matrices(hb2_partition *p, int64_t cat, int64_t n, const int64_t *nodeIds, int64_t K,
+                             const double *M, const double *w);
+
+/* Replaces likefunc.cpp:10978-11123 (+ ComputeTreeBlockByBranch tree_evaluator.cpp:3556-4171) for ONE rate class:
+ * prunes the nodes in updateNodes (nUpdate < 0 or updateNodes == NULL => all nodes) and reduces at the root.
+ *   lnL            : sum_s f_s log L_s, already scale-corrected (what ComputeBlock returns at likefunc.cpp:11259)
+ *   siteL/siteScale: nullable; per-pattern (original order) L and count with L_true = L*2^(-64*count)
+ *                    (the storageVec / siteCorrectionCounts outputs, tree_evaluator.cpp:4080-4092, :84-87) */
+int hb2_evaluate(hb2_partition *p, int64_t cat, int64_t nUpdate, const int64_t *updateNodes,
+                 const double *rootFreqs, double *lnL, double *siteL, int64_t *siteScale);
+
+/* Fused replacement for the whole category loop PopulateConditionalProbabilities(WeightedSum) +
+ * SumUpSiteLikelihoods (likefunc2.cpp:484-908, 1446-1506): all C classes pruned in one pass,
+ * L_s = sum_c weights[c]*L_{c,s} combined on device, one lnL comes back.  Same outputs as hb2_evaluate. */
+int hb2_evaluate_classes(hb2_partition *p, const double *weights, int64_t nUpdate, const int64_t *updateNodes,
+                         const double *rootFreqs, double *lnL, double *siteL, int64_t *siteScale);
+
+/* FillInConditionals-style read-back (tree.cpp:3335): conditionals of internal node `inode` (0..I-1), class cat,
+ * as S*D doubles (original pattern order) and S binary exponents: true value = cond * 2^exp2. */
+int hb2_read_conditionals(hb2_partition *p, int64_t cat, int64_t inode, double *cond, int32_t *exp2);
+
+/* Read back the transition matrix currently cached for (cat, node): D*D doubles, row = parent state. */
+int hb2_read_transition(hb2_partition *p, int64_t cat, int64_t node, double *P);
+
+/* Multi-GPU (one process per GPU, patterns sharded by the caller: each rank creates its partition with its own
+ * pattern shard).  After hb2_comm_init every hb2_evaluate* returns the SUM over ranks of the partial lnL
+ * (a single fp64 ncclAllReduce on the partition's stream; per-pattern outputs stay local to the shard).
+ * uniqueId: the 128 bytes of an ncclUniqueId produced by hb2_comm_unique_id on rank 0 and broadcast by the host. */
+int hb2_comm_unique_id(void *uniqueId128);
+int hb2_comm_init(hb2_partition *p, int nRanks, int rank, const void *uniqueId128);
+
+/* Pair of SetupLFCaches in DeleteCaches (likefunc.cpp:10556-10601). */
+void hb2_destroy(hb2_partition *p);
+
+/* Introspection for tests/bench: kernel launches issued so far by this partition, and device pointers/timing. */
+int64_t hb2_launch_count(const hb2_partition *p);
+/* Runs the same work as hb2_evaluate_classes `iters` times with inputs already resident on the device
+ * (re-exponentiating every cached rate matrix and re-pruning the whole tree each time) and returns the mean
+ * device time per evaluation in milliseconds (CUDA events on the partition's stream).  stageMs (nullable, 3 doubles)
+ * receives the mean per-stage times {expm, pruning, root reduction}. */
+int hb2_time_resident(hb2_partition *p, const double *weights, const double *rootFreqs, int iters,
+                      double *msPerEval, double *stageMs, double *lnL);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYPHY_B200_H */

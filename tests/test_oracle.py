@@ -1,0 +1,62 @@
+"""CPU suite: the oracle (oracle/hb2_oracle.c) against the reference's golden vectors, and its own invariants."""
+import numpy as np
+import pytest
+
+from hyphy_b200 import synth
+from oracle import port
+from tests import golden_cases as gc
+
+
+@pytest.mark.parametrize("name", gc.SMALL + gc.MEDIUM)
+def test_oracle_matches_reference_golden(name):
+    w, g = gc.load(name)
+    lnl, site = port.lnl(w)
+    assert abs(lnl - g["lnL"]) <= 1e-11 * abs(g["lnL"])
+    np.testing.assert_allclose(site[w.site_to_pattern], g["site_lnL"], rtol=0, atol=1e-10)
+
+
+def test_oracle_expm_is_a_transition_matrix_and_semigroup():
+    Q = synth.mg94_rev_Q(0.7)
+    P1 = port.expm(Q * 0.05, sparse_storage=True)
+    P2 = port.expm(Q * 0.10, sparse_storage=True)
+    assert np.all(P1 >= -1e-18)
+    np.testing.assert_allclose(P1.sum(axis=1), 1.0, atol=1e-14)
+    np.testing.assert_allclose(P1 @ P1, P2, atol=1e-13)
+    # dense and sparse storage scalings agree to rounding
+    np.testing.assert_allclose(port.expm(Q * 0.05, sparse_storage=False), P1, atol=1e-14)
+
+
+def test_oracle_expm_zero_and_large():
+    Z = np.zeros((4, 4))
+    np.testing.assert_array_equal(port.expm(Z), np.eye(4))
+    Q = synth.hky85_Q(2.0, [0.3, 0.22, 0.24, 0.24])
+    Pinf = port.expm(Q * 500.0)
+    np.testing.assert_allclose(Pinf, np.tile([0.3, 0.22, 0.24, 0.24], (4, 1)), atol=1e-9)
+
+
+def test_oracle_scaler_convention():
+    """Deep tree: scaling must trigger and (L, count) must satisfy L_true = L * 2^(-64 count)."""
+    w, g = gc.load("mg94_200x64_c4_scaling")
+    P = np.stack([port.expm(w.Q_classes[0] * w.tree.t[b], True) for b in range(w.tree.n_branches)])
+    L, cnt = port.prune(w, P)
+    assert cnt.max() >= 1
+    assert np.all(L > 0) and np.all(L < 2.0 ** 64)
+
+
+def test_oracle_ambiguity_all_ones_equals_pruned_leaf():
+    """A fully missing leaf (all-ones vector) must not change the site likelihood versus any resolution sum."""
+    w = synth.nucleotide_workload(6, 40, seed=5)
+    P = np.stack([port.expm(w.Q_classes[0] * w.tree.t[b]) for b in range(w.tree.n_branches)])
+    base, _ = port.prune(w, P)
+    w2 = synth.nucleotide_workload(6, 40, seed=5)
+    w2.ambig = np.ones((1, 4))
+    total = np.zeros(w.S)
+    for st in range(4):
+        w3 = synth.nucleotide_workload(6, 40, seed=5)
+        w3.leaf_states = w.leaf_states.copy()
+        w3.leaf_states[0, :] = st
+        total += port.prune(w3, P)[0]
+    w2.leaf_states = w.leaf_states.copy()
+    w2.leaf_states[0, :] = -1
+    amb, _ = port.prune(w2, P)
+    np.testing.assert_allclose(amb, total, rtol=1e-13)
