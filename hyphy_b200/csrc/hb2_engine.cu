@@ -6,6 +6,7 @@
 // No CPU fallback exists on this path: every failure is an error code (fatal for the host).
 #include "../../include/hyphy_b200.h"
 #include "hb2_kernels_fp64.cuh"
+#include "hb2_kernels_tc.cuh"
 
 #include <climits>
 #include <cstdarg>
@@ -101,6 +102,10 @@ struct hb2_partition {
     std::vector<char> have_matrix;            // [C*B]
     std::vector<char> is_rate;                // [C*B] slot holds a rate matrix resident in d_Qres (for hb2_time_resident)
     double *d_Qres = nullptr;                 // [C][B][D*D] last rate matrices, resident copy
+    // tensor-core path (33..64 states unless HB2_FLAG_FORCE_FP64): fp32 conditionals + split/tiled P operands
+    bool use_tc = false;
+    float *d_condf = nullptr, *d_PB = nullptr, *d_PTf = nullptr;
+    int *d_err = nullptr;
     bool first_eval_done = false;
     std::vector<char> evaluated_cat;          // [C] whole tree pruned at least once
     int64_t launches = 0;
@@ -115,7 +120,7 @@ struct hb2_partition {
 namespace {
 
 int launch_expm(hb2_partition *p, const double *dQ, const int *d_dst, int n, int is_trans, const double *mix_w,
-                const int *mix_first, double *qres) {
+                const int *mix_first, double *qres, bool pack_tc = true) {
     if (n <= 0) return 0;
     hb2::ExpmArgs a{dQ, d_dst, mix_w, mix_first, p->d_PT, qres, (int)p->D, is_trans};
     switch (p->Dp) {
@@ -129,12 +134,24 @@ int launch_expm(hb2_partition *p, const double *dQ, const int *d_dst, int n, int
     }
     p->launches++;
     CU(cudaGetLastError());
+    if (p->use_tc && pack_tc) {
+        hb2::pack_tc_kernel<<<n, 256, 0, p->stream>>>(p->d_PT, d_dst, p->d_PB, p->d_PTf);
+        p->launches++;
+        CU(cudaGetLastError());
+    }
     return 0;
 }
 
 int launch_prune(hb2_partition *p, const hb2::PruneArgs &a, const int *d_jobs, int njobs, int ncls) {
     if (njobs <= 0) return 0;
-    if (p->Dp == 64) {
+    if (p->use_tc) {
+        hb2::PruneTcArgs t;
+        t.PB = p->d_PB; t.PTf = p->d_PTf; t.cond = p->d_condf; t.scal = a.scal; t.leaf = a.leaf; t.ambig = a.ambig; t.pi = a.pi;
+        t.rootL = a.rootL; t.rootE = a.rootE; t.tree = a.tree; t.err = p->d_err;
+        t.L = a.L; t.I = a.I; t.B = a.B; t.D = a.D; t.Sp = a.Sp; t.cat0 = a.cat0;
+        dim3 grid((unsigned)(p->Sp / hb2::TC_TILE_P), (unsigned)njobs, (unsigned)ncls);
+        hb2::prune64_tc_kernel<<<grid, 128, hb2::TC_SMEM_BYTES, p->stream>>>(t, d_jobs);
+    } else if (p->Dp == 64) {
         dim3 grid((unsigned)(p->Sp / hb2::TILE_P), (unsigned)njobs, (unsigned)ncls);
         hb2::prune64_kernel<<<grid, 256, 2 * 64 * hb2::LD64 * sizeof(double), p->stream>>>(a, d_jobs);
     } else {
@@ -303,9 +320,11 @@ int evaluate_impl(hb2_partition *p, int c0, int nc, const double *weights, int64
     const bool want_sites = siteL != nullptr || siteScale != nullptr;
     if (run_root(p, c0, nc, weights != nullptr, want_sites)) return 1;
     CU(cudaMemcpyAsync(hs + p->Dp + p->C, p->d_lnL, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaMemcpyAsync(hs + p->Dp + p->C + 1, p->d_err, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
     if (siteL) CU(cudaMemcpyAsync(siteL, p->d_siteL, p->S * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     if (siteScale) CU(cudaMemcpyAsync(siteScale, p->d_siteScale, p->S * sizeof(long long), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaStreamSynchronize(p->stream));
+    if (*reinterpret_cast<int *>(hs + p->Dp + p->C + 1) != 0) return fail("device-side barrier timeout in the tcgen05 pruning kernel");
     *lnL = hs[p->Dp + p->C];
     for (int c = c0; c < c0 + nc; c++) p->evaluated_cat[c] = 1;
     return 0;
@@ -345,7 +364,8 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
     hb2_partition *p = new hb2_partition();
     p->device = device; p->flags = flags; p->S = S; p->D = D; p->L = L; p->I = I; p->C = C; p->B = L + I - 1; p->nAmb = nAmb;
     p->Dp = Dp;
-    const int64_t tile = (Dp == 64) ? hb2::TILE_P : 128;
+    p->use_tc = (Dp == 64) && !(flags & HB2_FLAG_FORCE_FP64);
+    const int64_t tile = (Dp == 64 && !p->use_tc) ? hb2::TILE_P : 128;
     p->Sp = (S + tile - 1) / tile * tile;
     p->parents.assign(flatParents, flatParents + L + I);
     p->children.assign(I, {});
@@ -378,7 +398,20 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
     CUP(cudaMalloc(&p->d_leaf, L * Sp * sizeof(int)));
     CUP(cudaMalloc(&p->d_ambig, std::max<int64_t>(nAmb, 1) * Dp * sizeof(double)));
     CUP(cudaMalloc(&p->d_freq, Sp * sizeof(double)));
-    CUP(cudaMalloc(&p->d_cond, (size_t)C * I * Sp * Dp * sizeof(double)));
+    if (p->use_tc) {
+        CUP(cudaMalloc(&p->d_condf, (size_t)C * I * Sp * 64 * sizeof(float)));
+        CUP(cudaMalloc(&p->d_PB, (size_t)C * p->B * hb2::TC_PB_FLOATS * sizeof(float)));
+        CUP(cudaMalloc(&p->d_PTf, (size_t)C * p->B * 4096 * sizeof(float)));
+        CUP(cudaMemsetAsync(p->d_condf, 0, (size_t)C * I * Sp * 64 * sizeof(float), p->stream));
+        CUP(cudaMemsetAsync(p->d_PB, 0, (size_t)C * p->B * hb2::TC_PB_FLOATS * sizeof(float), p->stream));
+        CUP(cudaMemsetAsync(p->d_PTf, 0, (size_t)C * p->B * 4096 * sizeof(float), p->stream));
+        CUP(cudaFuncSetAttribute(hb2::prune64_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::TC_SMEM_BYTES));
+    } else {
+        CUP(cudaMalloc(&p->d_cond, (size_t)C * I * Sp * Dp * sizeof(double)));
+        CUP(cudaMemsetAsync(p->d_cond, 0, (size_t)C * I * Sp * Dp * sizeof(double), p->stream));
+    }
+    CUP(cudaMalloc(&p->d_err, sizeof(int)));
+    CUP(cudaMemsetAsync(p->d_err, 0, sizeof(int), p->stream));
     CUP(cudaMalloc(&p->d_scal, (size_t)C * I * Sp * sizeof(int)));
     CUP(cudaMalloc(&p->d_PT, (size_t)C * p->B * dpdp * sizeof(double)));
     CUP(cudaMalloc(&p->d_Qres, (size_t)C * p->B * dd * sizeof(double)));
@@ -404,7 +437,6 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
     CUP(cudaMallocHost(&p->h_dst, p->q_capacity * sizeof(int)));
     CUP(cudaMallocHost(&p->h_small, (Dp + C + 8) * sizeof(double)));
     CUP(cudaMallocHost(&p->h_jobs, I * sizeof(int)));
-    CUP(cudaMemsetAsync(p->d_cond, 0, (size_t)C * I * Sp * Dp * sizeof(double), p->stream));
     CUP(cudaMemsetAsync(p->d_scal, 0, (size_t)C * I * Sp * sizeof(int), p->stream));
     CUP(cudaMemsetAsync(p->d_PT, 0, (size_t)C * p->B * dpdp * sizeof(double), p->stream));
     CUP(cudaMemsetAsync(p->d_rootL, 0, (size_t)C * Sp * sizeof(double), p->stream));
@@ -484,7 +516,7 @@ int hb2_set_mixture_matrices(hb2_partition *p, int64_t cat, int64_t n, const int
         CU(cudaMemcpyAsync(p->d_dst, p->h_dst, n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
         CU(cudaMemcpyAsync(p->d_mix_w, hw.data(), n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
         CU(cudaMemcpyAsync(p->d_mix_first, hf.data(), n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
-        if (launch_expm(p, p->d_Q, p->d_dst, (int)n, 0, p->d_mix_w, p->d_mix_first, nullptr)) return 1;
+        if (launch_expm(p, p->d_Q, p->d_dst, (int)n, 0, p->d_mix_w, p->d_mix_first, nullptr, k == K - 1)) return 1;
         CU(cudaStreamSynchronize(p->stream));
     }
     for (int64_t i = 0; i < n; i++) { p->have_matrix[cat * p->B + nodeIds[i]] = 1; p->is_rate[cat * p->B + nodeIds[i]] = 0; }
@@ -514,6 +546,11 @@ int hb2_read_conditionals(hb2_partition *p, int64_t cat, int64_t inode, double *
     std::vector<double> tmp((size_t)p->Sp * p->Dp);
     std::vector<int> te(p->Sp);
     CU(cudaStreamSynchronize(p->stream));
+    if (p->use_tc) {
+        std::vector<float> tf(tmp.size());
+        CU(cudaMemcpy(tf.data(), p->d_condf + ((size_t)cat * p->I + inode) * p->Sp * 64, tf.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < tf.size(); k++) tmp[k] = tf[k];
+    } else
     CU(cudaMemcpy(tmp.data(), p->d_cond + ((size_t)cat * p->I + inode) * p->Sp * p->Dp, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(te.data(), p->d_scal + ((size_t)cat * p->I + inode) * p->Sp, te.size() * sizeof(int), cudaMemcpyDeviceToHost));
     for (int64_t s = 0; s < p->S; s++) {
@@ -568,7 +605,7 @@ void hb2_destroy(hb2_partition *p) {
     if (p->comm) g_nccl.CommDestroy(p->comm);
     void *dev[] = {p->d_leaf, p->d_scal, p->d_rootE, p->d_child_start, p->d_child_ids, p->d_jobs, p->d_dst, p->d_flag,
                    p->d_mix_first, p->d_ambig, p->d_freq, p->d_cond, p->d_PT, p->d_Q, p->d_pi, p->d_rootL, p->d_weights,
-                   p->d_partial, p->d_lnL, p->d_siteL, p->d_mix_w, p->d_siteScale, p->d_Qres};
+                   p->d_partial, p->d_lnL, p->d_siteL, p->d_mix_w, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err};
     for (void *d : dev) if (d) cudaFree(d);
     if (p->h_Q) cudaFreeHost(p->h_Q);
     if (p->h_small) cudaFreeHost(p->h_small);
@@ -581,6 +618,7 @@ void hb2_destroy(hb2_partition *p) {
 }
 
 int64_t hb2_launch_count(const hb2_partition *p) { return p ? p->launches : 0; }
+int hb2_precision_mode(const hb2_partition *p) { return (p && p->use_tc) ? 1 : 0; }
 
 int hb2_time_resident(hb2_partition *p, const double *weights, const double *rootFreqs, int iters, double *msPerEval,
                       double *stageMs, double *lnL) {

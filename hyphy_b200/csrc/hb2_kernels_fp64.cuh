@@ -50,23 +50,26 @@ __device__ __forceinline__ double exp2i(int e) {   // exact 2^e for |e| < 1022
 }
 
 // ------------------------------------------------------------------------------------------------
-// 64x64x64 fp64 tile product, 256 threads, each thread owns a 4x4 block of C:
-//   acc[i][j] += sum_k A[(4*ty+i)*LD64 + k] * B[k*LD64 + 4*tx + j]
-// A rows are read as broadcasts (two distinct rows per warp, 16 banks apart thanks to LD64), B as 32-byte vectors.
+// 64x64x64 fp64 tile product, 256 threads; thread (tx,ty) owns rows 4ty..4ty+3 and columns
+// {2tx, 2tx+1, 32+2tx, 33+2tx} of C (col_of):  acc[i][j] += sum_k A[(4*ty+i)*LD64 + k] * B[k*LD64 + col_of(tx,j)]
+// A rows are read as broadcasts (two distinct rows per warp, 16 banks apart thanks to LD64); each B read is one
+// 16-byte vector per thread, 256 contiguous bytes per half-warp: conflict-free.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int col_of(int tx, int j) { return (j < 2) ? 2 * tx + j : 32 + 2 * tx + (j - 2); }
+
 __device__ __forceinline__ void tile_mm64(const double *__restrict__ A, const double *__restrict__ Bm,
                                           int tx, int ty, double (&acc)[4][4]) {
     const double *a0 = A + (4 * ty) * LD64;
-    const double *b0 = Bm + 4 * tx;
+    const double *b0 = Bm + 2 * tx;
 #pragma unroll 4
     for (int k = 0; k < 64; k += 2) {
         double2 a[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) a[i] = *reinterpret_cast<const double2 *>(a0 + i * LD64 + k);
         double2 b00 = *reinterpret_cast<const double2 *>(b0 + k * LD64);
-        double2 b01 = *reinterpret_cast<const double2 *>(b0 + k * LD64 + 2);
+        double2 b01 = *reinterpret_cast<const double2 *>(b0 + k * LD64 + 32);
         double2 b10 = *reinterpret_cast<const double2 *>(b0 + (k + 1) * LD64);
-        double2 b11 = *reinterpret_cast<const double2 *>(b0 + (k + 1) * LD64 + 2);
+        double2 b11 = *reinterpret_cast<const double2 *>(b0 + (k + 1) * LD64 + 32);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             acc[i][0] = fma(a[i].x, b00.x, acc[i][0]);
@@ -100,12 +103,10 @@ struct ExpmArgs {
     int is_trans;           // 1: input already a transition matrix -> just transpose/pad
 };
 
-__device__ __forceinline__ double taylor_c(int k) {
-    const double c[16] = {1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
-                          1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0, 1.0 / 87178291200.0,
-                          1.0 / 1307674368000.0};
-    return c[k];
-}
+__constant__ double c_taylor[16] = {1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320,
+                                    1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0,
+                                    1.0 / 87178291200.0, 1.0 / 1307674368000.0};
+__device__ __forceinline__ double taylor_c(int k) { return c_taylor[k]; }
 
 __global__ void __launch_bounds__(256, 1) expm64_kernel(ExpmArgs a) {
     extern __shared__ __align__(16) double sm[];
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(256, 1) expm64_kernel(ExpmArgs a) {
         for (int i = 0; i < 4; i++)
 #pragma unroll
             for (int j = 0; j < 4; j += 2)
-                *reinterpret_cast<double2 *>(M + (4 * ty + i) * LD64 + 4 * tx + j) = make_double2(acc[i][j], acc[i][j + 1]);
+                *reinterpret_cast<double2 *>(M + (4 * ty + i) * LD64 + col_of(tx, j)) = make_double2(acc[i][j], acc[i][j + 1]);
     };
     zero(); tile_mm64(A1, A1, tx, ty, acc); store(A2);
     __syncthreads();
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(256, 1) expm64_kernel(ExpmArgs a) {
     zero(); tile_mm64(A2, A2, tx, ty, acc); store(A4);
     // R = B3 = c12 I + c13 A + c14 A2 + c15 A3
     auto poly_block = [&](int q, int i, int j) -> double {
-        int r = 4 * ty + i, c = 4 * tx + j, o = r * LD64 + c;
+        int r = 4 * ty + i, c = col_of(tx, j), o = r * LD64 + c;
         double v = taylor_c(4 * q + 1) * A1[o] + taylor_c(4 * q + 2) * A2[o];
         if (r == c) v += taylor_c(4 * q);
         return v;   // the A3 term is added by the caller after the barrier that publishes A3
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(256, 1) expm64_kernel(ExpmArgs a) {
     for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            int o = (4 * ty + i) * LD64 + 4 * tx + j;
+            int o = (4 * ty + i) * LD64 + col_of(tx, j);
             R[o] = poly_block(3, i, j) + taylor_c(15) * A3[o];
         }
     __syncthreads();
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(256, 1) expm64_kernel(ExpmArgs a) {
         for (int i = 0; i < 4; i++)
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                int o = (4 * ty + i) * LD64 + 4 * tx + j;
+                int o = (4 * ty + i) * LD64 + col_of(tx, j);
                 R[o] = acc[i][j] + poly_block(q, i, j) + taylor_c(4 * q + 3) * A3[o];
             }
         __syncthreads();
@@ -367,8 +368,8 @@ __global__ void __launch_bounds__(256, 2) prune64_kernel(PruneArgs a, const int 
                 const int code = a.leaf[(size_t)child * Sp + s0 + 4 * ty + i];
                 double m0, m1, m2, m3;
                 if (code >= 0) {
-                    const double2 *p = reinterpret_cast<const double2 *>(PT + (size_t)code * 64 + 4 * tx);
-                    double2 q0 = __ldg(p), q1 = __ldg(p + 1);
+                    const double2 *p = reinterpret_cast<const double2 *>(PT + (size_t)code * 64 + 2 * tx);
+                    double2 q0 = __ldg(p), q1 = __ldg(p + 16);
                     m0 = q0.x; m1 = q0.y; m2 = q1.x; m3 = q1.y;
                 } else {
                     const double *amb = a.ambig + (size_t)(-code - 1) * 64;
@@ -376,8 +377,8 @@ __global__ void __launch_bounds__(256, 2) prune64_kernel(PruneArgs a, const int 
                     for (int j = 0; j < a.D; j++) {
                         const double w = __ldg(amb + j);
                         if (w != 0.0) {
-                            const double2 *p = reinterpret_cast<const double2 *>(PT + (size_t)j * 64 + 4 * tx);
-                            double2 q0 = __ldg(p), q1 = __ldg(p + 1);
+                            const double2 *p = reinterpret_cast<const double2 *>(PT + (size_t)j * 64 + 2 * tx);
+                            double2 q0 = __ldg(p), q1 = __ldg(p + 16);
                             m0 = fma(w, q0.x, m0); m1 = fma(w, q0.y, m1); m2 = fma(w, q1.x, m2); m3 = fma(w, q1.y, m3);
                         }
                     }
@@ -426,11 +427,11 @@ __global__ void __launch_bounds__(256, 2) prune64_kernel(PruneArgs a, const int 
         }
         ex[i] += e;
         const int row = 4 * ty + i;
-        *reinterpret_cast<double2 *>(outp + (size_t)row * 64 + 4 * tx) = make_double2(v[i][0], v[i][1]);
-        *reinterpret_cast<double2 *>(outp + (size_t)row * 64 + 4 * tx + 2) = make_double2(v[i][2], v[i][3]);
+        *reinterpret_cast<double2 *>(outp + (size_t)row * 64 + 2 * tx) = make_double2(v[i][0], v[i][1]);
+        *reinterpret_cast<double2 *>(outp + (size_t)row * 64 + 32 + 2 * tx) = make_double2(v[i][2], v[i][3]);
         if (tx == 0) a.scal[((size_t)cat * a.I + par) * Sp + s0 + row] = ex[i];
         if (is_root) {
-            double r = v[i][0] * a.pi[4 * tx] + v[i][1] * a.pi[4 * tx + 1] + v[i][2] * a.pi[4 * tx + 2] + v[i][3] * a.pi[4 * tx + 3];
+            double r = v[i][0] * a.pi[2 * tx] + v[i][1] * a.pi[2 * tx + 1] + v[i][2] * a.pi[32 + 2 * tx] + v[i][3] * a.pi[33 + 2 * tx];
 #pragma unroll
             for (int o = 1; o < 16; o <<= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
             if (tx == 0) {

@@ -1,0 +1,304 @@
+// hb2_kernels_tc.cuh -- tcgen05 (5th-gen tensor core) pruning path for 33..64-state models (sm_100a only).
+//
+// The 61-state codon update  parent[s][n] *= sum_k P[n][k] * child[s][k]  is a dense contraction batched over
+// patterns:  D[128 patterns][64 parent states] = X[128][64 child states] * P^T.  tcgen05 has no fp64 kind, so the
+// contraction runs as an error-compensated split in kind::tf32 with fp32 accumulation in TMEM:
+//        X = Xh + Xl,  P = Ph + Pl   (each part exactly representable in tf32, round-to-nearest splits)
+//        D = Xl*Ph + Xh*Pl + Xh*Ph   (the dropped Xl*Pl term is ~2^-22 relative)
+// All operands are non-negative, so there is no cancellation and the relative error of D is bounded by the
+// representation error of the splits (~2^-22) plus fp32 accumulation.  Conditionals are stored in fp32, renormalised
+// per (node, pattern) to max in [0.5,1) with an int32 binary exponent, so fp32 range is never an issue.
+//
+// Operand staging:
+//   A (= X, 128 x 64, K-major) comes from TENSOR MEMORY: each of the 128 threads owns one pattern (one TMEM lane),
+//     loads its fp32 row from HBM, splits it in registers and writes Xh / Xl with tcgen05.st (columns 64..191).
+//   B (= P, 64 x 64, K-major) comes from SHARED MEMORY in the canonical no-swizzle UMMA layout (8x16-byte core
+//     matrices; LBO = 1024 B between K chunks, SBO = 128 B between 8-row groups).  The expm stage writes P already
+//     split and tiled that way (pack_tc_kernel), so one 32 KB cp.async.bulk (TMA engine, mbarrier completion) per
+//     child stages Ph and Pl.
+//   D (128 x 64 fp32) lives in TMEM columns 0..63; it is read back with tcgen05.ld, one row per thread, multiplied
+//     into the running product of the parent held in registers.
+//
+// Replaces (for D in 33..64) reference tree_evaluator.cpp:3875-4008 (_hy_mvp_blocked<61> + _hy_vvmult_sum<61>).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "hb2_kernels_fp64.cuh"
+
+namespace hb2 {
+
+constexpr int TC_TILE_P = 128;                 // patterns per CTA (= UMMA M = TMEM lanes)
+constexpr int TC_PB_FLOATS = 2 * 4096;         // per (class, branch): Ph tile + Pl tile in canonical layout
+constexpr int TC_SMEM_BYTES = 2 * 32768 + 1024; // two B stages (one used for now; also caps residency at 2 CTAs/SM) + barriers
+constexpr uint32_t TC_TMEM_COLS = 256;         // D: 0..63, Xh: 64..127, Xl: 128..191
+
+struct PruneTcArgs {
+    const float *PB;                // [C][B][2][16][64][4] canonical K-major tiles of P (hi, lo)
+    const float *PTf;               // [C][B][64][64] fp32 copy of PT (leaf column gather)
+    float *cond;                    // [C][I][Sp][64] fp32 conditionals
+    int *scal;                      // [C][I][Sp]
+    const int *leaf;                // [L][Sp]
+    const double *ambig;            // [nAmb][64]
+    const double *pi;               // [64]
+    double *rootL;                  // [C][Sp]
+    int *rootE;                     // [C][Sp]
+    TreeDev tree;
+    int *err;                       // device error flag (mbarrier timeout)
+    int L, I, B, D, Sp, cat0;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug must surface as an error flag (host returns an error), never as a hung GPU.
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int *err_flag) {
+    const uint32_t addr = smem_u32(bar);
+    for (int it = 0; it < (1 << 22); it++) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P1;\n\t"
+            "}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    atomicExch(err_flag, 1);
+    return false;
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc], kind::tf32, M=128, N=64, K=8
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+#define HB2_TMEM_ST16(taddr, r, o)                                                                                   \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" \
+                 ::"r"(taddr), "r"(r[o + 0]), "r"(r[o + 1]), "r"(r[o + 2]), "r"(r[o + 3]), "r"(r[o + 4]), "r"(r[o + 5]),   \
+                 "r"(r[o + 6]), "r"(r[o + 7]), "r"(r[o + 8]), "r"(r[o + 9]), "r"(r[o + 10]), "r"(r[o + 11]),            \
+                 "r"(r[o + 12]), "r"(r[o + 13]), "r"(r[o + 14]), "r"(r[o + 15]) : "memory")
+#define HB2_TMEM_LD16(taddr, r, o)                                                                                   \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+                 : "=r"(r[o + 0]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3]), "=r"(r[o + 4]), "=r"(r[o + 5]),      \
+                   "=r"(r[o + 6]), "=r"(r[o + 7]), "=r"(r[o + 8]), "=r"(r[o + 9]), "=r"(r[o + 10]), "=r"(r[o + 11]),    \
+                   "=r"(r[o + 12]), "=r"(r[o + 13]), "=r"(r[o + 14]), "=r"(r[o + 15])                                    \
+                 : "r"(taddr) : "memory")
+
+// UMMA shared-memory descriptor, SWIZZLE_NONE, K-major: start>>4 | (LBO>>4)<<16 | (SBO>>4)<<32 | version 1 @46
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 16) | ((uint64_t)(128u >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor: c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major both, N=64 (8<<17), M=128 (8<<24)
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+// ------------------------------------------------------------------------------------------------------------------
+// PT (fp64, transposed) -> tensor-path operands: canonical hi/lo tiles of P and an fp32 copy of PT.  One CTA per slot.
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_tc_kernel(const double *__restrict__ PT, const int *__restrict__ slots,
+                                                       float *__restrict__ PB, float *__restrict__ PTf) {
+    const size_t slot = slots[blockIdx.x];
+    const double *src = PT + slot * 4096;
+    float *pb = PB + slot * TC_PB_FLOATS;
+    float *pf = PTf + slot * 4096;
+    for (int o = threadIdx.x; o < 4096; o += 256) {
+        const int chunk = o >> 8, n = (o >> 2) & 63, kk = chunk * 4 + (o & 3);
+        const double p = src[kk * 64 + n];              // P[n][kk] = PT[kk][n]
+        const float hi = tf32_rn((float)p);
+        const float lo = tf32_rn((float)(p - (double)hi));
+        pb[o] = hi;
+        pb[4096 + o] = lo;
+        pf[o] = (float)src[o];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fused pruning update on tcgen05.  grid = (Sp/128, jobs, classes), block = 128 threads (thread t <-> pattern t).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void renorm_f32(float (&v)[64], int &ex) {
+    float m = 0.f;
+#pragma unroll
+    for (int k = 0; k < 64; k++) m = fmaxf(m, v[k]);
+    if (m > 0.f && m < INFINITY) {
+        const int e = (int)((__float_as_uint(m) >> 23) & 0xffu) - 126;       // m = f * 2^e, f in [0.5,1) (normal m)
+        if (e != 0) {
+            const float s1 = __uint_as_float((uint32_t)(127 - e / 2) << 23), s2 = __uint_as_float((uint32_t)(127 - (e - e / 2)) << 23);
+#pragma unroll
+            for (int k = 0; k < 64; k++) v[k] = v[k] * s1 * s2;
+            ex += e;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128, 2) prune64_tc_kernel(PruneTcArgs a, const int *__restrict__ jobs) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float *Bs = reinterpret_cast<float *>(smem);                         // [2][4096] Ph, Pl
+    uint64_t *bar_b = reinterpret_cast<uint64_t *>(smem + 2 * 32768);
+    uint64_t *bar_mma = bar_b + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_b + 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int par = jobs[blockIdx.y];
+    const int cat = a.cat0 + blockIdx.z;
+    const size_t Sp = a.Sp;
+    const size_t s = (size_t)blockIdx.x * TC_TILE_P + tid;
+
+    if (tid == 0) {
+        mbar_init(bar_b, 1);
+        mbar_init(bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);      // this warp's TMEM lane quarter
+    const uint64_t bdesc_hi = make_b_desc(smem_u32(Bs));
+    const uint64_t bdesc_lo = make_b_desc(smem_u32(Bs + 4096));
+
+    float v[64];
+#pragma unroll
+    for (int k = 0; k < 64; k++) v[k] = 1.f;
+    int ex = 0;
+    uint32_t phase = 0;
+    const int c_begin = a.tree.child_start[par], c_end = a.tree.child_start[par + 1];
+    for (int ci = c_begin; ci < c_end; ci++) {
+        const int child = a.tree.child_ids[ci];
+        const size_t slot = (size_t)cat * a.B + child;
+        if (child < a.L) {
+            const int code = a.leaf[(size_t)child * Sp + s];
+            const float *PTf = a.PTf + slot * 4096;
+            if (code >= 0) {
+                const float4 *row = reinterpret_cast<const float4 *>(PTf + (size_t)code * 64);
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    const float4 r = __ldg(row + q);
+                    v[4 * q] *= r.x; v[4 * q + 1] *= r.y; v[4 * q + 2] *= r.z; v[4 * q + 3] *= r.w;
+                }
+            } else {
+                float acc[64];
+#pragma unroll
+                for (int k = 0; k < 64; k++) acc[k] = 0.f;
+                const double *amb = a.ambig + (size_t)(-code - 1) * 64;
+                for (int j = 0; j < a.D; j++) {
+                    if (__ldg(amb + j) != 0.0) {
+                        const float4 *row = reinterpret_cast<const float4 *>(PTf + (size_t)j * 64);
+#pragma unroll
+                        for (int q = 0; q < 16; q++) {
+                            const float4 r = __ldg(row + q);
+                            acc[4 * q] += r.x; acc[4 * q + 1] += r.y; acc[4 * q + 2] += r.z; acc[4 * q + 3] += r.w;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 64; k++) v[k] *= acc[k];
+            }
+        } else {
+            const int cin = child - a.L;
+            // (A) stage Ph|Pl of this branch: one 32 KB bulk copy (TMA engine), completion on bar_b
+            if (tid == 0) {
+                mbar_expect_tx(bar_b, 32768u);
+                bulk_g2s(Bs, a.PB + slot * TC_PB_FLOATS, 32768u, bar_b);
+            }
+            // (B) this thread's pattern row -> split -> TMEM (Xh at cols 64.., Xl at cols 128..)
+            {
+                const float4 *xr = reinterpret_cast<const float4 *>(a.cond + (((size_t)cat * a.I + cin) * Sp + s) * 64);
+                uint32_t hi[64], lo[64];
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    const float4 x = xr[q];
+                    const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const float h = tf32_rn(xs[u]);
+                        hi[4 * q + u] = __float_as_uint(h);
+                        lo[4 * q + u] = __float_as_uint(xs[u] - h);
+                    }
+                }
+#pragma unroll
+                for (int o = 0; o < 64; o += 16) {
+                    HB2_TMEM_ST16(lane_addr + 64 + o, hi, o);
+                    HB2_TMEM_ST16(lane_addr + 128 + o, lo, o);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            }
+            ex += a.scal[((size_t)cat * a.I + cin) * Sp + s];
+            tc_fence_before();
+            __syncthreads();                 // A operand complete in TMEM; every thread is done reading the previous D
+            if (tid == 0) {
+                tc_fence_after();
+                mbar_wait(bar_b, phase, a.err);
+                // small terms first: Xl*Ph, Xh*Pl, then Xh*Ph (8 K-steps of 8 each)
+#pragma unroll
+                for (int kk = 0; kk < 8; kk++)
+                    tc_mma_tf32_ts(tmem_base, tmem_base + 128 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, kk > 0);
+#pragma unroll
+                for (int kk = 0; kk < 8; kk++)
+                    tc_mma_tf32_ts(tmem_base, tmem_base + 64 + kk * 8, bdesc_lo + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u);
+#pragma unroll
+                for (int kk = 0; kk < 8; kk++)
+                    tc_mma_tf32_ts(tmem_base, tmem_base + 64 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u);
+                tc_commit(bar_mma);
+            }
+            __syncwarp();
+            mbar_wait(bar_mma, phase, a.err);
+            tc_fence_after();
+            {
+                uint32_t d[64];
+#pragma unroll
+                for (int o = 0; o < 64; o += 16) HB2_TMEM_LD16(lane_addr + o, d, o);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < 64; k++) v[k] *= __uint_as_float(d[k]);
+            }
+            phase ^= 1u;
+        }
+        renorm_f32(v, ex);
+    }
+    // write the parent's conditionals (already renormalised after the last child) and the root reduction
+    {
+        float4 *outp = reinterpret_cast<float4 *>(a.cond + (((size_t)cat * a.I + par) * Sp + s) * 64);
+#pragma unroll
+        for (int q = 0; q < 16; q++) outp[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        a.scal[((size_t)cat * a.I + par) * Sp + s] = ex;
+        if (par == a.I - 1) {
+            double r = 0.0;
+#pragma unroll
+            for (int k = 0; k < 64; k++) r = fma((double)v[k], a.pi[k], r);
+            a.rootL[(size_t)cat * Sp + s] = r;
+            a.rootE[(size_t)cat * Sp + s] = ex;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace hb2

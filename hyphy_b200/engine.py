@@ -42,6 +42,7 @@ ABI = [
     ("hb2_comm_init", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     ("hb2_destroy", None, [C.c_void_p]),
     ("hb2_launch_count", C.c_int64, [C.c_void_p]),
+    ("hb2_precision_mode", C.c_int, [C.c_void_p]),
     ("hb2_time_resident", C.c_int, [C.c_void_p, _dp, _dp, C.c_int, _dp, _dp, _dp]),
 ]
 
@@ -180,6 +181,10 @@ class Partition:
     @property
     def launch_count(self) -> int:
         return int(self._lib.hb2_launch_count(self._h))
+
+    @property
+    def precision_mode(self) -> int:
+        return int(self._lib.hb2_precision_mode(self._h))
 
     def time_resident(self, weights, root_freqs, iters=10):
         w, pw = _d(weights)

@@ -105,6 +105,9 @@ void hb2_destroy(hb2_partition *p);
 
 /* Introspection for tests/bench: kernel launches issued so far by this partition, and device pointers/timing. */
 int64_t hb2_launch_count(const hb2_partition *p);
+/* 0: fp64 pruning kernels (4/20-state register kernels, or HB2_FLAG_FORCE_FP64);
+ * 1: tcgen05 tensor-core pruning, error-compensated 3xTF32 split with fp32 conditionals (33..64 states). */
+int hb2_precision_mode(const hb2_partition *p);
 /* Runs the same work as hb2_evaluate_classes `iters` times with inputs already resident on the device
  * (re-exponentiating every cached rate matrix and re-pruning the whole tree each time) and returns the mean
  * device time per evaluation in milliseconds (CUDA events on the partition's stream).  stageMs (nullable, 3 doubles)
