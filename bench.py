@@ -8,8 +8,10 @@ A "step" is ONE full likelihood-function evaluation: every one of the B*C rate m
 the whole tree pruned for all patterns and classes, root reduction, one fp64 lnL back.
   value : evaluations/s with the inputs already resident in HBM (device time, CUDA events on the engine's stream,
           K steps, max over ranks).
-  e2e   : the same through the public C-ABI call sequence a host makes (hb2_set_matrices_packed + hb2_evaluate_classes)
-          with HOST buffers: the H2D copy of that step's matrices and the D2H read of lnL are inside the timed region.
+  e2e   : the same through the public C-ABI call sequence a host makes per evaluation (hb2_set_matrices_compiled for
+          every class + hb2_evaluate_classes) with HOST buffers: the H2D copy of that step's formula values and the D2H
+          read of lnL are inside the timed region.  e2e_dense is the same with dense D*D rate matrices
+          (hb2_set_matrices_packed), i.e. without the compiled-template hand-over.
 Multi-GPU: patterns are sharded across ranks (strong scaling of one alignment); one fp64 ncclAllReduce per evaluation.
 The oracle / reference binary under oracle/ is used only for cpu_baseline and --impl reference.
 """
@@ -171,6 +173,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fp64", action="store_true", help="force the fp64 pruning kernels (HB2_FLAG_FORCE_FP64)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -193,7 +196,8 @@ def main():
     S = w.S
     # contiguous pattern shards, balanced by count
     lo, hi = rank * S // world, (rank + 1) * S // world
-    lf = LikelihoodFunction(w, device=local_rank, pattern_slice=slice(lo, hi) if world > 1 else None)
+    lf = LikelihoodFunction(w, device=local_rank, flags=1 if args.fp64 else 0,
+                            pattern_slice=slice(lo, hi) if world > 1 else None)
     if world > 1:
         uid = [Partition.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -220,22 +224,34 @@ def main():
         pinned.append(t)
     Qts = [t.numpy() for t in pinned]
 
+    lf.set_template()                                # static half of the compiled model matrix, once
+    Vs = [torch.from_numpy(np.ascontiguousarray(w.compiled_values(perturb=1e-4 * k))).pin_memory().numpy() for k in range(n_variants)]
+
     def e2e_step(k):
+        lf.set_all_compiled(Vs[k % n_variants])
+        return lf.compute()
+
+    def e2e_dense_step(k):
         q = Qts[k % n_variants]
         for c in range(w.C):
             lf.part.set_matrices(c, lf.all_nodes, q[c])
         return lf.compute()
 
+    def timed(step):
+        for k in range(args.warmup):
+            step(k)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            step(k)
+        barrier()
+        return max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+
     lnl0 = e2e_step(0)                              # also the first (whole-tree) evaluation
-    for k in range(args.warmup):
-        e2e_step(k)
+    lnl_dense = e2e_dense_step(0)
     # ---- e2e: public API with host buffers ---------------------------------------------------------
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        e2e_step(k)
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    e2e_dense_ms = timed(e2e_dense_step)
+    e2e_ms = timed(e2e_step)
     # ---- resident: device time by CUDA events on the engine's stream ---------------------------------
     lf.part.set_matrices(0, lf.all_nodes, Qts[0][0])
     for c in range(1, w.C):
@@ -277,14 +293,19 @@ def main():
                     "tensor_frac_of_tf32_peak": ((flops / world) / (prune_ms * 1e-3) / 1e12) / (pk["bf16_tflops"] / 2) if tc_mode else None,
                     "fp64_tflops_expm": expm_flops / (stage[0] * 1e-3) / 1e12 if stage[0] > 0 else None,
                     "stage_ms": {"expm": stage[0], "pruning": stage[1], "root": stage[2]}}
-        h2d = int(w.C * w.tree.n_branches * w.D * w.D * 8 + w.C * w.tree.n_branches * 4 + (64 + w.C) * 8)
+        nF = w.compiled_template()[2]
+        h2d = int(w.C * w.tree.n_branches * nF * 8 + w.C * w.tree.n_branches * 4 + (64 + w.C) * 8 + w.tree.n_internal * 4)
+        h2d_dense = int(w.C * w.tree.n_branches * w.D * w.D * 8 + w.C * w.tree.n_branches * 4 + (64 + w.C) * 8 + w.tree.n_internal * 4)
         line = {"metric": METRIC, "value": 1000.0 / ms, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "tf32x3 (tcgen05, fp32 accumulate) pruning + f64 expm/root" if tc_mode else "f64",
                 "data": "synthetic",
                 "config": {"workload": NAME, "patterns": S, "branches": w.tree.n_branches, "states": w.D, "classes": w.C,
                            "sharding": f"patterns/{world}", "l2": "inputs larger than L2 (830 MB of conditionals per evaluation)"},
-                "e2e": {"value": 1000.0 / e2e_ms, "unit": "evals/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8},
+                "e2e": {"value": 1000.0 / e2e_ms, "unit": "evals/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
+                        "api": "hb2_set_matrices_compiled x C + hb2_evaluate_classes"},
+                "e2e_dense": {"value": 1000.0 / e2e_dense_ms, "unit": "evals/s", "ms_per_step": e2e_dense_ms, "h2d_bytes_per_step": h2d_dense,
+                              "d2h_bytes_per_step": 12, "api": "hb2_set_matrices_packed x C + hb2_evaluate_classes", "lnL": lnl_dense},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "lnL": lnl0, "lnL_resident": lnl_res}
         if not args.no_cpu_baseline and world == 1:
             try:

@@ -102,6 +102,12 @@ struct hb2_partition {
     std::vector<char> have_matrix;            // [C*B]
     std::vector<char> is_rate;                // [C*B] slot holds a rate matrix resident in d_Qres (for hb2_time_resident)
     double *d_Qres = nullptr;                 // [C][B][D*D] last rate matrices, resident copy
+    // compiled rate-matrix template (hb2_set_rate_template) and its per-evaluation formula values
+    int64_t t_nnz = 0, t_nF = 0;
+    bool t_has_colfreq = false;
+    int *d_t_index = nullptr, *d_t_formula = nullptr, *d_vdst = nullptr, *h_vdst = nullptr;
+    double *d_t_colfreq = nullptr, *d_V = nullptr, *h_V = nullptr;
+    int64_t n_vpending = 0;
     // tensor-core path (33..64 states unless HB2_FLAG_FORCE_FP64): fp32 conditionals + split/tiled P operands
     bool use_tc = false;
     float *d_condf = nullptr, *d_PB = nullptr, *d_PTf = nullptr;
@@ -122,7 +128,13 @@ namespace {
 int launch_expm(hb2_partition *p, const double *dQ, const int *d_dst, int n, int is_trans, const double *mix_w,
                 const int *mix_first, double *qres, bool pack_tc = true) {
     if (n <= 0) return 0;
-    hb2::ExpmArgs a{dQ, d_dst, mix_w, mix_first, p->d_PT, qres, (int)p->D, is_trans};
+    hb2::ExpmArgs a{};
+    a.Q = dQ; a.dst = d_dst; a.mix_w = mix_w; a.mix_first = mix_first; a.PT = p->d_PT; a.Qres = qres; a.D = (int)p->D;
+    a.is_trans = is_trans;
+    if (is_trans == 2) {                       // compiled template: dQ points at the formula values [n][nF]
+        a.is_trans = 0; a.Q = nullptr; a.V = dQ; a.tmpl_index = p->d_t_index; a.tmpl_formula = p->d_t_formula;
+        a.tmpl_colfreq = p->t_has_colfreq ? p->d_t_colfreq : nullptr; a.tmpl_nnz = (int)p->t_nnz; a.nF = (int)p->t_nF;
+    }
     switch (p->Dp) {
         case 64: hb2::expm64_kernel<<<n, 256, 5 * 64 * hb2::LD64 * sizeof(double), p->stream>>>(a); break;
         case 4: hb2::expm_small_kernel<4><<<n, 128, hb2::expm_small_smem_bytes(4), p->stream>>>(a); break;
@@ -171,7 +183,21 @@ int launch_prune(hb2_partition *p, const hb2::PruneArgs &a, const int *d_jobs, i
 }
 
 // Flush matrices handed over since the last evaluation: one H2D copy + one (or two) expm launches.
+int flush_compiled(hb2_partition *p) {
+    const int64_t n = p->n_vpending;
+    if (n == 0) return 0;
+    CU(cudaMemcpyAsync(p->d_V, p->h_V, n * p->t_nF * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CU(cudaMemcpyAsync(p->d_vdst, p->h_vdst, n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    CU(cudaEventRecord(p->ev_staging, p->stream));
+    p->staging_busy = true;
+    if (launch_expm(p, p->d_V, p->d_vdst, (int)n, 2, nullptr, nullptr, p->d_Qres)) return 1;
+    for (int64_t k = 0; k < n; k++) p->is_rate[p->h_vdst[k]] = 1;
+    p->n_vpending = 0;
+    return 0;
+}
+
 int flush_matrices(hb2_partition *p) {
+    if (flush_compiled(p)) return 1;
     const int64_t n = p->n_pending;
     if (n == 0) return 0;
     const size_t dd = (size_t)p->D * p->D;
@@ -523,6 +549,57 @@ int hb2_set_mixture_matrices(hb2_partition *p, int64_t cat, int64_t n, const int
     return 0;
 }
 
+int hb2_set_rate_template(hb2_partition *p, int64_t nnz, const int64_t *entryIndex, const int64_t *entryFormula,
+                          int64_t nFormulas, const double *colFreq) {
+    if (!p) return fail("null partition");
+    if (nnz < 1 || nFormulas < 1 || !entryIndex || !entryFormula) return fail("bad template arguments");
+    CU(cudaSetDevice(p->device));
+    if (flush_matrices(p)) return 1;
+    CU(cudaStreamSynchronize(p->stream));
+    std::vector<int> idx(nnz), frm(nnz);
+    for (int64_t e = 0; e < nnz; e++) {
+        if (entryIndex[e] < 0 || entryIndex[e] >= p->D * p->D) return fail("template entry %lld: index %lld out of range", (long long)e, (long long)entryIndex[e]);
+        if (entryFormula[e] < 0 || entryFormula[e] >= nFormulas) return fail("template entry %lld: formula %lld out of range", (long long)e, (long long)entryFormula[e]);
+        idx[e] = (int)entryIndex[e]; frm[e] = (int)entryFormula[e];
+    }
+    void *old[] = {p->d_t_index, p->d_t_formula, p->d_t_colfreq, p->d_V, p->d_vdst};
+    for (void *d : old) if (d) cudaFree(d);
+    if (p->h_V) cudaFreeHost(p->h_V);
+    if (p->h_vdst) cudaFreeHost(p->h_vdst);
+    p->d_t_index = p->d_t_formula = p->d_vdst = nullptr; p->d_t_colfreq = p->d_V = nullptr; p->h_V = nullptr; p->h_vdst = nullptr;
+    CU(cudaMalloc(&p->d_t_index, nnz * sizeof(int)));
+    CU(cudaMalloc(&p->d_t_formula, nnz * sizeof(int)));
+    CU(cudaMalloc(&p->d_t_colfreq, p->D * sizeof(double)));
+    CU(cudaMalloc(&p->d_V, (size_t)p->q_capacity * nFormulas * sizeof(double)));
+    CU(cudaMalloc(&p->d_vdst, p->q_capacity * sizeof(int)));
+    CU(cudaMallocHost(&p->h_V, (size_t)p->q_capacity * nFormulas * sizeof(double)));
+    CU(cudaMallocHost(&p->h_vdst, p->q_capacity * sizeof(int)));
+    CU(cudaMemcpy(p->d_t_index, idx.data(), nnz * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(p->d_t_formula, frm.data(), nnz * sizeof(int), cudaMemcpyHostToDevice));
+    p->t_has_colfreq = colFreq != nullptr;
+    if (colFreq) CU(cudaMemcpy(p->d_t_colfreq, colFreq, p->D * sizeof(double), cudaMemcpyHostToDevice));
+    p->t_nnz = nnz; p->t_nF = nFormulas; p->n_vpending = 0;
+    return 0;
+}
+
+int hb2_set_matrices_compiled(hb2_partition *p, int64_t cat, int64_t n, const int64_t *nodeIds, const double *formulaValues) {
+    if (!p) return fail("null partition");
+    if (p->t_nnz == 0) return fail("hb2_set_rate_template has not been called");
+    if (n < 0 || (n > 0 && (!nodeIds || !formulaValues))) return fail("bad compiled matrix list");
+    if (cat < 0) cat = 0;
+    if (cat >= p->C) return fail("rate class %lld out of range (C=%lld)", (long long)cat, (long long)p->C);
+    for (int64_t k = 0; k < n; k++) {
+        if (nodeIds[k] < 0 || nodeIds[k] >= p->B) return fail("node id %lld has no branch", (long long)nodeIds[k]);
+        if (p->n_vpending == p->q_capacity) { cudaSetDevice(p->device); if (flush_compiled(p)) return 1; }
+        if (p->staging_busy) { CU(cudaEventSynchronize(p->ev_staging)); p->staging_busy = false; }
+        memcpy(p->h_V + p->n_vpending * p->t_nF, formulaValues + k * p->t_nF, p->t_nF * sizeof(double));
+        p->h_vdst[p->n_vpending] = (int)(cat * p->B + nodeIds[k]);
+        p->have_matrix[cat * p->B + nodeIds[k]] = 1;
+        p->n_vpending++;
+    }
+    return 0;
+}
+
 int hb2_evaluate(hb2_partition *p, int64_t cat, int64_t nUpdate, const int64_t *updateNodes, const double *rootFreqs,
                  double *lnL, double *siteL, int64_t *siteScale) {
     if (!p) return fail("null partition");
@@ -605,12 +682,14 @@ void hb2_destroy(hb2_partition *p) {
     if (p->comm) g_nccl.CommDestroy(p->comm);
     void *dev[] = {p->d_leaf, p->d_scal, p->d_rootE, p->d_child_start, p->d_child_ids, p->d_jobs, p->d_dst, p->d_flag,
                    p->d_mix_first, p->d_ambig, p->d_freq, p->d_cond, p->d_PT, p->d_Q, p->d_pi, p->d_rootL, p->d_weights,
-                   p->d_partial, p->d_lnL, p->d_siteL, p->d_mix_w, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err};
+                   p->d_partial, p->d_lnL, p->d_siteL, p->d_mix_w, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_t_index, p->d_t_formula, p->d_vdst, p->d_t_colfreq, p->d_V};
     for (void *d : dev) if (d) cudaFree(d);
     if (p->h_Q) cudaFreeHost(p->h_Q);
     if (p->h_small) cudaFreeHost(p->h_small);
     if (p->h_jobs) cudaFreeHost(p->h_jobs);
     if (p->h_dst) cudaFreeHost(p->h_dst);
+    if (p->h_V) cudaFreeHost(p->h_V);
+    if (p->h_vdst) cudaFreeHost(p->h_vdst);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
     if (p->ev_staging) cudaEventDestroy(p->ev_staging);
     if (p->stream) cudaStreamDestroy(p->stream);

@@ -101,7 +101,51 @@ struct ExpmArgs {
     double *Qres;           // nullable [slots][D*D]: resident copy of the rate matrices, written while loading
     int D;
     int is_trans;           // 1: input already a transition matrix -> just transpose/pad
+    // compiled-template input (replaces dense Q when tmpl_nnz > 0): Q[row][col] = V[blk][formula[e]] * colfreq[col],
+    // diagonal = -(off-diagonal row sum); mirrors _CompiledMatrixData + MultByFreqs (reference matrix.h:69, matrix.cpp:1546)
+    const double *V;        // [n][nF] formula values per matrix
+    const int *tmpl_index;  // [nnz] row*D + col
+    const int *tmpl_formula;// [nnz]
+    const double *tmpl_colfreq;  // nullable [D]
+    int tmpl_nnz, nF;
 };
+
+// Builds A1[j][i] = Q[i][j] (transposed, zero padded, leading dimension LD) from dense or compiled input and leaves a
+// dense resident copy in Qres when asked.  All threads of the CTA call it; ends with a barrier.
+template <int DP, int LD, int NT>
+__device__ __forceinline__ void load_rate_matrix(const ExpmArgs &a, double *A1, int tid) {
+    const int D = a.D;
+    const size_t slot = a.dst[blockIdx.x];
+    if (a.tmpl_nnz > 0) {
+        for (int idx = tid; idx < DP * LD; idx += NT) A1[idx] = 0.0;
+        __syncthreads();
+        const double *V = a.V + (size_t)blockIdx.x * a.nF;
+        for (int e = tid; e < a.tmpl_nnz; e += NT) {
+            const int rc = a.tmpl_index[e], r = rc / D, c = rc - r * D;
+            double v = V[a.tmpl_formula[e]];
+            if (a.tmpl_colfreq) v *= a.tmpl_colfreq[c];
+            if (r != c) A1[c * LD + r] = v;
+        }
+        __syncthreads();
+        if (tid < D) {
+            double s = 0.0;
+            for (int c = 0; c < D; c++) if (c != tid) s += A1[c * LD + tid];
+            A1[tid * LD + tid] = -s;
+        }
+        __syncthreads();
+        if (a.Qres)
+            for (int idx = tid; idx < D * D; idx += NT) { const int i = idx / D, j = idx - i * D; a.Qres[slot * D * D + idx] = A1[j * LD + i]; }
+    } else {
+        const double *Q = a.Q + (size_t)blockIdx.x * D * D;
+        for (int idx = tid; idx < DP * DP; idx += NT) {
+            const int i = idx / DP, j = idx - i * DP;
+            const double v = (i < D && j < D) ? Q[(size_t)i * D + j] : 0.0;
+            A1[j * LD + i] = v;
+            if (a.Qres && i < D && j < D) a.Qres[slot * D * D + (size_t)i * D + j] = v;
+        }
+    }
+    __syncthreads();
+}
 
 __constant__ double c_taylor[16] = {1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320,
                                     1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0,
@@ -115,17 +159,9 @@ __global__ void __launch_bounds__(256, 1) expm64_kernel(ExpmArgs a) {
     __shared__ int s_shift;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int D = a.D;
-    const double *Q = a.Q + (size_t)blockIdx.x * D * D;
     double *out = a.PT + (size_t)a.dst[blockIdx.x] * 4096;
 
-    // load transposed + zero padded: A1[j][i] = Q[i][j]
-    for (int idx = tid; idx < 64 * 64; idx += 256) {
-        int i = idx >> 6, j = idx & 63;
-        double v = (i < D && j < D) ? Q[(size_t)i * D + j] : 0.0;
-        A1[j * LD64 + i] = v;
-        if (a.Qres && i < D && j < D) a.Qres[(size_t)a.dst[blockIdx.x] * D * D + (size_t)i * D + j] = v;
-    }
-    __syncthreads();
+    load_rate_matrix<64, LD64, 256>(a, A1, tid);
     if (a.is_trans) {
         for (int idx = tid; idx < 4096; idx += 256) out[idx] = A1[(idx >> 6) * LD64 + (idx & 63)];
         return;
@@ -244,15 +280,8 @@ __global__ void __launch_bounds__(128) expm_small_kernel(ExpmArgs a) {
     __shared__ double red[DP];
     __shared__ int s_shift;
     const int tid = threadIdx.x, D = a.D;
-    const double *Q = a.Q + (size_t)blockIdx.x * D * D;
     double *out = a.PT + (size_t)a.dst[blockIdx.x] * DP * DP;
-    for (int idx = tid; idx < DP * DP; idx += 128) {
-        int i = idx / DP, j = idx % DP;
-        const double v = (i < D && j < D) ? Q[(size_t)i * D + j] : 0.0;
-        A1[j * LD + i] = v;
-        if (a.Qres && i < D && j < D) a.Qres[(size_t)a.dst[blockIdx.x] * D * D + (size_t)i * D + j] = v;
-    }
-    __syncthreads();
+    load_rate_matrix<DP, LD, 128>(a, A1, tid);
     if (a.is_trans) {
         for (int idx = tid; idx < DP * DP; idx += 128) out[idx] = A1[(idx / DP) * LD + idx % DP];
         return;

@@ -9,6 +9,12 @@
 // representation error of the splits (~2^-22) plus fp32 accumulation.  Conditionals are stored in fp32, renormalised
 // per (node, pattern) to max in [0.5,1) with an int32 binary exponent, so fp32 range is never an issue.
 //
+// Anchors.  The tensor core accumulates in fp32 with truncation (measured on B200: -8e-8 mean relative error per
+// K=64 contraction), which would bias lnL by ~-1.6e-7*|lnL|.  Conditional vectors are sharply peaked (1-3 codons carry
+// almost all the mass), so each thread pulls the entries >= 2^-6 of its row (at most 8, "anchors") out of the tensor
+// operand and multiplies them on the CUDA cores with round-to-nearest fp32 FMAs against fp32 rows of P^T while the
+// MMAs run; the tensor core only contracts the diffuse remainder, whose truncation bias is scaled down by its share.
+//
 // Operand staging:
 //   A (= X, 128 x 64, K-major) comes from TENSOR MEMORY: each of the 128 threads owns one pattern (one TMEM lane),
 //     loads its fp32 row from HBM, splits it in registers and writes Xh / Xl with tcgen05.st (columns 64..191).
@@ -31,6 +37,8 @@ constexpr int TC_TILE_P = 128;                 // patterns per CTA (= UMMA M = T
 constexpr int TC_PB_FLOATS = 2 * 4096;         // per (class, branch): Ph tile + Pl tile in canonical layout
 constexpr int TC_SMEM_BYTES = 2 * 32768 + 1024; // two B stages (one used for now; also caps residency at 2 CTAs/SM) + barriers
 constexpr uint32_t TC_TMEM_COLS = 256;         // D: 0..63, Xh: 64..127, Xl: 128..191
+constexpr int TC_MAX_ANCHORS = 8;              // per pattern and child
+constexpr float TC_ANCHOR_THR = 0.015625f;     // 2^-6 (rows are normalised to max in [0.5,1))
 
 struct PruneTcArgs {
     const float *PB;                // [C][B][2][16][64][4] canonical K-major tiles of P (hi, lo)
@@ -158,6 +166,8 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_kernel(PruneTcArgs a, const
     uint64_t *bar_b = reinterpret_cast<uint64_t *>(smem + 2 * 32768);
     uint64_t *bar_mma = bar_b + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_b + 2);
+    int *s_ak = reinterpret_cast<int *>(smem + 32768);                   // [TC_MAX_ANCHORS][128] anchor state
+    float *s_av = reinterpret_cast<float *>(smem + 32768 + TC_MAX_ANCHORS * 128 * 4);   // [TC_MAX_ANCHORS][128] anchor value
     const int tid = threadIdx.x, warp = tid >> 5;
     const int par = jobs[blockIdx.y];
     const int cat = a.cat0 + blockIdx.z;
@@ -225,16 +235,23 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_kernel(PruneTcArgs a, const
                 mbar_expect_tx(bar_b, 32768u);
                 bulk_g2s(Bs, a.PB + slot * TC_PB_FLOATS, 32768u, bar_b);
             }
-            // (B) this thread's pattern row -> split -> TMEM (Xh at cols 64.., Xl at cols 128..)
+            // (B) this thread's pattern row -> anchors out -> split -> TMEM (Xh at cols 64.., Xl at cols 128..)
+            int na = 0;
             {
                 const float4 *xr = reinterpret_cast<const float4 *>(a.cond + (((size_t)cat * a.I + cin) * Sp + s) * 64);
                 uint32_t hi[64], lo[64];
 #pragma unroll
                 for (int q = 0; q < 16; q++) {
                     const float4 x = xr[q];
-                    const float xs[4] = {x.x, x.y, x.z, x.w};
+                    float xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
+                        if (xs[u] >= TC_ANCHOR_THR && na < TC_MAX_ANCHORS) {
+                            s_ak[na * 128 + tid] = 4 * q + u;
+                            s_av[na * 128 + tid] = xs[u];
+                            na++;
+                            xs[u] = 0.f;
+                        }
                         const float h = tf32_rn(xs[u]);
                         hi[4 * q + u] = __float_as_uint(h);
                         lo[4 * q + u] = __float_as_uint(xs[u] - h);
@@ -266,15 +283,33 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_kernel(PruneTcArgs a, const
                 tc_commit(bar_mma);
             }
             __syncwarp();
+            // anchors on the CUDA cores while the tensor core works: acc[n] = sum_a x[k_a] * P[n][k_a], fp32 RN
+            float acc[64];
+#pragma unroll
+            for (int k = 0; k < 64; k++) acc[k] = 0.f;
+            {
+                const float *PTf = a.PTf + slot * 4096;
+                for (int ai = 0; ai < na; ai++) {
+                    const int ka = s_ak[ai * 128 + tid];
+                    const float xv = s_av[ai * 128 + tid];
+                    const float4 *row = reinterpret_cast<const float4 *>(PTf + (size_t)ka * 64);
+#pragma unroll
+                    for (int q = 0; q < 16; q++) {
+                        const float4 r = __ldg(row + q);
+                        acc[4 * q] = fmaf(xv, r.x, acc[4 * q]); acc[4 * q + 1] = fmaf(xv, r.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(xv, r.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(xv, r.w, acc[4 * q + 3]);
+                    }
+                }
+            }
             mbar_wait(bar_mma, phase, a.err);
             tc_fence_after();
-            {
-                uint32_t d[64];
 #pragma unroll
-                for (int o = 0; o < 64; o += 16) HB2_TMEM_LD16(lane_addr + o, d, o);
+            for (int o = 0; o < 64; o += 16) {
+                uint32_t d[16];
+                HB2_TMEM_LD16(lane_addr + o, d, 0);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int k = 0; k < 64; k++) v[k] *= __uint_as_float(d[k]);
+                for (int k = 0; k < 16; k++) v[o + k] *= (__uint_as_float(d[k]) + acc[o + k]);
             }
             phase ^= 1u;
         }

@@ -33,6 +33,8 @@ ABI = [
                              C.c_int64, _ip, C.c_int, C.c_int]),
     ("hb2_set_matrices", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _ip, C.POINTER(_dp), C.c_int]),
     ("hb2_set_matrices_packed", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _ip, _dp, C.c_int]),
+    ("hb2_set_rate_template", C.c_int, [C.c_void_p, C.c_int64, _ip, _ip, C.c_int64, _dp]),
+    ("hb2_set_matrices_compiled", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _ip, _dp]),
     ("hb2_set_mixture_matrices", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _ip, C.c_int64, _dp, _dp]),
     ("hb2_evaluate", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _ip, _dp, _dp, _dp, _ip]),
     ("hb2_evaluate_classes", C.c_int, [C.c_void_p, _dp, C.c_int64, _ip, _dp, _dp, _dp, _ip]),
@@ -121,6 +123,23 @@ class Partition:
         keep = [np.ascontiguousarray(m, dtype=np.float64) for m in mats]
         arr = (_dp * len(keep))(*[m.ctypes.data_as(_dp) for m in keep])
         _check(self._lib.hb2_set_matrices(self._h, int(cat), len(ids), pids, arr, int(kind)))
+
+    def set_rate_template(self, entry_index, entry_formula, n_formulas, col_freq=None):
+        ei, pei = _i(entry_index)
+        ef, pef = _i(entry_formula)
+        assert ei.shape == ef.shape
+        pcf = None
+        if col_freq is not None:
+            cf, pcf = _d(col_freq)
+            assert cf.shape == (self.D,)
+        self.n_formulas = int(n_formulas)
+        _check(self._lib.hb2_set_rate_template(self._h, len(ei), pei, pef, int(n_formulas), pcf))
+
+    def set_matrices_compiled(self, cat, node_ids, values):
+        ids, pids = _i(node_ids)
+        v, pv = _d(values)
+        assert v.shape == (len(ids), self.n_formulas)
+        _check(self._lib.hb2_set_matrices_compiled(self._h, int(cat), len(ids), pids, pv))
 
     def set_mixture_matrices(self, cat, node_ids, M, w):
         ids, pids = _i(node_ids)
@@ -230,6 +249,17 @@ class LikelihoodFunction:
         Qt = self.w.Qt() if Qt is None else Qt
         for c in range(self.w.C):
             self.part.set_matrices(c, self.all_nodes, Qt[c], kind)
+
+    def set_template(self):
+        """Hand the model's compiled template over once (the static half of _CompiledMatrixData)."""
+        ei, ef, nf, cf = self.w.compiled_template()
+        self.part.set_rate_template(ei, ef, nf, cf)
+
+    def set_all_compiled(self, values=None):
+        """Per-evaluation half: formula values [C, B, nF] for every branch and class."""
+        values = self.w.compiled_values() if values is None else values
+        for c in range(self.w.C):
+            self.part.set_matrices_compiled(c, self.all_nodes, values[c])
 
     def compute_block(self, cat=0, update_nodes=None, want_sites=False):
         return self.part.evaluate(cat, self.w.pi, update_nodes, want_sites)

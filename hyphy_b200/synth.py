@@ -231,6 +231,7 @@ class Workload:
     site_to_pattern: np.ndarray    # int64 [sites]
     site_chars: list | None = None  # per leaf, the character string (for FASTA export to the reference)
     meta: dict = dataclasses.field(default_factory=dict)
+    _tmpl: tuple | None = None
 
     @property
     def S(self):
@@ -239,6 +240,54 @@ class Workload:
     @property
     def C(self):
         return len(self.Q_classes)
+
+    # -- compact ("compiled") form of the same matrices: the static template and per-evaluation formula values,
+    #    the shape in which the reference itself holds a model matrix (_CompiledMatrixData, matrix.h:69-80)
+    def _formulas(self):
+        """Returns (entry_index[nnz], entry_formula[nnz], per-class base value of each formula [C, nF], col_freq|None);
+        the formula VALUE for branch b is base * t_b."""
+        if getattr(self, "_tmpl", None) is not None:
+            return self._tmpl
+        kind = self.meta.get("kind")
+        D = self.D
+        if kind == "codon":
+            th = dict(zip(["AC", "AG", "AT", "CG", "CT", "GT"], self.meta["theta"]))
+            keys, ei, ef = {}, [], []
+            for i, j, pf, nonsyn, nm in mg94_entries(self.meta["theta"], np.array(self.meta["posfreq"])):
+                key = (nm, nonsyn, pf)
+                if key not in keys:
+                    keys[key] = len(keys)
+                ei.append(i * D + j)
+                ef.append(keys[key])
+            omegas = self.meta["omegas"]
+            base = np.array([[th[nm] * pf * (om if nonsyn else 1.0) for (nm, nonsyn, pf) in keys] for om in omegas])
+            cf = None
+        elif kind == "nuc":
+            ei, ef = [], []
+            for i in range(4):
+                for j in range(4):
+                    if i != j:
+                        ei.append(i * 4 + j)
+                        ef.append(1 if ((i + j) in (2, 4) and abs(i - j) == 2) else 0)
+            base = np.array([[1.0, self.meta["kappa"]]])
+            cf = np.asarray(self.pi, dtype=np.float64)
+        else:                                   # generic: every off-diagonal entry is its own formula
+            ei = [i * D + j for i in range(D) for j in range(D) if i != j]
+            ef = list(range(len(ei)))
+            base = np.array([[Q[i, j] for i in range(D) for j in range(D) if i != j] for Q in self.Q_classes])
+            cf = None
+        self._tmpl = (np.array(ei, dtype=np.int64), np.array(ef, dtype=np.int64), base, cf)
+        return self._tmpl
+
+    def compiled_template(self):
+        ei, ef, base, cf = self._formulas()
+        return ei, ef, base.shape[1], cf
+
+    def compiled_values(self, perturb: float = 0.0) -> np.ndarray:
+        """Formula values [C, B, nF] (what the host evaluates per branch: cmd->formulaValues, matrix.cpp:3131)."""
+        _, _, base, _ = self._formulas()
+        nb = self.tree.n_branches
+        return base[:, None, :] * (self.tree.t[:nb, None] * (1.0 + perturb))[None, :, :]
 
     def Qt(self, perturb: float = 0.0) -> np.ndarray:
         """Dense Q*t for every (class, branch node): float64 [C, L+I-1, D, D].  `perturb` scales all

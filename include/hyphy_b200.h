@@ -67,6 +67,22 @@ int hb2_set_matrices(hb2_partition *p, int64_t cat, int64_t n, const int64_t *no
 int hb2_set_matrices_packed(hb2_partition *p, int64_t cat, int64_t n, const int64_t *nodeIds,
                             const double *M, int kind);
 
+/* Compact hand-over of rate matrices (removes the 8*D*D bytes per matrix of H2D traffic and lets the device do
+ * what _Matrix::EvaluateSimple's scatter (matrix.cpp:3094-3321) and MultByFreqs (matrix.cpp:1546-1677) do on the host).
+ * The reference compiles a model matrix into _CompiledMatrixData (include/matrix.h:69-80): a list of unique formulas
+ * (formulasToEval), per-evaluation numeric formulaValues[], and formulaRefs[] mapping every stored off-diagonal entry
+ * to its formula.  hb2_set_rate_template takes that static part once per model:
+ *   entryIndex[e]   = row*D + col of stored entry e (theIndex), off-diagonal
+ *   entryFormula[e] = formulaRefs[e] in [0, nFormulas)
+ *   colFreq         = nullable D doubles: entry (r,c) is multiplied by colFreq[c] (MultByFreqs; NULL when the model
+ *                     was declared with the "do not multiply by frequencies" flag)
+ * hb2_set_matrices_compiled then hands over, per evaluation, only formulaValues (n * nFormulas doubles, one row per
+ * listed node); the engine scatters them, applies colFreq, sets diagonal = -(row sum) and exponentiates. */
+int hb2_set_rate_template(hb2_partition *p, int64_t nnz, const int64_t *entryIndex, const int64_t *entryFormula,
+                          int64_t nFormulas, const double *colFreq);
+int hb2_set_matrices_compiled(hb2_partition *p, int64_t cat, int64_t n, const int64_t *nodeIds,
+                              const double *formulaValues);
+
 /* Explicit-form mixtures P = sum_k w_k Exp(Q_k) per branch (BS-REL; tree.cpp:3047-3089):
  * K components for each listed node, M packed [n][K][D*D], w packed [n][K]. */
 int hb2_set_mixture_matrices(hb2_partition *p, int64_t cat, int64_t n, const int64_t *nodeIds, int64_t K,

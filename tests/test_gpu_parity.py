@@ -139,6 +139,41 @@ def test_host_transition_matrices_path(mode):
     assert abs(lnl - g["lnL"]) <= max(tol(w, mode)[0], 1e-12) * abs(g["lnL"])
 
 
+@pytest.mark.parametrize("name", ["mg94_30x100_c4_ambig", "c1_hky85_8x500"])
+def test_compiled_template_equals_dense_matrices(name, mode):
+    """hb2_set_rate_template + hb2_set_matrices_compiled (the reference's _CompiledMatrixData hand-over, incl. the
+    MultByFreqs column multiplier for HKY85) must give the matrices and lnL of the dense hand-over."""
+    w, g = gc.load(name)
+    lf = LF(w, mode)
+    lf.set_all_matrices()
+    dense = lf.compute()
+    Pd = lf.part.read_transition(w.C - 1, 4)
+    lf.close()
+    lf = LF(w, mode)
+    lf.set_template()
+    lf.set_all_compiled()
+    comp = lf.compute()
+    np.testing.assert_allclose(lf.part.read_transition(w.C - 1, 4), Pd, rtol=0, atol=1e-14)
+    # partial update through the compiled path
+    w.tree.t[2] *= 1.3
+    V = w.compiled_values()
+    for c in range(w.C):
+        lf.part.set_matrices_compiled(c, [2], V[c, 2:3])
+    upd = lf.compute(update_nodes=[2])
+    ref, _ = port.lnl(w)
+    w.tree.t[2] /= 1.3
+    lf.close()
+    assert abs(comp - dense) <= 1e-12 * abs(dense)
+    assert abs(upd - ref) <= tol(w, mode)[0] * abs(ref)
+    with pytest.raises(engine.EngineError, match="hb2_set_rate_template"):
+        lf2 = LF(w, mode)
+        try:
+            lf2.part.n_formulas = 3
+            lf2.part.set_matrices_compiled(0, [0], np.zeros((1, 3)))
+        finally:
+            lf2.close()
+
+
 def test_partial_update_equals_full_recompute(mode):
     """DetermineNodesForUpdate semantics (tree.cpp:3117): change one branch, pass only that node; the engine must
     re-prune its ancestors and reuse every other cached conditional."""
