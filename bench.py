@@ -194,14 +194,12 @@ def main():
 
     w = synth.codon_workload(WORKLOAD["taxa"], WORKLOAD["codons"], WORKLOAD["classes"])
     S = w.S
-    # contiguous pattern shards, balanced by count
-    lo, hi = rank * S // world, (rank + 1) * S // world
+    from hyphy_b200.sharding import shard_bounds, exchange_unique_id
+    lo, hi = shard_bounds(S, world, rank)            # contiguous pattern shards, balanced by count
     lf = LikelihoodFunction(w, device=local_rank, flags=1 if args.fp64 else 0,
                             pattern_slice=slice(lo, hi) if world > 1 else None)
     if world > 1:
-        uid = [Partition.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        lf.part.comm_init(world, rank, uid[0])
+        lf.part.comm_init(world, rank, exchange_unique_id(dist, rank, Partition.comm_unique_id))
 
     def barrier():
         if dist is not None:
