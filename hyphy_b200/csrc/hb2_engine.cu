@@ -11,6 +11,7 @@
 #include <climits>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <string>
@@ -112,6 +113,11 @@ struct hb2_partition {
     bool use_tc = false;
     float *d_condf = nullptr, *d_PB = nullptr, *d_PTf = nullptr;
     int *d_err = nullptr;
+    // persistent walk kernel (one launch per evaluation): plan buffers, epoch flags, residency
+    bool use_walk = false;
+    int walk_max_resident = 0;
+    int epoch = 0;
+    int *d_done = nullptr, *d_walk = nullptr, *h_walk = nullptr;
     bool first_eval_done = false;
     std::vector<char> evaluated_cat;          // [C] whole tree pruned at least once
     int64_t launches = 0;
@@ -276,7 +282,81 @@ hb2::PruneArgs prune_args(hb2_partition *p, int cat0) {
     return a;
 }
 
+// Walk plan: lanes of internal nodes (height-major order inside a lane), children re-ordered and tagged.
+// Layout of the int buffer: lane_start[K+1] | lane_jobs[nJobs] | job_child_start[I+1] | job_child[L+I]
+int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector<int>> &levels) {
+    const int I = (int)p->I, L = (int)p->L;
+    const int T = (int)(p->Sp / hb2::TC_TILE_P);
+    const int CT = ncls * T;
+    int K = std::max(1, std::min(8, p->walk_max_resident / std::max(CT, 1)));
+    int total = 0;
+    for (auto &lv : levels) total += (int)lv.size();
+    if (total == 0) return 0;
+    K = std::min(K, total);
+    const int nslots = (K == 1) ? std::min(CT, p->walk_max_resident) : CT;
+    std::vector<char> dirty(I, 0);
+    for (auto &lv : levels) for (int n : lv) dirty[n] = 1;
+    std::vector<int> lane_of(I, -1), lane_last(K, -1), lane_total(K, 0);
+    std::vector<std::vector<int>> lanes(K);
+    std::vector<int> chain_child(I, -1);
+    for (auto &lv : levels) {
+        if (lv.empty()) continue;
+        std::vector<int> lvl_count(K, 0);
+        const int cap = ((int)lv.size() + K - 1) / K;
+        for (int n : lv) {
+            // preferred lane: the one whose last job is this node's highest dirty internal child (register hand-over)
+            int best = -1, best_h = -1;
+            for (int ch : p->children[n]) {
+                if (ch < L) continue;
+                const int ci = ch - L;
+                if (dirty[ci] && lane_of[ci] >= 0 && lane_last[lane_of[ci]] == ci && p->height[ci] > best_h) { best = ci; best_h = p->height[ci]; }
+            }
+            int lane = -1;
+            if (best >= 0 && lvl_count[lane_of[best]] < cap) { lane = lane_of[best]; chain_child[n] = best; }
+            if (lane < 0) {
+                for (int r = 0; r < K; r++)
+                    if (lane < 0 || lvl_count[r] < lvl_count[lane] || (lvl_count[r] == lvl_count[lane] && lane_total[r] < lane_total[lane])) lane = r;
+            }
+            lane_of[n] = lane; lane_last[lane] = n; lvl_count[lane]++; lane_total[lane]++;
+            lanes[lane].push_back(n);
+        }
+    }
+    int *buf = p->h_walk;
+    int *lane_start = buf, *lane_jobs = buf + (K + 1), *jcs = lane_jobs + total, *jc = jcs + (I + 1);
+    int off = 0;
+    for (int r = 0; r < K; r++) { lane_start[r] = off; for (int n : lanes[r]) lane_jobs[off++] = n; }
+    lane_start[K] = off;
+    int co = 0;
+    for (int n = 0; n < I; n++) {
+        jcs[n] = co;
+        if (!dirty[n]) continue;
+        if (chain_child[n] >= 0) jc[co++] = (chain_child[n] + L) | hb2::WALK_CHAIN;
+        for (int ch : p->children[n]) if (ch < L) jc[co++] = ch;                          // leaves: no waiting
+        for (int ch : p->children[n]) {
+            if (ch < L || ch - L == chain_child[n]) continue;
+            const int ci = ch - L;
+            jc[co++] = ch | ((dirty[ci] && lane_of[ci] != lane_of[n]) ? hb2::WALK_WAIT : 0);
+        }
+    }
+    jcs[I] = co;
+    const int nints = (K + 1) + total + (I + 1) + co;
+    CU(cudaMemcpyAsync(p->d_walk, p->h_walk, nints * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    hb2::PruneArgs a = prune_args(p, cat0);
+    hb2::WalkArgs w;
+    hb2::PruneTcArgs &t = w.a;
+    t.PB = p->d_PB; t.PTf = p->d_PTf; t.cond = p->d_condf; t.scal = a.scal; t.leaf = a.leaf; t.ambig = a.ambig; t.pi = a.pi;
+    t.rootL = a.rootL; t.rootE = a.rootE; t.tree = a.tree; t.err = p->d_err;
+    t.L = a.L; t.I = a.I; t.B = a.B; t.D = a.D; t.Sp = a.Sp; t.cat0 = a.cat0;
+    w.lane_start = p->d_walk; w.lane_jobs = p->d_walk + (K + 1); w.job_child_start = w.lane_jobs + total; w.job_child = w.job_child_start + (I + 1);
+    w.done = p->d_done; w.epoch = ++p->epoch; w.K = K; w.T = T; w.ncls = ncls; w.nslots = nslots;
+    hb2::prune64_tc_walk_kernel<<<nslots * K, 128, hb2::TC_SMEM_BYTES, p->stream>>>(w);
+    p->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int run_pruning(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector<int>> &levels) {
+    if (p->use_tc && p->use_walk) return run_walk(p, cat0, ncls, levels);
     // upload all job lists in one copy
     int total = 0;
     for (auto &lv : levels) total += (int)lv.size();
@@ -350,7 +430,7 @@ int evaluate_impl(hb2_partition *p, int c0, int nc, const double *weights, int64
     if (siteL) CU(cudaMemcpyAsync(siteL, p->d_siteL, p->S * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     if (siteScale) CU(cudaMemcpyAsync(siteScale, p->d_siteScale, p->S * sizeof(long long), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaStreamSynchronize(p->stream));
-    if (*reinterpret_cast<int *>(hs + p->Dp + p->C + 1) != 0) return fail("device-side barrier timeout in the tcgen05 pruning kernel");
+    if (*reinterpret_cast<int *>(hs + p->Dp + p->C + 1) != 0) return fail("device-side wait timed out in the tcgen05 pruning kernel (code %d)", *reinterpret_cast<int *>(hs + p->Dp + p->C + 1));
     *lnL = hs[p->Dp + p->C];
     for (int c = c0; c < c0 + nc; c++) p->evaluated_cat[c] = 1;
     return 0;
@@ -432,6 +512,22 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
         CUP(cudaMemsetAsync(p->d_PB, 0, (size_t)C * p->B * hb2::TC_PB_FLOATS * sizeof(float), p->stream));
         CUP(cudaMemsetAsync(p->d_PTf, 0, (size_t)C * p->B * 4096 * sizeof(float), p->stream));
         CUP(cudaFuncSetAttribute(hb2::prune64_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::TC_SMEM_BYTES));
+        CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::TC_SMEM_BYTES));
+        {
+            const char *env = getenv("HB2_TC_WALK");
+            p->use_walk = !(env && env[0] == '0');
+            int per_sm = 0, sms = 0;
+            CUP(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hb2::prune64_tc_walk_kernel, 128, hb2::TC_SMEM_BYTES));
+            CUP(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+            p->walk_max_resident = std::min(per_sm, 2) * sms;          // TMEM: 256 of 512 columns per CTA -> at most 2 per SM
+            if (p->walk_max_resident < 1) p->use_walk = false;
+            const size_t T = Sp / hb2::TC_TILE_P;
+            CUP(cudaMalloc(&p->d_done, (size_t)C * I * T * sizeof(int)));
+            CUP(cudaMemsetAsync(p->d_done, 0, (size_t)C * I * T * sizeof(int), p->stream));
+            const size_t walk_ints = 16 + (size_t)I + (I + 1) + (L + I);
+            CUP(cudaMalloc(&p->d_walk, walk_ints * sizeof(int)));
+            CUP(cudaMallocHost(&p->h_walk, walk_ints * sizeof(int)));
+        }
     } else {
         CUP(cudaMalloc(&p->d_cond, (size_t)C * I * Sp * Dp * sizeof(double)));
         CUP(cudaMemsetAsync(p->d_cond, 0, (size_t)C * I * Sp * Dp * sizeof(double), p->stream));
@@ -564,6 +660,7 @@ int hb2_set_rate_template(hb2_partition *p, int64_t nnz, const int64_t *entryInd
     }
     void *old[] = {p->d_t_index, p->d_t_formula, p->d_t_colfreq, p->d_V, p->d_vdst};
     for (void *d : old) if (d) cudaFree(d);
+    if (p->h_walk) cudaFreeHost(p->h_walk);
     if (p->h_V) cudaFreeHost(p->h_V);
     if (p->h_vdst) cudaFreeHost(p->h_vdst);
     p->d_t_index = p->d_t_formula = p->d_vdst = nullptr; p->d_t_colfreq = p->d_V = nullptr; p->h_V = nullptr; p->h_vdst = nullptr;
@@ -682,7 +779,7 @@ void hb2_destroy(hb2_partition *p) {
     if (p->comm) g_nccl.CommDestroy(p->comm);
     void *dev[] = {p->d_leaf, p->d_scal, p->d_rootE, p->d_child_start, p->d_child_ids, p->d_jobs, p->d_dst, p->d_flag,
                    p->d_mix_first, p->d_ambig, p->d_freq, p->d_cond, p->d_PT, p->d_Q, p->d_pi, p->d_rootL, p->d_weights,
-                   p->d_partial, p->d_lnL, p->d_siteL, p->d_mix_w, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_t_index, p->d_t_formula, p->d_vdst, p->d_t_colfreq, p->d_V};
+                   p->d_partial, p->d_lnL, p->d_siteL, p->d_mix_w, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_done, p->d_walk, p->d_t_index, p->d_t_formula, p->d_vdst, p->d_t_colfreq, p->d_V};
     for (void *d : dev) if (d) cudaFree(d);
     if (p->h_Q) cudaFreeHost(p->h_Q);
     if (p->h_small) cudaFreeHost(p->h_small);

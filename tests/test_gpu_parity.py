@@ -1,8 +1,8 @@
 """GPU suite (pytest -m gpu): the CUDA path, called through the C ABI, against the oracle and the reference's
 golden vectors.  north_star's contract is |dlnL| < 1e-6*|lnL|.  Two precisions are exercised:
   fp64 : HB2_FLAG_FORCE_FP64 -- fp64 kernels everywhere, held to 1e-10 (parity reference on the device)
-  tc   : default flags -- 33..64-state models run on tcgen05 (error-compensated 3xTF32, fp32 conditionals), held to
-         2.5e-7 (4x inside the contract); other state counts use the fp64 register kernels in both modes.
+  tc   : default flags -- 33..64-state models run on tcgen05 (error-compensated 3xTF32 + anchors, fp32 conditionals),
+         held to 1e-7 (10x inside the contract); other state counts use the fp64 register kernels in both modes.
 Measured errors are appended to gpurun_out/parity_errors.jsonl for DESIGN.md."""
 import json
 import os
@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 
 RTOL_CONTRACT = 1e-6
 MODES = {"fp64": (engine.FLAG_FORCE_FP64, 1e-10, 1e-8),     # flags, lnL rtol required, per-site atol
-         "tc": (engine.FLAG_DEFAULT, 2.5e-7, 5e-4)}
+         "tc": (engine.FLAG_DEFAULT, 1e-7, 5e-5)}
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -191,10 +191,12 @@ def test_partial_update_equals_full_recompute(mode):
         ref, _ = port.lnl(w)
         assert abs(got - ref) <= rtol * abs(ref)
         assert got != base
-    # idempotence: nothing changed, empty update list -> same value, and a forced full recompute agrees bit for bit
+    # idempotence: nothing changed, empty update list -> same value; a forced full recompute agrees (bit for bit on the
+    # fp64 path; the walk kernel may fold a node's children in a different order, i.e. fp32 rounding noise)
     again = lf.compute(update_nodes=[])
     full = lf.compute(update_nodes=None)
-    assert again == got and full == got
+    assert again == got
+    assert full == got if (mode == "fp64" or w.D <= 32) else abs(full - got) <= 1e-8 * abs(got)
     lf.close()
     gc._cache.pop("mg94_30x100_c4_ambig", None)          # this test edited the cached workload's branch lengths
 
@@ -313,7 +315,7 @@ def test_full_size_properties(mode):
 
 def test_tensor_path_against_fp64_path_deep_and_wide():
     """The tcgen05 path against the fp64 kernels on the same device, on shapes chosen to stress error accumulation
-    (500 taxa: ~1000 contractions per pattern) and short/long branch mixes.  Contract: 1e-6; required here: 2.5e-7."""
+    (500 taxa: ~1000 contractions per pattern) and short/long branch mixes.  Contract: 1e-6; required here: 1e-7."""
     for (taxa, codons, C, mean_t) in [(500, 96, 4, 0.05), (200, 128, 1, 0.005), (64, 256, 4, 0.3)]:
         w = synth.codon_workload(taxa, codons, C, seed=77, mean_t=mean_t)
         res = {}
@@ -325,4 +327,4 @@ def test_tensor_path_against_fp64_path_deep_and_wide():
         a, b = res["fp64"][0], res["tc"][0]
         site = np.abs(_site_lnl(res["fp64"][1], res["fp64"][2]) - _site_lnl(res["tc"][1], res["tc"][2])).max()
         record("tc_vs_fp64", w.name + f"_t{mean_t}", "tc", b, a, float(site))
-        assert abs(a - b) <= 2.5e-7 * abs(a), (w.name, a, b)
+        assert abs(a - b) <= 1e-7 * abs(a), (w.name, a, b)
