@@ -114,6 +114,7 @@ struct hb2_partition {
     float *d_condf = nullptr, *d_PB = nullptr, *d_PTf = nullptr;
     int *d_err = nullptr;
     // persistent walk kernel (one launch per evaluation): plan buffers, epoch flags, residency
+    bool expm_dfma = false;                   // HB2_EXPM_DFMA=1: previous FFMA-style fp64 expm kernel (A/B testing)
     bool use_walk = false;
     int walk_max_resident = 0;
     int epoch = 0;
@@ -141,8 +142,17 @@ int launch_expm(hb2_partition *p, const double *dQ, const int *d_dst, int n, int
         a.is_trans = 0; a.Q = nullptr; a.V = dQ; a.tmpl_index = p->d_t_index; a.tmpl_formula = p->d_t_formula;
         a.tmpl_colfreq = p->t_has_colfreq ? p->d_t_colfreq : nullptr; a.tmpl_nnz = (int)p->t_nnz; a.nF = (int)p->t_nF;
     }
+    bool packed = false;
     switch (p->Dp) {
-        case 64: hb2::expm64_kernel<<<n, 256, 5 * 64 * hb2::LD64 * sizeof(double), p->stream>>>(a); break;
+        case 64:
+            if (p->expm_dfma) {
+                hb2::expm64_kernel<<<n, 256, 5 * 64 * hb2::LD64 * sizeof(double), p->stream>>>(a);
+            } else {
+                hb2::ExpmTcOut tco{nullptr, nullptr};
+                if (p->use_tc && pack_tc && !mix_w) { tco.PB = p->d_PB; tco.PTf = p->d_PTf; packed = true; }
+                hb2::expm64_dmma_kernel<<<n, 256, 4 * 64 * hb2::LD64 * sizeof(double), p->stream>>>(a, tco);
+            }
+            break;
         case 4: hb2::expm_small_kernel<4><<<n, 128, hb2::expm_small_smem_bytes(4), p->stream>>>(a); break;
         case 8: hb2::expm_small_kernel<8><<<n, 128, hb2::expm_small_smem_bytes(8), p->stream>>>(a); break;
         case 16: hb2::expm_small_kernel<16><<<n, 128, hb2::expm_small_smem_bytes(16), p->stream>>>(a); break;
@@ -152,7 +162,7 @@ int launch_expm(hb2_partition *p, const double *dQ, const int *d_dst, int n, int
     }
     p->launches++;
     CU(cudaGetLastError());
-    if (p->use_tc && pack_tc) {
+    if (p->use_tc && pack_tc && !packed) {
         hb2::pack_tc_kernel<<<n, 256, 0, p->stream>>>(p->d_PT, d_dst, p->d_PB, p->d_PTf);
         p->launches++;
         CU(cudaGetLastError());
@@ -323,8 +333,15 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
     }
     int *buf = p->h_walk;
     int *lane_start = buf, *lane_jobs = buf + (K + 1), *jcs = lane_jobs + total, *jc = jcs + (I + 1);
+    // a node's tile must be published (epoch flag) iff a dirty parent in ANOTHER lane consumes it
+    std::vector<char> publish(I, 0);
+    for (int n = 0; n < I; n++) {
+        if (!dirty[n]) continue;
+        const int64_t par = p->parents[L + n];
+        if (par >= 0 && dirty[par] && lane_of[par] != lane_of[n]) publish[n] = 1;
+    }
     int off = 0;
-    for (int r = 0; r < K; r++) { lane_start[r] = off; for (int n : lanes[r]) lane_jobs[off++] = n; }
+    for (int r = 0; r < K; r++) { lane_start[r] = off; for (int n : lanes[r]) lane_jobs[off++] = n | (publish[n] ? hb2::WALK_PUBLISH : 0); }
     lane_start[K] = off;
     int co = 0;
     for (int n = 0; n < I; n++) {
@@ -347,9 +364,10 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
     t.PB = p->d_PB; t.PTf = p->d_PTf; t.cond = p->d_condf; t.scal = a.scal; t.leaf = a.leaf; t.ambig = a.ambig; t.pi = a.pi;
     t.rootL = a.rootL; t.rootE = a.rootE; t.tree = a.tree; t.err = p->d_err;
     t.L = a.L; t.I = a.I; t.B = a.B; t.D = a.D; t.Sp = a.Sp; t.cat0 = a.cat0;
-    w.lane_start = p->d_walk; w.lane_jobs = p->d_walk + (K + 1); w.job_child_start = w.lane_jobs + total; w.job_child = w.job_child_start + (I + 1);
+    w.plan = p->d_walk; w.plan_ints = nints; w.n_jobs = total;
     w.done = p->d_done; w.epoch = ++p->epoch; w.K = K; w.T = T; w.ncls = ncls; w.nslots = nslots;
-    hb2::prune64_tc_walk_kernel<<<nslots * K, 128, hb2::TC_SMEM_BYTES, p->stream>>>(w);
+    if (getenv("HB2_DEBUG")) fprintf(stderr, "[hb2] walk: jobs=%d K=%d T=%d ncls=%d nslots=%d grid=%d resident=%d plan_ints=%d\n", total, K, T, ncls, nslots, nslots * K, p->walk_max_resident, nints);
+    hb2::prune64_tc_walk_kernel<<<nslots * K, 128, hb2::WALK_SMEM_BYTES, p->stream>>>(w);
     p->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -512,12 +530,13 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
         CUP(cudaMemsetAsync(p->d_PB, 0, (size_t)C * p->B * hb2::TC_PB_FLOATS * sizeof(float), p->stream));
         CUP(cudaMemsetAsync(p->d_PTf, 0, (size_t)C * p->B * 4096 * sizeof(float), p->stream));
         CUP(cudaFuncSetAttribute(hb2::prune64_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::TC_SMEM_BYTES));
-        CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::TC_SMEM_BYTES));
+        CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::WALK_SMEM_BYTES));
         {
             const char *env = getenv("HB2_TC_WALK");
             p->use_walk = !(env && env[0] == '0');
             int per_sm = 0, sms = 0;
-            CUP(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hb2::prune64_tc_walk_kernel, 128, hb2::TC_SMEM_BYTES));
+            CUP(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hb2::prune64_tc_walk_kernel, 128, hb2::WALK_SMEM_BYTES));
+            if (getenv("HB2_DEBUG")) fprintf(stderr, "[hb2] walk kernel occupancy: %d CTAs/SM\n", per_sm);
             CUP(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
             p->walk_max_resident = std::min(per_sm, 2) * sms;          // TMEM: 256 of 512 columns per CTA -> at most 2 per SM
             if (p->walk_max_resident < 1) p->use_walk = false;
@@ -525,6 +544,7 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
             CUP(cudaMalloc(&p->d_done, (size_t)C * I * T * sizeof(int)));
             CUP(cudaMemsetAsync(p->d_done, 0, (size_t)C * I * T * sizeof(int), p->stream));
             const size_t walk_ints = 16 + (size_t)I + (I + 1) + (L + I);
+            if (walk_ints > (size_t)hb2::WALK_MAX_PLAN_INTS) p->use_walk = false;   // plan does not fit in shared memory: per-level launches
             CUP(cudaMalloc(&p->d_walk, walk_ints * sizeof(int)));
             CUP(cudaMallocHost(&p->h_walk, walk_ints * sizeof(int)));
         }
@@ -585,6 +605,8 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
     if (Dp == 32) CUP(cudaFuncSetAttribute(hb2::expm_small_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hb2::expm_small_smem_bytes(32)));
     if (Dp == 64) {
         CUP(cudaFuncSetAttribute(hb2::expm64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(5 * 64 * hb2::LD64 * sizeof(double))));
+        CUP(cudaFuncSetAttribute(hb2::expm64_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * 64 * hb2::LD64 * sizeof(double))));
+        { const char *env = getenv("HB2_EXPM_DFMA"); p->expm_dfma = env && env[0] == '1'; }
         CUP(cudaFuncSetAttribute(hb2::prune64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 64 * hb2::LD64 * sizeof(double))));
     }
 #undef CUP

@@ -270,6 +270,190 @@ __global__ void __launch_bounds__(256, 1) expm64_kernel(ExpmArgs a) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// expm64_dmma_kernel: same contract as expm64_kernel, products on the FP64 tensor pipe (mma.sync.m8n8k4.f64, DMMA)
+// and a Paterson-Stockmeyer polynomial whose degree follows the norm:
+//   p(A) = sum_{q=0..Q} A3^q * (c_{3q} I + c_{3q+1} A + c_{3q+2} A2),   A3 = A^3,   degree 3Q+2,   2+Q products,
+//   Q chosen so that theta^(3Q+3)/(3Q+3)! <= 1e-16 with theta = ||A||/2^s <= 0.975; s squarings follow.
+// 8 warps; warp (wr,wc) owns rows 16wr..16wr+15 and columns 32wc..32wc+31 of the product as 2x4 m8n8 tiles; lane
+// (g = lane/4, q = lane%4) holds element (row 16wr+8i+g, col 32wc+8j+2q+e) in acc[i][j][e].
+// Optional fused epilogue for the tensor-core pruning path: PB (hi/lo canonical tiles of P) and PTf (fp32 PT).
+// ------------------------------------------------------------------------------------------------
+__constant__ double c_taylor18[18] = {1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320,
+                                      1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0,
+                                      1.0 / 87178291200.0, 1.0 / 1307674368000.0, 1.0 / 20922789888000.0,
+                                      1.0 / 355687428096000.0};
+
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void tile_mm64_dmma(const double *__restrict__ A, const double *__restrict__ Bm, int wr, int wc,
+                                               int g, int q, double (&acc)[2][4][2]) {
+    const double *a0 = A + (16 * wr + g) * LD64 + q;
+    const double *b0 = Bm + q * LD64 + 32 * wc + g;
+#pragma unroll 4
+    for (int k0 = 0; k0 < 64; k0 += 4) {
+        const double x0 = a0[k0], x1 = a0[8 * LD64 + k0];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const double b = b0[k0 * LD64 + 8 * j];
+            dmma884(acc[0][j], x0, b);
+            dmma884(acc[1][j], x1, b);
+        }
+    }
+}
+
+struct ExpmTcOut {
+    float *PB;      // nullable: [slots][2][4096] canonical hi/lo tiles (see hb2_kernels_tc.cuh)
+    float *PTf;     // [slots][4096]
+};
+
+__device__ __forceinline__ float tf32_rn_dev(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(256, 1) expm64_dmma_kernel(ExpmArgs a, ExpmTcOut tc) {
+    extern __shared__ __align__(16) double sm[];
+    double *A1 = sm, *A2 = A1 + 64 * LD64, *A3 = A2 + 64 * LD64, *R = A3 + 64 * LD64;
+    __shared__ double red[64];
+    __shared__ int s_shift, s_Q;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wr = warp >> 1, wc = warp & 1, g = lane >> 2, q4 = lane & 3;
+    const int D = a.D;
+    const size_t slot = a.dst[blockIdx.x];
+    double *out = a.PT + slot * 4096;
+
+    load_rate_matrix<64, LD64, 256>(a, A1, tid);
+    if (a.is_trans) {
+        for (int idx = tid; idx < 4096; idx += 256) R[(idx >> 6) * LD64 + (idx & 63)] = A1[(idx >> 6) * LD64 + (idx & 63)];
+        __syncthreads();
+    } else {
+        if (tid < 64) {
+            double s = 0.0;
+            for (int j = 0; j < 64; j++) s += fabs(A1[j * LD64 + tid]);
+            red[tid] = s;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double m = 0.0;
+            bool bad = false;
+            for (int i = 0; i < 64; i++) { if (!(red[i] == red[i]) || isinf(red[i])) bad = true; m = fmax(m, red[i]); }
+            int shift = 0, Q = 1;
+            if (!bad && m > 0.975) {
+                int e = 0;
+                frexp(m / 0.975, &e);              // m/0.975 = f*2^e, f in [0.5,1)  ->  m/2^e <= 0.975
+                shift = max(e, 0);
+            }
+            const double theta = bad ? 0.0 : ldexp(m, -shift);
+            Q = theta <= 0.0064 ? 1 : theta <= 0.069 ? 2 : theta <= 0.245 ? 3 : theta <= 0.55 ? 4 : 5;
+            s_shift = bad ? -1 : shift;
+            s_Q = Q;
+        }
+        __syncthreads();
+        const int shift = s_shift, Q = s_Q;
+        if (shift < 0 || shift > 900) {           // NaN/inf or absurd rates: propagate NaN (host sees NaN lnL)
+            for (int idx = tid; idx < 4096; idx += 256) out[idx] = __longlong_as_double(0x7ff8000000000000LL);
+            if (tc.PB) {
+                for (int idx = tid; idx < 8192; idx += 256) tc.PB[slot * 8192 + idx] = __int_as_float(0x7fc00000);
+                for (int idx = tid; idx < 4096; idx += 256) tc.PTf[slot * 4096 + idx] = __int_as_float(0x7fc00000);
+            }
+            return;
+        }
+        if (shift > 0) {
+            const double sc = exp2i(-shift);
+            for (int idx = tid; idx < 64 * 64; idx += 256) A1[(idx >> 6) * LD64 + (idx & 63)] *= sc;
+            __syncthreads();
+        }
+        double acc[2][4][2];
+        auto zero = [&]() {
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+        };
+        auto off = [&](int i, int j) { return (16 * wr + 8 * i + g) * LD64 + 32 * wc + 8 * j + 2 * q4; };
+        auto store = [&](double *M) {
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) *reinterpret_cast<double2 *>(M + off(i, j)) = make_double2(acc[i][j][0], acc[i][j][1]);
+        };
+        zero(); tile_mm64_dmma(A1, A1, wr, wc, g, q4, acc); store(A2);
+        __syncthreads();
+        zero(); tile_mm64_dmma(A2, A1, wr, wc, g, q4, acc); store(A3);
+        // R = B_Q, then R = R*A3 + B_q for q = Q-1..0   (polynomials in A commute)
+        auto poly = [&](int qq, int i, int j, int e) -> double {
+            const int r = 16 * wr + 8 * i + g, c = 32 * wc + 8 * j + 2 * q4 + e, o = r * LD64 + c;
+            double v = c_taylor18[3 * qq + 1] * A1[o] + c_taylor18[3 * qq + 2] * A2[o];
+            if (r == c) v += c_taylor18[3 * qq];
+            return v;
+        };
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                *reinterpret_cast<double2 *>(R + off(i, j)) = make_double2(poly(Q, i, j, 0), poly(Q, i, j, 1));
+        __syncthreads();
+        for (int qq = Q - 1; qq >= 0; qq--) {
+            zero(); tile_mm64_dmma(R, A3, wr, wc, g, q4, acc);
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    *reinterpret_cast<double2 *>(R + off(i, j)) = make_double2(acc[i][j][0] + poly(qq, i, j, 0), acc[i][j][1] + poly(qq, i, j, 1));
+            __syncthreads();
+        }
+        for (int s = 0; s < shift; s++) {
+            zero(); tile_mm64_dmma(R, R, wr, wc, g, q4, acc);
+            __syncthreads();
+            store(R);
+            __syncthreads();
+        }
+        // clamp negatives, zero the padding, repair: column k of PT (= row k of P) must sum to 1
+        for (int idx = tid; idx < 64 * 64; idx += 256) {
+            int j = idx >> 6, kk = idx & 63;
+            double v = R[j * LD64 + kk];
+            if (j >= D || kk >= D) v = 0.0; else if (v < 0.0) v = 0.0;
+            R[j * LD64 + kk] = v;
+        }
+        __syncthreads();
+        if (tid < 64) {
+            double s = 0.0;
+            for (int j = 0; j < 64; j++) if (j != tid) s += R[j * LD64 + tid];
+            if (tid < D) R[tid * LD64 + tid] = fmax(1.0 - s, 0.0);
+        }
+        __syncthreads();
+    }
+    if (a.mix_w) {
+        const double w = a.mix_w[blockIdx.x];
+        const bool first = a.mix_first[blockIdx.x] != 0;
+        for (int idx = tid; idx < 4096; idx += 256) {
+            double v = w * R[(idx >> 6) * LD64 + (idx & 63)];
+            out[idx] = first ? v : out[idx] + v;
+        }
+    } else {
+        for (int idx = tid; idx < 4096; idx += 256) out[idx] = R[(idx >> 6) * LD64 + (idx & 63)];
+        if (tc.PB) {
+            float *pb = tc.PB + slot * 8192;
+            float *pf = tc.PTf + slot * 4096;
+            for (int o = tid; o < 4096; o += 256) {
+                const int chunk = o >> 8, n = (o >> 2) & 63, kk = chunk * 4 + (o & 3);
+                const double pv = R[kk * LD64 + n];          // P[n][kk] = PT[kk][n]
+                const float hi = tf32_rn_dev((float)pv);
+                pb[o] = hi;
+                pb[4096 + o] = tf32_rn_dev((float)(pv - (double)hi));
+                pf[o] = (float)R[(o >> 6) * LD64 + (o & 63)];
+            }
+        }
+    }
+}
+
 // Small state spaces (Dp <= 32): one CTA of 128 threads per matrix, plain shared-memory products.
 constexpr size_t expm_small_smem_bytes(int DP) { return (size_t)6 * DP * (DP + 1) * sizeof(double); }
 template <int DP>

@@ -347,19 +347,28 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_kernel(PruneTcArgs a, const
 // step (the spine of deep trees) is taken straight from registers -- no memory round trip on the critical path.
 // All K lanes of a (c,t) must be co-resident (host guarantees grid <= resident capacity); with K == 1 there are no
 // cross-CTA waits at all and a CTA may loop over several (c,t) pairs.
+//
+// Latency engineering (the pass is bound by tree depth x per-node latency, not by bandwidth):
+//   * the plan (jobs, children) is copied to shared memory once;
+//   * P tiles are double-buffered: the bulk copy for the NEXT contraction is issued right after the current MMAs;
+//   * leaf codes are loaded and their P^T rows prefetched into L1 at job start, consumed after the contractions;
+//   * epoch flags are published (fence + st.release by one thread of warp 3) only for nodes that another lane consumes.
+// Job encoding : internal index | WALK_PUBLISH.
 // Child encoding: id | WALK_WAIT (produced in this evaluation by another lane) | WALK_CHAIN (produced by the previous
 // job of this lane: first child of the job, comes from registers).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int WALK_WAIT = 1 << 30;
 constexpr int WALK_CHAIN = 1 << 29;
+constexpr int WALK_PUBLISH = 1 << 30;
 constexpr int WALK_ID_MASK = (1 << 29) - 1;
+constexpr int WALK_MAX_PLAN_INTS = 6144;       // plan must fit in shared memory (else the host uses per-level launches)
+constexpr int WALK_LEAF_CACHE = 4;             // leaf children per job whose codes are fetched up front
+constexpr int WALK_SMEM_BYTES = 2 * 32768 + TC_MAX_ANCHORS * 128 * 8 + WALK_LEAF_CACHE * 128 * 4 + WALK_MAX_PLAN_INTS * 4 + 64;
 
 struct WalkArgs {
     PruneTcArgs a;
-    const int *lane_start;      // [K+1] offsets into lane_jobs
-    const int *lane_jobs;       // internal indices, lane-major, each lane sorted by (height, index)
-    const int *job_child_start; // [I+1]
-    const int *job_child;       // encoded children of every internal node (chain child first)
+    const int *plan;            // lane_start[K+1] | lane_jobs[nJobs] | job_child_start[I+1] | job_child[...]
+    int plan_ints, n_jobs;
     int *done;                  // [C][I][T] epoch of the last evaluation that produced the tile
     int epoch, K, T, ncls, nslots;
 };
@@ -372,21 +381,26 @@ __device__ __forceinline__ int ld_acquire(const int *p) {
 __device__ __forceinline__ void st_release(int *p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const PruneTcArgs &a = w.a;
-    float *Bs = reinterpret_cast<float *>(smem);
-    uint64_t *bar_b = reinterpret_cast<uint64_t *>(smem + 2 * 32768);
-    uint64_t *bar_mma = bar_b + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_b + 2);
-    int *s_ak = reinterpret_cast<int *>(smem + 32768);
-    float *s_av = reinterpret_cast<float *>(smem + 32768 + TC_MAX_ANCHORS * 128 * 4);
+    float *Bs = reinterpret_cast<float *>(smem);                                   // 2 stages x (Ph | Pl)
+    int *s_ak = reinterpret_cast<int *>(smem + 65536);                             // [TC_MAX_ANCHORS][128]
+    float *s_av = reinterpret_cast<float *>(smem + 65536 + TC_MAX_ANCHORS * 128 * 4);
+    int *s_code = reinterpret_cast<int *>(smem + 65536 + TC_MAX_ANCHORS * 128 * 8); // [WALK_LEAF_CACHE][128]
+    int *s_plan = s_code + WALK_LEAF_CACHE * 128;
+    uint64_t *bar_b = reinterpret_cast<uint64_t *>(s_plan + WALK_MAX_PLAN_INTS);    // [2]
+    uint64_t *bar_mma = bar_b + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_mma + 1);
     const int tid = threadIdx.x, warp = tid >> 5;
     const size_t Sp = a.Sp;
 
+    for (int i = tid; i < w.plan_ints; i += 128) s_plan[i] = w.plan[i];
     if (tid == 0) {
         mbar_init(bar_b, 1);
+        mbar_init(bar_b + 1, 1);
         mbar_init(bar_mma, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -399,34 +413,188 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const uint64_t bdesc_hi = make_b_desc(smem_u32(Bs));
-    const uint64_t bdesc_lo = make_b_desc(smem_u32(Bs + 4096));
-    uint32_t phase = 0;
+    const int *lane_start = s_plan, *lane_jobs = s_plan + (w.K + 1), *jcs = lane_jobs + w.n_jobs, *jc = jcs + (a.I + 1);
+    uint32_t n_mma = 0;                      // contractions issued so far by this CTA (selects P stage and barrier parities)
 
     const int r = blockIdx.x % w.K;
-    const int j_begin = w.lane_start[r], j_end = w.lane_start[r + 1];
+    const int j_begin = lane_start[r], j_end = lane_start[r + 1];
+
+    // next contraction (internal child) at or after position (j, ci) of this lane's plan; -1 if none
+    auto next_mma_child = [&](int j, int ci) -> int {
+        for (; j < j_end; j++) {
+            const int par = lane_jobs[j] & WALK_ID_MASK;
+            const int ce = jcs[par + 1];
+            if (ci < 0) ci = jcs[par];
+            for (; ci < ce; ci++)
+                if ((jc[ci] & WALK_ID_MASK) >= a.L) return jc[ci] & WALK_ID_MASK;
+            ci = -1;
+        }
+        return -1;
+    };
+    auto issue_p_tile = [&](int cat, int child, uint32_t m) {           // thread 0 only
+        const uint32_t stage = m & 1u;
+        mbar_expect_tx(bar_b + stage, 32768u);
+        bulk_g2s(Bs + stage * 8192, a.PB + ((size_t)cat * a.B + child) * TC_PB_FLOATS, 32768u, bar_b + stage);
+    };
+
     for (int ct = blockIdx.x / w.K; ct < w.ncls * w.T; ct += w.nslots) {
         const int cat = a.cat0 + ct / w.T;
         const int tile = ct % w.T;
         const size_t s = (size_t)tile * TC_TILE_P + tid;
         float v[64];
         int ex = 0;
+        if (tid == 0) {
+            const int first = next_mma_child(j_begin, -1);
+            if (first >= 0) issue_p_tile(cat, first, n_mma);
+        }
         for (int j = j_begin; j < j_end; j++) {
-            const int par = w.lane_jobs[j];
-            const int c_begin = w.job_child_start[par], c_end = w.job_child_start[par + 1];
-            const bool chain0 = (w.job_child[c_begin] & WALK_CHAIN) != 0;
+            const int job = lane_jobs[j];
+            const int par = job & WALK_ID_MASK;
+            const int c_begin = jcs[par], c_end = jcs[par + 1];
+            const bool chain0 = (jc[c_begin] & WALK_CHAIN) != 0;
             if (!chain0) {
 #pragma unroll
                 for (int k = 0; k < 64; k++) v[k] = 1.f;
                 ex = 0;
             }
+            // leaf children: fetch the codes now and pull their P^T rows towards L1; they are folded in after the contractions
+            {
+                int nl = 0;
+                for (int ci = c_begin; ci < c_end && nl < WALK_LEAF_CACHE; ci++) {
+                    const int child = jc[ci] & WALK_ID_MASK;
+                    if (child >= a.L) continue;
+                    const int code = __ldg(a.leaf + (size_t)child * Sp + s);
+                    s_code[nl * 128 + tid] = code;
+                    if (code >= 0) {
+                        const float *row = a.PTf + ((size_t)cat * a.B + child) * 4096 + (size_t)code * 64;
+                        prefetch_l1(row);
+                        prefetch_l1(row + 32);
+                    }
+                    nl++;
+                }
+            }
+            // contractions (internal children)
             for (int ci = c_begin; ci < c_end; ci++) {
-                const int enc = w.job_child[ci];
+                const int enc = jc[ci];
                 const int child = enc & WALK_ID_MASK;
+                if (child < a.L) continue;
                 const size_t slot = (size_t)cat * a.B + child;
-                if (child < a.L) {
-                    const int code = a.leaf[(size_t)child * Sp + s];
+                const int cin = child - a.L;
+                const uint32_t stage = n_mma & 1u;
+                int na = 0;
+                {
+                    uint32_t hi[64], lo[64];
+                    if (enc & WALK_CHAIN) {
+#pragma unroll
+                        for (int k = 0; k < 64; k++) {
+                            float x = v[k];
+                            v[k] = 1.f;
+                            if (x >= TC_ANCHOR_THR && na < TC_MAX_ANCHORS) {
+                                s_ak[na * 128 + tid] = k; s_av[na * 128 + tid] = x; na++; x = 0.f;
+                            }
+                            const float h = tf32_rn(x);
+                            hi[k] = __float_as_uint(h);
+                            lo[k] = __float_as_uint(x - h);
+                        }
+                    } else {
+                        if (enc & WALK_WAIT) {
+                            const int *flag = w.done + ((size_t)cat * a.I + cin) * w.T + tile;
+                            int it = 0;
+                            while (ld_acquire(flag) < w.epoch) {
+                                if (++it > (1 << 24)) { atomicExch(a.err, 2); break; }
+                            }
+                        }
+                        const float4 *xr = reinterpret_cast<const float4 *>(a.cond + (((size_t)cat * a.I + cin) * Sp + s) * 64);
+#pragma unroll
+                        for (int q = 0; q < 16; q++) {
+                            const float4 x4 = __ldcg(xr + q);      // may have been produced by another SM in this launch
+                            float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                if (xs[u] >= TC_ANCHOR_THR && na < TC_MAX_ANCHORS) {
+                                    s_ak[na * 128 + tid] = 4 * q + u; s_av[na * 128 + tid] = xs[u]; na++; xs[u] = 0.f;
+                                }
+                                const float h = tf32_rn(xs[u]);
+                                hi[4 * q + u] = __float_as_uint(h);
+                                lo[4 * q + u] = __float_as_uint(xs[u] - h);
+                            }
+                        }
+                        ex += __ldcg(a.scal + ((size_t)cat * a.I + cin) * Sp + s);
+                    }
+#pragma unroll
+                    for (int o = 0; o < 64; o += 16) {
+                        HB2_TMEM_ST16(lane_addr + 64 + o, hi, o);
+                        HB2_TMEM_ST16(lane_addr + 128 + o, lo, o);
+                    }
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                }
+                // anchor rows towards L1 before the barrier
+                for (int ai = 0; ai < na; ai++) {
+                    const float *row = a.PTf + slot * 4096 + (size_t)s_ak[ai * 128 + tid] * 64;
+                    prefetch_l1(row);
+                    prefetch_l1(row + 32);
+                }
+                tc_fence_before();
+                __syncthreads();             // A operand complete in TMEM; every thread is done reading the previous D
+                if (tid == 0) {
+                    tc_fence_after();
+                    mbar_wait(bar_b + stage, (n_mma >> 1) & 1u, a.err);
+                    const uint64_t bdesc_hi = make_b_desc(smem_u32(Bs + stage * 8192));
+                    const uint64_t bdesc_lo = make_b_desc(smem_u32(Bs + stage * 8192 + 4096));
+#pragma unroll
+                    for (int kk = 0; kk < 8; kk++)
+                        tc_mma_tf32_ts(tmem_base, tmem_base + 128 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, kk > 0);
+#pragma unroll
+                    for (int kk = 0; kk < 8; kk++)
+                        tc_mma_tf32_ts(tmem_base, tmem_base + 64 + kk * 8, bdesc_lo + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u);
+#pragma unroll
+                    for (int kk = 0; kk < 8; kk++)
+                        tc_mma_tf32_ts(tmem_base, tmem_base + 64 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u);
+                    tc_commit(bar_mma);
+                    // stage the P tile of the next contraction of this lane into the other buffer
+                    const int nxt = next_mma_child(j, ci + 1);
+                    if (nxt >= 0) issue_p_tile(cat, nxt, n_mma + 1);
+                }
+                __syncwarp();
+                float acc[64];
+#pragma unroll
+                for (int k = 0; k < 64; k++) acc[k] = 0.f;
+                {
                     const float *PTf = a.PTf + slot * 4096;
+                    for (int ai = 0; ai < na; ai++) {
+                        const int ka = s_ak[ai * 128 + tid];
+                        const float xv = s_av[ai * 128 + tid];
+                        const float4 *row = reinterpret_cast<const float4 *>(PTf + (size_t)ka * 64);
+#pragma unroll
+                        for (int q = 0; q < 16; q++) {
+                            const float4 rr = __ldg(row + q);
+                            acc[4 * q] = fmaf(xv, rr.x, acc[4 * q]); acc[4 * q + 1] = fmaf(xv, rr.y, acc[4 * q + 1]);
+                            acc[4 * q + 2] = fmaf(xv, rr.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(xv, rr.w, acc[4 * q + 3]);
+                        }
+                    }
+                }
+                mbar_wait(bar_mma, n_mma & 1u, a.err);
+                tc_fence_after();
+#pragma unroll
+                for (int o = 0; o < 64; o += 16) {
+                    uint32_t d[16];
+                    HB2_TMEM_LD16(lane_addr + o, d, 0);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int k = 0; k < 16; k++) v[o + k] *= (__uint_as_float(d[k]) + acc[o + k]);
+                }
+                n_mma++;
+                renorm_f32(v, ex);
+            }
+            // leaf children
+            {
+                int nl = 0;
+                for (int ci = c_begin; ci < c_end; ci++) {
+                    const int child = jc[ci] & WALK_ID_MASK;
+                    if (child >= a.L) continue;
+                    const int code = (nl < WALK_LEAF_CACHE) ? s_code[nl * 128 + tid] : __ldg(a.leaf + (size_t)child * Sp + s);
+                    nl++;
+                    const float *PTf = a.PTf + ((size_t)cat * a.B + child) * 4096;
                     if (code >= 0) {
                         const float4 *row = reinterpret_cast<const float4 *>(PTf + (size_t)code * 64);
 #pragma unroll
@@ -452,109 +620,10 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
 #pragma unroll
                         for (int k = 0; k < 64; k++) v[k] *= acc[k];
                     }
-                } else {
-                    const int cin = child - a.L;
-                    if (tid == 0) {          // stage Ph|Pl early: it does not depend on the child's data
-                        mbar_expect_tx(bar_b, 32768u);
-                        bulk_g2s(Bs, a.PB + slot * TC_PB_FLOATS, 32768u, bar_b);
-                    }
-                    int na = 0;
-                    {
-                        uint32_t hi[64], lo[64];
-                        if (enc & WALK_CHAIN) {
-                            // the child is the previous job of this lane: its conditionals are still in registers
-#pragma unroll
-                            for (int k = 0; k < 64; k++) {
-                                float x = v[k];
-                                v[k] = 1.f;
-                                if (x >= TC_ANCHOR_THR && na < TC_MAX_ANCHORS) {
-                                    s_ak[na * 128 + tid] = k; s_av[na * 128 + tid] = x; na++; x = 0.f;
-                                }
-                                const float h = tf32_rn(x);
-                                hi[k] = __float_as_uint(h);
-                                lo[k] = __float_as_uint(x - h);
-                            }
-                        } else {
-                            if (enc & WALK_WAIT) {
-                                const int *flag = w.done + ((size_t)cat * a.I + cin) * w.T + tile;
-                                int it = 0;
-                                while (ld_acquire(flag) < w.epoch) {
-                                    if (++it > (1 << 24)) { atomicExch(a.err, 2); break; }
-                                }
-                            }
-                            const float4 *xr = reinterpret_cast<const float4 *>(a.cond + (((size_t)cat * a.I + cin) * Sp + s) * 64);
-#pragma unroll
-                            for (int q = 0; q < 16; q++) {
-                                const float4 x4 = __ldcg(xr + q);      // produced by another SM in this launch: bypass L1
-                                float xs[4] = {x4.x, x4.y, x4.z, x4.w};
-#pragma unroll
-                                for (int u = 0; u < 4; u++) {
-                                    if (xs[u] >= TC_ANCHOR_THR && na < TC_MAX_ANCHORS) {
-                                        s_ak[na * 128 + tid] = 4 * q + u; s_av[na * 128 + tid] = xs[u]; na++; xs[u] = 0.f;
-                                    }
-                                    const float h = tf32_rn(xs[u]);
-                                    hi[4 * q + u] = __float_as_uint(h);
-                                    lo[4 * q + u] = __float_as_uint(xs[u] - h);
-                                }
-                            }
-                            ex += __ldcg(a.scal + ((size_t)cat * a.I + cin) * Sp + s);
-                        }
-#pragma unroll
-                        for (int o = 0; o < 64; o += 16) {
-                            HB2_TMEM_ST16(lane_addr + 64 + o, hi, o);
-                            HB2_TMEM_ST16(lane_addr + 128 + o, lo, o);
-                        }
-                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                    }
-                    tc_fence_before();
-                    __syncthreads();
-                    if (tid == 0) {
-                        tc_fence_after();
-                        mbar_wait(bar_b, phase, a.err);
-#pragma unroll
-                        for (int kk = 0; kk < 8; kk++)
-                            tc_mma_tf32_ts(tmem_base, tmem_base + 128 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, kk > 0);
-#pragma unroll
-                        for (int kk = 0; kk < 8; kk++)
-                            tc_mma_tf32_ts(tmem_base, tmem_base + 64 + kk * 8, bdesc_lo + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u);
-#pragma unroll
-                        for (int kk = 0; kk < 8; kk++)
-                            tc_mma_tf32_ts(tmem_base, tmem_base + 64 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u);
-                        tc_commit(bar_mma);
-                    }
-                    __syncwarp();
-                    float acc[64];
-#pragma unroll
-                    for (int k = 0; k < 64; k++) acc[k] = 0.f;
-                    {
-                        const float *PTf = a.PTf + slot * 4096;
-                        for (int ai = 0; ai < na; ai++) {
-                            const int ka = s_ak[ai * 128 + tid];
-                            const float xv = s_av[ai * 128 + tid];
-                            const float4 *row = reinterpret_cast<const float4 *>(PTf + (size_t)ka * 64);
-#pragma unroll
-                            for (int q = 0; q < 16; q++) {
-                                const float4 rr = __ldg(row + q);
-                                acc[4 * q] = fmaf(xv, rr.x, acc[4 * q]); acc[4 * q + 1] = fmaf(xv, rr.y, acc[4 * q + 1]);
-                                acc[4 * q + 2] = fmaf(xv, rr.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(xv, rr.w, acc[4 * q + 3]);
-                            }
-                        }
-                    }
-                    mbar_wait(bar_mma, phase, a.err);
-                    tc_fence_after();
-#pragma unroll
-                    for (int o = 0; o < 64; o += 16) {
-                        uint32_t d[16];
-                        HB2_TMEM_LD16(lane_addr + o, d, 0);
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                        for (int k = 0; k < 16; k++) v[o + k] *= (__uint_as_float(d[k]) + acc[o + k]);
-                    }
-                    phase ^= 1u;
+                    renorm_f32(v, ex);
                 }
-                renorm_f32(v, ex);
             }
-            // publish this tile of the parent: conditionals, exponent, (root reduction), then the epoch flag
+            // this tile of the parent: conditionals, exponent, (root reduction); epoch flag only if another lane consumes it
             {
                 float4 *outp = reinterpret_cast<float4 *>(a.cond + (((size_t)cat * a.I + par) * Sp + s) * 64);
 #pragma unroll
@@ -568,11 +637,15 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                     a.rootE[(size_t)cat * Sp + s] = ex;
                 }
             }
-            __threadfence();
-            tc_fence_before();
-            __syncthreads();
-            if (tid == 0) st_release(w.done + ((size_t)cat * a.I + par) * w.T + tile, w.epoch);
+            if (job & WALK_PUBLISH) {
+                __syncthreads();
+                if (tid == 96) {
+                    __threadfence();
+                    st_release(w.done + ((size_t)cat * a.I + par) * w.T + tile, w.epoch);
+                }
+            }
         }
+        __syncthreads();     // all contractions of this (class, tile) are complete before the next one re-arms the P stages
     }
     tc_fence_before();
     __syncthreads();
