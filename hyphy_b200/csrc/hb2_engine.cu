@@ -114,6 +114,7 @@ struct hb2_partition {
     float *d_condf = nullptr, *d_PB = nullptr, *d_PTf = nullptr;
     int *d_err = nullptr;
     // persistent walk kernel (one launch per evaluation): plan buffers, epoch flags, residency
+    bool small_walk = true;                   // HB2_SMALL_WALK=0: per-level launches of prune_small_kernel (A/B testing)
     bool expm_dfma = false;                   // HB2_EXPM_DFMA=1: previous FFMA-style fp64 expm kernel (A/B testing)
     bool use_walk = false;
     int walk_max_resident = 0;
@@ -331,8 +332,6 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
             lanes[lane].push_back(n);
         }
     }
-    int *buf = p->h_walk;
-    int *lane_start = buf, *lane_jobs = buf + (K + 1), *jcs = lane_jobs + total, *jc = jcs + (I + 1);
     // a node's tile must be published (epoch flag) iff a dirty parent in ANOTHER lane consumes it
     std::vector<char> publish(I, 0);
     for (int n = 0; n < I; n++) {
@@ -340,23 +339,29 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
         const int64_t par = p->parents[L + n];
         if (par >= 0 && dirty[par] && lane_of[par] != lane_of[n]) publish[n] = 1;
     }
-    int off = 0;
-    for (int r = 0; r < K; r++) { lane_start[r] = off; for (int n : lanes[r]) lane_jobs[off++] = n | (publish[n] ? hb2::WALK_PUBLISH : 0); }
-    lane_start[K] = off;
-    int co = 0;
-    for (int n = 0; n < I; n++) {
-        jcs[n] = co;
-        if (!dirty[n]) continue;
-        if (chain_child[n] >= 0) jc[co++] = (chain_child[n] + L) | hb2::WALK_CHAIN;
-        for (int ch : p->children[n]) if (ch < L) jc[co++] = ch;                          // leaves: no waiting
-        for (int ch : p->children[n]) {
-            if (ch < L || ch - L == chain_child[n]) continue;
-            const int ci = ch - L;
-            jc[co++] = ch | ((dirty[ci] && lane_of[ci] != lane_of[n]) ? hb2::WALK_WAIT : 0);
+    // flatten every lane into steps (one per child): chain child first, then leaves, then the other internal children
+    int *buf = p->h_walk;
+    int *lane_start = buf;                       // [K+1], steps start at int offset 16 (int2-aligned)
+    int *steps = buf + 16;
+    int ns = 0;
+    for (int r = 0; r < K; r++) {
+        lane_start[r] = ns;
+        for (int n : lanes[r]) {
+            const int first = ns;
+            auto push = [&](int enc) { steps[2 * ns] = enc; steps[2 * ns + 1] = n; ns++; };
+            if (chain_child[n] >= 0) push((chain_child[n] + L) | hb2::WALK_CHAIN);
+            for (int ch : p->children[n]) if (ch < L) push(ch);
+            for (int ch : p->children[n]) {
+                if (ch < L || ch - L == chain_child[n]) continue;
+                const int ci = ch - L;
+                push(ch | ((dirty[ci] && lane_of[ci] != lane_of[n]) ? hb2::WALK_WAIT : 0));
+            }
+            steps[2 * first + 1] |= hb2::STEP_FIRST;
+            steps[2 * (ns - 1) + 1] |= hb2::STEP_LAST | (publish[n] ? hb2::STEP_PUBLISH : 0);
         }
     }
-    jcs[I] = co;
-    const int nints = (K + 1) + total + (I + 1) + co;
+    lane_start[K] = ns;
+    const int nints = 16 + 2 * ns;
     CU(cudaMemcpyAsync(p->d_walk, p->h_walk, nints * sizeof(int), cudaMemcpyHostToDevice, p->stream));
     hb2::PruneArgs a = prune_args(p, cat0);
     hb2::WalkArgs w;
@@ -364,10 +369,34 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
     t.PB = p->d_PB; t.PTf = p->d_PTf; t.cond = p->d_condf; t.scal = a.scal; t.leaf = a.leaf; t.ambig = a.ambig; t.pi = a.pi;
     t.rootL = a.rootL; t.rootE = a.rootE; t.tree = a.tree; t.err = p->d_err;
     t.L = a.L; t.I = a.I; t.B = a.B; t.D = a.D; t.Sp = a.Sp; t.cat0 = a.cat0;
-    w.plan = p->d_walk; w.plan_ints = nints; w.n_jobs = total;
+    w.lane_start = p->d_walk; w.steps = reinterpret_cast<const int2 *>(p->d_walk + 16);
     w.done = p->d_done; w.epoch = ++p->epoch; w.K = K; w.T = T; w.ncls = ncls; w.nslots = nslots;
-    if (getenv("HB2_DEBUG")) fprintf(stderr, "[hb2] walk: jobs=%d K=%d T=%d ncls=%d nslots=%d grid=%d resident=%d plan_ints=%d\n", total, K, T, ncls, nslots, nslots * K, p->walk_max_resident, nints);
+    if (getenv("HB2_DEBUG")) fprintf(stderr, "[hb2] walk: jobs=%d steps=%d K=%d T=%d ncls=%d nslots=%d grid=%d resident=%d\n", total, ns, K, T, ncls, nslots, nslots * K, p->walk_max_resident);
     hb2::prune64_tc_walk_kernel<<<nslots * K, 128, hb2::WALK_SMEM_BYTES, p->stream>>>(w);
+    p->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// Small state spaces: one launch, one thread per pattern walking the dirty nodes in post-order.
+int run_small_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector<int>> &levels) {
+    std::vector<int> jobs;
+    for (auto &lv : levels) jobs.insert(jobs.end(), lv.begin(), lv.end());
+    if (jobs.empty()) return 0;
+    std::sort(jobs.begin(), jobs.end());                 // internal indices ascending == post-order
+    std::copy(jobs.begin(), jobs.end(), p->h_jobs);
+    CU(cudaMemcpyAsync(p->d_jobs, p->h_jobs, jobs.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    hb2::PruneArgs a = prune_args(p, cat0);
+    dim3 grid((unsigned)(p->Sp / 128), (unsigned)ncls);
+    const int n = (int)jobs.size();
+    switch (p->Dp) {
+        case 4: hb2::prune_small_walk_kernel<4><<<grid, 128, 0, p->stream>>>(a, p->d_jobs, n); break;
+        case 8: hb2::prune_small_walk_kernel<8><<<grid, 128, 0, p->stream>>>(a, p->d_jobs, n); break;
+        case 16: hb2::prune_small_walk_kernel<16><<<grid, 128, 0, p->stream>>>(a, p->d_jobs, n); break;
+        case 24: hb2::prune_small_walk_kernel<24><<<grid, 128, 0, p->stream>>>(a, p->d_jobs, n); break;
+        case 32: hb2::prune_small_walk_kernel<32><<<grid, 128, 0, p->stream>>>(a, p->d_jobs, n); break;
+        default: return fail("unsupported padded state count %d", p->Dp);
+    }
     p->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -375,6 +404,7 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
 
 int run_pruning(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector<int>> &levels) {
     if (p->use_tc && p->use_walk) return run_walk(p, cat0, ncls, levels);
+    if (p->Dp <= 32 && p->small_walk) return run_small_walk(p, cat0, ncls, levels);
     // upload all job lists in one copy
     int total = 0;
     for (auto &lv : levels) total += (int)lv.size();
@@ -535,16 +565,21 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
             const char *env = getenv("HB2_TC_WALK");
             p->use_walk = !(env && env[0] == '0');
             int per_sm = 0, sms = 0;
+            CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             CUP(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hb2::prune64_tc_walk_kernel, 128, hb2::WALK_SMEM_BYTES));
-            if (getenv("HB2_DEBUG")) fprintf(stderr, "[hb2] walk kernel occupancy: %d CTAs/SM\n", per_sm);
+            if (getenv("HB2_DEBUG")) {
+                cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, hb2::prune64_tc_walk_kernel);
+                cudaDeviceProp dp; cudaGetDeviceProperties(&dp, device);
+                fprintf(stderr, "[hb2] walk kernel occupancy: %d CTAs/SM (regs/thread %d, static smem %zu, dyn smem %d, regs/SM %d, smem/SM %zu, smem/block optin %zu, reserved/block %zu)\n",
+                        per_sm, fa.numRegs, fa.sharedSizeBytes, hb2::WALK_SMEM_BYTES, dp.regsPerMultiprocessor, dp.sharedMemPerMultiprocessor, dp.sharedMemPerBlockOptin, dp.reservedSharedMemPerBlock);
+            }
             CUP(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
             p->walk_max_resident = std::min(per_sm, 2) * sms;          // TMEM: 256 of 512 columns per CTA -> at most 2 per SM
             if (p->walk_max_resident < 1) p->use_walk = false;
             const size_t T = Sp / hb2::TC_TILE_P;
             CUP(cudaMalloc(&p->d_done, (size_t)C * I * T * sizeof(int)));
             CUP(cudaMemsetAsync(p->d_done, 0, (size_t)C * I * T * sizeof(int), p->stream));
-            const size_t walk_ints = 16 + (size_t)I + (I + 1) + (L + I);
-            if (walk_ints > (size_t)hb2::WALK_MAX_PLAN_INTS) p->use_walk = false;   // plan does not fit in shared memory: per-level launches
+            const size_t walk_ints = 16 + 2 * (size_t)(L + I);
             CUP(cudaMalloc(&p->d_walk, walk_ints * sizeof(int)));
             CUP(cudaMallocHost(&p->h_walk, walk_ints * sizeof(int)));
         }
@@ -607,6 +642,8 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
         CUP(cudaFuncSetAttribute(hb2::expm64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(5 * 64 * hb2::LD64 * sizeof(double))));
         CUP(cudaFuncSetAttribute(hb2::expm64_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * 64 * hb2::LD64 * sizeof(double))));
         { const char *env = getenv("HB2_EXPM_DFMA"); p->expm_dfma = env && env[0] == '1'; }
+    }
+    { const char *env = getenv("HB2_SMALL_WALK"); p->small_walk = !(env && env[0] == '0');
         CUP(cudaFuncSetAttribute(hb2::prune64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 64 * hb2::LD64 * sizeof(double))));
     }
 #undef CUP
@@ -745,7 +782,10 @@ int hb2_read_conditionals(hb2_partition *p, int64_t cat, int64_t inode, double *
     if (p->use_tc) {
         std::vector<float> tf(tmp.size());
         CU(cudaMemcpy(tf.data(), p->d_condf + ((size_t)cat * p->I + inode) * p->Sp * 64, tf.size() * sizeof(float), cudaMemcpyDeviceToHost));
-        for (size_t k = 0; k < tf.size(); k++) tmp[k] = tf[k];
+        // device layout per tile of 128 patterns: [16 chunks][128 patterns][4 floats]
+        for (int64_t s = 0; s < p->Sp; s++)
+            for (int k = 0; k < 64; k++)
+                tmp[s * 64 + k] = tf[(((size_t)(s / 128) * 16 + k / 4) * 128 + s % 128) * 4 + k % 4];
     } else
     CU(cudaMemcpy(tmp.data(), p->d_cond + ((size_t)cat * p->I + inode) * p->Sp * p->Dp, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(te.data(), p->d_scal + ((size_t)cat * p->I + inode) * p->Sp, te.size() * sizeof(int), cudaMemcpyDeviceToHost));

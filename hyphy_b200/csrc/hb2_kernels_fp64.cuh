@@ -738,6 +738,95 @@ __global__ void __launch_bounds__(128) prune_small_kernel(PruneArgs a, const int
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Small state spaces, whole pruning pass in ONE launch: thread s owns pattern s and walks the dirty internal nodes in
+// post-order.  Every dependency is thread-local (a child's conditionals were written by the same thread earlier in the
+// same launch, or are a valid cache from an earlier evaluation), so there is no synchronisation of any kind; P^T of a
+// branch is read by all threads at the same address (L1 broadcast).  HBM traffic per evaluation is the algorithmic
+// minimum: one coalesced write and (at most) one read of Dp*8+4 bytes per (node, pattern) plus 4 B per leaf state.
+// grid = (Sp/128, classes), block = 128.  jobs = dirty internal indices, ascending (= post-order).
+// ------------------------------------------------------------------------------------------------
+template <int DP>
+__global__ void __launch_bounds__(128) prune_small_walk_kernel(PruneArgs a, const int *__restrict__ jobs, int njobs) {
+    const int tid = threadIdx.x;
+    const int cat = a.cat0 + blockIdx.y;
+    const size_t Sp = a.Sp;
+    const size_t s = (size_t)blockIdx.x * 128 + tid;
+    for (int jb = 0; jb < njobs; jb++) {
+        const int par = __ldg(jobs + jb);
+        double v[DP];
+#pragma unroll
+        for (int k = 0; k < DP; k++) v[k] = 1.0;
+        int ex = 0;
+        const int c_begin = __ldg(a.tree.child_start + par), c_end = __ldg(a.tree.child_start + par + 1);
+        for (int ci = c_begin; ci < c_end; ci++) {
+            const int child = __ldg(a.tree.child_ids + ci);
+            const double *PT = a.PT + ((size_t)cat * a.B + child) * DP * DP;
+            if (child < a.L) {
+                const int code = __ldg(a.leaf + (size_t)child * Sp + s);
+                if (code >= 0) {
+                    const double2 *row = reinterpret_cast<const double2 *>(PT + (size_t)code * DP);
+#pragma unroll
+                    for (int k = 0; k < DP; k += 2) { const double2 r = __ldg(row + k / 2); v[k] *= r.x; v[k + 1] *= r.y; }
+                } else {
+                    const double *amb = a.ambig + (size_t)(-code - 1) * DP;
+                    double acc[DP];
+#pragma unroll
+                    for (int k = 0; k < DP; k++) acc[k] = 0.0;
+                    for (int j = 0; j < a.D; j++) {
+                        const double wgt = __ldg(amb + j);
+                        const double2 *row = reinterpret_cast<const double2 *>(PT + (size_t)j * DP);
+#pragma unroll
+                        for (int k = 0; k < DP; k += 2) { const double2 r = __ldg(row + k / 2); acc[k] = fma(wgt, r.x, acc[k]); acc[k + 1] = fma(wgt, r.y, acc[k + 1]); }
+                    }
+#pragma unroll
+                    for (int k = 0; k < DP; k++) v[k] *= acc[k];
+                }
+            } else {
+                const int cin = child - a.L;
+                const double2 *X = reinterpret_cast<const double2 *>(a.cond + (((size_t)cat * a.I + cin) * Sp + s) * DP);
+                double x[DP];
+#pragma unroll
+                for (int j = 0; j < DP; j += 2) { const double2 t = X[j / 2]; x[j] = t.x; x[j + 1] = t.y; }
+                double acc[DP];
+#pragma unroll
+                for (int k = 0; k < DP; k++) acc[k] = 0.0;
+#pragma unroll
+                for (int j = 0; j < DP; j++) {
+                    const double2 *row = reinterpret_cast<const double2 *>(PT + (size_t)j * DP);
+#pragma unroll
+                    for (int k = 0; k < DP; k += 2) { const double2 r = __ldg(row + k / 2); acc[k] = fma(x[j], r.x, acc[k]); acc[k + 1] = fma(x[j], r.y, acc[k + 1]); }
+                }
+#pragma unroll
+                for (int k = 0; k < DP; k++) v[k] *= acc[k];
+                ex += a.scal[((size_t)cat * a.I + cin) * Sp + s];
+            }
+        }
+        double m = 0.0;
+#pragma unroll
+        for (int k = 0; k < DP; k++) m = fmax(m, v[k]);
+        if (m > 0.0 && m < INFINITY) {
+            const int e = ilogb(m) + 1;
+            const double s1 = exp2i(-(e / 2)), s2 = exp2i(-(e - e / 2));
+#pragma unroll
+            for (int k = 0; k < DP; k++) v[k] = v[k] * s1 * s2;
+            ex += e;
+        }
+        double2 *outp = reinterpret_cast<double2 *>(a.cond + (((size_t)cat * a.I + par) * Sp + s) * DP);
+#pragma unroll
+        for (int k = 0; k < DP; k += 2) outp[k / 2] = make_double2(v[k], v[k + 1]);
+        a.scal[((size_t)cat * a.I + par) * Sp + s] = ex;
+        if (par == a.I - 1) {
+            double r = 0.0;
+#pragma unroll
+            for (int k = 0; k < DP; k++) r = fma(v[k], a.pi[k], r);
+            a.rootL[(size_t)cat * Sp + s] = r;
+            a.rootE[(size_t)cat * Sp + s] = ex;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Root reduction: rate-class mixture + log + pattern frequency + block partial sums.
 //   L_s = sum_c w_c * rootL[c][s] * 2^(rootE[c][s]);  lnL_s = log(sum_c w_c rootL 2^(e_c-emax)) + emax ln2

@@ -43,7 +43,7 @@ constexpr float TC_ANCHOR_THR = 0.015625f;     // 2^-6 (rows are normalised to m
 struct PruneTcArgs {
     const float *PB;                // [C][B][2][16][64][4] canonical K-major tiles of P (hi, lo)
     const float *PTf;               // [C][B][64][64] fp32 copy of PT (leaf column gather)
-    float *cond;                    // [C][I][Sp][64] fp32 conditionals
+    float *cond;                    // [C][I][Sp/128][16 chunks][128 patterns][4] fp32 conditionals (tile-wise K-major chunks)
     int *scal;                      // [C][I][Sp]
     const int *leaf;                // [L][Sp]
     const double *ambig;            // [nAmb][64]
@@ -238,11 +238,11 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_kernel(PruneTcArgs a, const
             // (B) this thread's pattern row -> anchors out -> split -> TMEM (Xh at cols 64.., Xl at cols 128..)
             int na = 0;
             {
-                const float4 *xr = reinterpret_cast<const float4 *>(a.cond + (((size_t)cat * a.I + cin) * Sp + s) * 64);
+                const float4 *xr = reinterpret_cast<const float4 *>(a.cond) + ((((size_t)cat * a.I + cin) * (Sp / 128) + blockIdx.x) * 16) * 128 + tid;
                 uint32_t hi[64], lo[64];
 #pragma unroll
                 for (int q = 0; q < 16; q++) {
-                    const float4 x = xr[q];
+                    const float4 x = xr[(size_t)q * 128];
                     float xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
@@ -317,9 +317,9 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_kernel(PruneTcArgs a, const
     }
     // write the parent's conditionals (already renormalised after the last child) and the root reduction
     {
-        float4 *outp = reinterpret_cast<float4 *>(a.cond + (((size_t)cat * a.I + par) * Sp + s) * 64);
+        float4 *outp = reinterpret_cast<float4 *>(a.cond) + ((((size_t)cat * a.I + par) * (Sp / 128) + blockIdx.x) * 16) * 128 + tid;
 #pragma unroll
-        for (int q = 0; q < 16; q++) outp[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        for (int q = 0; q < 16; q++) outp[(size_t)q * 128] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         a.scal[((size_t)cat * a.I + par) * Sp + s] = ex;
         if (par == a.I - 1) {
             double r = 0.0;
@@ -341,34 +341,38 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_kernel(PruneTcArgs a, const
 // Persistent "walk" kernel: the whole pruning pass of one evaluation in ONE launch.
 //
 // Patterns are independent, so all dependencies are tile-local: tile t of node p needs tile t of p's children only.
-// CTA (c, t, r) owns rate class c, pattern tile t and "lane" r (one of K groups of internal nodes); it processes its
-// lane's nodes in (height, index) order.  A child computed by another lane of the same (c, t) is awaited through a
-// per-(class, node, tile) epoch flag in global memory (release/acquire); a child computed by THIS CTA in the previous
-// step (the spine of deep trees) is taken straight from registers -- no memory round trip on the critical path.
-// All K lanes of a (c,t) must be co-resident (host guarantees grid <= resident capacity); with K == 1 there are no
-// cross-CTA waits at all and a CTA may loop over several (c,t) pairs.
+// CTA (c, t, r) owns rate class c, pattern tile t and "lane" r (one of K groups of internal nodes); it executes its
+// lane's STEPS (one per child of every node of the lane, nodes in (height, index) order) back to back.  A child computed
+// by another lane of the same (c, t) is awaited through a per-(class, node, tile) epoch flag in global memory
+// (release/acquire); a child computed by THIS CTA in the previous job (the spine of deep trees) is taken straight from
+// registers.  All K lanes of a (c,t) must be co-resident (host guarantees grid <= resident capacity); with K == 1 there
+// are no cross-CTA waits at all and a CTA may loop over several (c,t) pairs.
 //
-// Latency engineering (the pass is bound by tree depth x per-node latency, not by bandwidth):
-//   * the plan (jobs, children) is copied to shared memory once;
-//   * P tiles are double-buffered: the bulk copy for the NEXT contraction is issued right after the current MMAs;
-//   * leaf codes are loaded and their P^T rows prefetched into L1 at job start, consumed after the contractions;
-//   * epoch flags are published (fence + st.release by one thread of warp 3) only for nodes that another lane consumes.
-// Job encoding : internal index | WALK_PUBLISH.
-// Child encoding: id | WALK_WAIT (produced in this evaluation by another lane) | WALK_CHAIN (produced by the previous
-// job of this lane: first child of the job, comes from registers).
+// The pass is bound by (tree depth x per-step latency), so every operand of step i+1 is staged while step i runs:
+//   * per step, the branch's fp32 P^T table (64 rows x 256 B, padded to 272 B rows) and -- for a contraction -- its
+//     Ph|Pl UMMA tiles are bulk-copied (TMA engine, mbarrier tx completion) into a 2-stage shared-memory ring by warp 0
+//     right after the step-begin barrier; leaf column gathers and anchor rows are then shared-memory reads;
+//   * the 32 KB conditional block of the next contraction is prefetched into L2 (cp.async.bulk.prefetch.L2) and the next
+//     leaf's state codes into a register;
+//   * conditionals are stored tile-wise as [16 chunks][128 patterns][4 floats] (the K-major UMMA core-matrix order), so
+//     thread t's 16-byte accesses are perfectly coalesced for both the producer and the consumer of a tile;
+//   * epoch flags are published (fence + st.release by one thread) only for nodes that another lane consumes.
+// Step encoding: x = child id | WALK_WAIT | WALK_CHAIN ; y = parent internal index | STEP_FIRST | STEP_LAST | STEP_PUBLISH.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int WALK_WAIT = 1 << 30;
 constexpr int WALK_CHAIN = 1 << 29;
-constexpr int WALK_PUBLISH = 1 << 30;
-constexpr int WALK_ID_MASK = (1 << 29) - 1;
-constexpr int WALK_MAX_PLAN_INTS = 6144;       // plan must fit in shared memory (else the host uses per-level launches)
-constexpr int WALK_LEAF_CACHE = 4;             // leaf children per job whose codes are fetched up front
-constexpr int WALK_SMEM_BYTES = 2 * 32768 + TC_MAX_ANCHORS * 128 * 8 + WALK_LEAF_CACHE * 128 * 4 + WALK_MAX_PLAN_INTS * 4 + 64;
+constexpr int WALK_ID_MASK = (1 << 28) - 1;
+constexpr int STEP_FIRST = 1 << 28;
+constexpr int STEP_LAST = 1 << 29;
+constexpr int STEP_PUBLISH = 1 << 30;
+constexpr int WALK_PT_ROW = 68;                // floats per padded P^T row in shared memory (272 B: conflict-free gathers)
+constexpr int WALK_STAGE_FLOATS = 64 * WALK_PT_ROW + 8192;     // P^T table + Ph|Pl tiles
+constexpr int WALK_SMEM_BYTES = 2 * WALK_STAGE_FLOATS * 4 + TC_MAX_ANCHORS * 128 * 8 + 64;
 
 struct WalkArgs {
     PruneTcArgs a;
-    const int *plan;            // lane_start[K+1] | lane_jobs[nJobs] | job_child_start[I+1] | job_child[...]
-    int plan_ints, n_jobs;
+    const int *lane_start;      // [K+1] offsets into steps
+    const int2 *steps;
     int *done;                  // [C][I][T] epoch of the last evaluation that produced the tile
     int epoch, K, T, ncls, nslots;
 };
@@ -381,26 +385,30 @@ __device__ __forceinline__ int ld_acquire(const int *p) {
 __device__ __forceinline__ void st_release(int *p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// float4 index of chunk q of pattern t in the conditional block of (cat, node, tile)
+__device__ __forceinline__ size_t cond_f4(int cat, int node, int tile, int q, int t, int I, int T) {
+    return ((((size_t)cat * I + node) * T + tile) * 16 + q) * 128 + t;
+}
 
 __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const PruneTcArgs &a = w.a;
-    float *Bs = reinterpret_cast<float *>(smem);                                   // 2 stages x (Ph | Pl)
-    int *s_ak = reinterpret_cast<int *>(smem + 65536);                             // [TC_MAX_ANCHORS][128]
-    float *s_av = reinterpret_cast<float *>(smem + 65536 + TC_MAX_ANCHORS * 128 * 4);
-    int *s_code = reinterpret_cast<int *>(smem + 65536 + TC_MAX_ANCHORS * 128 * 8); // [WALK_LEAF_CACHE][128]
-    int *s_plan = s_code + WALK_LEAF_CACHE * 128;
-    uint64_t *bar_b = reinterpret_cast<uint64_t *>(s_plan + WALK_MAX_PLAN_INTS);    // [2]
-    uint64_t *bar_mma = bar_b + 2;
+    float *stage_base = reinterpret_cast<float *>(smem);                           // 2 x [P^T table | Ph | Pl]
+    int *s_ak = reinterpret_cast<int *>(smem + 2 * WALK_STAGE_FLOATS * 4);          // [TC_MAX_ANCHORS][128]
+    float *s_av = reinterpret_cast<float *>(s_ak + TC_MAX_ANCHORS * 128);
+    uint64_t *bar_full = reinterpret_cast<uint64_t *>(s_av + TC_MAX_ANCHORS * 128); // [2]
+    uint64_t *bar_mma = bar_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_mma + 1);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const size_t Sp = a.Sp;
+    float4 *cond4 = reinterpret_cast<float4 *>(a.cond);
 
-    for (int i = tid; i < w.plan_ints; i += 128) s_plan[i] = w.plan[i];
     if (tid == 0) {
-        mbar_init(bar_b, 1);
-        mbar_init(bar_b + 1, 1);
+        mbar_init(bar_full, 1);
+        mbar_init(bar_full + 1, 1);
         mbar_init(bar_mma, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -413,28 +421,28 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const int *lane_start = s_plan, *lane_jobs = s_plan + (w.K + 1), *jcs = lane_jobs + w.n_jobs, *jc = jcs + (a.I + 1);
-    uint32_t n_mma = 0;                      // contractions issued so far by this CTA (selects P stage and barrier parities)
+    uint32_t n_step = 0, n_mma = 0;          // running counters: select ring stage / barrier parities
 
     const int r = blockIdx.x % w.K;
-    const int j_begin = lane_start[r], j_end = lane_start[r + 1];
+    const int i_begin = w.lane_start[r], i_end = w.lane_start[r + 1];
 
-    // next contraction (internal child) at or after position (j, ci) of this lane's plan; -1 if none
-    auto next_mma_child = [&](int j, int ci) -> int {
-        for (; j < j_end; j++) {
-            const int par = lane_jobs[j] & WALK_ID_MASK;
-            const int ce = jcs[par + 1];
-            if (ci < 0) ci = jcs[par];
-            for (; ci < ce; ci++)
-                if ((jc[ci] & WALK_ID_MASK) >= a.L) return jc[ci] & WALK_ID_MASK;
-            ci = -1;
+    // warp 0: stage the operands of one step into ring slot (m & 1)
+    auto stage_step = [&](int cat, int tile, int2 st, uint32_t m) {
+        const int child = st.x & WALK_ID_MASK;
+        const bool internal = child >= a.L;
+        float *dst = stage_base + (m & 1u) * WALK_STAGE_FLOATS;
+        uint64_t *bar = bar_full + (m & 1u);
+        const size_t slot = (size_t)cat * a.B + child;
+        if (lane == 0) mbar_expect_tx(bar, 16384u + (internal ? 32768u : 0u));
+        __syncwarp();
+        const float *src = a.PTf + slot * 4096;
+        bulk_g2s(dst + lane * WALK_PT_ROW, src + lane * 64, 256u, bar);
+        bulk_g2s(dst + (lane + 32) * WALK_PT_ROW, src + (lane + 32) * 64, 256u, bar);
+        if (lane == 0 && internal) {
+            bulk_g2s(dst + 64 * WALK_PT_ROW, a.PB + slot * TC_PB_FLOATS, 32768u, bar);
+            if (!(st.x & WALK_CHAIN))      // pull the child's conditional block towards L2 (it may still be in DRAM)
+                prefetch_l2_bulk(cond4 + cond_f4(cat, child - a.L, tile, 0, 0, a.I, w.T), 32768u);
         }
-        return -1;
-    };
-    auto issue_p_tile = [&](int cat, int child, uint32_t m) {           // thread 0 only
-        const uint32_t stage = m & 1u;
-        mbar_expect_tx(bar_b + stage, 32768u);
-        bulk_g2s(Bs + stage * 8192, a.PB + ((size_t)cat * a.B + child) * TC_PB_FLOATS, 32768u, bar_b + stage);
     };
 
     for (int ct = blockIdx.x / w.K; ct < w.ncls * w.T; ct += w.nslots) {
@@ -443,44 +451,61 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
         const size_t s = (size_t)tile * TC_TILE_P + tid;
         float v[64];
         int ex = 0;
-        if (tid == 0) {
-            const int first = next_mma_child(j_begin, -1);
-            if (first >= 0) issue_p_tile(cat, first, n_mma);
-        }
-        for (int j = j_begin; j < j_end; j++) {
-            const int job = lane_jobs[j];
-            const int par = job & WALK_ID_MASK;
-            const int c_begin = jcs[par], c_end = jcs[par + 1];
-            const bool chain0 = (jc[c_begin] & WALK_CHAIN) != 0;
-            if (!chain0) {
+        if (i_begin == i_end) continue;
+        int2 st = __ldg(w.steps + i_begin);
+        __syncthreads();                      // previous (class, tile): every read of the ring is complete
+        if (warp == 0) stage_step(cat, tile, st, n_step);
+        int next_code = 0;
+        if ((st.x & WALK_ID_MASK) < a.L) next_code = __ldg(a.leaf + (size_t)(st.x & WALK_ID_MASK) * Sp + s);
+        for (int i = i_begin; i < i_end; i++) {
+            const int enc = st.x;
+            const int child = enc & WALK_ID_MASK;
+            const int par = st.y & WALK_ID_MASK;
+            const int flags = st.y;
+            const int code = next_code;
+            int2 nx = make_int2(0, 0);
+            const bool has_next = (i + 1 < i_end);
+            if (has_next) nx = __ldg(w.steps + i + 1);
+            __syncthreads();                  // (1) everyone is done with step i-1: ring slot (n_step+1)&1 is free
+            if (has_next) {
+                if (warp == 0) stage_step(cat, tile, nx, n_step + 1);
+                if ((nx.x & WALK_ID_MASK) < a.L) next_code = __ldg(a.leaf + (size_t)(nx.x & WALK_ID_MASK) * Sp + s);
+            }
+            if ((flags & STEP_FIRST) && !(enc & WALK_CHAIN)) {
 #pragma unroll
                 for (int k = 0; k < 64; k++) v[k] = 1.f;
                 ex = 0;
             }
-            // leaf children: fetch the codes now and pull their P^T rows towards L1; they are folded in after the contractions
-            {
-                int nl = 0;
-                for (int ci = c_begin; ci < c_end && nl < WALK_LEAF_CACHE; ci++) {
-                    const int child = jc[ci] & WALK_ID_MASK;
-                    if (child >= a.L) continue;
-                    const int code = __ldg(a.leaf + (size_t)child * Sp + s);
-                    s_code[nl * 128 + tid] = code;
-                    if (code >= 0) {
-                        const float *row = a.PTf + ((size_t)cat * a.B + child) * 4096 + (size_t)code * 64;
-                        prefetch_l1(row);
-                        prefetch_l1(row + 32);
+            const float *tab = stage_base + (n_step & 1u) * WALK_STAGE_FLOATS;     // P^T table of this branch
+            if (child < a.L) {
+                mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
+                if (code >= 0) {
+                    const float4 *row = reinterpret_cast<const float4 *>(tab + code * WALK_PT_ROW);
+#pragma unroll
+                    for (int q = 0; q < 16; q++) {
+                        const float4 rr = row[q];
+                        v[4 * q] *= rr.x; v[4 * q + 1] *= rr.y; v[4 * q + 2] *= rr.z; v[4 * q + 3] *= rr.w;
                     }
-                    nl++;
+                } else {
+                    float acc[64];
+#pragma unroll
+                    for (int k = 0; k < 64; k++) acc[k] = 0.f;
+                    const double *amb = a.ambig + (size_t)(-code - 1) * 64;
+                    for (int jj = 0; jj < a.D; jj++) {
+                        if (__ldg(amb + jj) != 0.0) {
+                            const float4 *row = reinterpret_cast<const float4 *>(tab + jj * WALK_PT_ROW);
+#pragma unroll
+                            for (int q = 0; q < 16; q++) {
+                                const float4 rr = row[q];
+                                acc[4 * q] += rr.x; acc[4 * q + 1] += rr.y; acc[4 * q + 2] += rr.z; acc[4 * q + 3] += rr.w;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 64; k++) v[k] *= acc[k];
                 }
-            }
-            // contractions (internal children)
-            for (int ci = c_begin; ci < c_end; ci++) {
-                const int enc = jc[ci];
-                const int child = enc & WALK_ID_MASK;
-                if (child < a.L) continue;
-                const size_t slot = (size_t)cat * a.B + child;
+            } else {
                 const int cin = child - a.L;
-                const uint32_t stage = n_mma & 1u;
                 int na = 0;
                 {
                     uint32_t hi[64], lo[64];
@@ -504,10 +529,10 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                                 if (++it > (1 << 24)) { atomicExch(a.err, 2); break; }
                             }
                         }
-                        const float4 *xr = reinterpret_cast<const float4 *>(a.cond + (((size_t)cat * a.I + cin) * Sp + s) * 64);
+                        const float4 *xr = cond4 + cond_f4(cat, cin, tile, 0, tid, a.I, w.T);
 #pragma unroll
                         for (int q = 0; q < 16; q++) {
-                            const float4 x4 = __ldcg(xr + q);      // may have been produced by another SM in this launch
+                            const float4 x4 = __ldcg(xr + (size_t)q * 128);      // may have been produced by another SM in this launch
                             float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
                             for (int u = 0; u < 4; u++) {
@@ -528,19 +553,13 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                     }
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 }
-                // anchor rows towards L1 before the barrier
-                for (int ai = 0; ai < na; ai++) {
-                    const float *row = a.PTf + slot * 4096 + (size_t)s_ak[ai * 128 + tid] * 64;
-                    prefetch_l1(row);
-                    prefetch_l1(row + 32);
-                }
                 tc_fence_before();
-                __syncthreads();             // A operand complete in TMEM; every thread is done reading the previous D
+                __syncthreads();             // (2) A operand complete in TMEM; every thread is done reading the previous D
                 if (tid == 0) {
                     tc_fence_after();
-                    mbar_wait(bar_b + stage, (n_mma >> 1) & 1u, a.err);
-                    const uint64_t bdesc_hi = make_b_desc(smem_u32(Bs + stage * 8192));
-                    const uint64_t bdesc_lo = make_b_desc(smem_u32(Bs + stage * 8192 + 4096));
+                    mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
+                    const uint64_t bdesc_hi = make_b_desc(smem_u32(tab + 64 * WALK_PT_ROW));
+                    const uint64_t bdesc_lo = make_b_desc(smem_u32(tab + 64 * WALK_PT_ROW + 4096));
 #pragma unroll
                     for (int kk = 0; kk < 8; kk++)
                         tc_mma_tf32_ts(tmem_base, tmem_base + 128 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, kk > 0);
@@ -551,23 +570,21 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                     for (int kk = 0; kk < 8; kk++)
                         tc_mma_tf32_ts(tmem_base, tmem_base + 64 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u);
                     tc_commit(bar_mma);
-                    // stage the P tile of the next contraction of this lane into the other buffer
-                    const int nxt = next_mma_child(j, ci + 1);
-                    if (nxt >= 0) issue_p_tile(cat, nxt, n_mma + 1);
                 }
                 __syncwarp();
+                // anchors on the CUDA cores while the tensor core works (rows of the P^T table in shared memory)
                 float acc[64];
 #pragma unroll
                 for (int k = 0; k < 64; k++) acc[k] = 0.f;
-                {
-                    const float *PTf = a.PTf + slot * 4096;
+                if (na > 0) {
+                    mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
                     for (int ai = 0; ai < na; ai++) {
                         const int ka = s_ak[ai * 128 + tid];
                         const float xv = s_av[ai * 128 + tid];
-                        const float4 *row = reinterpret_cast<const float4 *>(PTf + (size_t)ka * 64);
+                        const float4 *row = reinterpret_cast<const float4 *>(tab + ka * WALK_PT_ROW);
 #pragma unroll
                         for (int q = 0; q < 16; q++) {
-                            const float4 rr = __ldg(row + q);
+                            const float4 rr = row[q];
                             acc[4 * q] = fmaf(xv, rr.x, acc[4 * q]); acc[4 * q + 1] = fmaf(xv, rr.y, acc[4 * q + 1]);
                             acc[4 * q + 2] = fmaf(xv, rr.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(xv, rr.w, acc[4 * q + 3]);
                         }
@@ -584,50 +601,14 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                     for (int k = 0; k < 16; k++) v[o + k] *= (__uint_as_float(d[k]) + acc[o + k]);
                 }
                 n_mma++;
-                renorm_f32(v, ex);
             }
-            // leaf children
-            {
-                int nl = 0;
-                for (int ci = c_begin; ci < c_end; ci++) {
-                    const int child = jc[ci] & WALK_ID_MASK;
-                    if (child >= a.L) continue;
-                    const int code = (nl < WALK_LEAF_CACHE) ? s_code[nl * 128 + tid] : __ldg(a.leaf + (size_t)child * Sp + s);
-                    nl++;
-                    const float *PTf = a.PTf + ((size_t)cat * a.B + child) * 4096;
-                    if (code >= 0) {
-                        const float4 *row = reinterpret_cast<const float4 *>(PTf + (size_t)code * 64);
+            renorm_f32(v, ex);
+            n_step++;
+            if (flags & STEP_LAST) {
+                // this tile of the parent: conditionals, exponent, (root reduction); epoch flag only if another lane consumes it
+                float4 *outp = cond4 + cond_f4(cat, par, tile, 0, tid, a.I, w.T);
 #pragma unroll
-                        for (int q = 0; q < 16; q++) {
-                            const float4 rr = __ldg(row + q);
-                            v[4 * q] *= rr.x; v[4 * q + 1] *= rr.y; v[4 * q + 2] *= rr.z; v[4 * q + 3] *= rr.w;
-                        }
-                    } else {
-                        float acc[64];
-#pragma unroll
-                        for (int k = 0; k < 64; k++) acc[k] = 0.f;
-                        const double *amb = a.ambig + (size_t)(-code - 1) * 64;
-                        for (int jj = 0; jj < a.D; jj++) {
-                            if (__ldg(amb + jj) != 0.0) {
-                                const float4 *row = reinterpret_cast<const float4 *>(PTf + (size_t)jj * 64);
-#pragma unroll
-                                for (int q = 0; q < 16; q++) {
-                                    const float4 rr = __ldg(row + q);
-                                    acc[4 * q] += rr.x; acc[4 * q + 1] += rr.y; acc[4 * q + 2] += rr.z; acc[4 * q + 3] += rr.w;
-                                }
-                            }
-                        }
-#pragma unroll
-                        for (int k = 0; k < 64; k++) v[k] *= acc[k];
-                    }
-                    renorm_f32(v, ex);
-                }
-            }
-            // this tile of the parent: conditionals, exponent, (root reduction); epoch flag only if another lane consumes it
-            {
-                float4 *outp = reinterpret_cast<float4 *>(a.cond + (((size_t)cat * a.I + par) * Sp + s) * 64);
-#pragma unroll
-                for (int q = 0; q < 16; q++) __stcg(outp + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+                for (int q = 0; q < 16; q++) __stcg(outp + (size_t)q * 128, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
                 __stcg(a.scal + ((size_t)cat * a.I + par) * Sp + s, ex);
                 if (par == a.I - 1) {
                     double rr = 0.0;
@@ -636,16 +617,16 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                     a.rootL[(size_t)cat * Sp + s] = rr;
                     a.rootE[(size_t)cat * Sp + s] = ex;
                 }
-            }
-            if (job & WALK_PUBLISH) {
-                __syncthreads();
-                if (tid == 96) {
-                    __threadfence();
-                    st_release(w.done + ((size_t)cat * a.I + par) * w.T + tile, w.epoch);
+                if (flags & STEP_PUBLISH) {
+                    __syncthreads();
+                    if (tid == 96) {
+                        __threadfence();
+                        st_release(w.done + ((size_t)cat * a.I + par) * w.T + tile, w.epoch);
+                    }
                 }
             }
+            st = nx;
         }
-        __syncthreads();     // all contractions of this (class, tile) are complete before the next one re-arms the P stages
     }
     tc_fence_before();
     __syncthreads();
