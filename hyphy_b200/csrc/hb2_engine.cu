@@ -555,10 +555,10 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
     if (p->use_tc) {
         CUP(cudaMalloc(&p->d_condf, (size_t)C * I * Sp * 64 * sizeof(float)));
         CUP(cudaMalloc(&p->d_PB, (size_t)C * p->B * hb2::TC_PB_FLOATS * sizeof(float)));
-        CUP(cudaMalloc(&p->d_PTf, (size_t)C * p->B * 4096 * sizeof(float)));
+        CUP(cudaMalloc(&p->d_PTf, (size_t)C * p->B * hb2::TC_PTF_FLOATS * sizeof(float)));
         CUP(cudaMemsetAsync(p->d_condf, 0, (size_t)C * I * Sp * 64 * sizeof(float), p->stream));
         CUP(cudaMemsetAsync(p->d_PB, 0, (size_t)C * p->B * hb2::TC_PB_FLOATS * sizeof(float), p->stream));
-        CUP(cudaMemsetAsync(p->d_PTf, 0, (size_t)C * p->B * 4096 * sizeof(float), p->stream));
+        CUP(cudaMemsetAsync(p->d_PTf, 0, (size_t)C * p->B * hb2::TC_PTF_FLOATS * sizeof(float), p->stream));
         CUP(cudaFuncSetAttribute(hb2::prune64_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::TC_SMEM_BYTES));
         CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::WALK_SMEM_BYTES));
         {
@@ -574,6 +574,7 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
                         per_sm, fa.numRegs, fa.sharedSizeBytes, hb2::WALK_SMEM_BYTES, dp.regsPerMultiprocessor, dp.sharedMemPerMultiprocessor, dp.sharedMemPerBlockOptin, dp.reservedSharedMemPerBlock);
             }
             CUP(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+            if (const char *ov = getenv("HB2_WALK_CTAS_PER_SM")) per_sm = atoi(ov);      // bring-up override
             p->walk_max_resident = std::min(per_sm, 2) * sms;          // TMEM: 256 of 512 columns per CTA -> at most 2 per SM
             if (p->walk_max_resident < 1) p->use_walk = false;
             const size_t T = Sp / hb2::TC_TILE_P;

@@ -308,7 +308,7 @@ __device__ __forceinline__ void tile_mm64_dmma(const double *__restrict__ A, con
 
 struct ExpmTcOut {
     float *PB;      // nullable: [slots][2][4096] canonical hi/lo tiles (see hb2_kernels_tc.cuh)
-    float *PTf;     // [slots][4096]
+    float *PTf;     // [slots][64 rows][68 floats] (rows padded: conflict-free shared-memory gathers after a flat bulk copy)
 };
 
 __device__ __forceinline__ float tf32_rn_dev(float x) {
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(256, 1) expm64_dmma_kernel(ExpmArgs a, ExpmTcO
             for (int idx = tid; idx < 4096; idx += 256) out[idx] = __longlong_as_double(0x7ff8000000000000LL);
             if (tc.PB) {
                 for (int idx = tid; idx < 8192; idx += 256) tc.PB[slot * 8192 + idx] = __int_as_float(0x7fc00000);
-                for (int idx = tid; idx < 4096; idx += 256) tc.PTf[slot * 4096 + idx] = __int_as_float(0x7fc00000);
+                for (int idx = tid; idx < 4352; idx += 256) tc.PTf[slot * 4352 + idx] = __int_as_float(0x7fc00000);
             }
             return;
         }
@@ -441,14 +441,14 @@ __global__ void __launch_bounds__(256, 1) expm64_dmma_kernel(ExpmArgs a, ExpmTcO
         for (int idx = tid; idx < 4096; idx += 256) out[idx] = R[(idx >> 6) * LD64 + (idx & 63)];
         if (tc.PB) {
             float *pb = tc.PB + slot * 8192;
-            float *pf = tc.PTf + slot * 4096;
+            float *pf = tc.PTf + slot * 4352;           // rows padded to 68 floats (TC_PTF_ROW)
             for (int o = tid; o < 4096; o += 256) {
                 const int chunk = o >> 8, n = (o >> 2) & 63, kk = chunk * 4 + (o & 3);
                 const double pv = R[kk * LD64 + n];          // P[n][kk] = PT[kk][n]
                 const float hi = tf32_rn_dev((float)pv);
                 pb[o] = hi;
                 pb[4096 + o] = tf32_rn_dev((float)(pv - (double)hi));
-                pf[o] = (float)R[(o >> 6) * LD64 + (o & 63)];
+                pf[(o >> 6) * 68 + (o & 63)] = (float)R[(o >> 6) * LD64 + (o & 63)];
             }
         }
     }

@@ -35,6 +35,8 @@ namespace hb2 {
 
 constexpr int TC_TILE_P = 128;                 // patterns per CTA (= UMMA M = TMEM lanes)
 constexpr int TC_PB_FLOATS = 2 * 4096;         // per (class, branch): Ph tile + Pl tile in canonical layout
+constexpr int TC_PTF_ROW = 68;                 // floats per row of the fp32 P^T table (64 + 4 padding: 272-byte rows)
+constexpr int TC_PTF_FLOATS = 64 * TC_PTF_ROW; // per (class, branch)
 constexpr int TC_SMEM_BYTES = 2 * 32768 + 1024; // two B stages (one used for now; also caps residency at 2 CTAs/SM) + barriers
 constexpr uint32_t TC_TMEM_COLS = 256;         // D: 0..63, Xh: 64..127, Xl: 128..191
 constexpr int TC_MAX_ANCHORS = 8;              // per pattern and child
@@ -42,7 +44,7 @@ constexpr float TC_ANCHOR_THR = 0.015625f;     // 2^-6 (rows are normalised to m
 
 struct PruneTcArgs {
     const float *PB;                // [C][B][2][16][64][4] canonical K-major tiles of P (hi, lo)
-    const float *PTf;               // [C][B][64][64] fp32 copy of PT (leaf column gather)
+    const float *PTf;               // [C][B][64][68] fp32 copy of PT, padded rows (leaf column gather, anchors)
     float *cond;                    // [C][I][Sp/128][16 chunks][128 patterns][4] fp32 conditionals (tile-wise K-major chunks)
     int *scal;                      // [C][I][Sp]
     const int *leaf;                // [L][Sp]
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const double *__restrict__
     const size_t slot = slots[blockIdx.x];
     const double *src = PT + slot * 4096;
     float *pb = PB + slot * TC_PB_FLOATS;
-    float *pf = PTf + slot * 4096;
+    float *pf = PTf + slot * TC_PTF_FLOATS;
     for (int o = threadIdx.x; o < 4096; o += 256) {
         const int chunk = o >> 8, n = (o >> 2) & 63, kk = chunk * 4 + (o & 3);
         const double p = src[kk * 64 + n];              // P[n][kk] = PT[kk][n]
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const double *__restrict__
         const float lo = tf32_rn((float)(p - (double)hi));
         pb[o] = hi;
         pb[4096 + o] = lo;
-        pf[o] = (float)src[o];
+        pf[(o >> 6) * TC_PTF_ROW + (o & 63)] = (float)src[o];
     }
 }
 
@@ -202,9 +204,9 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_kernel(PruneTcArgs a, const
         const size_t slot = (size_t)cat * a.B + child;
         if (child < a.L) {
             const int code = a.leaf[(size_t)child * Sp + s];
-            const float *PTf = a.PTf + slot * 4096;
+            const float *PTf = a.PTf + slot * TC_PTF_FLOATS;
             if (code >= 0) {
-                const float4 *row = reinterpret_cast<const float4 *>(PTf + (size_t)code * 64);
+                const float4 *row = reinterpret_cast<const float4 *>(PTf + (size_t)code * TC_PTF_ROW);
 #pragma unroll
                 for (int q = 0; q < 16; q++) {
                     const float4 r = __ldg(row + q);
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_kernel(PruneTcArgs a, const
                 const double *amb = a.ambig + (size_t)(-code - 1) * 64;
                 for (int j = 0; j < a.D; j++) {
                     if (__ldg(amb + j) != 0.0) {
-                        const float4 *row = reinterpret_cast<const float4 *>(PTf + (size_t)j * 64);
+                        const float4 *row = reinterpret_cast<const float4 *>(PTf + (size_t)j * TC_PTF_ROW);
 #pragma unroll
                         for (int q = 0; q < 16; q++) {
                             const float4 r = __ldg(row + q);
@@ -288,11 +290,11 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_kernel(PruneTcArgs a, const
 #pragma unroll
             for (int k = 0; k < 64; k++) acc[k] = 0.f;
             {
-                const float *PTf = a.PTf + slot * 4096;
+                const float *PTf = a.PTf + slot * TC_PTF_FLOATS;
                 for (int ai = 0; ai < na; ai++) {
                     const int ka = s_ak[ai * 128 + tid];
                     const float xv = s_av[ai * 128 + tid];
-                    const float4 *row = reinterpret_cast<const float4 *>(PTf + (size_t)ka * 64);
+                    const float4 *row = reinterpret_cast<const float4 *>(PTf + (size_t)ka * TC_PTF_ROW);
 #pragma unroll
                     for (int q = 0; q < 16; q++) {
                         const float4 r = __ldg(row + q);
@@ -365,7 +367,7 @@ constexpr int WALK_ID_MASK = (1 << 28) - 1;
 constexpr int STEP_FIRST = 1 << 28;
 constexpr int STEP_LAST = 1 << 29;
 constexpr int STEP_PUBLISH = 1 << 30;
-constexpr int WALK_PT_ROW = 68;                // floats per padded P^T row in shared memory (272 B: conflict-free gathers)
+constexpr int WALK_PT_ROW = TC_PTF_ROW;        // same padded rows in shared memory: one flat bulk copy stages the table
 constexpr int WALK_STAGE_FLOATS = 64 * WALK_PT_ROW + 8192;     // P^T table + Ph|Pl tiles
 constexpr int WALK_SMEM_BYTES = 2 * WALK_STAGE_FLOATS * 4 + TC_MAX_ANCHORS * 128 * 8 + 64;
 
@@ -402,7 +404,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
     uint64_t *bar_full = reinterpret_cast<uint64_t *>(s_av + TC_MAX_ANCHORS * 128); // [2]
     uint64_t *bar_mma = bar_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_mma + 1);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const size_t Sp = a.Sp;
     float4 *cond4 = reinterpret_cast<float4 *>(a.cond);
 
@@ -422,23 +424,21 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     uint32_t n_step = 0, n_mma = 0;          // running counters: select ring stage / barrier parities
+    bool bailed = false;                     // a dependency wait timed out: stop waiting, the host reports the error
 
     const int r = blockIdx.x % w.K;
     const int i_begin = w.lane_start[r], i_end = w.lane_start[r + 1];
 
-    // warp 0: stage the operands of one step into ring slot (m & 1)
+    // thread 0: stage the operands of one step into ring slot (m & 1): two flat bulk copies + one L2 prefetch
     auto stage_step = [&](int cat, int tile, int2 st, uint32_t m) {
         const int child = st.x & WALK_ID_MASK;
         const bool internal = child >= a.L;
         float *dst = stage_base + (m & 1u) * WALK_STAGE_FLOATS;
         uint64_t *bar = bar_full + (m & 1u);
         const size_t slot = (size_t)cat * a.B + child;
-        if (lane == 0) mbar_expect_tx(bar, 16384u + (internal ? 32768u : 0u));
-        __syncwarp();
-        const float *src = a.PTf + slot * 4096;
-        bulk_g2s(dst + lane * WALK_PT_ROW, src + lane * 64, 256u, bar);
-        bulk_g2s(dst + (lane + 32) * WALK_PT_ROW, src + (lane + 32) * 64, 256u, bar);
-        if (lane == 0 && internal) {
+        mbar_expect_tx(bar, (uint32_t)(TC_PTF_FLOATS * 4) + (internal ? 32768u : 0u));
+        bulk_g2s(dst, a.PTf + slot * TC_PTF_FLOATS, (uint32_t)(TC_PTF_FLOATS * 4), bar);
+        if (internal) {
             bulk_g2s(dst + 64 * WALK_PT_ROW, a.PB + slot * TC_PB_FLOATS, 32768u, bar);
             if (!(st.x & WALK_CHAIN))      // pull the child's conditional block towards L2 (it may still be in DRAM)
                 prefetch_l2_bulk(cond4 + cond_f4(cat, child - a.L, tile, 0, 0, a.I, w.T), 32768u);
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
         if (i_begin == i_end) continue;
         int2 st = __ldg(w.steps + i_begin);
         __syncthreads();                      // previous (class, tile): every read of the ring is complete
-        if (warp == 0) stage_step(cat, tile, st, n_step);
+        if (tid == 0) stage_step(cat, tile, st, n_step);
         int next_code = 0;
         if ((st.x & WALK_ID_MASK) < a.L) next_code = __ldg(a.leaf + (size_t)(st.x & WALK_ID_MASK) * Sp + s);
         for (int i = i_begin; i < i_end; i++) {
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
             if (has_next) nx = __ldg(w.steps + i + 1);
             __syncthreads();                  // (1) everyone is done with step i-1: ring slot (n_step+1)&1 is free
             if (has_next) {
-                if (warp == 0) stage_step(cat, tile, nx, n_step + 1);
+                if (tid == 0) stage_step(cat, tile, nx, n_step + 1);
                 if ((nx.x & WALK_ID_MASK) < a.L) next_code = __ldg(a.leaf + (size_t)(nx.x & WALK_ID_MASK) * Sp + s);
             }
             if ((flags & STEP_FIRST) && !(enc & WALK_CHAIN)) {
@@ -525,8 +525,8 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                         if (enc & WALK_WAIT) {
                             const int *flag = w.done + ((size_t)cat * a.I + cin) * w.T + tile;
                             int it = 0;
-                            while (ld_acquire(flag) < w.epoch) {
-                                if (++it > (1 << 24)) { atomicExch(a.err, 2); break; }
+                            while (!bailed && ld_acquire(flag) < w.epoch) {
+                                if (++it > (1 << 21)) { atomicExch(a.err, 2); bailed = true; }   // never hang the GPU
                             }
                         }
                         const float4 *xr = cond4 + cond_f4(cat, cin, tile, 0, tid, a.I, w.T);
