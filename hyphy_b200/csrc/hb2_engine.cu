@@ -574,6 +574,15 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
                         per_sm, fa.numRegs, fa.sharedSizeBytes, hb2::WALK_SMEM_BYTES, dp.regsPerMultiprocessor, dp.sharedMemPerMultiprocessor, dp.sharedMemPerBlockOptin, dp.reservedSharedMemPerBlock);
             }
             CUP(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+            {   // the occupancy API reports 1 CTA/SM for this kernel on B200 although ncu (launch__occupancy_limit_* = 2) and a
+                // forced 2-per-SM run with cross-CTA dependencies (r01g) show two are co-resident; derive it from the resources
+                cudaFuncAttributes fa; CUP(cudaFuncGetAttributes(&fa, hb2::prune64_tc_walk_kernel));
+                cudaDeviceProp dp; CUP(cudaGetDeviceProperties(&dp, device));
+                const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * 128;
+                const size_t smem_per_cta = (size_t)hb2::WALK_SMEM_BYTES + fa.sharedSizeBytes + dp.reservedSharedMemPerBlock;
+                const int by_res = std::min(dp.regsPerMultiprocessor / std::max(regs_per_cta, 1), (int)(dp.sharedMemPerMultiprocessor / smem_per_cta));
+                per_sm = std::max(per_sm, std::min(by_res, 2));
+            }
             if (const char *ov = getenv("HB2_WALK_CTAS_PER_SM")) per_sm = atoi(ov);      // bring-up override
             p->walk_max_resident = std::min(per_sm, 2) * sms;          // TMEM: 256 of 512 columns per CTA -> at most 2 per SM
             if (p->walk_max_resident < 1) p->use_walk = false;

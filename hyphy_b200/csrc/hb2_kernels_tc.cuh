@@ -147,16 +147,18 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const double *__restrict__
 // ------------------------------------------------------------------------------------------------------------------
 // Fused pruning update on tcgen05.  grid = (Sp/128, jobs, classes), block = 128 threads (thread t <-> pattern t).
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void renorm_f32(float (&v)[64], int &ex) {
+// Power-of-two renormalisation of a pattern's 64 conditionals: max -> [0.5,1).  `force` = false only rescales when the
+// maximum has drifted below 2^-32 (cheap guard between the children of one node); true at the end of a node.
+__device__ __forceinline__ void renorm_f32(float (&v)[64], int &ex, bool force = true) {
     float m = 0.f;
 #pragma unroll
     for (int k = 0; k < 64; k++) m = fmaxf(m, v[k]);
-    if (m > 0.f && m < INFINITY) {
-        const int e = (int)((__float_as_uint(m) >> 23) & 0xffu) - 126;       // m = f * 2^e, f in [0.5,1) (normal m)
+    if (m > 0.f && m < INFINITY && (force || m < 2.3283064e-10f)) {
+        const int e = max((int)((__float_as_uint(m) >> 23) & 0xffu) - 126, -125);   // m = f * 2^e, f in [0.5,1) (normal m)
         if (e != 0) {
-            const float s1 = __uint_as_float((uint32_t)(127 - e / 2) << 23), s2 = __uint_as_float((uint32_t)(127 - (e - e / 2)) << 23);
+            const float sc = __uint_as_float((uint32_t)(127 - e) << 23);           // 2^-e, exact
 #pragma unroll
-            for (int k = 0; k < 64; k++) v[k] = v[k] * s1 * s2;
+            for (int k = 0; k < 64; k++) v[k] *= sc;
             ex += e;
         }
     }
@@ -453,6 +455,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
         int ex = 0;
         if (i_begin == i_end) continue;
         int2 st = __ldg(w.steps + i_begin);
+        int2 nx = (i_begin + 1 < i_end) ? __ldg(w.steps + i_begin + 1) : make_int2(0, 0);
         __syncthreads();                      // previous (class, tile): every read of the ring is complete
         if (tid == 0) stage_step(cat, tile, st, n_step);
         int next_code = 0;
@@ -463,9 +466,8 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
             const int par = st.y & WALK_ID_MASK;
             const int flags = st.y;
             const int code = next_code;
-            int2 nx = make_int2(0, 0);
             const bool has_next = (i + 1 < i_end);
-            if (has_next) nx = __ldg(w.steps + i + 1);
+            const int2 nx2 = (i + 2 < i_end) ? __ldg(w.steps + i + 2) : make_int2(0, 0);   // descriptors run two steps ahead
             __syncthreads();                  // (1) everyone is done with step i-1: ring slot (n_step+1)&1 is free
             if (has_next) {
                 if (tid == 0) stage_step(cat, tile, nx, n_step + 1);
@@ -602,7 +604,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                 }
                 n_mma++;
             }
-            renorm_f32(v, ex);
+            renorm_f32(v, ex, (flags & STEP_LAST) != 0);
             n_step++;
             if (flags & STEP_LAST) {
                 // this tile of the parent: conditionals, exponent, (root reduction); epoch flag only if another lane consumes it
@@ -626,6 +628,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                 }
             }
             st = nx;
+            nx = nx2;
         }
     }
     tc_fence_before();
