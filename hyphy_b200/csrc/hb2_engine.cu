@@ -117,6 +117,7 @@ struct hb2_partition {
     bool small_walk = true;                   // HB2_SMALL_WALK=0: per-level launches of prune_small_kernel (A/B testing)
     bool expm_dfma = false;                   // HB2_EXPM_DFMA=1: previous FFMA-style fp64 expm kernel (A/B testing)
     bool use_walk = false;
+    bool walk_split = true;                   // two threads per pattern (256-thread CTAs); HB2_WALK_SPLIT=0 selects the 128-thread kernel
     int walk_max_resident = 0;
     int epoch = 0;
     int *d_done = nullptr, *d_walk = nullptr, *h_walk = nullptr;
@@ -372,7 +373,8 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
     w.lane_start = p->d_walk; w.steps = reinterpret_cast<const int2 *>(p->d_walk + 16);
     w.done = p->d_done; w.epoch = ++p->epoch; w.K = K; w.T = T; w.ncls = ncls; w.nslots = nslots;
     if (getenv("HB2_DEBUG")) fprintf(stderr, "[hb2] walk: jobs=%d steps=%d K=%d T=%d ncls=%d nslots=%d grid=%d resident=%d\n", total, ns, K, T, ncls, nslots, nslots * K, p->walk_max_resident);
-    hb2::prune64_tc_walk_kernel<<<nslots * K, 128, hb2::WALK_SMEM_BYTES, p->stream>>>(w);
+    if (p->walk_split) hb2::prune64_tc_walk2_kernel<<<nslots * K, 256, hb2::WALK2_SMEM_BYTES, p->stream>>>(w);
+    else hb2::prune64_tc_walk_kernel<<<nslots * K, 128, hb2::WALK_SMEM_BYTES, p->stream>>>(w);
     p->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -561,6 +563,9 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
         CUP(cudaMemsetAsync(p->d_PTf, 0, (size_t)C * p->B * hb2::TC_PTF_FLOATS * sizeof(float), p->stream));
         CUP(cudaFuncSetAttribute(hb2::prune64_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::TC_SMEM_BYTES));
         CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::WALK_SMEM_BYTES));
+        CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::WALK2_SMEM_BYTES));
+        CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        { const char *env = getenv("HB2_WALK_SPLIT"); p->walk_split = !(env && env[0] == '0'); }
         {
             const char *env = getenv("HB2_TC_WALK");
             p->use_walk = !(env && env[0] == '0');
@@ -576,10 +581,12 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
             CUP(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
             {   // the occupancy API reports 1 CTA/SM for this kernel on B200 although ncu (launch__occupancy_limit_* = 2) and a
                 // forced 2-per-SM run with cross-CTA dependencies (r01g) show two are co-resident; derive it from the resources
-                cudaFuncAttributes fa; CUP(cudaFuncGetAttributes(&fa, hb2::prune64_tc_walk_kernel));
+                cudaFuncAttributes fa;
+                if (p->walk_split) CUP(cudaFuncGetAttributes(&fa, hb2::prune64_tc_walk2_kernel));
+                else CUP(cudaFuncGetAttributes(&fa, hb2::prune64_tc_walk_kernel));
                 cudaDeviceProp dp; CUP(cudaGetDeviceProperties(&dp, device));
-                const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * 128;
-                const size_t smem_per_cta = (size_t)hb2::WALK_SMEM_BYTES + fa.sharedSizeBytes + dp.reservedSharedMemPerBlock;
+                const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * (p->walk_split ? 256 : 128);
+                const size_t smem_per_cta = (size_t)(p->walk_split ? hb2::WALK2_SMEM_BYTES : hb2::WALK_SMEM_BYTES) + fa.sharedSizeBytes + dp.reservedSharedMemPerBlock;
                 const int by_res = std::min(dp.regsPerMultiprocessor / std::max(regs_per_cta, 1), (int)(dp.sharedMemPerMultiprocessor / smem_per_cta));
                 per_sm = std::max(per_sm, std::min(by_res, 2));
             }

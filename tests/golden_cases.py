@@ -26,3 +26,17 @@ SMALL = ["c1_hky85_8x500", "nuc_300x200_scaling", "mg94_8x60_c1", "mg94_8x60_c4_
          "mg94_200x64_c4_scaling"]
 MEDIUM = ["c2_mg94_50x1000_c1"]
 FULL = ["ns_mg94_200x2000_c4"]
+
+
+def load_smallcodon():
+    """The reference's own test tests/hbltests/SimpleOptimizations/SmallCodon.bf (golden lnL at :37) at the parameter
+    values the reference binary fitted (tools/make_smallcodon_fixture.py).  Returns (workload, Qt[1,B,61,61], fixture)."""
+    from hyphy_b200 import synth
+    g = np.load(os.path.join(GOLDEN_DIR, "smallcodon_fit.npz"))
+    L = int(g["n_leaves"])
+    fp = g["flat_parents"]
+    I = len(fp) - L
+    tree = synth.FlatTree(L, I, fp, [f"n{k}" for k in range(L + I)], np.zeros(L + I), "")
+    w = synth.Workload("smallcodon_fit", tree, 61, g["pi"], [np.eye(61)], np.array([1.0]), g["leaf_states"], g["ambig"].reshape(-1, 61),
+                       g["pattern_freq"], np.zeros(0, dtype=np.int64))
+    return w, g["Qt"][None], {"lnL_reference_run": float(g["lnL_reference_run"]), "lnL_golden": float(g["lnL_golden"])}

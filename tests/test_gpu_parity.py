@@ -77,6 +77,19 @@ def test_lnl_matches_reference_golden(name, mode):
     assert np.all(sl > 0) and np.all(sl <= 1.0)
 
 
+def test_reference_own_golden_smallcodon(mode):
+    """The reference's own golden vector: tests/hbltests/SimpleOptimizations/SmallCodon.bf:37 (-3189.516375 +- 0.002),
+    evaluated at the parameters the reference binary fitted."""
+    w, Qt, g = gc.load_smallcodon()
+    lf = LF(w, mode)
+    lf.set_all_matrices(Qt)
+    lnl = lf.compute()
+    lf.close()
+    record("smallcodon", "SmallCodon.bf", mode, lnl, g["lnL_reference_run"])
+    assert abs(lnl - g["lnL_reference_run"]) <= tol(w, mode)[0] * abs(lnl)
+    assert abs(lnl - g["lnL_golden"]) < 0.002
+
+
 @pytest.mark.parametrize("name", ["mg94_8x60_c4_ambig", "c1_hky85_8x500", "mg94_200x64_c4_scaling"])
 def test_per_class_compute_block_matches_oracle(name, mode):
     """ComputeBlock semantics: one rate class at a time with (L, scaler count) outputs, combined on the host the

@@ -60,3 +60,12 @@ def test_oracle_ambiguity_all_ones_equals_pruned_leaf():
     w2.leaf_states[0, :] = -1
     amb, _ = port.prune(w2, P)
     np.testing.assert_allclose(amb, total, rtol=1e-13)
+
+
+def test_oracle_reproduces_reference_own_golden_smallcodon():
+    """SmallCodon.bf:37 expects -3189.516375 +- 2*OPTIMIZATION_PRECISION (0.002); at the parameters the reference binary
+    itself fitted, the oracle must give the reference's lnL (fixed-parameter parity on real HIV-1 RT data)."""
+    w, Qt, g = gc.load_smallcodon()
+    lnl, _ = port.lnl(w, Qt=Qt)
+    assert abs(lnl - g["lnL_reference_run"]) <= 1e-11 * abs(lnl)
+    assert abs(lnl - g["lnL_golden"]) < 0.002
