@@ -263,9 +263,10 @@ def main():
     ms, stage, lnl_res = lf.part.time_resident(w.class_weights, w.pi, iters=args.steps)
     barrier()
     launches = lf.part.launch_count - launches0
-    # the timed region is a few tens of ms; keep the identical load running ~1 s so nvidia-smi (100 ms period) sees it
-    t_end = time.time() + 1.0
-    while time.time() < t_end:
+    # the timed region is a few tens of ms; keep the identical load running ~1 s so nvidia-smi (100 ms period) sees it.
+    # The repeat count is derived from the rank-reduced time so every rank issues the same number of all-reduces.
+    extra = int(min(200, max(1, round(1000.0 / max(max_over_ranks(ms) * args.steps, 1e-3)))))
+    for _ in range(extra):
         lf.part.time_resident(w.class_weights, w.pi, iters=args.steps)
     clocks = sampler.stop()
     tc_mode = lf.part.precision_mode == 1

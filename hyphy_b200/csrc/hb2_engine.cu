@@ -103,6 +103,7 @@ struct hb2_partition {
     std::vector<char> have_matrix;            // [C*B]
     std::vector<char> is_rate;                // [C*B] slot holds a rate matrix resident in d_Qres (for hb2_time_resident)
     double *d_Qres = nullptr;                 // [C][B][D*D] last rate matrices, resident copy
+    double *d_mix_scratch = nullptr;          // [capacity][4096] expm scratch for mixture components (allocated on first use)
     // compiled rate-matrix template (hb2_set_rate_template) and its per-evaluation formula values
     int64_t t_nnz = 0, t_nF = 0;
     bool t_has_colfreq = false;
@@ -140,6 +141,7 @@ int launch_expm(hb2_partition *p, const double *dQ, const int *d_dst, int n, int
     hb2::ExpmArgs a{};
     a.Q = dQ; a.dst = d_dst; a.mix_w = mix_w; a.mix_first = mix_first; a.PT = p->d_PT; a.Qres = qres; a.D = (int)p->D;
     a.is_trans = is_trans;
+    a.park = mix_w ? p->d_mix_scratch : nullptr;
     if (is_trans == 2) {                       // compiled template: dQ points at the formula values [n][nF]
         a.is_trans = 0; a.Q = nullptr; a.V = dQ; a.tmpl_index = p->d_t_index; a.tmpl_formula = p->d_t_formula;
         a.tmpl_colfreq = p->t_has_colfreq ? p->d_t_colfreq : nullptr; a.tmpl_nnz = (int)p->t_nnz; a.nF = (int)p->t_nF;
@@ -152,7 +154,7 @@ int launch_expm(hb2_partition *p, const double *dQ, const int *d_dst, int n, int
             } else {
                 hb2::ExpmTcOut tco{nullptr, nullptr};
                 if (p->use_tc && pack_tc && !mix_w) { tco.PB = p->d_PB; tco.PTf = p->d_PTf; packed = true; }
-                hb2::expm64_dmma_kernel<<<n, 256, 4 * 64 * hb2::LD64 * sizeof(double), p->stream>>>(a, tco);
+                hb2::expm64_dmma_kernel<<<n, 256, 3 * 64 * hb2::LD64 * sizeof(double), p->stream>>>(a, tco);
             }
             break;
         case 4: hb2::expm_small_kernel<4><<<n, 128, hb2::expm_small_smem_bytes(4), p->stream>>>(a); break;
@@ -657,7 +659,8 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
     if (Dp == 32) CUP(cudaFuncSetAttribute(hb2::expm_small_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hb2::expm_small_smem_bytes(32)));
     if (Dp == 64) {
         CUP(cudaFuncSetAttribute(hb2::expm64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(5 * 64 * hb2::LD64 * sizeof(double))));
-        CUP(cudaFuncSetAttribute(hb2::expm64_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * 64 * hb2::LD64 * sizeof(double))));
+        CUP(cudaFuncSetAttribute(hb2::expm64_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * 64 * hb2::LD64 * sizeof(double))));
+        CUP(cudaFuncSetAttribute(hb2::expm64_dmma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         { const char *env = getenv("HB2_EXPM_DFMA"); p->expm_dfma = env && env[0] == '1'; }
     }
     { const char *env = getenv("HB2_SMALL_WALK"); p->small_walk = !(env && env[0] == '0');
@@ -699,6 +702,7 @@ int hb2_set_mixture_matrices(hb2_partition *p, int64_t cat, int64_t n, const int
     if (n > p->q_capacity) return fail("too many nodes");
     CU(cudaSetDevice(p->device));
     if (flush_matrices(p)) return 1;         // keep ordering with plain matrices staged earlier
+    if (!p->d_mix_scratch && p->Dp == 64) CU(cudaMalloc(&p->d_mix_scratch, (size_t)p->q_capacity * 4096 * sizeof(double)));
     const size_t dd = (size_t)p->D * p->D;
     std::vector<double> hw(n);
     std::vector<int> hf(n);
@@ -858,7 +862,7 @@ void hb2_destroy(hb2_partition *p) {
     if (p->comm) g_nccl.CommDestroy(p->comm);
     void *dev[] = {p->d_leaf, p->d_scal, p->d_rootE, p->d_child_start, p->d_child_ids, p->d_jobs, p->d_dst, p->d_flag,
                    p->d_mix_first, p->d_ambig, p->d_freq, p->d_cond, p->d_PT, p->d_Q, p->d_pi, p->d_rootL, p->d_weights,
-                   p->d_partial, p->d_lnL, p->d_siteL, p->d_mix_w, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_done, p->d_walk, p->d_t_index, p->d_t_formula, p->d_vdst, p->d_t_colfreq, p->d_V};
+                   p->d_partial, p->d_lnL, p->d_siteL, p->d_mix_w, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_done, p->d_walk, p->d_t_index, p->d_t_formula, p->d_vdst, p->d_t_colfreq, p->d_V};
     for (void *d : dev) if (d) cudaFree(d);
     if (p->h_Q) cudaFreeHost(p->h_Q);
     if (p->h_small) cudaFreeHost(p->h_small);

@@ -108,6 +108,7 @@ struct ExpmArgs {
     const int *tmpl_formula;// [nnz]
     const double *tmpl_colfreq;  // nullable [D]
     int tmpl_nnz, nF;
+    double *park;           // nullable [n][4096] scratch for expm64_dmma_kernel (needed when PT[slot] must not be clobbered: mixtures)
 };
 
 // Builds A1[j][i] = Q[i][j] (transposed, zero padded, leading dimension LD) from dense or compiled input and leaves a
@@ -317,9 +318,13 @@ __device__ __forceinline__ float tf32_rn_dev(float x) {
     return __uint_as_float(r);
 }
 
-__global__ void __launch_bounds__(256, 1) expm64_dmma_kernel(ExpmArgs a, ExpmTcOut tc) {
+__global__ void __launch_bounds__(256, 2) expm64_dmma_kernel(ExpmArgs a, ExpmTcOut tc) {
+    // Three shared 64x64 fp64 buffers (101 KB) so that TWO CTAs share an SM and one CTA's load/norm/epilogue phases
+    // overlap the other's DMMA products:  X0 = A -> later R,  X1 = A^2,  X2 = A^3.  The polynomial blocks need A at the
+    // thread's own output positions after X0 has become R: those values are parked in the (not yet written) output
+    // slot PT[slot] in global memory (L2 resident, same [row][col] layout) and re-read per Horner step.
     extern __shared__ __align__(16) double sm[];
-    double *A1 = sm, *A2 = A1 + 64 * LD64, *A3 = A2 + 64 * LD64, *R = A3 + 64 * LD64;
+    double *X0 = sm, *X1 = X0 + 64 * LD64, *X2 = X1 + 64 * LD64;
     __shared__ double red[64];
     __shared__ int s_shift, s_Q;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -327,32 +332,34 @@ __global__ void __launch_bounds__(256, 1) expm64_dmma_kernel(ExpmArgs a, ExpmTcO
     const int D = a.D;
     const size_t slot = a.dst[blockIdx.x];
     double *out = a.PT + slot * 4096;
+    double *park = a.park ? a.park + (size_t)blockIdx.x * 4096 : out;
+    double *R = X0;
 
-    load_rate_matrix<64, LD64, 256>(a, A1, tid);
-    if (a.is_trans) {
-        for (int idx = tid; idx < 4096; idx += 256) R[(idx >> 6) * LD64 + (idx & 63)] = A1[(idx >> 6) * LD64 + (idx & 63)];
-        __syncthreads();
-    } else {
+    load_rate_matrix<64, LD64, 256>(a, X0, tid);
+    if (!a.is_trans) {
         if (tid < 64) {
             double s = 0.0;
-            for (int j = 0; j < 64; j++) s += fabs(A1[j * LD64 + tid]);
+            for (int j = 0; j < 64; j++) s += fabs(X0[j * LD64 + tid]);
             red[tid] = s;
         }
         __syncthreads();
-        if (tid == 0) {
-            double m = 0.0;
-            bool bad = false;
-            for (int i = 0; i < 64; i++) { if (!(red[i] == red[i]) || isinf(red[i])) bad = true; m = fmax(m, red[i]); }
-            int shift = 0, Q = 1;
-            if (!bad && m > 0.975) {
-                int e = 0;
-                frexp(m / 0.975, &e);              // m/0.975 = f*2^e, f in [0.5,1)  ->  m/2^e <= 0.975
-                shift = max(e, 0);
+        if (tid < 32) {                      // warp-parallel max / NaN scan of the 64 row sums
+            double m = fmax(red[tid], red[tid + 32]);
+            bool bad = !(red[tid] == red[tid]) || !(red[tid + 32] == red[tid + 32]) || isinf(red[tid]) || isinf(red[tid + 32]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+            bad = __any_sync(0xffffffffu, bad);
+            if (tid == 0) {
+                int shift = 0;
+                if (!bad && m > 0.975) {
+                    int e = 0;
+                    frexp(m / 0.975, &e);          // m/0.975 = f*2^e, f in [0.5,1)  ->  m/2^e <= 0.975
+                    shift = max(e, 0);
+                }
+                const double theta = bad ? 0.0 : ldexp(m, -shift);
+                s_Q = theta <= 0.0064 ? 1 : theta <= 0.069 ? 2 : theta <= 0.245 ? 3 : theta <= 0.55 ? 4 : 5;
+                s_shift = bad ? -1 : shift;
             }
-            const double theta = bad ? 0.0 : ldexp(m, -shift);
-            Q = theta <= 0.0064 ? 1 : theta <= 0.069 ? 2 : theta <= 0.245 ? 3 : theta <= 0.55 ? 4 : 5;
-            s_shift = bad ? -1 : shift;
-            s_Q = Q;
         }
         __syncthreads();
         const int shift = s_shift, Q = s_Q;
@@ -364,9 +371,14 @@ __global__ void __launch_bounds__(256, 1) expm64_dmma_kernel(ExpmArgs a, ExpmTcO
             }
             return;
         }
-        if (shift > 0) {
+        {   // scale A in place and park a copy in the output slot (coalesced)
             const double sc = exp2i(-shift);
-            for (int idx = tid; idx < 64 * 64; idx += 256) A1[(idx >> 6) * LD64 + (idx & 63)] *= sc;
+            for (int idx = tid; idx < 64 * 64; idx += 256) {
+                const int o = (idx >> 6) * LD64 + (idx & 63);
+                const double v = X0[o] * sc;
+                X0[o] = v;
+                park[idx] = v;
+            }
             __syncthreads();
         }
         double acc[2][4][2];
@@ -377,36 +389,43 @@ __global__ void __launch_bounds__(256, 1) expm64_dmma_kernel(ExpmArgs a, ExpmTcO
                 for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
         };
         auto off = [&](int i, int j) { return (16 * wr + 8 * i + g) * LD64 + 32 * wc + 8 * j + 2 * q4; };
+        auto goff = [&](int i, int j) { return (16 * wr + 8 * i + g) * 64 + 32 * wc + 8 * j + 2 * q4; };
         auto store = [&](double *M) {
 #pragma unroll
             for (int i = 0; i < 2; i++)
 #pragma unroll
                 for (int j = 0; j < 4; j++) *reinterpret_cast<double2 *>(M + off(i, j)) = make_double2(acc[i][j][0], acc[i][j][1]);
         };
-        zero(); tile_mm64_dmma(A1, A1, wr, wc, g, q4, acc); store(A2);
+        zero(); tile_mm64_dmma(X0, X0, wr, wc, g, q4, acc); store(X1);
         __syncthreads();
-        zero(); tile_mm64_dmma(A2, A1, wr, wc, g, q4, acc); store(A3);
-        // R = B_Q, then R = R*A3 + B_q for q = Q-1..0   (polynomials in A commute)
-        auto poly = [&](int qq, int i, int j, int e) -> double {
-            const int r = 16 * wr + 8 * i + g, c = 32 * wc + 8 * j + 2 * q4 + e, o = r * LD64 + c;
-            double v = c_taylor18[3 * qq + 1] * A1[o] + c_taylor18[3 * qq + 2] * A2[o];
-            if (r == c) v += c_taylor18[3 * qq];
+        zero(); tile_mm64_dmma(X1, X0, wr, wc, g, q4, acc); store(X2);
+        __syncthreads();                             // every warp is done reading A from X0: it becomes R
+        // R = B_Q, then R = R*A3 + B_q for q = Q-1..0, with B_q = c_{3q} I + c_{3q+1} A + c_{3q+2} A^2 at own positions
+        auto poly2 = [&](int qq, int i, int j) -> double2 {
+            const int r = 16 * wr + 8 * i + g, c = 32 * wc + 8 * j + 2 * q4;
+            const double2 a1 = __ldcg(reinterpret_cast<const double2 *>(park + goff(i, j)));
+            const double2 a2 = *reinterpret_cast<const double2 *>(X1 + off(i, j));
+            double2 v = make_double2(c_taylor18[3 * qq + 1] * a1.x + c_taylor18[3 * qq + 2] * a2.x,
+                                     c_taylor18[3 * qq + 1] * a1.y + c_taylor18[3 * qq + 2] * a2.y);
+            if (r == c) v.x += c_taylor18[3 * qq];
+            if (r == c + 1) v.y += c_taylor18[3 * qq];
             return v;
         };
 #pragma unroll
         for (int i = 0; i < 2; i++)
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                *reinterpret_cast<double2 *>(R + off(i, j)) = make_double2(poly(Q, i, j, 0), poly(Q, i, j, 1));
+            for (int j = 0; j < 4; j++) *reinterpret_cast<double2 *>(R + off(i, j)) = poly2(Q, i, j);
         __syncthreads();
         for (int qq = Q - 1; qq >= 0; qq--) {
-            zero(); tile_mm64_dmma(R, A3, wr, wc, g, q4, acc);
+            zero(); tile_mm64_dmma(R, X2, wr, wc, g, q4, acc);
             __syncthreads();
 #pragma unroll
             for (int i = 0; i < 2; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++)
-                    *reinterpret_cast<double2 *>(R + off(i, j)) = make_double2(acc[i][j][0] + poly(qq, i, j, 0), acc[i][j][1] + poly(qq, i, j, 1));
+                for (int j = 0; j < 4; j++) {
+                    const double2 pv = poly2(qq, i, j);
+                    *reinterpret_cast<double2 *>(R + off(i, j)) = make_double2(acc[i][j][0] + pv.x, acc[i][j][1] + pv.y);
+                }
             __syncthreads();
         }
         for (int s = 0; s < shift; s++) {
@@ -423,11 +442,14 @@ __global__ void __launch_bounds__(256, 1) expm64_dmma_kernel(ExpmArgs a, ExpmTcO
             R[j * LD64 + kk] = v;
         }
         __syncthreads();
-        if (tid < 64) {
+        {   // column sums by all 256 threads: 4 threads per column, 16 rows each
+            const int col = tid & 63, part = tid >> 6;
             double s = 0.0;
-            for (int j = 0; j < 64; j++) if (j != tid) s += R[j * LD64 + tid];
-            if (tid < D) R[tid * LD64 + tid] = fmax(1.0 - s, 0.0);
+            for (int j = part * 16; j < part * 16 + 16; j++) if (j != col) s += R[j * LD64 + col];
+            X1[part * 64 + col] = s;                 // X1 (A^2) is no longer needed
         }
+        __syncthreads();
+        if (tid < D) R[tid * LD64 + tid] = fmax(1.0 - (X1[tid] + X1[64 + tid] + X1[128 + tid] + X1[192 + tid]), 0.0);
         __syncthreads();
     }
     if (a.mix_w) {
