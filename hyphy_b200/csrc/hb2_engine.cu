@@ -375,8 +375,36 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
     w.lane_start = p->d_walk; w.steps = reinterpret_cast<const int2 *>(p->d_walk + 16);
     w.done = p->d_done; w.epoch = ++p->epoch; w.K = K; w.T = T; w.ncls = ncls; w.nslots = nslots;
     if (getenv("HB2_DEBUG")) fprintf(stderr, "[hb2] walk: jobs=%d steps=%d K=%d T=%d ncls=%d nslots=%d grid=%d resident=%d\n", total, ns, K, T, ncls, nslots, nslots * K, p->walk_max_resident);
+    w.trace = nullptr; w.trace_cta = 0;
+    const char *trace_path = getenv("HB2_WALK_TRACE");
+    long long *d_trace = nullptr;
+    if (trace_path && !p->walk_split) {          // bring-up aid: per-step clock stamps of one CTA -> text file
+        const char *tc = getenv("HB2_WALK_TRACE_CTA");
+        w.trace_cta = tc ? atoi(tc) : 0;
+        CU(cudaMalloc(&d_trace, (size_t)(ns + 1) * 8 * sizeof(long long)));
+        CU(cudaMemsetAsync(d_trace, 0, (size_t)(ns + 1) * 8 * sizeof(long long), p->stream));
+        w.trace = d_trace;
+    }
     if (p->walk_split) hb2::prune64_tc_walk2_kernel<<<nslots * K, 256, hb2::WALK2_SMEM_BYTES, p->stream>>>(w);
     else hb2::prune64_tc_walk_kernel<<<nslots * K, 128, hb2::WALK_SMEM_BYTES, p->stream>>>(w);
+    if (d_trace) {
+        std::vector<long long> ht((size_t)(ns + 1) * 8);
+        CU(cudaStreamSynchronize(p->stream));
+        CU(cudaMemcpy(ht.data(), d_trace, ht.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(d_trace);
+        if (FILE *f = fopen(trace_path, "w")) {
+            const int r = w.trace_cta % K;
+            fprintf(f, "# cta %d lane %d steps %d..%d ; columns: child_enc parent_flags t_begin bar1 staged/ready tableready|split bar2 bfull mma_done end (cycles rel. to first)\n", w.trace_cta, r, lane_start[r], lane_start[r + 1]);
+            const long long t00 = ht[1];
+            for (int i = 0; i < lane_start[r + 1] - lane_start[r]; i++) {
+                const long long *q = ht.data() + (size_t)i * 8;
+                fprintf(f, "%d 0x%x 0x%x", i, (unsigned)(q[0] >> 32), (unsigned)(q[0] & 0xffffffff));
+                for (int c = 1; c < 8; c++) fprintf(f, " %lld", q[c] ? q[c] - t00 : -1LL);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
     p->launches++;
     CU(cudaGetLastError());
     return 0;

@@ -150,9 +150,10 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const double *__restrict__
 // Power-of-two renormalisation of a pattern's 64 conditionals: max -> [0.5,1).  `force` = false only rescales when the
 // maximum has drifted below 2^-32 (cheap guard between the children of one node); true at the end of a node.
 __device__ __forceinline__ void renorm_f32(float (&v)[64], int &ex, bool force = true) {
-    float m = 0.f;
+    float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];          // four independent chains instead of one of length 64
 #pragma unroll
-    for (int k = 0; k < 64; k++) m = fmaxf(m, v[k]);
+    for (int k = 4; k < 64; k += 4) { m0 = fmaxf(m0, v[k]); m1 = fmaxf(m1, v[k + 1]); m2 = fmaxf(m2, v[k + 2]); m3 = fmaxf(m3, v[k + 3]); }
+    const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
     if (m > 0.f && m < INFINITY && (force || m < 2.3283064e-10f)) {
         const int e = max((int)((__float_as_uint(m) >> 23) & 0xffu) - 126, -125);   // m = f * 2^e, f in [0.5,1) (normal m)
         if (e != 0) {
@@ -379,6 +380,8 @@ struct WalkArgs {
     const int2 *steps;
     int *done;                  // [C][I][T] epoch of the last evaluation that produced the tile
     int epoch, K, T, ncls, nslots;
+    long long *trace;           // nullable debug buffer: 8 clock64 stamps per step of CTA `trace_cta` (HB2_WALK_TRACE)
+    int trace_cta;
 };
 
 __device__ __forceinline__ int ld_acquire(const int *p) {
@@ -468,6 +471,9 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
             const int code = next_code;
             const bool has_next = (i + 1 < i_end);
             const int2 nx2 = (i + 2 < i_end) ? __ldg(w.steps + i + 2) : make_int2(0, 0);   // descriptors run two steps ahead
+            const bool tr = w.trace && tid == 0 && (int)blockIdx.x == w.trace_cta;
+            long long *trp = tr ? w.trace + (size_t)(i - i_begin) * 8 : nullptr;
+            if (tr) { trp[0] = ((long long)st.x << 32) | (unsigned)st.y; trp[1] = clock64(); }
             __syncthreads();                  // (1) everyone is done with step i-1: ring slot (n_step+1)&1 is free
             if (has_next) {
                 if (tid == 0) stage_step(cat, tile, nx, n_step + 1);
@@ -479,8 +485,10 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                 ex = 0;
             }
             const float *tab = stage_base + (n_step & 1u) * WALK_STAGE_FLOATS;     // P^T table of this branch
+            if (tr) trp[2] = clock64();
             if (child < a.L) {
                 mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
+                if (tr) trp[3] = clock64();
                 if (code >= 0) {
                     const float4 *row = reinterpret_cast<const float4 *>(tab + code * WALK_PT_ROW);
 #pragma unroll
@@ -508,7 +516,12 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                 }
             } else {
                 const int cin = child - a.L;
-                int na = 0;
+                // Anchors without a serial dependency: one independent compare per element builds a 64-bit mask and
+                // zeroes the element in the tensor operand; the (few) set bits are then enumerated with ffs and their
+                // values re-read from the child's conditional block in L2 (the row this thread itself loaded or, on a
+                // chain, stored a moment ago), eight loads in flight.
+                uint32_t am0 = 0, am1 = 0, am2 = 0, am3 = 0;
+                const float4 *xrow = cond4 + cond_f4(cat, cin, tile, 0, tid, a.I, w.T);
                 {
                     uint32_t hi[64], lo[64];
                     if (enc & WALK_CHAIN) {
@@ -516,9 +529,9 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                         for (int k = 0; k < 64; k++) {
                             float x = v[k];
                             v[k] = 1.f;
-                            if (x >= TC_ANCHOR_THR && na < TC_MAX_ANCHORS) {
-                                s_ak[na * 128 + tid] = k; s_av[na * 128 + tid] = x; na++; x = 0.f;
-                            }
+                            const bool big = x >= TC_ANCHOR_THR;
+                            if (big) { if (k < 16) am0 |= 1u << k; else if (k < 32) am1 |= 1u << (k - 16); else if (k < 48) am2 |= 1u << (k - 32); else am3 |= 1u << (k - 48); }
+                            x = big ? 0.f : x;
                             const float h = tf32_rn(x);
                             hi[k] = __float_as_uint(h);
                             lo[k] = __float_as_uint(x - h);
@@ -531,19 +544,19 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                                 if (++it > (1 << 21)) { atomicExch(a.err, 2); bailed = true; }   // never hang the GPU
                             }
                         }
-                        const float4 *xr = cond4 + cond_f4(cat, cin, tile, 0, tid, a.I, w.T);
 #pragma unroll
                         for (int q = 0; q < 16; q++) {
-                            const float4 x4 = __ldcg(xr + (size_t)q * 128);      // may have been produced by another SM in this launch
+                            const float4 x4 = __ldcg(xrow + (size_t)q * 128);      // may have been produced by another SM in this launch
                             float xs[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
                             for (int u = 0; u < 4; u++) {
-                                if (xs[u] >= TC_ANCHOR_THR && na < TC_MAX_ANCHORS) {
-                                    s_ak[na * 128 + tid] = 4 * q + u; s_av[na * 128 + tid] = xs[u]; na++; xs[u] = 0.f;
-                                }
-                                const float h = tf32_rn(xs[u]);
-                                hi[4 * q + u] = __float_as_uint(h);
-                                lo[4 * q + u] = __float_as_uint(xs[u] - h);
+                                const int kq = 4 * q + u;
+                                const bool big = xs[u] >= TC_ANCHOR_THR;
+                                if (big) { if (kq < 16) am0 |= 1u << kq; else if (kq < 32) am1 |= 1u << (kq - 16); else if (kq < 48) am2 |= 1u << (kq - 32); else am3 |= 1u << (kq - 48); }
+                                const float x = big ? 0.f : xs[u];
+                                const float h = tf32_rn(x);
+                                hi[kq] = __float_as_uint(h);
+                                lo[kq] = __float_as_uint(x - h);
                             }
                         }
                         ex += __ldcg(a.scal + ((size_t)cat * a.I + cin) * Sp + s);
@@ -555,11 +568,28 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                     }
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 }
+                unsigned long long amask = (unsigned long long)(am0 | (am1 << 16)) | ((unsigned long long)(am2 | (am3 << 16)) << 32);
+                int ak[TC_MAX_ANCHORS];
+                float av[TC_MAX_ANCHORS];
+                const float *xrow_f = reinterpret_cast<const float *>(xrow);
+#pragma unroll
+                for (int ai = 0; ai < TC_MAX_ANCHORS; ai++) {
+                    ak[ai] = -1; av[ai] = 0.f;
+                    if (amask) {
+                        const int kk = __ffsll((long long)amask) - 1;
+                        amask &= amask - 1;
+                        ak[ai] = kk;
+                        av[ai] = __ldcg(xrow_f + ((size_t)(kk >> 2) * 128) * 4 + (kk & 3));
+                    }
+                }
+                if (tr) trp[3] = clock64();
                 tc_fence_before();
                 __syncthreads();             // (2) A operand complete in TMEM; every thread is done reading the previous D
+                if (tr) trp[4] = clock64();
                 if (tid == 0) {
                     tc_fence_after();
                     mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
+                    if (tr) trp[5] = clock64();
                     const uint64_t bdesc_hi = make_b_desc(smem_u32(tab + 64 * WALK_PT_ROW));
                     const uint64_t bdesc_lo = make_b_desc(smem_u32(tab + 64 * WALK_PT_ROW + 4096));
 #pragma unroll
@@ -578,12 +608,12 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                 float acc[64];
 #pragma unroll
                 for (int k = 0; k < 64; k++) acc[k] = 0.f;
-                if (na > 0) {
-                    mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
-                    for (int ai = 0; ai < na; ai++) {
-                        const int ka = s_ak[ai * 128 + tid];
-                        const float xv = s_av[ai * 128 + tid];
-                        const float4 *row = reinterpret_cast<const float4 *>(tab + ka * WALK_PT_ROW);
+                mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
+#pragma unroll
+                for (int ai = 0; ai < TC_MAX_ANCHORS; ai++) {
+                    if (ak[ai] >= 0) {
+                        const float xv = av[ai];
+                        const float4 *row = reinterpret_cast<const float4 *>(tab + ak[ai] * WALK_PT_ROW);
 #pragma unroll
                         for (int q = 0; q < 16; q++) {
                             const float4 rr = row[q];
@@ -592,7 +622,20 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                         }
                     }
                 }
+                while (amask) {                  // more than TC_MAX_ANCHORS entries above the threshold (diffuse vectors): rare
+                    const int kk = __ffsll((long long)amask) - 1;
+                    amask &= amask - 1;
+                    const float xv = __ldcg(xrow_f + ((size_t)(kk >> 2) * 128) * 4 + (kk & 3));
+                    const float4 *row = reinterpret_cast<const float4 *>(tab + kk * WALK_PT_ROW);
+#pragma unroll
+                    for (int q = 0; q < 16; q++) {
+                        const float4 rr = row[q];
+                        acc[4 * q] = fmaf(xv, rr.x, acc[4 * q]); acc[4 * q + 1] = fmaf(xv, rr.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(xv, rr.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(xv, rr.w, acc[4 * q + 3]);
+                    }
+                }
                 mbar_wait(bar_mma, n_mma & 1u, a.err);
+                if (tr) trp[6] = clock64();
                 tc_fence_after();
 #pragma unroll
                 for (int o = 0; o < 64; o += 16) {
@@ -627,6 +670,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                     }
                 }
             }
+            if (tr) trp[7] = clock64();
             st = nx;
             nx = nx2;
         }
