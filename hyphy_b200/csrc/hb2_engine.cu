@@ -381,14 +381,14 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
     if (trace_path && !p->walk_split) {          // bring-up aid: per-step clock stamps of one CTA -> text file
         const char *tc = getenv("HB2_WALK_TRACE_CTA");
         w.trace_cta = tc ? atoi(tc) : 0;
-        CU(cudaMalloc(&d_trace, (size_t)(ns + 1) * 8 * sizeof(long long)));
-        CU(cudaMemsetAsync(d_trace, 0, (size_t)(ns + 1) * 8 * sizeof(long long), p->stream));
+        CU(cudaMalloc(&d_trace, (size_t)(ns + 1) * 12 * sizeof(long long)));
+        CU(cudaMemsetAsync(d_trace, 0, (size_t)(ns + 1) * 12 * sizeof(long long), p->stream));
         w.trace = d_trace;
     }
     if (p->walk_split) hb2::prune64_tc_walk2_kernel<<<nslots * K, 256, hb2::WALK2_SMEM_BYTES, p->stream>>>(w);
     else hb2::prune64_tc_walk_kernel<<<nslots * K, 128, hb2::WALK_SMEM_BYTES, p->stream>>>(w);
     if (d_trace) {
-        std::vector<long long> ht((size_t)(ns + 1) * 8);
+        std::vector<long long> ht((size_t)(ns + 1) * 12);
         CU(cudaStreamSynchronize(p->stream));
         CU(cudaMemcpy(ht.data(), d_trace, ht.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(d_trace);
@@ -397,9 +397,9 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
             fprintf(f, "# cta %d lane %d steps %d..%d ; columns: child_enc parent_flags t_begin bar1 staged/ready tableready|split bar2 bfull mma_done end (cycles rel. to first)\n", w.trace_cta, r, lane_start[r], lane_start[r + 1]);
             const long long t00 = ht[1];
             for (int i = 0; i < lane_start[r + 1] - lane_start[r]; i++) {
-                const long long *q = ht.data() + (size_t)i * 8;
+                const long long *q = ht.data() + (size_t)i * 12;
                 fprintf(f, "%d 0x%x 0x%x", i, (unsigned)(q[0] >> 32), (unsigned)(q[0] & 0xffffffff));
-                for (int c = 1; c < 8; c++) fprintf(f, " %lld", q[c] ? q[c] - t00 : -1LL);
+                for (int c = 1; c < 12; c++) fprintf(f, " %lld", q[c] ? q[c] - t00 : -1LL);
                 fprintf(f, "\n");
             }
             fclose(f);

@@ -100,10 +100,10 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem,
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
         "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
+// round-to-nearest (ties away from zero) to tf32, i.e. what cvt.rna.tf32.f32 computes, but with two full-rate integer
+// instructions: the conversion instruction issues at a quarter of the ALU rate and dominated the operand-split phase
 __device__ __forceinline__ float tf32_rn(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 #define HB2_TMEM_ST16(taddr, r, o)                                                                                   \
     asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" \
@@ -409,14 +409,14 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
     uint64_t *bar_full = reinterpret_cast<uint64_t *>(s_av + TC_MAX_ANCHORS * 128); // [2]
     uint64_t *bar_mma = bar_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_mma + 1);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const size_t Sp = a.Sp;
     float4 *cond4 = reinterpret_cast<float4 *>(a.cond);
 
     if (tid == 0) {
         mbar_init(bar_full, 1);
         mbar_init(bar_full + 1, 1);
-        mbar_init(bar_mma, 1);
+        mbar_init(bar_mma, 4);               // one tcgen05.commit per issuing warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
             const bool has_next = (i + 1 < i_end);
             const int2 nx2 = (i + 2 < i_end) ? __ldg(w.steps + i + 2) : make_int2(0, 0);   // descriptors run two steps ahead
             const bool tr = w.trace && tid == 0 && (int)blockIdx.x == w.trace_cta;
-            long long *trp = tr ? w.trace + (size_t)(i - i_begin) * 8 : nullptr;
+            long long *trp = tr ? w.trace + (size_t)(i - i_begin) * 12 : nullptr;
             if (tr) { trp[0] = ((long long)st.x << 32) | (unsigned)st.y; trp[1] = clock64(); }
             __syncthreads();                  // (1) everyone is done with step i-1: ring slot (n_step+1)&1 is free
             if (has_next) {
@@ -561,12 +561,22 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                         }
                         ex += __ldcg(a.scal + ((size_t)cat * a.I + cin) * Sp + s);
                     }
+                    if (tr) trp[8] = clock64();
 #pragma unroll
                     for (int o = 0; o < 64; o += 16) {
                         HB2_TMEM_ST16(lane_addr + 64 + o, hi, o);
                         HB2_TMEM_ST16(lane_addr + 128 + o, lo, o);
                     }
+                    {   // D starts from zero: the 24 MMAs are issued by four threads in parallel, all accumulating
+                        uint32_t zz[16];
+#pragma unroll
+                        for (int z = 0; z < 16; z++) zz[z] = 0u;
+#pragma unroll
+                        for (int o = 0; o < 64; o += 16) HB2_TMEM_ST16(lane_addr + o, zz, 0);
+                    }
+                    if (tr) trp[9] = clock64();
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    if (tr) trp[10] = clock64();
                 }
                 unsigned long long amask = (unsigned long long)(am0 | (am1 << 16)) | ((unsigned long long)(am2 | (am3 << 16)) << 32);
                 int ak[TC_MAX_ANCHORS];
@@ -586,21 +596,22 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                 tc_fence_before();
                 __syncthreads();             // (2) A operand complete in TMEM; every thread is done reading the previous D
                 if (tr) trp[4] = clock64();
-                if (tid == 0) {
+                if (lane == 0) {
+                    // A single thread issues one tcgen05.mma every ~190 cycles (measured, tools/tc_mma_timing.cu); four
+                    // issuing threads (one per warp) overlap that latency: the 24 accumulating MMAs take ~1450 cycles
+                    // instead of ~4700.  MMA m: term = m/8 (0: Xl*Ph, 1: Xh*Pl, 2: Xh*Ph), K-step = m%8.
                     tc_fence_after();
                     mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
                     if (tr) trp[5] = clock64();
                     const uint64_t bdesc_hi = make_b_desc(smem_u32(tab + 64 * WALK_PT_ROW));
                     const uint64_t bdesc_lo = make_b_desc(smem_u32(tab + 64 * WALK_PT_ROW + 4096));
 #pragma unroll
-                    for (int kk = 0; kk < 8; kk++)
-                        tc_mma_tf32_ts(tmem_base, tmem_base + 128 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, kk > 0);
-#pragma unroll
-                    for (int kk = 0; kk < 8; kk++)
-                        tc_mma_tf32_ts(tmem_base, tmem_base + 64 + kk * 8, bdesc_lo + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u);
-#pragma unroll
-                    for (int kk = 0; kk < 8; kk++)
-                        tc_mma_tf32_ts(tmem_base, tmem_base + 64 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u);
+                    for (int j = 0; j < 6; j++) {
+                        const int m = warp + 4 * j, term = m >> 3, kk = m & 7;
+                        const uint32_t a_col = (term == 0) ? 128u : 64u;
+                        const uint64_t bd = (term == 1) ? bdesc_lo : bdesc_hi;
+                        tc_mma_tf32_ts(tmem_base, tmem_base + a_col + kk * 8, bd + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u);
+                    }
                     tc_commit(bar_mma);
                 }
                 __syncwarp();

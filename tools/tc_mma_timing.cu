@@ -27,19 +27,24 @@ __global__ void __launch_bounds__(128) k(const float *Bt, long long *out, int na
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     if (tid == 0) { mbar_expect_tx(bar_b, 32768u); bulk_g2s(Bs, Bt, 32768u, bar_b); }
     tc_fence_before(); __syncthreads();
-    if (tid == 0) {
+    // a_from_smem is reused as the number of issuing threads (lane 0 of warps 0..n-1); bar_mma expects n commits
+    const int nissue = a_from_smem < 1 ? 1 : a_from_smem;
+    if (tid == 0) { mbar_init(bar_mma, nissue); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    if ((tid & 31) == 0 && warp < nissue) {
         tc_fence_after();
         mbar_wait(bar_b, 0, &err);
         const uint64_t dh = make_b_desc(smem_u32(Bs));
         for (int rep = 0; rep < 3; rep++) {
             long long t0 = clock64();
-            for (int m = 0; m < nmma; m++)
-                tc_mma_tf32_ts(tmem_base + (uint32_t)(m % nacc) * 64u, tmem_base + 384 + (m % 8) * 8, dh + (uint64_t)((m % 8) * 2 * 1024 >> 4), TC_IDESC, m >= nacc);
+#pragma unroll 1
+            for (int m = warp; m < nmma; m += nissue)
+                tc_mma_tf32_ts(tmem_base + (uint32_t)(m % nacc) * 64u, tmem_base + 384 + (m % 8) * 8, dh + (uint64_t)((m % 8) * 2 * 1024 >> 4), TC_IDESC, 1u);
             long long t1 = clock64();
             tc_commit(bar_mma);
             mbar_wait(bar_mma, rep & 1, &err);
             long long t2 = clock64();
-            out[rep * 2] = t1 - t0; out[rep * 2 + 1] = t2 - t0;
+            if (tid == 0) { out[rep * 2] = t1 - t0; out[rep * 2 + 1] = t2 - t0; }
         }
     }
     tc_fence_before(); __syncthreads();
@@ -52,12 +57,13 @@ int main() {
     cudaMalloc(&dB, 8192 * 4); cudaMalloc(&dO, 64);
     cudaMemcpy(dB, Bt.data(), 8192 * 4, cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-    for (int nmma : {8, 24, 48})
-        for (int nacc : {1, 2, 3, 4, 6}) {
-            k<<<1, 128, TC_SMEM_BYTES>>>(dB, dO, nacc, nmma, 0);
+    for (int nmma : {24, 48})
+        for (int nacc : {1, 4})
+        for (int nissue : {1, 2, 4}) {
+            k<<<1, 128, TC_SMEM_BYTES>>>(dB, dO, nacc, nmma, nissue);
             cudaError_t e = cudaDeviceSynchronize();
             long long h[6]; cudaMemcpy(h, dO, 48, cudaMemcpyDeviceToHost);
-            printf("nmma=%d accumulators=%d : issue %lld cyc, issue->complete %lld cyc (%.1f per MMA)  [%s]\n", nmma, nacc, h[4], h[5], (double)h[5] / nmma, cudaGetErrorString(e));
+            printf("issuers=%d nmma=%d accumulators=%d : issue %lld cyc, issue->complete %lld cyc (%.1f per MMA)  [%s]\n", nissue, nmma, nacc, h[4], h[5], (double)h[5] / nmma, cudaGetErrorString(e));
         }
     return 0;
 }
