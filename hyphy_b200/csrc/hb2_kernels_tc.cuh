@@ -39,7 +39,8 @@ constexpr int TC_PTF_ROW = 68;                 // floats per row of the fp32 P^T
 constexpr int TC_PTF_FLOATS = 64 * TC_PTF_ROW; // per (class, branch)
 constexpr int TC_SMEM_BYTES = 2 * 32768 + 1024; // two B stages (one used for now; also caps residency at 2 CTAs/SM) + barriers
 constexpr uint32_t TC_TMEM_COLS = 256;         // D: 0..63, Xh: 64..127, Xl: 128..191
-constexpr int TC_MAX_ANCHORS = 8;              // per pattern and child
+constexpr int TC_MAX_ANCHORS = 8;              // per pattern and child (list capacity of the per-level and split-row kernels)
+constexpr int WALK_FAST_ANCHORS = 4;           // anchors handled by the unrolled fast path of the walk kernel; more go to a loop
 constexpr float TC_ANCHOR_THR = 0.015625f;     // 2^-6 (rows are normalised to max in [0.5,1))
 
 struct PruneTcArgs {
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
     if (tid == 0) {
         mbar_init(bar_full, 1);
         mbar_init(bar_full + 1, 1);
-        mbar_init(bar_mma, 4);               // one tcgen05.commit per issuing warp
+        mbar_init(bar_mma, 2);               // one tcgen05.commit per issuing thread (warps 0 and 1)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -567,23 +568,16 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                         HB2_TMEM_ST16(lane_addr + 64 + o, hi, o);
                         HB2_TMEM_ST16(lane_addr + 128 + o, lo, o);
                     }
-                    {   // D starts from zero: the 24 MMAs are issued by four threads in parallel, all accumulating
-                        uint32_t zz[16];
-#pragma unroll
-                        for (int z = 0; z < 16; z++) zz[z] = 0u;
-#pragma unroll
-                        for (int o = 0; o < 64; o += 16) HB2_TMEM_ST16(lane_addr + o, zz, 0);
-                    }
                     if (tr) trp[9] = clock64();
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     if (tr) trp[10] = clock64();
                 }
                 unsigned long long amask = (unsigned long long)(am0 | (am1 << 16)) | ((unsigned long long)(am2 | (am3 << 16)) << 32);
-                int ak[TC_MAX_ANCHORS];
-                float av[TC_MAX_ANCHORS];
+                int ak[WALK_FAST_ANCHORS];
+                float av[WALK_FAST_ANCHORS];
                 const float *xrow_f = reinterpret_cast<const float *>(xrow);
 #pragma unroll
-                for (int ai = 0; ai < TC_MAX_ANCHORS; ai++) {
+                for (int ai = 0; ai < WALK_FAST_ANCHORS; ai++) {
                     ak[ai] = -1; av[ai] = 0.f;
                     if (amask) {
                         const int kk = __ffsll((long long)amask) - 1;
@@ -596,22 +590,24 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                 tc_fence_before();
                 __syncthreads();             // (2) A operand complete in TMEM; every thread is done reading the previous D
                 if (tr) trp[4] = clock64();
-                if (lane == 0) {
-                    // A single thread issues one tcgen05.mma every ~190 cycles (measured, tools/tc_mma_timing.cu); four
-                    // issuing threads (one per warp) overlap that latency: the 24 accumulating MMAs take ~1450 cycles
-                    // instead of ~4700.  MMA m: term = m/8 (0: Xl*Ph, 1: Xh*Pl, 2: Xh*Ph), K-step = m%8.
+                if (lane == 0 && warp < 2) {
+                    // One thread issues a tcgen05.mma only every ~100-190 cycles (tools/tc_mma_timing.cu: 24 MMAs take 4770
+                    // cycles from one thread, 2560 from two, 1460 from four).  Two threads issue here, each into its OWN
+                    // accumulator (warp 0: even K-steps -> D0 = columns 0..63, warp 1: odd K-steps -> D1 = columns
+                    // 192..255) in a fixed order (small terms first), so the result is bit-reproducible; D0 + D1 is formed
+                    // in registers after the read-back.
                     tc_fence_after();
                     mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
                     if (tr) trp[5] = clock64();
                     const uint64_t bdesc_hi = make_b_desc(smem_u32(tab + 64 * WALK_PT_ROW));
                     const uint64_t bdesc_lo = make_b_desc(smem_u32(tab + 64 * WALK_PT_ROW + 4096));
+                    const uint32_t dcol = warp ? 192u : 0u;
 #pragma unroll
-                    for (int j = 0; j < 6; j++) {
-                        const int m = warp + 4 * j, term = m >> 3, kk = m & 7;
-                        const uint32_t a_col = (term == 0) ? 128u : 64u;
-                        const uint64_t bd = (term == 1) ? bdesc_lo : bdesc_hi;
-                        tc_mma_tf32_ts(tmem_base, tmem_base + a_col + kk * 8, bd + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u);
-                    }
+                    for (int j = 0; j < 4; j++) { const int kk = 2 * j + warp; tc_mma_tf32_ts(tmem_base + dcol, tmem_base + 128 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, j > 0); }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { const int kk = 2 * j + warp; tc_mma_tf32_ts(tmem_base + dcol, tmem_base + 64 + kk * 8, bdesc_lo + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u); }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { const int kk = 2 * j + warp; tc_mma_tf32_ts(tmem_base + dcol, tmem_base + 64 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u); }
                     tc_commit(bar_mma);
                 }
                 __syncwarp();
@@ -621,7 +617,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                 for (int k = 0; k < 64; k++) acc[k] = 0.f;
                 mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
 #pragma unroll
-                for (int ai = 0; ai < TC_MAX_ANCHORS; ai++) {
+                for (int ai = 0; ai < WALK_FAST_ANCHORS; ai++) {
                     if (ak[ai] >= 0) {
                         const float xv = av[ai];
                         const float4 *row = reinterpret_cast<const float4 *>(tab + ak[ai] * WALK_PT_ROW);
@@ -650,11 +646,12 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                 tc_fence_after();
 #pragma unroll
                 for (int o = 0; o < 64; o += 16) {
-                    uint32_t d[16];
+                    uint32_t d[16], d1[16];
                     HB2_TMEM_LD16(lane_addr + o, d, 0);
+                    HB2_TMEM_LD16(lane_addr + 192 + o, d1, 0);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int k = 0; k < 16; k++) v[o + k] *= (__uint_as_float(d[k]) + acc[o + k]);
+                    for (int k = 0; k < 16; k++) v[o + k] *= ((__uint_as_float(d[k]) + __uint_as_float(d1[k])) + acc[o + k]);
                 }
                 n_mma++;
             }
