@@ -118,7 +118,7 @@ struct hb2_partition {
     bool small_walk = true;                   // HB2_SMALL_WALK=0: per-level launches of prune_small_kernel (A/B testing)
     bool expm_dfma = false;                   // HB2_EXPM_DFMA=1: previous FFMA-style fp64 expm kernel (A/B testing)
     bool use_walk = false;
-    bool walk_split = true;                   // two threads per pattern (256-thread CTAs); HB2_WALK_SPLIT=0 selects the 128-thread kernel
+    bool walk_split = false;                  // HB2_WALK_SPLIT=1: two threads per pattern (256-thread CTAs); measured no faster (r01h), kept for study
     int walk_max_resident = 0;
     int epoch = 0;
     int *d_done = nullptr, *d_walk = nullptr, *h_walk = nullptr;
@@ -595,7 +595,7 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
         CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::WALK_SMEM_BYTES));
         CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::WALK2_SMEM_BYTES));
         CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        { const char *env = getenv("HB2_WALK_SPLIT"); p->walk_split = !(env && env[0] == '0'); }
+        { const char *env = getenv("HB2_WALK_SPLIT"); p->walk_split = env && env[0] == '1'; }
         {
             const char *env = getenv("HB2_TC_WALK");
             p->use_walk = !(env && env[0] == '0');
