@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fp64", action="store_true", help="force the fp64 pruning kernels (HB2_FLAG_FORCE_FP64)")
+    ap.add_argument("--emulate-shard", default="", help="debug: R/W -> run rank R's pattern shard of a W-rank job on one GPU, no collectives")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -189,15 +190,22 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        # control plane (barriers, id exchange, max-over-ranks of the timings) over gloo; the DATA path -- the per-evaluation
+        # sum of partial log-likelihoods -- is the engine's own NCCL communicator (hb2_comm_init) on the engine's stream.
+        # (A second, torch-owned NCCL communicator in the same process made cudaMemcpyAsync on the engine's stream fail with
+        # "invalid argument" right after torch's first MAX all-reduce on this box: gpurun r01n/r01p.)
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("gloo")
 
     w = synth.codon_workload(WORKLOAD["taxa"], WORKLOAD["codons"], WORKLOAD["classes"])
     S = w.S
     from hyphy_b200.sharding import shard_bounds, exchange_unique_id
     lo, hi = shard_bounds(S, world, rank)            # contiguous pattern shards, balanced by count
+    if args.emulate_shard:
+        er, ew = (int(x) for x in args.emulate_shard.split("/"))
+        lo, hi = shard_bounds(S, ew, er)
     lf = LikelihoodFunction(w, device=local_rank, flags=1 if args.fp64 else 0,
-                            pattern_slice=slice(lo, hi) if world > 1 else None)
+                            pattern_slice=slice(lo, hi) if (world > 1 or args.emulate_shard) else None)
     if world > 1:
         lf.part.comm_init(world, rank, exchange_unique_id(dist, rank, Partition.comm_unique_id))
 
@@ -209,7 +217,7 @@ def main():
     def max_over_ranks(x):
         if dist is None:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        t = torch.tensor([x], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 

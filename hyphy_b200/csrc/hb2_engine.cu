@@ -365,7 +365,17 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
     }
     lane_start[K] = ns;
     const int nints = 16 + 2 * ns;
-    CU(cudaMemcpyAsync(p->d_walk, p->h_walk, nints * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    {
+        cudaError_t ce = cudaMemcpyAsync(p->d_walk, p->h_walk, nints * sizeof(int), cudaMemcpyHostToDevice, p->stream);
+        if (ce != cudaSuccess) {
+            int cur = -1; cudaGetDevice(&cur);
+            cudaPointerAttributes pa{}, pb{};
+            cudaError_t e1 = cudaPointerGetAttributes(&pa, p->d_walk), e2 = cudaPointerGetAttributes(&pb, p->h_walk);
+            return fail("walk plan upload failed: %s; nints=%d ns=%d K=%d total=%d cur_dev=%d part_dev=%d d_walk=%p(type %d dev %d err %d) h_walk=%p(type %d dev %d err %d) stream=%p query=%d",
+                        cudaGetErrorString(ce), nints, ns, K, total, cur, p->device, (void *)p->d_walk, (int)pa.type, pa.device, (int)e1,
+                        (void *)p->h_walk, (int)pb.type, pb.device, (int)e2, (void *)p->stream, (int)cudaStreamQuery(p->stream));
+        }
+    }
     hb2::PruneArgs a = prune_args(p, cat0);
     hb2::WalkArgs w;
     hb2::PruneTcArgs &t = w.a;
