@@ -289,11 +289,23 @@ def main():
         prune_launches = (launches // args.steps) - (4 if tc_mode else 3)     # minus expm, (pack), combine, final_sum
         prune_ms = stage[1]
         achieved_gbs = (byts / world) / (prune_ms * 1e-3) / 1e9
-        kname = ("prune64_tc_kernel (tcgen05 3xTF32 fused pruning update, all tree levels)" if tc_mode
-                 else "prune64_kernel (fp64 fused pruning update, all tree levels)")
+        single_launch = prune_launches == 1
+        kname = ("prune64_tc_walk_kernel (tcgen05 3xTF32 fused pruning pass, whole tree in one launch)" if (tc_mode and single_launch)
+                 else "prune64_tc_kernel (tcgen05 3xTF32 fused pruning update, one launch per tree level)" if tc_mode
+                 else "prune64_kernel (fp64 fused pruning update, one launch per tree level)")
+        # DRAM traffic of that kernel from the committed `ncu --set full` capture of this same command (profiles/)
+        traffic, traffic_src = None, None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "walk_kernel_latest.json")))["kernels"][0]
+            if tc_mode and single_launch and world == 1:
+                unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+                traffic = sum(prof[k]["value"] * unit[prof[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                traffic_src = "profiles/walk_kernel_latest.json (ncu --set full, per launch)"
+        except Exception:
+            pass
         roofline = {"kernel": kname, "bound": "hbm",
                     "achieved": achieved_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / pk["hbm_gbs"],
-                    "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({pk_kind})",
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": f"MEASURED_PEAKS.json ({pk_kind})",
                     "launches_per_eval": prune_launches, "avg_launch_ms": prune_ms / max(prune_launches, 1),
                     "algorithmic_bytes_per_eval": byts, "algorithmic_flops_per_eval": flops,
                     "tflops_pruning": (flops / world) / (prune_ms * 1e-3) / 1e12,

@@ -329,6 +329,22 @@ def test_full_size_properties(mode):
     assert abs(b - 2 * a) <= 1e-11 * abs(b)
 
 
+def test_more_class_tile_pairs_than_resident_ctas(mode):
+    """12000 patterns x 4 classes = 376 (class, tile) pairs > 296 co-resident CTAs: the walk kernel must loop over pairs
+    inside a CTA (K = 1 path); also exercises pattern padding (12000 is not a multiple of 128)."""
+    w = synth.codon_workload(16, 12000, 4, seed=99, mean_t=0.4)
+    assert w.S * w.C > 296 * 128
+    lf = LF(w, mode)
+    lf.set_template()
+    lf.set_all_compiled()
+    got, sl, ss = lf.compute(want_sites=True)
+    lf.close()
+    ref, site = port.lnl(w)
+    record("bigS", w.name, mode, got, ref, float(np.abs(_site_lnl(sl, ss) - site).max()))
+    assert abs(got - ref) <= tol(w, mode)[0] * abs(ref)
+    assert np.abs(_site_lnl(sl, ss) - site).max() <= tol(w, mode)[1]
+
+
 def test_tensor_path_against_fp64_path_deep_and_wide():
     """The tcgen05 path against the fp64 kernels on the same device, on shapes chosen to stress error accumulation
     (500 taxa: ~1000 contractions per pattern) and short/long branch mixes.  Contract: 1e-6; required here: 1e-7."""
