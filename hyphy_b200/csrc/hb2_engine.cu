@@ -701,10 +701,11 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
         CUP(cudaFuncSetAttribute(hb2::expm64_dmma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         { const char *env = getenv("HB2_EXPM_DFMA"); p->expm_dfma = env && env[0] == '1'; }
     }
-    { const char *env = getenv("HB2_SMALL_WALK"); p->small_walk = !(env && env[0] == '0');
+    {
         CUP(cudaFuncSetAttribute(hb2::prune64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 64 * hb2::LD64 * sizeof(double))));
     }
 #undef CUP
+    { const char *env = getenv("HB2_SMALL_WALK"); p->small_walk = !(env && env[0] == '0'); }
     p->have_matrix.assign(C * p->B, 0);
     p->is_rate.assign(C * p->B, 0);
     p->evaluated_cat.assign(C, 0);

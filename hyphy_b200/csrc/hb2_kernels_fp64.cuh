@@ -769,8 +769,15 @@ __global__ void __launch_bounds__(128) prune_small_kernel(PruneArgs a, const int
 // minimum: one coalesced write and (at most) one read of Dp*8+4 bytes per (node, pattern) plus 4 B per leaf state.
 // grid = (Sp/128, classes), block = 128.  jobs = dirty internal indices, ascending (= post-order).
 // ------------------------------------------------------------------------------------------------
+// Occupancy matters here more than anywhere: a pattern's walk is long and sequential, so patterns beyond the resident
+// thread capacity form a second wave that doubles the time (r01r: 200k patterns at 10 CTAs/SM = 1.06 waves).  For 4/8
+// states the register budget is capped so that 16 CTAs/SM (2048 threads) are resident.
 template <int DP>
-__global__ void __launch_bounds__(128) prune_small_walk_kernel(PruneArgs a, const int *__restrict__ jobs, int njobs) {
+__global__ void __launch_bounds__(128, (DP <= 8) ? 16 : 1) prune_small_walk_kernel(PruneArgs a, const int *__restrict__ jobs, int njobs) {
+    // 16..32 states: the branch's P^T is staged in shared memory once per child (all threads of the CTA walk the same
+    // job list in lockstep) and read as broadcasts; 4/8 states read the 16/64 doubles straight through L1.
+    constexpr bool kStage = DP > 8;
+    __shared__ double Ps[kStage ? DP * DP : 1];
     const int tid = threadIdx.x;
     const int cat = a.cat0 + blockIdx.y;
     const size_t Sp = a.Sp;
@@ -784,13 +791,21 @@ __global__ void __launch_bounds__(128) prune_small_walk_kernel(PruneArgs a, cons
         const int c_begin = __ldg(a.tree.child_start + par), c_end = __ldg(a.tree.child_start + par + 1);
         for (int ci = c_begin; ci < c_end; ci++) {
             const int child = __ldg(a.tree.child_ids + ci);
-            const double *PT = a.PT + ((size_t)cat * a.B + child) * DP * DP;
+            const double *PTg = a.PT + ((size_t)cat * a.B + child) * DP * DP;
+            const double *PT = PTg;
+            if (kStage) {
+                __syncthreads();
+                for (int idx = tid; idx < DP * DP / 2; idx += 128)
+                    reinterpret_cast<double2 *>(Ps)[idx] = __ldg(reinterpret_cast<const double2 *>(PTg) + idx);
+                __syncthreads();
+                PT = Ps;
+            }
             if (child < a.L) {
                 const int code = __ldg(a.leaf + (size_t)child * Sp + s);
                 if (code >= 0) {
                     const double2 *row = reinterpret_cast<const double2 *>(PT + (size_t)code * DP);
 #pragma unroll
-                    for (int k = 0; k < DP; k += 2) { const double2 r = __ldg(row + k / 2); v[k] *= r.x; v[k + 1] *= r.y; }
+                    for (int k = 0; k < DP; k += 2) { const double2 r = kStage ? row[k / 2] : __ldg(row + k / 2); v[k] *= r.x; v[k + 1] *= r.y; }
                 } else {
                     const double *amb = a.ambig + (size_t)(-code - 1) * DP;
                     double acc[DP];
@@ -800,7 +815,7 @@ __global__ void __launch_bounds__(128) prune_small_walk_kernel(PruneArgs a, cons
                         const double wgt = __ldg(amb + j);
                         const double2 *row = reinterpret_cast<const double2 *>(PT + (size_t)j * DP);
 #pragma unroll
-                        for (int k = 0; k < DP; k += 2) { const double2 r = __ldg(row + k / 2); acc[k] = fma(wgt, r.x, acc[k]); acc[k + 1] = fma(wgt, r.y, acc[k + 1]); }
+                        for (int k = 0; k < DP; k += 2) { const double2 r = kStage ? row[k / 2] : __ldg(row + k / 2); acc[k] = fma(wgt, r.x, acc[k]); acc[k + 1] = fma(wgt, r.y, acc[k + 1]); }
                     }
 #pragma unroll
                     for (int k = 0; k < DP; k++) v[k] *= acc[k];
@@ -818,7 +833,7 @@ __global__ void __launch_bounds__(128) prune_small_walk_kernel(PruneArgs a, cons
                 for (int j = 0; j < DP; j++) {
                     const double2 *row = reinterpret_cast<const double2 *>(PT + (size_t)j * DP);
 #pragma unroll
-                    for (int k = 0; k < DP; k += 2) { const double2 r = __ldg(row + k / 2); acc[k] = fma(x[j], r.x, acc[k]); acc[k + 1] = fma(x[j], r.y, acc[k + 1]); }
+                    for (int k = 0; k < DP; k += 2) { const double2 r = kStage ? row[k / 2] : __ldg(row + k / 2); acc[k] = fma(x[j], r.x, acc[k]); acc[k + 1] = fma(x[j], r.y, acc[k + 1]); }
                 }
 #pragma unroll
                 for (int k = 0; k < DP; k++) v[k] *= acc[k];
