@@ -769,11 +769,9 @@ __global__ void __launch_bounds__(128) prune_small_kernel(PruneArgs a, const int
 // minimum: one coalesced write and (at most) one read of Dp*8+4 bytes per (node, pattern) plus 4 B per leaf state.
 // grid = (Sp/128, classes), block = 128.  jobs = dirty internal indices, ascending (= post-order).
 // ------------------------------------------------------------------------------------------------
-// Occupancy matters here more than anywhere: a pattern's walk is long and sequential, so patterns beyond the resident
-// thread capacity form a second wave that doubles the time (r01r: 200k patterns at 10 CTAs/SM = 1.06 waves).  For 4/8
-// states the register budget is capped so that 16 CTAs/SM (2048 threads) are resident.
+// (Forcing 16 CTAs/SM for 4 states -- 32 registers, spills -- was slower: 1.39 vs 1.18 ms at 256 x 200k, r01s.)
 template <int DP>
-__global__ void __launch_bounds__(128, (DP <= 8) ? 16 : 1) prune_small_walk_kernel(PruneArgs a, const int *__restrict__ jobs, int njobs) {
+__global__ void __launch_bounds__(128) prune_small_walk_kernel(PruneArgs a, const int *__restrict__ jobs, int njobs) {
     // 16..32 states: the branch's P^T is staged in shared memory once per child (all threads of the CTA walk the same
     // job list in lockstep) and read as broadcasts; 4/8 states read the 16/64 doubles straight through L1.
     constexpr bool kStage = DP > 8;
