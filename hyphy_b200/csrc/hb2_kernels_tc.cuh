@@ -72,11 +72,10 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int *e
     const uint32_t addr = smem_u32(bar);
     for (int it = 0; it < (1 << 22); it++) {
         uint32_t ok;
-        // test_wait polls without the suspend window of try_wait: the waits on this path are short and latency-critical
         asm volatile(
             "{\n\t"
             ".reg .pred P1;\n\t"
-            "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, P1;\n\t"
             "}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
         if (ok) return true;
@@ -430,61 +429,26 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    uint32_t n_mma = 0;                      // contractions issued so far (parity of bar_mma)
+    uint32_t n_step = 0, n_mma = 0;          // running counters: select ring stage / barrier parities
     bool bailed = false;                     // a dependency wait timed out: stop waiting, the host reports the error
 
     const int r = blockIdx.x % w.K;
     const int i_begin = w.lane_start[r], i_end = w.lane_start[r + 1];
 
-    // ring bookkeeping: slot staged for the current step and its mbarrier parity; cnt[] = stagings issued per slot
-    uint32_t cnt0 = 0, cnt1 = 0;
-    auto claim = [&](int slot) -> uint32_t { uint32_t par; if (slot == 0) { par = cnt0 & 1u; cnt0++; } else { par = cnt1 & 1u; cnt1++; } return par; };
-    // thread 0: stage the operands of one step into ring slot `slot`
-    auto stage_to = [&](int cat, int tile, int2 st, int slot) {
+    // thread 0: stage the operands of one step into ring slot (m & 1): two flat bulk copies + one L2 prefetch
+    auto stage_step = [&](int cat, int tile, int2 st, uint32_t m) {
         const int child = st.x & WALK_ID_MASK;
         const bool internal = child >= a.L;
-        float *dst = stage_base + slot * WALK_STAGE_FLOATS;
-        uint64_t *bar = bar_full + slot;
-        const size_t slotid = (size_t)cat * a.B + child;
+        float *dst = stage_base + (m & 1u) * WALK_STAGE_FLOATS;
+        uint64_t *bar = bar_full + (m & 1u);
+        const size_t slot = (size_t)cat * a.B + child;
         mbar_expect_tx(bar, (uint32_t)(TC_PTF_FLOATS * 4) + (internal ? 32768u : 0u));
-        bulk_g2s(dst, a.PTf + slotid * TC_PTF_FLOATS, (uint32_t)(TC_PTF_FLOATS * 4), bar);
+        bulk_g2s(dst, a.PTf + slot * TC_PTF_FLOATS, (uint32_t)(TC_PTF_FLOATS * 4), bar);
         if (internal) {
-            bulk_g2s(dst + 64 * WALK_PT_ROW, a.PB + slotid * TC_PB_FLOATS, 32768u, bar);
-            if (!(st.x & WALK_CHAIN)) prefetch_l2_bulk(cond4 + cond_f4(cat, child - a.L, tile, 0, 0, a.I, w.T), 32768u);
+            bulk_g2s(dst + 64 * WALK_PT_ROW, a.PB + slot * TC_PB_FLOATS, 32768u, bar);
+            if (!(st.x & WALK_CHAIN))      // pull the child's conditional block towards L2 (it may still be in DRAM)
+                prefetch_l2_bulk(cond4 + cond_f4(cat, child - a.L, tile, 0, 0, a.I, w.T), 32768u);
         }
-    };
-    // fold one leaf child into v: column gather from the staged P^T table (ambiguous states: sum of the allowed columns)
-    auto leaf_fold = [&](float (&v)[64], const float *tab, int code) {
-        if (code >= 0) {
-            const float4 *row = reinterpret_cast<const float4 *>(tab + code * WALK_PT_ROW);
-#pragma unroll
-            for (int q = 0; q < 16; q++) {
-                const float4 rr = row[q];
-                v[4 * q] *= rr.x; v[4 * q + 1] *= rr.y; v[4 * q + 2] *= rr.z; v[4 * q + 3] *= rr.w;
-            }
-        } else {
-            float acc[64];
-#pragma unroll
-            for (int k = 0; k < 64; k++) acc[k] = 0.f;
-            const double *amb = a.ambig + (size_t)(-code - 1) * 64;
-            for (int jj = 0; jj < a.D; jj++) {
-                if (__ldg(amb + jj) != 0.0) {
-                    const float4 *row = reinterpret_cast<const float4 *>(tab + jj * WALK_PT_ROW);
-#pragma unroll
-                    for (int q = 0; q < 16; q++) {
-                        const float4 rr = row[q];
-                        acc[4 * q] += rr.x; acc[4 * q + 1] += rr.y; acc[4 * q + 2] += rr.z; acc[4 * q + 3] += rr.w;
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 64; k++) v[k] *= acc[k];
-        }
-    };
-    auto step_at = [&](int i) -> int2 { return (i < i_end) ? __ldg(w.steps + i) : make_int2(0, 0); };
-    auto leaf_code = [&](int2 st, size_t s) -> int {
-        const int child = st.x & WALK_ID_MASK;
-        return (child < a.L) ? __ldg(a.leaf + (size_t)child * Sp + s) : 0;
     };
 
     for (int ct = blockIdx.x / w.K; ct < w.ncls * w.T; ct += w.nslots) {
@@ -494,45 +458,69 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
         float v[64];
         int ex = 0;
         if (i_begin == i_end) continue;
-        int i = i_begin;
-        int2 st = step_at(i), nx = step_at(i + 1), nx2 = step_at(i + 2);
+        int2 st = __ldg(w.steps + i_begin);
+        int2 nx = (i_begin + 1 < i_end) ? __ldg(w.steps + i_begin + 1) : make_int2(0, 0);
         __syncthreads();                      // previous (class, tile): every read of the ring is complete
-        int cur_slot = 0;
-        uint32_t cur_par = claim(0);
-        if (tid == 0) stage_to(cat, tile, st, 0);
-        int code = leaf_code(st, s);
-        while (i < i_end) {
+        if (tid == 0) stage_step(cat, tile, st, n_step);
+        int next_code = 0;
+        if ((st.x & WALK_ID_MASK) < a.L) next_code = __ldg(a.leaf + (size_t)(st.x & WALK_ID_MASK) * Sp + s);
+        for (int i = i_begin; i < i_end; i++) {
             const int enc = st.x;
             const int child = enc & WALK_ID_MASK;
+            const int par = st.y & WALK_ID_MASK;
+            const int flags = st.y;
+            const int code = next_code;
             const bool has_next = (i + 1 < i_end);
+            const int2 nx2 = (i + 2 < i_end) ? __ldg(w.steps + i + 2) : make_int2(0, 0);   // descriptors run two steps ahead
             const bool tr = w.trace && tid == 0 && (int)blockIdx.x == w.trace_cta;
             long long *trp = tr ? w.trace + (size_t)(i - i_begin) * 12 : nullptr;
             if (tr) { trp[0] = ((long long)st.x << 32) | (unsigned)st.y; trp[1] = clock64(); }
-            __syncthreads();                  // (1) everyone is done with the previous step: the other ring slot is free
-            const int nxt_slot = cur_slot ^ 1;
-            uint32_t nxt_par = 0;
-            int code_nx = 0;
+            __syncthreads();                  // (1) everyone is done with step i-1: ring slot (n_step+1)&1 is free
             if (has_next) {
-                nxt_par = claim(nxt_slot);
-                if (tid == 0) stage_to(cat, tile, nx, nxt_slot);
-                code_nx = leaf_code(nx, s);
+                if (tid == 0) stage_step(cat, tile, nx, n_step + 1);
+                if ((nx.x & WALK_ID_MASK) < a.L) next_code = __ldg(a.leaf + (size_t)(nx.x & WALK_ID_MASK) * Sp + s);
             }
-            if ((st.y & STEP_FIRST) && !(enc & WALK_CHAIN)) {
+            if ((flags & STEP_FIRST) && !(enc & WALK_CHAIN)) {
 #pragma unroll
                 for (int k = 0; k < 64; k++) v[k] = 1.f;
                 ex = 0;
             }
-            const float *tab = stage_base + cur_slot * WALK_STAGE_FLOATS;
+            const float *tab = stage_base + (n_step & 1u) * WALK_STAGE_FLOATS;     // P^T table of this branch
             if (tr) trp[2] = clock64();
-            bool fused = false;
-            uint32_t par3 = 0;
-            int code_nx2 = 0;
             if (child < a.L) {
-                mbar_wait(bar_full + cur_slot, cur_par, a.err);
+                mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
                 if (tr) trp[3] = clock64();
-                leaf_fold(v, tab, code);
+                if (code >= 0) {
+                    const float4 *row = reinterpret_cast<const float4 *>(tab + code * WALK_PT_ROW);
+#pragma unroll
+                    for (int q = 0; q < 16; q++) {
+                        const float4 rr = row[q];
+                        v[4 * q] *= rr.x; v[4 * q + 1] *= rr.y; v[4 * q + 2] *= rr.z; v[4 * q + 3] *= rr.w;
+                    }
+                } else {
+                    float acc[64];
+#pragma unroll
+                    for (int k = 0; k < 64; k++) acc[k] = 0.f;
+                    const double *amb = a.ambig + (size_t)(-code - 1) * 64;
+                    for (int jj = 0; jj < a.D; jj++) {
+                        if (__ldg(amb + jj) != 0.0) {
+                            const float4 *row = reinterpret_cast<const float4 *>(tab + jj * WALK_PT_ROW);
+#pragma unroll
+                            for (int q = 0; q < 16; q++) {
+                                const float4 rr = row[q];
+                                acc[4 * q] += rr.x; acc[4 * q + 1] += rr.y; acc[4 * q + 2] += rr.z; acc[4 * q + 3] += rr.w;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 64; k++) v[k] *= acc[k];
+                }
             } else {
                 const int cin = child - a.L;
+                // Anchors without a serial dependency: one independent compare per element builds a 64-bit mask and
+                // zeroes the element in the tensor operand; the (few) set bits are then enumerated with ffs and their
+                // values re-read from the child's conditional block in L2 (the row this thread itself loaded or, on a
+                // chain, stored a moment ago), eight loads in flight.
                 uint32_t am0 = 0, am1 = 0, am2 = 0, am3 = 0;
                 const float4 *xrow = cond4 + cond_f4(cat, cin, tile, 0, tid, a.I, w.T);
                 {
@@ -584,46 +572,6 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     if (tr) trp[10] = clock64();
                 }
-                if (tr) trp[3] = clock64();
-                tc_fence_before();
-                __syncthreads();             // (2) A operand complete in TMEM; every thread is done reading the previous D
-                if (tr) trp[4] = clock64();
-                if (lane == 0 && warp < 2) {
-                    // One thread issues a tcgen05.mma only every ~100-190 cycles (tools/tc_mma_timing.cu: 24 MMAs take 4770
-                    // cycles from one thread, 2560 from two, 1460 from four).  Two threads issue here, each into its OWN
-                    // accumulator (warp 0: even K-steps -> D0 = columns 0..63, warp 1: odd K-steps -> D1 = columns
-                    // 192..255) in a fixed order (small terms first), so the result is bit-reproducible; D0 + D1 is formed
-                    // in registers after the read-back.
-                    tc_fence_after();
-                    mbar_wait(bar_full + cur_slot, cur_par, a.err);
-                    if (tr) trp[5] = clock64();
-                    const uint64_t bdesc_hi = make_b_desc(smem_u32(tab + 64 * WALK_PT_ROW));
-                    const uint64_t bdesc_lo = make_b_desc(smem_u32(tab + 64 * WALK_PT_ROW + 4096));
-                    const uint32_t dcol = warp ? 192u : 0u;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) { const int kk = 2 * j + warp; tc_mma_tf32_ts(tmem_base + dcol, tmem_base + 128 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, j > 0); }
-#pragma unroll
-                    for (int j = 0; j < 4; j++) { const int kk = 2 * j + warp; tc_mma_tf32_ts(tmem_base + dcol, tmem_base + 64 + kk * 8, bdesc_lo + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u); }
-#pragma unroll
-                    for (int j = 0; j < 4; j++) { const int kk = 2 * j + warp; tc_mma_tf32_ts(tmem_base + dcol, tmem_base + 64 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u); }
-                    tc_commit(bar_mma);
-                }
-                __syncwarp();
-                // ---- in the shadow of the MMAs -------------------------------------------------------------------------
-                // (a) a leaf sibling (next step of the same node) is folded in right here: its table was staged in the other
-                //     ring slot at barrier (1); afterwards that slot is re-staged with the step after it
-                fused = has_next && (nx.x & WALK_ID_MASK) < a.L && !(nx.y & STEP_FIRST);
-                if (fused) {
-                    mbar_wait(bar_full + nxt_slot, nxt_par, a.err);
-                    leaf_fold(v, stage_base + nxt_slot * WALK_STAGE_FLOATS, code_nx);
-                    __syncthreads();         // (3) every thread has finished reading the sibling's table
-                    if (i + 2 < i_end) {
-                        par3 = claim(nxt_slot);
-                        if (tid == 0) stage_to(cat, tile, nx2, nxt_slot);
-                        code_nx2 = leaf_code(nx2, s);
-                    }
-                }
-                // (b) anchors: enumerate (values re-read from L2) and contract on the CUDA cores
                 unsigned long long amask = (unsigned long long)(am0 | (am1 << 16)) | ((unsigned long long)(am2 | (am3 << 16)) << 32);
                 int ak[WALK_FAST_ANCHORS];
                 float av[WALK_FAST_ANCHORS];
@@ -638,10 +586,36 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                         av[ai] = __ldcg(xrow_f + ((size_t)(kk >> 2) * 128) * 4 + (kk & 3));
                     }
                 }
+                if (tr) trp[3] = clock64();
+                tc_fence_before();
+                __syncthreads();             // (2) A operand complete in TMEM; every thread is done reading the previous D
+                if (tr) trp[4] = clock64();
+                if (lane == 0 && warp < 2) {
+                    // One thread issues a tcgen05.mma only every ~100-190 cycles (tools/tc_mma_timing.cu: 24 MMAs take 4770
+                    // cycles from one thread, 2560 from two, 1460 from four).  Two threads issue here, each into its OWN
+                    // accumulator (warp 0: even K-steps -> D0 = columns 0..63, warp 1: odd K-steps -> D1 = columns
+                    // 192..255) in a fixed order (small terms first), so the result is bit-reproducible; D0 + D1 is formed
+                    // in registers after the read-back.
+                    tc_fence_after();
+                    mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
+                    if (tr) trp[5] = clock64();
+                    const uint64_t bdesc_hi = make_b_desc(smem_u32(tab + 64 * WALK_PT_ROW));
+                    const uint64_t bdesc_lo = make_b_desc(smem_u32(tab + 64 * WALK_PT_ROW + 4096));
+                    const uint32_t dcol = warp ? 192u : 0u;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { const int kk = 2 * j + warp; tc_mma_tf32_ts(tmem_base + dcol, tmem_base + 128 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, j > 0); }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { const int kk = 2 * j + warp; tc_mma_tf32_ts(tmem_base + dcol, tmem_base + 64 + kk * 8, bdesc_lo + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u); }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) { const int kk = 2 * j + warp; tc_mma_tf32_ts(tmem_base + dcol, tmem_base + 64 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u); }
+                    tc_commit(bar_mma);
+                }
+                __syncwarp();
+                // anchors on the CUDA cores while the tensor core works (rows of the P^T table in shared memory)
                 float acc[64];
 #pragma unroll
                 for (int k = 0; k < 64; k++) acc[k] = 0.f;
-                mbar_wait(bar_full + cur_slot, cur_par, a.err);
+                mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
 #pragma unroll
                 for (int ai = 0; ai < WALK_FAST_ANCHORS; ai++) {
                     if (ak[ai] >= 0) {
@@ -655,7 +629,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                         }
                     }
                 }
-                while (amask) {                  // more than WALK_FAST_ANCHORS entries above the threshold (diffuse vectors): rare
+                while (amask) {                  // more than TC_MAX_ANCHORS entries above the threshold (diffuse vectors): rare
                     const int kk = __ffsll((long long)amask) - 1;
                     amask &= amask - 1;
                     const float xv = __ldcg(xrow_f + ((size_t)(kk >> 2) * 128) * 4 + (kk & 3));
@@ -681,9 +655,8 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                 }
                 n_mma++;
             }
-            const int flags = fused ? nx.y : st.y;            // the fused sibling carries the node's LAST / PUBLISH bits
-            const int par = flags & WALK_ID_MASK;
             renorm_f32(v, ex, (flags & STEP_LAST) != 0);
+            n_step++;
             if (flags & STEP_LAST) {
                 // this tile of the parent: conditionals, exponent, (root reduction); epoch flag only if another lane consumes it
                 float4 *outp = cond4 + cond_f4(cat, par, tile, 0, tid, a.I, w.T);
@@ -706,15 +679,8 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                 }
             }
             if (tr) trp[7] = clock64();
-            if (fused) {
-                i += 2;
-                st = nx2; nx = step_at(i + 1); nx2 = step_at(i + 2);
-                cur_slot = nxt_slot; cur_par = par3; code = code_nx2;
-            } else {
-                i += 1;
-                st = nx; nx = nx2; nx2 = step_at(i + 2);
-                cur_slot = nxt_slot; cur_par = nxt_par; code = code_nx;
-            }
+            st = nx;
+            nx = nx2;
         }
     }
     tc_fence_before();

@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libhyphy_b200.so")
+LIB_PATH = os.environ.get("HB2_LIB") or os.path.join(PKG, "libhyphy_b200.so")   # HB2_LIB: A/B another build of the engine
 
 MATRIX_RATE = 0
 MATRIX_TRANS = 1

@@ -360,3 +360,22 @@ def test_tensor_path_against_fp64_path_deep_and_wide():
         site = np.abs(_site_lnl(res["fp64"][1], res["fp64"][2]) - _site_lnl(res["tc"][1], res["tc"][2])).max()
         record("tc_vs_fp64", w.name + f"_t{mean_t}", "tc", b, a, float(site))
         assert abs(a - b) <= 1e-7 * abs(a), (w.name, a, b)
+
+
+def test_repeated_evaluations_are_bit_identical(mode):
+    """Race hunt at full size: every CTA of the persistent walk kernel hands tiles to other CTAs through epoch flags and
+    re-uses its shared-memory ring dozens of times per evaluation; a protocol slip shows up as a handful of patterns
+    changing between identical evaluations (tools/stress_determinism.py is the long version of this test)."""
+    w, _ = gc.load("ns_mg94_200x2000_c4")
+    Qt = w.Qt()
+    base = None
+    for _ in range(3):
+        lf = LF(w, mode)
+        lf.set_all_matrices(Qt)
+        for _ in range(10):
+            lnl, site, scc = lf.compute(want_sites=True)
+            if base is None:
+                base = (lnl, site.copy(), scc.copy())
+            assert lnl == base[0]
+            assert np.array_equal(site, base[1]) and np.array_equal(scc, base[2])
+        lf.close()
