@@ -286,7 +286,7 @@ def main():
         pk, pk_kind = peaks()
         flops, byts, expm_flops = algorithmic_work(w, S, 4 if tc_mode else 8)
         # dominant kernel: the fused pruning update (one launch per tree level); per-launch = per-evaluation / levels
-        prune_launches = (launches // args.steps) - (4 if tc_mode else 3)     # minus expm, (pack), combine, final_sum
+        prune_launches = (launches // args.steps) - 3     # minus expm (packs the tensor operands itself), combine, final_sum
         prune_ms = stage[1]
         achieved_gbs = (byts / world) / (prune_ms * 1e-3) / 1e9
         single_launch = prune_launches == 1

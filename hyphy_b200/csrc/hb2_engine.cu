@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -118,10 +119,10 @@ struct hb2_partition {
     bool small_walk = true;                   // HB2_SMALL_WALK=0: per-level launches of prune_small_kernel (A/B testing)
     bool expm_dfma = false;                   // HB2_EXPM_DFMA=1: previous FFMA-style fp64 expm kernel (A/B testing)
     bool use_walk = false;
-    bool walk_split = false;                  // HB2_WALK_SPLIT=1: two threads per pattern (256-thread CTAs); measured no faster (r01h), kept for study
     int walk_max_resident = 0;
     int epoch = 0;
     int *d_done = nullptr, *d_walk = nullptr, *h_walk = nullptr;
+    int walk_lane_cap = 8;              // lanes (CTAs) that share one (class, tile) pair; HB2_WALK_LANES overrides
     bool first_eval_done = false;
     std::vector<char> evaluated_cat;          // [C] whole tree pruned at least once
     int64_t launches = 0;
@@ -302,7 +303,8 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
     const int I = (int)p->I, L = (int)p->L;
     const int T = (int)(p->Sp / hb2::TC_TILE_P);
     const int CT = ncls * T;
-    int K = std::max(1, std::min(8, p->walk_max_resident / std::max(CT, 1)));
+    int kmax = p->walk_lane_cap;
+    int K = std::max(1, std::min(kmax, p->walk_max_resident / std::max(CT, 1)));
     int total = 0;
     for (auto &lv : levels) total += (int)lv.size();
     if (total == 0) return 0;
@@ -343,15 +345,20 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
         if (par >= 0 && dirty[par] && lane_of[par] != lane_of[n]) publish[n] = 1;
     }
     // flatten every lane into steps (one per child): chain child first, then leaves, then the other internal children
-    int *buf = p->h_walk;
-    int *lane_start = buf;                       // [K+1], steps start at int offset 16 (int2-aligned)
-    int *steps = buf + 16;
+    int *buf = p->h_walk;                        // header (lane_start | first | second contraction of each lane), then int4 steps
+    int *lane_start = buf;
+    int *steps = buf + hb2::WALK_HDR_INTS;
     int ns = 0;
     for (int r = 0; r < K; r++) {
         lane_start[r] = ns;
+        std::vector<int> contractions;           // step indices of this lane's tensor-core steps, in execution order
         for (int n : lanes[r]) {
             const int first = ns;
-            auto push = [&](int enc) { steps[2 * ns] = enc; steps[2 * ns + 1] = n; ns++; };
+            auto push = [&](int enc) {
+                steps[4 * ns] = enc; steps[4 * ns + 1] = n; steps[4 * ns + 2] = -1; steps[4 * ns + 3] = 0;
+                if ((enc & hb2::WALK_ID_MASK) >= L) contractions.push_back(ns);
+                ns++;
+            };
             if (chain_child[n] >= 0) push((chain_child[n] + L) | hb2::WALK_CHAIN);
             for (int ch : p->children[n]) if (ch < L) push(ch);
             for (int ch : p->children[n]) {
@@ -359,22 +366,22 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
                 const int ci = ch - L;
                 push(ch | ((dirty[ci] && lane_of[ci] != lane_of[n]) ? hb2::WALK_WAIT : 0));
             }
-            steps[2 * first + 1] |= hb2::STEP_FIRST;
-            steps[2 * (ns - 1) + 1] |= hb2::STEP_LAST | (publish[n] ? hb2::STEP_PUBLISH : 0);
+            steps[4 * first + 1] |= hb2::STEP_FIRST;
+            steps[4 * (ns - 1) + 1] |= hb2::STEP_LAST | (publish[n] ? hb2::STEP_PUBLISH : 0);
         }
+        // ring refill links: the kernel stages the first two contractions of a lane up front, then contraction j hands its
+        // shared-memory slot to contraction j + 2
+        auto stage_enc = [&](size_t j) { return j < contractions.size() ? (steps[4 * contractions[j]] & (hb2::WALK_ID_MASK | hb2::WALK_CHAIN)) : -1; };
+        buf[hb2::WALK_HDR_FIRST + r] = stage_enc(0);
+        buf[hb2::WALK_HDR_SECOND + r] = stage_enc(1);
+        for (size_t j = 0; j < contractions.size(); j++) steps[4 * contractions[j] + 2] = stage_enc(j + 2);
     }
     lane_start[K] = ns;
-    const int nints = 16 + 2 * ns;
+    const int nints = hb2::WALK_HDR_INTS + 4 * ns;
     {
         cudaError_t ce = cudaMemcpyAsync(p->d_walk, p->h_walk, nints * sizeof(int), cudaMemcpyHostToDevice, p->stream);
-        if (ce != cudaSuccess) {
-            int cur = -1; cudaGetDevice(&cur);
-            cudaPointerAttributes pa{}, pb{};
-            cudaError_t e1 = cudaPointerGetAttributes(&pa, p->d_walk), e2 = cudaPointerGetAttributes(&pb, p->h_walk);
-            return fail("walk plan upload failed: %s; nints=%d ns=%d K=%d total=%d cur_dev=%d part_dev=%d d_walk=%p(type %d dev %d err %d) h_walk=%p(type %d dev %d err %d) stream=%p query=%d",
-                        cudaGetErrorString(ce), nints, ns, K, total, cur, p->device, (void *)p->d_walk, (int)pa.type, pa.device, (int)e1,
-                        (void *)p->h_walk, (int)pb.type, pb.device, (int)e2, (void *)p->stream, (int)cudaStreamQuery(p->stream));
-        }
+        if (ce != cudaSuccess)
+            return fail("walk plan upload failed: %s (ints=%d steps=%d lanes=%d device=%d)", cudaGetErrorString(ce), nints, ns, K, p->device);
     }
     hb2::PruneArgs a = prune_args(p, cat0);
     hb2::WalkArgs w;
@@ -382,21 +389,20 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
     t.PB = p->d_PB; t.PTf = p->d_PTf; t.cond = p->d_condf; t.scal = a.scal; t.leaf = a.leaf; t.ambig = a.ambig; t.pi = a.pi;
     t.rootL = a.rootL; t.rootE = a.rootE; t.tree = a.tree; t.err = p->d_err;
     t.L = a.L; t.I = a.I; t.B = a.B; t.D = a.D; t.Sp = a.Sp; t.cat0 = a.cat0;
-    w.lane_start = p->d_walk; w.steps = reinterpret_cast<const int2 *>(p->d_walk + 16);
+    w.hdr = p->d_walk; w.steps = reinterpret_cast<const int4 *>(p->d_walk + hb2::WALK_HDR_INTS);
     w.done = p->d_done; w.epoch = ++p->epoch; w.K = K; w.T = T; w.ncls = ncls; w.nslots = nslots;
     if (getenv("HB2_DEBUG")) fprintf(stderr, "[hb2] walk: jobs=%d steps=%d K=%d T=%d ncls=%d nslots=%d grid=%d resident=%d\n", total, ns, K, T, ncls, nslots, nslots * K, p->walk_max_resident);
     w.trace = nullptr; w.trace_cta = 0;
     const char *trace_path = getenv("HB2_WALK_TRACE");
     long long *d_trace = nullptr;
-    if (trace_path && !p->walk_split) {          // bring-up aid: per-step clock stamps of one CTA -> text file
+    if (trace_path) {          // bring-up aid: per-step clock stamps of one CTA -> text file
         const char *tc = getenv("HB2_WALK_TRACE_CTA");
         w.trace_cta = tc ? atoi(tc) : 0;
         CU(cudaMalloc(&d_trace, (size_t)(ns + 1) * 12 * sizeof(long long)));
         CU(cudaMemsetAsync(d_trace, 0, (size_t)(ns + 1) * 12 * sizeof(long long), p->stream));
         w.trace = d_trace;
     }
-    if (p->walk_split) hb2::prune64_tc_walk2_kernel<<<nslots * K, 256, hb2::WALK2_SMEM_BYTES, p->stream>>>(w);
-    else hb2::prune64_tc_walk_kernel<<<nslots * K, 128, hb2::WALK_SMEM_BYTES, p->stream>>>(w);
+    hb2::prune64_tc_walk_kernel<<<nslots * K, 128, hb2::WALK_SMEM_BYTES, p->stream>>>(w);
     if (d_trace) {
         std::vector<long long> ht((size_t)(ns + 1) * 12);
         CU(cudaStreamSynchronize(p->stream));
@@ -603,14 +609,12 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
         CUP(cudaMemsetAsync(p->d_PTf, 0, (size_t)C * p->B * hb2::TC_PTF_FLOATS * sizeof(float), p->stream));
         CUP(cudaFuncSetAttribute(hb2::prune64_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::TC_SMEM_BYTES));
         CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::WALK_SMEM_BYTES));
-        CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::WALK2_SMEM_BYTES));
-        CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        { const char *env = getenv("HB2_WALK_SPLIT"); p->walk_split = env && env[0] == '1'; }
         {
             const char *env = getenv("HB2_TC_WALK");
             p->use_walk = !(env && env[0] == '0');
             int per_sm = 0, sms = 0;
-            CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            // two CTAs x 64 KB of ring per SM; the rest of the 256 KB stays L1 for the P^T tables read through it
+            CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 60));
             CUP(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hb2::prune64_tc_walk_kernel, 128, hb2::WALK_SMEM_BYTES));
             if (getenv("HB2_DEBUG")) {
                 cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, hb2::prune64_tc_walk_kernel);
@@ -622,21 +626,21 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
             {   // the occupancy API reports 1 CTA/SM for this kernel on B200 although ncu (launch__occupancy_limit_* = 2) and a
                 // forced 2-per-SM run with cross-CTA dependencies (r01g) show two are co-resident; derive it from the resources
                 cudaFuncAttributes fa;
-                if (p->walk_split) CUP(cudaFuncGetAttributes(&fa, hb2::prune64_tc_walk2_kernel));
-                else CUP(cudaFuncGetAttributes(&fa, hb2::prune64_tc_walk_kernel));
+                CUP(cudaFuncGetAttributes(&fa, hb2::prune64_tc_walk_kernel));
                 cudaDeviceProp dp; CUP(cudaGetDeviceProperties(&dp, device));
-                const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * (p->walk_split ? 256 : 128);
-                const size_t smem_per_cta = (size_t)(p->walk_split ? hb2::WALK2_SMEM_BYTES : hb2::WALK_SMEM_BYTES) + fa.sharedSizeBytes + dp.reservedSharedMemPerBlock;
+                const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * 128;
+                const size_t smem_per_cta = (size_t)hb2::WALK_SMEM_BYTES + fa.sharedSizeBytes + dp.reservedSharedMemPerBlock;
                 const int by_res = std::min(dp.regsPerMultiprocessor / std::max(regs_per_cta, 1), (int)(dp.sharedMemPerMultiprocessor / smem_per_cta));
                 per_sm = std::max(per_sm, std::min(by_res, 2));
             }
             if (const char *ov = getenv("HB2_WALK_CTAS_PER_SM")) per_sm = atoi(ov);      // bring-up override
+            if (const char *ov = getenv("HB2_WALK_LANES")) p->walk_lane_cap = std::max(1, std::min(atoi(ov), hb2::WALK_MAX_LANES));
             p->walk_max_resident = std::min(per_sm, 2) * sms;          // TMEM: 256 of 512 columns per CTA -> at most 2 per SM
             if (p->walk_max_resident < 1) p->use_walk = false;
             const size_t T = Sp / hb2::TC_TILE_P;
             CUP(cudaMalloc(&p->d_done, (size_t)C * I * T * sizeof(int)));
             CUP(cudaMemsetAsync(p->d_done, 0, (size_t)C * I * T * sizeof(int), p->stream));
-            const size_t walk_ints = 16 + 2 * (size_t)(L + I);
+            const size_t walk_ints = hb2::WALK_HDR_INTS + 4 * (size_t)(L + I);
             CUP(cudaMalloc(&p->d_walk, walk_ints * sizeof(int)));
             CUP(cudaMallocHost(&p->h_walk, walk_ints * sizeof(int)));
         }
@@ -779,7 +783,6 @@ int hb2_set_rate_template(hb2_partition *p, int64_t nnz, const int64_t *entryInd
     }
     void *old[] = {p->d_t_index, p->d_t_formula, p->d_t_colfreq, p->d_V, p->d_vdst};
     for (void *d : old) if (d) cudaFree(d);
-    if (p->h_walk) cudaFreeHost(p->h_walk);
     if (p->h_V) cudaFreeHost(p->h_V);
     if (p->h_vdst) cudaFreeHost(p->h_vdst);
     p->d_t_index = p->d_t_formula = p->d_vdst = nullptr; p->d_t_colfreq = p->d_V = nullptr; p->h_V = nullptr; p->h_vdst = nullptr;

@@ -354,16 +354,22 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_kernel(PruneTcArgs a, const
 // registers.  All K lanes of a (c,t) must be co-resident (host guarantees grid <= resident capacity); with K == 1 there
 // are no cross-CTA waits at all and a CTA may loop over several (c,t) pairs.
 //
-// The pass is bound by (tree depth x per-step latency), so every operand of step i+1 is staged while step i runs:
-//   * per step, the branch's fp32 P^T table (64 rows x 256 B, padded to 272 B rows) and -- for a contraction -- its
-//     Ph|Pl UMMA tiles are bulk-copied (TMA engine, mbarrier tx completion) into a 2-stage shared-memory ring by warp 0
-//     right after the step-begin barrier; leaf column gathers and anchor rows are then shared-memory reads;
-//   * the 32 KB conditional block of the next contraction is prefetched into L2 (cp.async.bulk.prefetch.L2) and the next
-//     leaf's state codes into a register;
+// The pass is bound by (tree depth x per-step latency), so a step synchronises as little as it can:
+//   * only the Ph|Pl UMMA tiles of CONTRACTIONS are staged in shared memory (2-slot ring, 32 KB bulk copies, mbarrier
+//     tx completion).  Thread 0 refills a slot the moment it has seen the MMAs that read it complete (bar_mma) -- the
+//     tensor core is the slot's only reader, so no CTA barrier guards the ring; the host links every contraction to the
+//     one two ahead of it in the lane (step.z);
+//   * the fp32 P^T table of a branch (leaf column gathers, anchor rows) is read straight from global memory through L1
+//     (read-only during this launch); each thread prefetches the row of its next leaf one step ahead.  A leaf step has
+//     no barrier at all;
+//   * a contraction has ONE CTA barrier: A operand complete in TMEM / previous D read by everyone;
+//   * the 32 KB conditional block of an upcoming contraction is prefetched into L2 when its tiles are staged;
 //   * conditionals are stored tile-wise as [16 chunks][128 patterns][4 floats] (the K-major UMMA core-matrix order), so
 //     thread t's 16-byte accesses are perfectly coalesced for both the producer and the consumer of a tile;
 //   * epoch flags are published (fence + st.release by one thread) only for nodes that another lane consumes.
-// Step encoding: x = child id | WALK_WAIT | WALK_CHAIN ; y = parent internal index | STEP_FIRST | STEP_LAST | STEP_PUBLISH.
+// Step: x = child id | WALK_WAIT | WALK_CHAIN ; y = parent internal index | STEP_FIRST | STEP_LAST | STEP_PUBLISH ;
+//       z = (contractions only) child id | WALK_CHAIN of the lane's contraction two ahead, or -1 ; w = reserved.
+// Plan header (ints): lane_start[K+1] at 0, first contraction of each lane at 64, second at 128 (same encoding as z).
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int WALK_WAIT = 1 << 30;
 constexpr int WALK_CHAIN = 1 << 29;
@@ -371,17 +377,17 @@ constexpr int WALK_ID_MASK = (1 << 28) - 1;
 constexpr int STEP_FIRST = 1 << 28;
 constexpr int STEP_LAST = 1 << 29;
 constexpr int STEP_PUBLISH = 1 << 30;
-constexpr int WALK_PT_ROW = TC_PTF_ROW;        // same padded rows in shared memory: one flat bulk copy stages the table
-constexpr int WALK_STAGE_FLOATS = 64 * WALK_PT_ROW + 8192;     // P^T table + Ph|Pl tiles
-constexpr int WALK_SMEM_BYTES = 2 * WALK_STAGE_FLOATS * 4 + TC_MAX_ANCHORS * 128 * 8 + 64;
+constexpr int WALK_MAX_LANES = 63;
+constexpr int WALK_HDR_FIRST = 64, WALK_HDR_SECOND = 128, WALK_HDR_INTS = 192;
+constexpr int WALK_SMEM_BYTES = 2 * TC_PB_FLOATS * 4 + 64;
 
 struct WalkArgs {
     PruneTcArgs a;
-    const int *lane_start;      // [K+1] offsets into steps
-    const int2 *steps;
+    const int *hdr;             // plan header (see above)
+    const int4 *steps;
     int *done;                  // [C][I][T] epoch of the last evaluation that produced the tile
     int epoch, K, T, ncls, nslots;
-    long long *trace;           // nullable debug buffer: 8 clock64 stamps per step of CTA `trace_cta` (HB2_WALK_TRACE)
+    long long *trace;           // nullable debug buffer: 12 clock64 stamps per step of CTA `trace_cta` (HB2_WALK_TRACE)
     int trace_cta;
 };
 
@@ -396,6 +402,7 @@ __device__ __forceinline__ void st_release(int *p, int v) {
 __device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // float4 index of chunk q of pattern t in the conditional block of (cat, node, tile)
 __device__ __forceinline__ size_t cond_f4(int cat, int node, int tile, int q, int t, int I, int T) {
     return ((((size_t)cat * I + node) * T + tile) * 16 + q) * 128 + t;
@@ -404,10 +411,8 @@ __device__ __forceinline__ size_t cond_f4(int cat, int node, int tile, int q, in
 __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const PruneTcArgs &a = w.a;
-    float *stage_base = reinterpret_cast<float *>(smem);                           // 2 x [P^T table | Ph | Pl]
-    int *s_ak = reinterpret_cast<int *>(smem + 2 * WALK_STAGE_FLOATS * 4);          // [TC_MAX_ANCHORS][128]
-    float *s_av = reinterpret_cast<float *>(s_ak + TC_MAX_ANCHORS * 128);
-    uint64_t *bar_full = reinterpret_cast<uint64_t *>(s_av + TC_MAX_ANCHORS * 128); // [2]
+    float *Bs = reinterpret_cast<float *>(smem);                                   // 2 x [Ph | Pl]
+    uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + 2 * TC_PB_FLOATS * 4); // [2]
     uint64_t *bar_mma = bar_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_mma + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -429,26 +434,33 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    uint32_t n_step = 0, n_mma = 0;          // running counters: select ring stage / barrier parities
+    uint32_t n_int = 0;                      // contractions done by this CTA: ring slot n_int & 1, parities from it
     bool bailed = false;                     // a dependency wait timed out: stop waiting, the host reports the error
 
     const int r = blockIdx.x % w.K;
-    const int i_begin = w.lane_start[r], i_end = w.lane_start[r + 1];
+    const int i_begin = __ldg(w.hdr + r), i_end = __ldg(w.hdr + r + 1);
+    const int first_c = __ldg(w.hdr + WALK_HDR_FIRST + r), second_c = __ldg(w.hdr + WALK_HDR_SECOND + r);
 
-    // thread 0: stage the operands of one step into ring slot (m & 1): two flat bulk copies + one L2 prefetch
-    auto stage_step = [&](int cat, int tile, int2 st, uint32_t m) {
-        const int child = st.x & WALK_ID_MASK;
-        const bool internal = child >= a.L;
-        float *dst = stage_base + (m & 1u) * WALK_STAGE_FLOATS;
+    // thread 0: stage the Ph|Pl tiles of contraction number m (of this CTA) into ring slot m & 1
+    auto stage_pb = [&](int cat, int tile, int zenc, uint32_t m) {
+        const int child = zenc & WALK_ID_MASK;
         uint64_t *bar = bar_full + (m & 1u);
-        const size_t slot = (size_t)cat * a.B + child;
-        mbar_expect_tx(bar, (uint32_t)(TC_PTF_FLOATS * 4) + (internal ? 32768u : 0u));
-        bulk_g2s(dst, a.PTf + slot * TC_PTF_FLOATS, (uint32_t)(TC_PTF_FLOATS * 4), bar);
-        if (internal) {
-            bulk_g2s(dst + 64 * WALK_PT_ROW, a.PB + slot * TC_PB_FLOATS, 32768u, bar);
-            if (!(st.x & WALK_CHAIN))      // pull the child's conditional block towards L2 (it may still be in DRAM)
-                prefetch_l2_bulk(cond4 + cond_f4(cat, child - a.L, tile, 0, 0, a.I, w.T), 32768u);
+        mbar_expect_tx(bar, 32768u);
+        bulk_g2s(Bs + (m & 1u) * TC_PB_FLOATS, a.PB + ((size_t)cat * a.B + child) * TC_PB_FLOATS, 32768u, bar);
+        if (!(zenc & WALK_CHAIN))            // pull the child's conditional block towards L2 (it may still be in DRAM)
+            prefetch_l2_bulk(cond4 + cond_f4(cat, child - a.L, tile, 0, 0, a.I, w.T), 32768u);
+    };
+    auto table_of = [&](int cat, int child) -> const float * { return a.PTf + ((size_t)cat * a.B + child) * TC_PTF_FLOATS; };
+    // state code of this thread's pattern at a leaf step (0 for contractions); its table row is prefetched into L1
+    auto leaf_code = [&](int cat, int4 st, size_t s) -> int {
+        const int child = st.x & WALK_ID_MASK;
+        if (child >= a.L) return 0;
+        const int code = __ldg(a.leaf + (size_t)child * Sp + s);
+        if (code >= 0) {
+            const char *row = reinterpret_cast<const char *>(table_of(cat, child) + code * TC_PTF_ROW);
+            prefetch_l1(row); prefetch_l1(row + 128); prefetch_l1(row + 255);
         }
+        return code;
     };
 
     for (int ct = blockIdx.x / w.K; ct < w.ncls * w.T; ct += w.nslots) {
@@ -458,43 +470,38 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
         float v[64];
         int ex = 0;
         if (i_begin == i_end) continue;
-        int2 st = __ldg(w.steps + i_begin);
-        int2 nx = (i_begin + 1 < i_end) ? __ldg(w.steps + i_begin + 1) : make_int2(0, 0);
-        __syncthreads();                      // previous (class, tile): every read of the ring is complete
-        if (tid == 0) stage_step(cat, tile, st, n_step);
-        int next_code = 0;
-        if ((st.x & WALK_ID_MASK) < a.L) next_code = __ldg(a.leaf + (size_t)(st.x & WALK_ID_MASK) * Sp + s);
+        // every MMA of the previous (class, tile) has completed and thread 0 has seen it: both ring slots are free
+        if (tid == 0) {
+            if (first_c >= 0) stage_pb(cat, tile, first_c, n_int);
+            if (second_c >= 0) stage_pb(cat, tile, second_c, n_int + 1);
+        }
+        int4 st = __ldg(w.steps + i_begin);
+        int4 nx = (i_begin + 1 < i_end) ? __ldg(w.steps + i_begin + 1) : make_int4(0, 0, -1, 0);
+        int next_code = leaf_code(cat, st, s);
         for (int i = i_begin; i < i_end; i++) {
             const int enc = st.x;
             const int child = enc & WALK_ID_MASK;
             const int par = st.y & WALK_ID_MASK;
             const int flags = st.y;
             const int code = next_code;
-            const bool has_next = (i + 1 < i_end);
-            const int2 nx2 = (i + 2 < i_end) ? __ldg(w.steps + i + 2) : make_int2(0, 0);   // descriptors run two steps ahead
+            const int4 nx2 = (i + 2 < i_end) ? __ldg(w.steps + i + 2) : make_int4(0, 0, -1, 0);   // descriptors run two steps ahead
             const bool tr = w.trace && tid == 0 && (int)blockIdx.x == w.trace_cta;
             long long *trp = tr ? w.trace + (size_t)(i - i_begin) * 12 : nullptr;
             if (tr) { trp[0] = ((long long)st.x << 32) | (unsigned)st.y; trp[1] = clock64(); }
-            __syncthreads();                  // (1) everyone is done with step i-1: ring slot (n_step+1)&1 is free
-            if (has_next) {
-                if (tid == 0) stage_step(cat, tile, nx, n_step + 1);
-                if ((nx.x & WALK_ID_MASK) < a.L) next_code = __ldg(a.leaf + (size_t)(nx.x & WALK_ID_MASK) * Sp + s);
-            }
+            if (i + 1 < i_end) next_code = leaf_code(cat, nx, s);
             if ((flags & STEP_FIRST) && !(enc & WALK_CHAIN)) {
 #pragma unroll
                 for (int k = 0; k < 64; k++) v[k] = 1.f;
                 ex = 0;
             }
-            const float *tab = stage_base + (n_step & 1u) * WALK_STAGE_FLOATS;     // P^T table of this branch
+            const float *tab = table_of(cat, child);                               // P^T table of this branch (global, via L1)
             if (tr) trp[2] = clock64();
             if (child < a.L) {
-                mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
-                if (tr) trp[3] = clock64();
                 if (code >= 0) {
-                    const float4 *row = reinterpret_cast<const float4 *>(tab + code * WALK_PT_ROW);
+                    const float4 *row = reinterpret_cast<const float4 *>(tab + code * TC_PTF_ROW);
 #pragma unroll
                     for (int q = 0; q < 16; q++) {
-                        const float4 rr = row[q];
+                        const float4 rr = __ldg(row + q);
                         v[4 * q] *= rr.x; v[4 * q + 1] *= rr.y; v[4 * q + 2] *= rr.z; v[4 * q + 3] *= rr.w;
                     }
                 } else {
@@ -504,10 +511,10 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                     const double *amb = a.ambig + (size_t)(-code - 1) * 64;
                     for (int jj = 0; jj < a.D; jj++) {
                         if (__ldg(amb + jj) != 0.0) {
-                            const float4 *row = reinterpret_cast<const float4 *>(tab + jj * WALK_PT_ROW);
+                            const float4 *row = reinterpret_cast<const float4 *>(tab + jj * TC_PTF_ROW);
 #pragma unroll
                             for (int q = 0; q < 16; q++) {
-                                const float4 rr = row[q];
+                                const float4 rr = __ldg(row + q);
                                 acc[4 * q] += rr.x; acc[4 * q + 1] += rr.y; acc[4 * q + 2] += rr.z; acc[4 * q + 3] += rr.w;
                             }
                         }
@@ -515,12 +522,13 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
 #pragma unroll
                     for (int k = 0; k < 64; k++) v[k] *= acc[k];
                 }
+                if (tr) trp[3] = clock64();
             } else {
                 const int cin = child - a.L;
                 // Anchors without a serial dependency: one independent compare per element builds a 64-bit mask and
                 // zeroes the element in the tensor operand; the (few) set bits are then enumerated with ffs and their
                 // values re-read from the child's conditional block in L2 (the row this thread itself loaded or, on a
-                // chain, stored a moment ago), eight loads in flight.
+                // chain, stored a moment ago).
                 uint32_t am0 = 0, am1 = 0, am2 = 0, am3 = 0;
                 const float4 *xrow = cond4 + cond_f4(cat, cin, tile, 0, tid, a.I, w.T);
                 {
@@ -572,23 +580,9 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     if (tr) trp[10] = clock64();
                 }
-                unsigned long long amask = (unsigned long long)(am0 | (am1 << 16)) | ((unsigned long long)(am2 | (am3 << 16)) << 32);
-                int ak[WALK_FAST_ANCHORS];
-                float av[WALK_FAST_ANCHORS];
-                const float *xrow_f = reinterpret_cast<const float *>(xrow);
-#pragma unroll
-                for (int ai = 0; ai < WALK_FAST_ANCHORS; ai++) {
-                    ak[ai] = -1; av[ai] = 0.f;
-                    if (amask) {
-                        const int kk = __ffsll((long long)amask) - 1;
-                        amask &= amask - 1;
-                        ak[ai] = kk;
-                        av[ai] = __ldcg(xrow_f + ((size_t)(kk >> 2) * 128) * 4 + (kk & 3));
-                    }
-                }
                 if (tr) trp[3] = clock64();
                 tc_fence_before();
-                __syncthreads();             // (2) A operand complete in TMEM; every thread is done reading the previous D
+                __syncthreads();             // the step's only CTA barrier: A operand complete in TMEM; previous D read by all
                 if (tr) trp[4] = clock64();
                 if (lane == 0 && warp < 2) {
                     // One thread issues a tcgen05.mma only every ~100-190 cycles (tools/tc_mma_timing.cu: 24 MMAs take 4770
@@ -597,10 +591,11 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                     // 192..255) in a fixed order (small terms first), so the result is bit-reproducible; D0 + D1 is formed
                     // in registers after the read-back.
                     tc_fence_after();
-                    mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
+                    mbar_wait(bar_full + (n_int & 1u), (n_int >> 1) & 1u, a.err);
                     if (tr) trp[5] = clock64();
-                    const uint64_t bdesc_hi = make_b_desc(smem_u32(tab + 64 * WALK_PT_ROW));
-                    const uint64_t bdesc_lo = make_b_desc(smem_u32(tab + 64 * WALK_PT_ROW + 4096));
+                    const float *bs = Bs + (n_int & 1u) * TC_PB_FLOATS;
+                    const uint64_t bdesc_hi = make_b_desc(smem_u32(bs));
+                    const uint64_t bdesc_lo = make_b_desc(smem_u32(bs + 4096));
                     const uint32_t dcol = warp ? 192u : 0u;
 #pragma unroll
                     for (int j = 0; j < 4; j++) { const int kk = 2 * j + warp; tc_mma_tf32_ts(tmem_base + dcol, tmem_base + 128 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, j > 0); }
@@ -611,38 +606,30 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                     tc_commit(bar_mma);
                 }
                 __syncwarp();
-                // anchors on the CUDA cores while the tensor core works (rows of the P^T table in shared memory)
+                // anchors on the CUDA cores while the tensor core works: values from L2, rows of the P^T table through L1
                 float acc[64];
 #pragma unroll
                 for (int k = 0; k < 64; k++) acc[k] = 0.f;
-                mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
-#pragma unroll
-                for (int ai = 0; ai < WALK_FAST_ANCHORS; ai++) {
-                    if (ak[ai] >= 0) {
-                        const float xv = av[ai];
-                        const float4 *row = reinterpret_cast<const float4 *>(tab + ak[ai] * WALK_PT_ROW);
+                {
+                    unsigned long long amask = (unsigned long long)(am0 | (am1 << 16)) | ((unsigned long long)(am2 | (am3 << 16)) << 32);
+                    const float *xrow_f = reinterpret_cast<const float *>(xrow);
+                    while (amask) {
+                        const int kk = __ffsll((long long)amask) - 1;
+                        amask &= amask - 1;
+                        const float xv = __ldcg(xrow_f + ((size_t)(kk >> 2) * 128) * 4 + (kk & 3));
+                        const float4 *row = reinterpret_cast<const float4 *>(tab + kk * TC_PTF_ROW);
 #pragma unroll
                         for (int q = 0; q < 16; q++) {
-                            const float4 rr = row[q];
+                            const float4 rr = __ldg(row + q);
                             acc[4 * q] = fmaf(xv, rr.x, acc[4 * q]); acc[4 * q + 1] = fmaf(xv, rr.y, acc[4 * q + 1]);
                             acc[4 * q + 2] = fmaf(xv, rr.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(xv, rr.w, acc[4 * q + 3]);
                         }
                     }
                 }
-                while (amask) {                  // more than TC_MAX_ANCHORS entries above the threshold (diffuse vectors): rare
-                    const int kk = __ffsll((long long)amask) - 1;
-                    amask &= amask - 1;
-                    const float xv = __ldcg(xrow_f + ((size_t)(kk >> 2) * 128) * 4 + (kk & 3));
-                    const float4 *row = reinterpret_cast<const float4 *>(tab + kk * WALK_PT_ROW);
-#pragma unroll
-                    for (int q = 0; q < 16; q++) {
-                        const float4 rr = row[q];
-                        acc[4 * q] = fmaf(xv, rr.x, acc[4 * q]); acc[4 * q + 1] = fmaf(xv, rr.y, acc[4 * q + 1]);
-                        acc[4 * q + 2] = fmaf(xv, rr.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(xv, rr.w, acc[4 * q + 3]);
-                    }
-                }
-                mbar_wait(bar_mma, n_mma & 1u, a.err);
+                mbar_wait(bar_mma, n_int & 1u, a.err);
                 if (tr) trp[6] = clock64();
+                // the tensor core was the only reader of this ring slot: refill it with the contraction two ahead
+                if (tid == 0 && st.z >= 0) stage_pb(cat, tile, st.z, n_int + 2);
                 tc_fence_after();
 #pragma unroll
                 for (int o = 0; o < 64; o += 16) {
@@ -653,10 +640,9 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
 #pragma unroll
                     for (int k = 0; k < 16; k++) v[o + k] *= ((__uint_as_float(d[k]) + __uint_as_float(d1[k])) + acc[o + k]);
                 }
-                n_mma++;
+                n_int++;
             }
             renorm_f32(v, ex, (flags & STEP_LAST) != 0);
-            n_step++;
             if (flags & STEP_LAST) {
                 // this tile of the parent: conditionals, exponent, (root reduction); epoch flag only if another lane consumes it
                 float4 *outp = cond4 + cond_f4(cat, par, tile, 0, tid, a.I, w.T);
@@ -690,292 +676,5 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
     }
 }
 
-
-// ------------------------------------------------------------------------------------------------------------------
-// Split-row variant of the walk kernel: 256 threads, TWO threads per pattern.  Warp w serves TMEM lane quarter (w & 3)
-// and state half (w >> 2): thread (w, lane) owns states [32h, 32h+32) of pattern 32*(w&3)+lane.  Per-thread work per
-// step halves and the SM holds twice as many warps (16 with 2 CTAs/SM) to hide latency; the step pipeline, ring,
-// flags and step encoding are those of prune64_tc_walk_kernel.  The two halves of a pattern meet in shared memory:
-// anchor lists (4 slots per half), partial row maxima (renormalisation) and partial root sums.
-// ------------------------------------------------------------------------------------------------------------------
-constexpr int WALK2_SMEM_BYTES = 2 * WALK_STAGE_FLOATS * 4 + TC_MAX_ANCHORS * 128 * 8 + 2 * 128 * 4 /*na*/ + 4 * 128 * 4 /*max, 2 parities*/ + 128 * 8 /*root*/ + 64;
-
-#define HB2_PAIR_SYNC(lq) asm volatile("bar.sync %0, 64;" ::"r"(1 + (lq)) : "memory")
-
-__global__ void __launch_bounds__(256, 2) prune64_tc_walk2_kernel(WalkArgs w) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    const PruneTcArgs &a = w.a;
-    float *stage_base = reinterpret_cast<float *>(smem);
-    int *s_ak = reinterpret_cast<int *>(smem + 2 * WALK_STAGE_FLOATS * 4);          // [8][128]: slots 4h..4h+3 belong to half h
-    float *s_av = reinterpret_cast<float *>(s_ak + TC_MAX_ANCHORS * 128);
-    int *s_na = reinterpret_cast<int *>(s_av + TC_MAX_ANCHORS * 128);               // [2][128]
-    float *s_pm = reinterpret_cast<float *>(s_na + 2 * 128);                        // [2 step parities][2 halves][128] partial row maxima
-    double *s_pr = reinterpret_cast<double *>(s_pm + 4 * 128);                      // [128] partial root sums (half 1)
-    uint64_t *bar_full = reinterpret_cast<uint64_t *>(s_pr + 128);                  // [2]
-    uint64_t *bar_mma = bar_full + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_mma + 1);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int lq = warp & 3, h = warp >> 2, t = lq * 32 + lane;
-    const size_t Sp = a.Sp;
-    float4 *cond4 = reinterpret_cast<float4 *>(a.cond);
-
-    if (tid == 0) {
-        mbar_init(bar_full, 1);
-        mbar_init(bar_full + 1, 1);
-        mbar_init(bar_mma, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    s_pm[h * 128 + t] = 1.f;
-    s_pm[256 + h * 128 + t] = 1.f;
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(lq * 32) << 16) + 32u * h;   // this thread's lane quarter and column half
-    uint32_t n_step = 0, n_mma = 0;
-    bool bailed = false;
-
-    const int r = blockIdx.x % w.K;
-    const int i_begin = w.lane_start[r], i_end = w.lane_start[r + 1];
-
-    auto stage_step = [&](int cat, int tile, int2 st, uint32_t m) {      // thread 0
-        const int child = st.x & WALK_ID_MASK;
-        const bool internal = child >= a.L;
-        float *dst = stage_base + (m & 1u) * WALK_STAGE_FLOATS;
-        uint64_t *bar = bar_full + (m & 1u);
-        const size_t slot = (size_t)cat * a.B + child;
-        mbar_expect_tx(bar, (uint32_t)(TC_PTF_FLOATS * 4) + (internal ? 32768u : 0u));
-        bulk_g2s(dst, a.PTf + slot * TC_PTF_FLOATS, (uint32_t)(TC_PTF_FLOATS * 4), bar);
-        if (internal) {
-            bulk_g2s(dst + 64 * WALK_PT_ROW, a.PB + slot * TC_PB_FLOATS, 32768u, bar);
-            if (!(st.x & WALK_CHAIN)) prefetch_l2_bulk(cond4 + cond_f4(cat, child - a.L, tile, 0, 0, a.I, w.T), 32768u);
-        }
-    };
-    auto scale_by = [&](float (&v)[32], int &ex, float m) {          // m = row maximum (both halves); exact power of two
-        const int e = max((int)((__float_as_uint(m) >> 23) & 0xffu) - 126, -125);
-        if (e != 0) {
-            const float sc = __uint_as_float((uint32_t)(127 - e) << 23);
-#pragma unroll
-            for (int k = 0; k < 32; k++) v[k] *= sc;
-            ex += e;
-        }
-    };
-
-    for (int ct = blockIdx.x / w.K; ct < w.ncls * w.T; ct += w.nslots) {
-        const int cat = a.cat0 + ct / w.T;
-        const int tile = ct % w.T;
-        const size_t s = (size_t)tile * TC_TILE_P + t;
-        float v[32];
-        int ex = 0;
-        if (i_begin == i_end) continue;
-        int2 st = __ldg(w.steps + i_begin);
-        int2 nx = (i_begin + 1 < i_end) ? __ldg(w.steps + i_begin + 1) : make_int2(0, 0);
-        __syncthreads();
-        if (tid == 0) stage_step(cat, tile, st, n_step);
-        int next_code = 0;
-        if ((st.x & WALK_ID_MASK) < a.L) next_code = __ldg(a.leaf + (size_t)(st.x & WALK_ID_MASK) * Sp + s);
-        bool fresh = true;                   // no partial maxima of this job published yet
-        for (int i = i_begin; i < i_end; i++) {
-            const int enc = st.x;
-            const int child = enc & WALK_ID_MASK;
-            const int par = st.y & WALK_ID_MASK;
-            const int flags = st.y;
-            const int code = next_code;
-            const bool has_next = (i + 1 < i_end);
-            const int2 nx2 = (i + 2 < i_end) ? __ldg(w.steps + i + 2) : make_int2(0, 0);
-            __syncthreads();                  // (1) step i-1 complete everywhere: ring slot (n_step+1)&1 free, s_pm/s_na of step i-1 visible
-            if (has_next) {
-                if (tid == 0) stage_step(cat, tile, nx, n_step + 1);
-                if ((nx.x & WALK_ID_MASK) < a.L) next_code = __ldg(a.leaf + (size_t)(nx.x & WALK_ID_MASK) * Sp + s);
-            }
-            if ((flags & STEP_FIRST) && !(enc & WALK_CHAIN)) {
-#pragma unroll
-                for (int k = 0; k < 32; k++) v[k] = 1.f;
-                ex = 0;
-                fresh = true;
-            } else if (!(flags & STEP_FIRST) && !fresh) {
-                // deferred underflow guard between the children of one node: the row maximum after the previous step
-                const float *pmp = s_pm + ((n_step + 1u) & 1u) * 256;          // written by both halves at the end of the previous step
-                const float m = fmaxf(pmp[t], pmp[128 + t]);
-                if (m > 0.f && m < 2.3283064e-10f) scale_by(v, ex, m);
-            }
-            const float *tab = stage_base + (n_step & 1u) * WALK_STAGE_FLOATS;
-            if (child < a.L) {
-                mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
-                if (code >= 0) {
-                    const float4 *row = reinterpret_cast<const float4 *>(tab + code * WALK_PT_ROW + 32 * h);
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        const float4 rr = row[q];
-                        v[4 * q] *= rr.x; v[4 * q + 1] *= rr.y; v[4 * q + 2] *= rr.z; v[4 * q + 3] *= rr.w;
-                    }
-                } else {
-                    float acc[32];
-#pragma unroll
-                    for (int k = 0; k < 32; k++) acc[k] = 0.f;
-                    const double *amb = a.ambig + (size_t)(-code - 1) * 64;
-                    for (int jj = 0; jj < a.D; jj++) {
-                        if (__ldg(amb + jj) != 0.0) {
-                            const float4 *row = reinterpret_cast<const float4 *>(tab + jj * WALK_PT_ROW + 32 * h);
-#pragma unroll
-                            for (int q = 0; q < 8; q++) {
-                                const float4 rr = row[q];
-                                acc[4 * q] += rr.x; acc[4 * q + 1] += rr.y; acc[4 * q + 2] += rr.z; acc[4 * q + 3] += rr.w;
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < 32; k++) v[k] *= acc[k];
-                }
-            } else {
-                const int cin = child - a.L;
-                int na = 0;
-                {
-                    uint32_t hi[32], lo[32];
-                    if (enc & WALK_CHAIN) {
-#pragma unroll
-                        for (int k = 0; k < 32; k++) {
-                            float x = v[k];
-                            v[k] = 1.f;
-                            if (x >= TC_ANCHOR_THR && na < 4) {
-                                s_ak[(4 * h + na) * 128 + t] = 32 * h + k; s_av[(4 * h + na) * 128 + t] = x; na++; x = 0.f;
-                            }
-                            const float hh = tf32_rn(x);
-                            hi[k] = __float_as_uint(hh);
-                            lo[k] = __float_as_uint(x - hh);
-                        }
-                    } else {
-                        if (enc & WALK_WAIT) {
-                            const int *flag = w.done + ((size_t)cat * a.I + cin) * w.T + tile;
-                            int it = 0;
-                            while (!bailed && ld_acquire(flag) < w.epoch) {
-                                if (++it > (1 << 21)) { atomicExch(a.err, 2); bailed = true; }
-                            }
-                        }
-                        const float4 *xr = cond4 + cond_f4(cat, cin, tile, 8 * h, t, a.I, w.T);
-#pragma unroll
-                        for (int q = 0; q < 8; q++) {
-                            const float4 x4 = __ldcg(xr + (size_t)q * 128);
-                            float xs[4] = {x4.x, x4.y, x4.z, x4.w};
-#pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                if (xs[u] >= TC_ANCHOR_THR && na < 4) {
-                                    s_ak[(4 * h + na) * 128 + t] = 32 * h + 4 * q + u; s_av[(4 * h + na) * 128 + t] = xs[u]; na++; xs[u] = 0.f;
-                                }
-                                const float hh = tf32_rn(xs[u]);
-                                hi[4 * q + u] = __float_as_uint(hh);
-                                lo[4 * q + u] = __float_as_uint(xs[u] - hh);
-                            }
-                        }
-                        ex += __ldcg(a.scal + ((size_t)cat * a.I + cin) * Sp + s);
-                    }
-                    s_na[h * 128 + t] = na;
-#pragma unroll
-                    for (int o = 0; o < 32; o += 16) {
-                        HB2_TMEM_ST16(lane_addr + 64 + o, hi, o);
-                        HB2_TMEM_ST16(lane_addr + 128 + o, lo, o);
-                    }
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                }
-                tc_fence_before();
-                __syncthreads();             // (2) A operand complete in TMEM, anchor lists of both halves visible
-                if (tid == 0) {
-                    tc_fence_after();
-                    mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
-                    const uint64_t bdesc_hi = make_b_desc(smem_u32(tab + 64 * WALK_PT_ROW));
-                    const uint64_t bdesc_lo = make_b_desc(smem_u32(tab + 64 * WALK_PT_ROW + 4096));
-#pragma unroll
-                    for (int kk = 0; kk < 8; kk++)
-                        tc_mma_tf32_ts(tmem_base, tmem_base + 128 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, kk > 0);
-#pragma unroll
-                    for (int kk = 0; kk < 8; kk++)
-                        tc_mma_tf32_ts(tmem_base, tmem_base + 64 + kk * 8, bdesc_lo + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u);
-#pragma unroll
-                    for (int kk = 0; kk < 8; kk++)
-                        tc_mma_tf32_ts(tmem_base, tmem_base + 64 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u);
-                    tc_commit(bar_mma);
-                }
-                __syncwarp();
-                // anchors of BOTH halves, outputs of this half, on the CUDA cores while the tensor core works
-                float acc[32];
-#pragma unroll
-                for (int k = 0; k < 32; k++) acc[k] = 0.f;
-                const int na0 = s_na[t], na1 = s_na[128 + t];
-                if (na0 + na1 > 0) {
-                    mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
-                    for (int ai = 0; ai < 8; ai++) {
-                        if (!(ai < na0 || (ai >= 4 && ai - 4 < na1))) continue;
-                        const int ka = s_ak[ai * 128 + t];
-                        const float xv = s_av[ai * 128 + t];
-                        const float4 *row = reinterpret_cast<const float4 *>(tab + ka * WALK_PT_ROW + 32 * h);
-#pragma unroll
-                        for (int q = 0; q < 8; q++) {
-                            const float4 rr = row[q];
-                            acc[4 * q] = fmaf(xv, rr.x, acc[4 * q]); acc[4 * q + 1] = fmaf(xv, rr.y, acc[4 * q + 1]);
-                            acc[4 * q + 2] = fmaf(xv, rr.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(xv, rr.w, acc[4 * q + 3]);
-                        }
-                    }
-                }
-                mbar_wait(bar_mma, n_mma & 1u, a.err);
-                tc_fence_after();
-#pragma unroll
-                for (int o = 0; o < 32; o += 16) {
-                    uint32_t d[16];
-                    HB2_TMEM_LD16(lane_addr + o, d, 0);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int k = 0; k < 16; k++) v[o + k] *= (__uint_as_float(d[k]) + acc[o + k]);
-                }
-                n_mma++;
-            }
-            // partial row maximum of this half (consumed by the guard of the next step, or right away at the end of the node)
-            float pm = 0.f;
-#pragma unroll
-            for (int k = 0; k < 32; k++) pm = fmaxf(pm, v[k]);
-            float *pmc = s_pm + (n_step & 1u) * 256;
-            pmc[h * 128 + t] = pm;
-            fresh = false;
-            n_step++;
-            if (flags & STEP_LAST) {
-                HB2_PAIR_SYNC(lq);            // both halves of every pattern of this lane quarter have published their maxima
-                const float m = fmaxf(pm, pmc[(1 - h) * 128 + t]);
-                if (m > 0.f && m < INFINITY) scale_by(v, ex, m);
-                float4 *outp = cond4 + cond_f4(cat, par, tile, 8 * h, t, a.I, w.T);
-#pragma unroll
-                for (int q = 0; q < 8; q++) __stcg(outp + (size_t)q * 128, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-                if (h == 0) __stcg(a.scal + ((size_t)cat * a.I + par) * Sp + s, ex);
-                if (par == a.I - 1) {
-                    double rr = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 32; k++) rr = fma((double)v[k], a.pi[32 * h + k], rr);
-                    if (h == 1) s_pr[t] = rr;
-                    HB2_PAIR_SYNC(lq);
-                    if (h == 0) {
-                        a.rootL[(size_t)cat * Sp + s] = rr + s_pr[t];
-                        a.rootE[(size_t)cat * Sp + s] = ex;
-                    }
-                }
-                if (flags & STEP_PUBLISH) {
-                    __syncthreads();
-                    if (tid == 96) {
-                        __threadfence();
-                        st_release(w.done + ((size_t)cat * a.I + par) * w.T + tile, w.epoch);
-                    }
-                }
-            }
-            st = nx;
-            nx = nx2;
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
-    }
-}
-
 }  // namespace hb2
+

@@ -4,7 +4,6 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-os.environ["HB2_WALK_SPLIT"] = "0"
 cta = sys.argv[1] if len(sys.argv) > 1 else "0"
 os.environ["HB2_WALK_TRACE"] = os.path.join(ROOT, "gpurun_out", f"walk_trace_cta{cta}.txt")
 os.environ["HB2_WALK_TRACE_CTA"] = cta
