@@ -14,7 +14,6 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
-
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -115,14 +114,15 @@ struct hb2_partition {
     bool use_tc = false;
     float *d_condf = nullptr, *d_PB = nullptr, *d_PTf = nullptr;
     int *d_err = nullptr;
-    // persistent walk kernel (one launch per evaluation): plan buffers, epoch flags, residency
+    // persistent walk kernel (one launch per evaluation): plan buffers, generation bits of the tagged hand-over, residency
     bool small_walk = true;                   // HB2_SMALL_WALK=0: per-level launches of prune_small_kernel (A/B testing)
     bool expm_dfma = false;                   // HB2_EXPM_DFMA=1: previous FFMA-style fp64 expm kernel (A/B testing)
     bool use_walk = false;
     int walk_max_resident = 0;
-    int epoch = 0;
-    int *d_done = nullptr, *d_walk = nullptr, *h_walk = nullptr;
-    int walk_lane_cap = 8;              // lanes (CTAs) that share one (class, tile) pair; HB2_WALK_LANES overrides
+    std::vector<int> walk_gen;          // [C][I] generation bit of each node's resident conditionals (tc walk path)
+    bool walk_reset = false;            // a pass was aborted: tags are inconsistent -> wipe and recompute everything
+    int *d_walk = nullptr, *h_walk = nullptr;
+    int walk_lane_cap = 8;              // lanes (CTAs) that share one (class, tile) pair; HB2_WALK_LANES overrides (<= 15)
     bool first_eval_done = false;
     std::vector<char> evaluated_cat;          // [C] whole tree pruned at least once
     int64_t launches = 0;
@@ -303,8 +303,7 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
     const int I = (int)p->I, L = (int)p->L;
     const int T = (int)(p->Sp / hb2::TC_TILE_P);
     const int CT = ncls * T;
-    int kmax = p->walk_lane_cap;
-    int K = std::max(1, std::min(kmax, p->walk_max_resident / std::max(CT, 1)));
+    int K = std::max(1, std::min(p->walk_lane_cap, p->walk_max_resident / std::max(CT, 1)));
     int total = 0;
     for (auto &lv : levels) total += (int)lv.size();
     if (total == 0) return 0;
@@ -337,28 +336,16 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
             lanes[lane].push_back(n);
         }
     }
-    // a node's tile must be published (epoch flag) iff a dirty parent in ANOTHER lane consumes it
-    std::vector<char> publish(I, 0);
-    for (int n = 0; n < I; n++) {
-        if (!dirty[n]) continue;
-        const int64_t par = p->parents[L + n];
-        if (par >= 0 && dirty[par] && lane_of[par] != lane_of[n]) publish[n] = 1;
-    }
     // flatten every lane into steps (one per child): chain child first, then leaves, then the other internal children
-    int *buf = p->h_walk;                        // header (lane_start | first | second contraction of each lane), then int4 steps
-    int *lane_start = buf;
-    int *steps = buf + hb2::WALK_HDR_INTS;
+    int *buf = p->h_walk;
+    int *lane_start = buf;                       // [K+1], steps start at int offset 16 (int2-aligned)
+    int *steps = buf + 16;
     int ns = 0;
     for (int r = 0; r < K; r++) {
         lane_start[r] = ns;
-        std::vector<int> contractions;           // step indices of this lane's tensor-core steps, in execution order
         for (int n : lanes[r]) {
             const int first = ns;
-            auto push = [&](int enc) {
-                steps[4 * ns] = enc; steps[4 * ns + 1] = n; steps[4 * ns + 2] = -1; steps[4 * ns + 3] = 0;
-                if ((enc & hb2::WALK_ID_MASK) >= L) contractions.push_back(ns);
-                ns++;
-            };
+            auto push = [&](int enc) { steps[2 * ns] = enc; steps[2 * ns + 1] = n; ns++; };
             if (chain_child[n] >= 0) push((chain_child[n] + L) | hb2::WALK_CHAIN);
             for (int ch : p->children[n]) if (ch < L) push(ch);
             for (int ch : p->children[n]) {
@@ -366,22 +353,29 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
                 const int ci = ch - L;
                 push(ch | ((dirty[ci] && lane_of[ci] != lane_of[n]) ? hb2::WALK_WAIT : 0));
             }
-            steps[4 * first + 1] |= hb2::STEP_FIRST;
-            steps[4 * (ns - 1) + 1] |= hb2::STEP_LAST | (publish[n] ? hb2::STEP_PUBLISH : 0);
+            steps[2 * first + 1] |= hb2::STEP_FIRST;
+            steps[2 * (ns - 1) + 1] |= hb2::STEP_LAST;
         }
-        // ring refill links: the kernel stages the first two contractions of a lane up front, then contraction j hands its
-        // shared-memory slot to contraction j + 2
-        auto stage_enc = [&](size_t j) { return j < contractions.size() ? (steps[4 * contractions[j]] & (hb2::WALK_ID_MASK | hb2::WALK_CHAIN)) : -1; };
-        buf[hb2::WALK_HDR_FIRST + r] = stage_enc(0);
-        buf[hb2::WALK_HDR_SECOND + r] = stage_enc(1);
-        for (size_t j = 0; j < contractions.size(); j++) steps[4 * contractions[j] + 2] = stage_enc(j + 2);
     }
     lane_start[K] = ns;
-    const int nints = hb2::WALK_HDR_INTS + 4 * ns;
+    // generation bits: every node re-pruned by this pass flips its bit (per class); the kernel tags what it writes with the
+    // new bit and awaits cross-lane children on it.  The table travels behind the steps.
+    for (int c = cat0; c < cat0 + ncls; c++)
+        for (int n = 0; n < I; n++)
+            if (dirty[n]) p->walk_gen[(size_t)c * I + n] ^= 1;
+    const int gen_off = 16 + 2 * ns;
+    std::copy(p->walk_gen.begin(), p->walk_gen.end(), buf + gen_off);
+    const int nints = gen_off + (int)p->walk_gen.size();
     {
         cudaError_t ce = cudaMemcpyAsync(p->d_walk, p->h_walk, nints * sizeof(int), cudaMemcpyHostToDevice, p->stream);
-        if (ce != cudaSuccess)
-            return fail("walk plan upload failed: %s (ints=%d steps=%d lanes=%d device=%d)", cudaGetErrorString(ce), nints, ns, K, p->device);
+        if (ce != cudaSuccess) {
+            int cur = -1; cudaGetDevice(&cur);
+            cudaPointerAttributes pa{}, pb{};
+            cudaError_t e1 = cudaPointerGetAttributes(&pa, p->d_walk), e2 = cudaPointerGetAttributes(&pb, p->h_walk);
+            return fail("walk plan upload failed: %s; nints=%d ns=%d K=%d total=%d cur_dev=%d part_dev=%d d_walk=%p(type %d dev %d err %d) h_walk=%p(type %d dev %d err %d) stream=%p query=%d",
+                        cudaGetErrorString(ce), nints, ns, K, total, cur, p->device, (void *)p->d_walk, (int)pa.type, pa.device, (int)e1,
+                        (void *)p->h_walk, (int)pb.type, pb.device, (int)e2, (void *)p->stream, (int)cudaStreamQuery(p->stream));
+        }
     }
     hb2::PruneArgs a = prune_args(p, cat0);
     hb2::WalkArgs w;
@@ -389,8 +383,8 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
     t.PB = p->d_PB; t.PTf = p->d_PTf; t.cond = p->d_condf; t.scal = a.scal; t.leaf = a.leaf; t.ambig = a.ambig; t.pi = a.pi;
     t.rootL = a.rootL; t.rootE = a.rootE; t.tree = a.tree; t.err = p->d_err;
     t.L = a.L; t.I = a.I; t.B = a.B; t.D = a.D; t.Sp = a.Sp; t.cat0 = a.cat0;
-    w.hdr = p->d_walk; w.steps = reinterpret_cast<const int4 *>(p->d_walk + hb2::WALK_HDR_INTS);
-    w.done = p->d_done; w.epoch = ++p->epoch; w.K = K; w.T = T; w.ncls = ncls; w.nslots = nslots;
+    w.lane_start = p->d_walk; w.steps = reinterpret_cast<const int2 *>(p->d_walk + 16);
+    w.gen = p->d_walk + gen_off; w.K = K; w.T = T; w.ncls = ncls; w.nslots = nslots;
     if (getenv("HB2_DEBUG")) fprintf(stderr, "[hb2] walk: jobs=%d steps=%d K=%d T=%d ncls=%d nslots=%d grid=%d resident=%d\n", total, ns, K, T, ncls, nslots, nslots * K, p->walk_max_resident);
     w.trace = nullptr; w.trace_cta = 0;
     const char *trace_path = getenv("HB2_WALK_TRACE");
@@ -502,6 +496,14 @@ int evaluate_impl(hb2_partition *p, int c0, int nc, const double *weights, int64
     CU(cudaSetDevice(p->device));
     if (check_ready(p, c0, nc)) return 1;
     if (flush_matrices(p)) return 1;
+    if (p->walk_reset) {                      // an earlier pass was aborted half-way: its tags are inconsistent
+        CU(cudaMemsetAsync(p->d_condf, 0, (size_t)p->C * p->I * p->Sp * 64 * sizeof(float), p->stream));
+        CU(cudaMemsetAsync(p->d_scal, 0, (size_t)p->C * p->I * p->Sp * sizeof(int), p->stream));
+        CU(cudaMemsetAsync(p->d_err, 0, sizeof(int), p->stream));
+        std::fill(p->walk_gen.begin(), p->walk_gen.end(), 0);
+        std::fill(p->evaluated_cat.begin(), p->evaluated_cat.end(), 0);
+        p->walk_reset = false;
+    }
     // small inputs: pi (padded) and class weights
     double *hs = p->h_small;
     for (int k = 0; k < p->Dp; k++) hs[k] = k < p->D ? rootFreqs[k] : 0.0;
@@ -526,6 +528,7 @@ int evaluate_impl(hb2_partition *p, int c0, int nc, const double *weights, int64
     if (siteL) CU(cudaMemcpyAsync(siteL, p->d_siteL, p->S * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     if (siteScale) CU(cudaMemcpyAsync(siteScale, p->d_siteScale, p->S * sizeof(long long), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaStreamSynchronize(p->stream));
+    if (*reinterpret_cast<int *>(hs + p->Dp + p->C + 1) != 0) p->walk_reset = p->use_tc && p->use_walk;
     if (*reinterpret_cast<int *>(hs + p->Dp + p->C + 1) != 0) return fail("device-side wait timed out in the tcgen05 pruning kernel (code %d)", *reinterpret_cast<int *>(hs + p->Dp + p->C + 1));
     *lnL = hs[p->Dp + p->C];
     for (int c = c0; c < c0 + nc; c++) p->evaluated_cat[c] = 1;
@@ -613,8 +616,7 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
             const char *env = getenv("HB2_TC_WALK");
             p->use_walk = !(env && env[0] == '0');
             int per_sm = 0, sms = 0;
-            // two CTAs x 64 KB of ring per SM; the rest of the 256 KB stays L1 for the P^T tables read through it
-            CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 60));
+            CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             CUP(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hb2::prune64_tc_walk_kernel, 128, hb2::WALK_SMEM_BYTES));
             if (getenv("HB2_DEBUG")) {
                 cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, hb2::prune64_tc_walk_kernel);
@@ -634,13 +636,12 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
                 per_sm = std::max(per_sm, std::min(by_res, 2));
             }
             if (const char *ov = getenv("HB2_WALK_CTAS_PER_SM")) per_sm = atoi(ov);      // bring-up override
-            if (const char *ov = getenv("HB2_WALK_LANES")) p->walk_lane_cap = std::max(1, std::min(atoi(ov), hb2::WALK_MAX_LANES));
+            if (const char *ov = getenv("HB2_WALK_LANES")) p->walk_lane_cap = std::max(1, std::min(atoi(ov), 15));
             p->walk_max_resident = std::min(per_sm, 2) * sms;          // TMEM: 256 of 512 columns per CTA -> at most 2 per SM
             if (p->walk_max_resident < 1) p->use_walk = false;
             const size_t T = Sp / hb2::TC_TILE_P;
-            CUP(cudaMalloc(&p->d_done, (size_t)C * I * T * sizeof(int)));
-            CUP(cudaMemsetAsync(p->d_done, 0, (size_t)C * I * T * sizeof(int), p->stream));
-            const size_t walk_ints = hb2::WALK_HDR_INTS + 4 * (size_t)(L + I);
+            p->walk_gen.assign((size_t)C * I, 0);       // matches the zero-filled conditional and exponent buffers
+            const size_t walk_ints = 16 + 2 * (size_t)(L + I) + (size_t)C * I;
             CUP(cudaMalloc(&p->d_walk, walk_ints * sizeof(int)));
             CUP(cudaMallocHost(&p->h_walk, walk_ints * sizeof(int)));
         }
@@ -848,13 +849,13 @@ int hb2_read_conditionals(hb2_partition *p, int64_t cat, int64_t inode, double *
         // device layout per tile of 128 patterns: [16 chunks][128 patterns][4 floats]
         for (int64_t s = 0; s < p->Sp; s++)
             for (int k = 0; k < 64; k++)
-                tmp[s * 64 + k] = tf[(((size_t)(s / 128) * 16 + k / 4) * 128 + s % 128) * 4 + k % 4];
+                tmp[s * 64 + k] = std::fabs(tf[(((size_t)(s / 128) * 16 + k / 4) * 128 + s % 128) * 4 + k % 4]);   // sign bit = walk tag
     } else
     CU(cudaMemcpy(tmp.data(), p->d_cond + ((size_t)cat * p->I + inode) * p->Sp * p->Dp, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(te.data(), p->d_scal + ((size_t)cat * p->I + inode) * p->Sp, te.size() * sizeof(int), cudaMemcpyDeviceToHost));
     for (int64_t s = 0; s < p->S; s++) {
         for (int64_t k = 0; k < p->D; k++) cond[s * p->D + k] = tmp[s * p->Dp + k];
-        exp2[s] = te[s];
+        exp2[s] = (p->use_tc && p->use_walk) ? (te[s] >> 1) : te[s];      // walk path: bit 0 is the generation tag
     }
     return 0;
 }
@@ -904,7 +905,7 @@ void hb2_destroy(hb2_partition *p) {
     if (p->comm) g_nccl.CommDestroy(p->comm);
     void *dev[] = {p->d_leaf, p->d_scal, p->d_rootE, p->d_child_start, p->d_child_ids, p->d_jobs, p->d_dst, p->d_flag,
                    p->d_mix_first, p->d_ambig, p->d_freq, p->d_cond, p->d_PT, p->d_Q, p->d_pi, p->d_rootL, p->d_weights,
-                   p->d_partial, p->d_lnL, p->d_siteL, p->d_mix_w, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_done, p->d_walk, p->d_t_index, p->d_t_formula, p->d_vdst, p->d_t_colfreq, p->d_V};
+                   p->d_partial, p->d_lnL, p->d_siteL, p->d_mix_w, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_walk, p->d_t_index, p->d_t_formula, p->d_vdst, p->d_t_colfreq, p->d_V};
     for (void *d : dev) if (d) cudaFree(d);
     if (p->h_Q) cudaFreeHost(p->h_Q);
     if (p->h_small) cudaFreeHost(p->h_small);

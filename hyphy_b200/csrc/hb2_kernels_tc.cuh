@@ -349,60 +349,58 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_kernel(PruneTcArgs a, const
 // Patterns are independent, so all dependencies are tile-local: tile t of node p needs tile t of p's children only.
 // CTA (c, t, r) owns rate class c, pattern tile t and "lane" r (one of K groups of internal nodes); it executes its
 // lane's STEPS (one per child of every node of the lane, nodes in (height, index) order) back to back.  A child computed
-// by another lane of the same (c, t) is awaited through a per-(class, node, tile) epoch flag in global memory
-// (release/acquire); a child computed by THIS CTA in the previous job (the spine of deep trees) is taken straight from
-// registers.  All K lanes of a (c,t) must be co-resident (host guarantees grid <= resident capacity); with K == 1 there
+// by another lane of the same (c, t) is awaited on the DATA ITSELF ("tags"): every node has a generation bit that the
+// host flips each time the node is re-pruned; the producer writes it into the sign bit of every conditional (they are
+// non-negative) and into bit 0 of the exponent word, and the consumer thread -- which needs exactly the 17 words the
+// producer thread of the same pattern wrote -- re-reads them until all carry the new bit.  No flag, no fence, no
+// barrier on either side, and a tile is consumed one L2 round trip after it was written.  A child computed by THIS CTA
+// in the previous job (the spine of deep trees) is taken straight from registers.  All K lanes of a (c,t) must be co-resident (host guarantees grid <= resident capacity); with K == 1 there
 // are no cross-CTA waits at all and a CTA may loop over several (c,t) pairs.
 //
-// The pass is bound by (tree depth x per-step latency), so a step synchronises as little as it can:
-//   * only the Ph|Pl UMMA tiles of CONTRACTIONS are staged in shared memory (2-slot ring, 32 KB bulk copies, mbarrier
-//     tx completion).  Thread 0 refills a slot the moment it has seen the MMAs that read it complete (bar_mma) -- the
-//     tensor core is the slot's only reader, so no CTA barrier guards the ring; the host links every contraction to the
-//     one two ahead of it in the lane (step.z);
-//   * the fp32 P^T table of a branch (leaf column gathers, anchor rows) is read straight from global memory through L1
-//     (read-only during this launch); each thread prefetches the row of its next leaf one step ahead.  A leaf step has
-//     no barrier at all;
-//   * a contraction has ONE CTA barrier: A operand complete in TMEM / previous D read by everyone;
-//   * the 32 KB conditional block of an upcoming contraction is prefetched into L2 when its tiles are staged;
+// The pass is bound by (tree depth x per-step latency), so every operand of step i+1 is staged while step i runs:
+//   * per step, the branch's fp32 P^T table (64 rows x 256 B, padded to 272 B rows) and -- for a contraction -- its
+//     Ph|Pl UMMA tiles are bulk-copied (TMA engine, mbarrier tx completion) into a 2-stage shared-memory ring by warp 0
+//     right after the step-begin barrier; leaf column gathers and anchor rows are then shared-memory reads;
+//   * the 32 KB conditional block of the next contraction is prefetched into L2 (cp.async.bulk.prefetch.L2) and the next
+//     leaf's state codes into a register;
 //   * conditionals are stored tile-wise as [16 chunks][128 patterns][4 floats] (the K-major UMMA core-matrix order), so
 //     thread t's 16-byte accesses are perfectly coalesced for both the producer and the consumer of a tile;
-//   * epoch flags are published (fence + st.release by one thread) only for nodes that another lane consumes.
-// Step: x = child id | WALK_WAIT | WALK_CHAIN ; y = parent internal index | STEP_FIRST | STEP_LAST | STEP_PUBLISH ;
-//       z = (contractions only) child id | WALK_CHAIN of the lane's contraction two ahead, or -1 ; w = reserved.
-// Plan header (ints): lane_start[K+1] at 0, first contraction of each lane at 64, second at 128 (same encoding as z).
+// Step encoding: x = child id | WALK_WAIT | WALK_CHAIN ; y = parent internal index | STEP_FIRST | STEP_LAST.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int WALK_WAIT = 1 << 30;
 constexpr int WALK_CHAIN = 1 << 29;
 constexpr int WALK_ID_MASK = (1 << 28) - 1;
 constexpr int STEP_FIRST = 1 << 28;
 constexpr int STEP_LAST = 1 << 29;
-constexpr int STEP_PUBLISH = 1 << 30;
-constexpr int WALK_MAX_LANES = 63;
-constexpr int WALK_HDR_FIRST = 64, WALK_HDR_SECOND = 128, WALK_HDR_INTS = 192;
-constexpr int WALK_SMEM_BYTES = 2 * TC_PB_FLOATS * 4 + 64;
+constexpr int WALK_PT_ROW = TC_PTF_ROW;        // same padded rows in shared memory: one flat bulk copy stages the table
+constexpr int WALK_STAGE_FLOATS = 64 * WALK_PT_ROW + 8192;     // P^T table + Ph|Pl tiles
+constexpr int WALK_SMEM_BYTES = 2 * WALK_STAGE_FLOATS * 4 + TC_MAX_ANCHORS * 128 * 8 + 64;
 
 struct WalkArgs {
     PruneTcArgs a;
-    const int *hdr;             // plan header (see above)
-    const int4 *steps;
-    int *done;                  // [C][I][T] epoch of the last evaluation that produced the tile
-    int epoch, K, T, ncls, nslots;
-    long long *trace;           // nullable debug buffer: 12 clock64 stamps per step of CTA `trace_cta` (HB2_WALK_TRACE)
+    const int *lane_start;      // [K+1] offsets into steps
+    const int2 *steps;
+    const int *gen;             // [C][I] generation bit of every node's conditionals AFTER this pass (see "tags" above)
+    int K, T, ncls, nslots;
+    long long *trace;           // nullable debug buffer: 8 clock64 stamps per step of CTA `trace_cta` (HB2_WALK_TRACE)
     int trace_cta;
 };
 
-__device__ __forceinline__ int ld_acquire(const int *p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// Tagged hand-over between CTAs: relaxed gpu-scope accesses, every 32-bit word carries its own validity bit, so no
+// ordering between the words (and no fence) is needed.
+__device__ __forceinline__ uint4 ld_relaxed_u4(const void *p) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release(int *p, int v) {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const void *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // float4 index of chunk q of pattern t in the conditional block of (cat, node, tile)
 __device__ __forceinline__ size_t cond_f4(int cat, int node, int tile, int q, int t, int I, int T) {
     return ((((size_t)cat * I + node) * T + tile) * 16 + q) * 128 + t;
@@ -411,8 +409,10 @@ __device__ __forceinline__ size_t cond_f4(int cat, int node, int tile, int q, in
 __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const PruneTcArgs &a = w.a;
-    float *Bs = reinterpret_cast<float *>(smem);                                   // 2 x [Ph | Pl]
-    uint64_t *bar_full = reinterpret_cast<uint64_t *>(smem + 2 * TC_PB_FLOATS * 4); // [2]
+    float *stage_base = reinterpret_cast<float *>(smem);                           // 2 x [P^T table | Ph | Pl]
+    int *s_ak = reinterpret_cast<int *>(smem + 2 * WALK_STAGE_FLOATS * 4);          // [TC_MAX_ANCHORS][128]
+    float *s_av = reinterpret_cast<float *>(s_ak + TC_MAX_ANCHORS * 128);
+    uint64_t *bar_full = reinterpret_cast<uint64_t *>(s_av + TC_MAX_ANCHORS * 128); // [2]
     uint64_t *bar_mma = bar_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_mma + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -434,33 +434,26 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    uint32_t n_int = 0;                      // contractions done by this CTA: ring slot n_int & 1, parities from it
+    uint32_t n_step = 0, n_mma = 0;          // running counters: select ring stage / barrier parities
     bool bailed = false;                     // a dependency wait timed out: stop waiting, the host reports the error
 
     const int r = blockIdx.x % w.K;
-    const int i_begin = __ldg(w.hdr + r), i_end = __ldg(w.hdr + r + 1);
-    const int first_c = __ldg(w.hdr + WALK_HDR_FIRST + r), second_c = __ldg(w.hdr + WALK_HDR_SECOND + r);
+    const int i_begin = w.lane_start[r], i_end = w.lane_start[r + 1];
 
-    // thread 0: stage the Ph|Pl tiles of contraction number m (of this CTA) into ring slot m & 1
-    auto stage_pb = [&](int cat, int tile, int zenc, uint32_t m) {
-        const int child = zenc & WALK_ID_MASK;
-        uint64_t *bar = bar_full + (m & 1u);
-        mbar_expect_tx(bar, 32768u);
-        bulk_g2s(Bs + (m & 1u) * TC_PB_FLOATS, a.PB + ((size_t)cat * a.B + child) * TC_PB_FLOATS, 32768u, bar);
-        if (!(zenc & WALK_CHAIN))            // pull the child's conditional block towards L2 (it may still be in DRAM)
-            prefetch_l2_bulk(cond4 + cond_f4(cat, child - a.L, tile, 0, 0, a.I, w.T), 32768u);
-    };
-    auto table_of = [&](int cat, int child) -> const float * { return a.PTf + ((size_t)cat * a.B + child) * TC_PTF_FLOATS; };
-    // state code of this thread's pattern at a leaf step (0 for contractions); its table row is prefetched into L1
-    auto leaf_code = [&](int cat, int4 st, size_t s) -> int {
+    // thread 0: stage the operands of one step into ring slot (m & 1): two flat bulk copies + one L2 prefetch
+    auto stage_step = [&](int cat, int tile, int2 st, uint32_t m) {
         const int child = st.x & WALK_ID_MASK;
-        if (child >= a.L) return 0;
-        const int code = __ldg(a.leaf + (size_t)child * Sp + s);
-        if (code >= 0) {
-            const char *row = reinterpret_cast<const char *>(table_of(cat, child) + code * TC_PTF_ROW);
-            prefetch_l1(row); prefetch_l1(row + 128); prefetch_l1(row + 255);
+        const bool internal = child >= a.L;
+        float *dst = stage_base + (m & 1u) * WALK_STAGE_FLOATS;
+        uint64_t *bar = bar_full + (m & 1u);
+        const size_t slot = (size_t)cat * a.B + child;
+        mbar_expect_tx(bar, (uint32_t)(TC_PTF_FLOATS * 4) + (internal ? 32768u : 0u));
+        bulk_g2s(dst, a.PTf + slot * TC_PTF_FLOATS, (uint32_t)(TC_PTF_FLOATS * 4), bar);
+        if (internal) {
+            bulk_g2s(dst + 64 * WALK_PT_ROW, a.PB + slot * TC_PB_FLOATS, 32768u, bar);
+            if (!(st.x & WALK_CHAIN))      // pull the child's conditional block towards L2 (it may still be in DRAM)
+                prefetch_l2_bulk(cond4 + cond_f4(cat, child - a.L, tile, 0, 0, a.I, w.T), 32768u);
         }
-        return code;
     };
 
     for (int ct = blockIdx.x / w.K; ct < w.ncls * w.T; ct += w.nslots) {
@@ -470,38 +463,49 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
         float v[64];
         int ex = 0;
         if (i_begin == i_end) continue;
-        // every MMA of the previous (class, tile) has completed and thread 0 has seen it: both ring slots are free
-        if (tid == 0) {
-            if (first_c >= 0) stage_pb(cat, tile, first_c, n_int);
-            if (second_c >= 0) stage_pb(cat, tile, second_c, n_int + 1);
-        }
-        int4 st = __ldg(w.steps + i_begin);
-        int4 nx = (i_begin + 1 < i_end) ? __ldg(w.steps + i_begin + 1) : make_int4(0, 0, -1, 0);
-        int next_code = leaf_code(cat, st, s);
+        int2 st = __ldg(w.steps + i_begin);
+        int2 nx = (i_begin + 1 < i_end) ? __ldg(w.steps + i_begin + 1) : make_int2(0, 0);
+        __syncthreads();                      // previous (class, tile): every read of the ring is complete
+        if (tid == 0) stage_step(cat, tile, st, n_step);
+        // fetched one step ahead: a leaf's state code, or (contractions) the generation bit the child's words must carry
+        auto step_aux = [&](int2 q) -> int {
+            const int ch = q.x & WALK_ID_MASK;
+            if (ch < a.L) return __ldg(a.leaf + (size_t)ch * Sp + s);
+            return (q.x & WALK_WAIT) ? __ldg(w.gen + (size_t)cat * a.I + (ch - a.L)) : 0;
+        };
+        int next_code = step_aux(st);
         for (int i = i_begin; i < i_end; i++) {
             const int enc = st.x;
             const int child = enc & WALK_ID_MASK;
             const int par = st.y & WALK_ID_MASK;
             const int flags = st.y;
             const int code = next_code;
-            const int4 nx2 = (i + 2 < i_end) ? __ldg(w.steps + i + 2) : make_int4(0, 0, -1, 0);   // descriptors run two steps ahead
+            const uint32_t tagbit = (flags & STEP_LAST) ? ((uint32_t)__ldg(w.gen + (size_t)cat * a.I + par) << 31) : 0u;   // used at the end
+            const bool has_next = (i + 1 < i_end);
+            const int2 nx2 = (i + 2 < i_end) ? __ldg(w.steps + i + 2) : make_int2(0, 0);   // descriptors run two steps ahead
             const bool tr = w.trace && tid == 0 && (int)blockIdx.x == w.trace_cta;
             long long *trp = tr ? w.trace + (size_t)(i - i_begin) * 12 : nullptr;
             if (tr) { trp[0] = ((long long)st.x << 32) | (unsigned)st.y; trp[1] = clock64(); }
-            if (i + 1 < i_end) next_code = leaf_code(cat, nx, s);
+            __syncthreads();                  // (1) everyone is done with step i-1: ring slot (n_step+1)&1 is free
+            if (has_next) {
+                if (tid == 0) stage_step(cat, tile, nx, n_step + 1);
+                next_code = step_aux(nx);
+            }
             if ((flags & STEP_FIRST) && !(enc & WALK_CHAIN)) {
 #pragma unroll
                 for (int k = 0; k < 64; k++) v[k] = 1.f;
                 ex = 0;
             }
-            const float *tab = table_of(cat, child);                               // P^T table of this branch (global, via L1)
+            const float *tab = stage_base + (n_step & 1u) * WALK_STAGE_FLOATS;     // P^T table of this branch
             if (tr) trp[2] = clock64();
             if (child < a.L) {
+                mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
+                if (tr) trp[3] = clock64();
                 if (code >= 0) {
-                    const float4 *row = reinterpret_cast<const float4 *>(tab + code * TC_PTF_ROW);
+                    const float4 *row = reinterpret_cast<const float4 *>(tab + code * WALK_PT_ROW);
 #pragma unroll
                     for (int q = 0; q < 16; q++) {
-                        const float4 rr = __ldg(row + q);
+                        const float4 rr = row[q];
                         v[4 * q] *= rr.x; v[4 * q + 1] *= rr.y; v[4 * q + 2] *= rr.z; v[4 * q + 3] *= rr.w;
                     }
                 } else {
@@ -511,10 +515,10 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                     const double *amb = a.ambig + (size_t)(-code - 1) * 64;
                     for (int jj = 0; jj < a.D; jj++) {
                         if (__ldg(amb + jj) != 0.0) {
-                            const float4 *row = reinterpret_cast<const float4 *>(tab + jj * TC_PTF_ROW);
+                            const float4 *row = reinterpret_cast<const float4 *>(tab + jj * WALK_PT_ROW);
 #pragma unroll
                             for (int q = 0; q < 16; q++) {
-                                const float4 rr = __ldg(row + q);
+                                const float4 rr = row[q];
                                 acc[4 * q] += rr.x; acc[4 * q + 1] += rr.y; acc[4 * q + 2] += rr.z; acc[4 * q + 3] += rr.w;
                             }
                         }
@@ -522,13 +526,12 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
 #pragma unroll
                     for (int k = 0; k < 64; k++) v[k] *= acc[k];
                 }
-                if (tr) trp[3] = clock64();
             } else {
                 const int cin = child - a.L;
                 // Anchors without a serial dependency: one independent compare per element builds a 64-bit mask and
                 // zeroes the element in the tensor operand; the (few) set bits are then enumerated with ffs and their
                 // values re-read from the child's conditional block in L2 (the row this thread itself loaded or, on a
-                // chain, stored a moment ago).
+                // chain, stored a moment ago), eight loads in flight.
                 uint32_t am0 = 0, am1 = 0, am2 = 0, am3 = 0;
                 const float4 *xrow = cond4 + cond_f4(cat, cin, tile, 0, tid, a.I, w.T);
                 {
@@ -546,29 +549,45 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                             lo[k] = __float_as_uint(x - h);
                         }
                     } else {
-                        if (enc & WALK_WAIT) {
-                            const int *flag = w.done + ((size_t)cat * a.I + cin) * w.T + tile;
-                            int it = 0;
-                            while (!bailed && ld_acquire(flag) < w.epoch) {
-                                if (++it > (1 << 21)) { atomicExch(a.err, 2); bailed = true; }   // never hang the GPU
+                        // A child produced by another lane during THIS launch is awaited on the data itself: every word
+                        // must carry the generation bit of this pass (sign bit of a conditional, bit 0 of the exponent
+                        // word).  Other children are resident; their bits are whatever pass produced them and are ignored.
+                        const bool await = (enc & WALK_WAIT) != 0;
+                        const uint32_t want = await ? ((uint32_t)code << 31) : 0u;
+                        const int *scp = a.scal + ((size_t)cat * a.I + cin) * Sp + s;
+                        uint4 x4[16];
+                        uint32_t sc;
+#pragma unroll
+                        for (int q = 0; q < 16; q++) x4[q] = __ldcg(reinterpret_cast<const uint4 *>(xrow + (size_t)q * 128));
+                        sc = (uint32_t)__ldcg(scp);
+                        if (await) {
+                            for (int it = 0; !bailed; it++) {
+                                uint32_t bad = (sc << 31) ^ want;
+#pragma unroll
+                                for (int q = 0; q < 16; q++) bad |= (x4[q].x ^ want) | (x4[q].y ^ want) | (x4[q].z ^ want) | (x4[q].w ^ want);
+                                if (!(bad >> 31)) break;
+                                if (it > (1 << 18)) { atomicExch(a.err, 2); bailed = true; }   // never hang the GPU
+#pragma unroll
+                                for (int q = 0; q < 16; q++) x4[q] = ld_relaxed_u4(xrow + (size_t)q * 128);
+                                sc = ld_relaxed_u32(scp);
                             }
                         }
 #pragma unroll
                         for (int q = 0; q < 16; q++) {
-                            const float4 x4 = __ldcg(xrow + (size_t)q * 128);      // may have been produced by another SM in this launch
-                            float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+                            const uint32_t xs[4] = {x4[q].x, x4[q].y, x4[q].z, x4[q].w};
 #pragma unroll
                             for (int u = 0; u < 4; u++) {
                                 const int kq = 4 * q + u;
-                                const bool big = xs[u] >= TC_ANCHOR_THR;
+                                const float xv = __uint_as_float(xs[u] & 0x7fffffffu);
+                                const bool big = xv >= TC_ANCHOR_THR;
                                 if (big) { if (kq < 16) am0 |= 1u << kq; else if (kq < 32) am1 |= 1u << (kq - 16); else if (kq < 48) am2 |= 1u << (kq - 32); else am3 |= 1u << (kq - 48); }
-                                const float x = big ? 0.f : xs[u];
+                                const float x = big ? 0.f : xv;
                                 const float h = tf32_rn(x);
                                 hi[kq] = __float_as_uint(h);
                                 lo[kq] = __float_as_uint(x - h);
                             }
                         }
-                        ex += __ldcg(a.scal + ((size_t)cat * a.I + cin) * Sp + s);
+                        ex += (int)sc >> 1;
                     }
                     if (tr) trp[8] = clock64();
 #pragma unroll
@@ -580,9 +599,23 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     if (tr) trp[10] = clock64();
                 }
+                unsigned long long amask = (unsigned long long)(am0 | (am1 << 16)) | ((unsigned long long)(am2 | (am3 << 16)) << 32);
+                int ak[WALK_FAST_ANCHORS];
+                float av[WALK_FAST_ANCHORS];
+                const float *xrow_f = reinterpret_cast<const float *>(xrow);
+#pragma unroll
+                for (int ai = 0; ai < WALK_FAST_ANCHORS; ai++) {
+                    ak[ai] = -1; av[ai] = 0.f;
+                    if (amask) {
+                        const int kk = __ffsll((long long)amask) - 1;
+                        amask &= amask - 1;
+                        ak[ai] = kk;
+                        av[ai] = __ldcg(xrow_f + ((size_t)(kk >> 2) * 128) * 4 + (kk & 3));   // sign bit = tag: stripped at the use, so the load stays in flight
+                    }
+                }
                 if (tr) trp[3] = clock64();
                 tc_fence_before();
-                __syncthreads();             // the step's only CTA barrier: A operand complete in TMEM; previous D read by all
+                __syncthreads();             // (2) A operand complete in TMEM; every thread is done reading the previous D
                 if (tr) trp[4] = clock64();
                 if (lane == 0 && warp < 2) {
                     // One thread issues a tcgen05.mma only every ~100-190 cycles (tools/tc_mma_timing.cu: 24 MMAs take 4770
@@ -591,11 +624,10 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                     // 192..255) in a fixed order (small terms first), so the result is bit-reproducible; D0 + D1 is formed
                     // in registers after the read-back.
                     tc_fence_after();
-                    mbar_wait(bar_full + (n_int & 1u), (n_int >> 1) & 1u, a.err);
+                    mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
                     if (tr) trp[5] = clock64();
-                    const float *bs = Bs + (n_int & 1u) * TC_PB_FLOATS;
-                    const uint64_t bdesc_hi = make_b_desc(smem_u32(bs));
-                    const uint64_t bdesc_lo = make_b_desc(smem_u32(bs + 4096));
+                    const uint64_t bdesc_hi = make_b_desc(smem_u32(tab + 64 * WALK_PT_ROW));
+                    const uint64_t bdesc_lo = make_b_desc(smem_u32(tab + 64 * WALK_PT_ROW + 4096));
                     const uint32_t dcol = warp ? 192u : 0u;
 #pragma unroll
                     for (int j = 0; j < 4; j++) { const int kk = 2 * j + warp; tc_mma_tf32_ts(tmem_base + dcol, tmem_base + 128 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, j > 0); }
@@ -606,30 +638,38 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                     tc_commit(bar_mma);
                 }
                 __syncwarp();
-                // anchors on the CUDA cores while the tensor core works: values from L2, rows of the P^T table through L1
+                // anchors on the CUDA cores while the tensor core works (rows of the P^T table in shared memory)
                 float acc[64];
 #pragma unroll
                 for (int k = 0; k < 64; k++) acc[k] = 0.f;
-                {
-                    unsigned long long amask = (unsigned long long)(am0 | (am1 << 16)) | ((unsigned long long)(am2 | (am3 << 16)) << 32);
-                    const float *xrow_f = reinterpret_cast<const float *>(xrow);
-                    while (amask) {
-                        const int kk = __ffsll((long long)amask) - 1;
-                        amask &= amask - 1;
-                        const float xv = __ldcg(xrow_f + ((size_t)(kk >> 2) * 128) * 4 + (kk & 3));
-                        const float4 *row = reinterpret_cast<const float4 *>(tab + kk * TC_PTF_ROW);
+                mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
+#pragma unroll
+                for (int ai = 0; ai < WALK_FAST_ANCHORS; ai++) {
+                    if (ak[ai] >= 0) {
+                        const float xv = fabsf(av[ai]);
+                        const float4 *row = reinterpret_cast<const float4 *>(tab + ak[ai] * WALK_PT_ROW);
 #pragma unroll
                         for (int q = 0; q < 16; q++) {
-                            const float4 rr = __ldg(row + q);
+                            const float4 rr = row[q];
                             acc[4 * q] = fmaf(xv, rr.x, acc[4 * q]); acc[4 * q + 1] = fmaf(xv, rr.y, acc[4 * q + 1]);
                             acc[4 * q + 2] = fmaf(xv, rr.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(xv, rr.w, acc[4 * q + 3]);
                         }
                     }
                 }
-                mbar_wait(bar_mma, n_int & 1u, a.err);
+                while (amask) {                  // more than TC_MAX_ANCHORS entries above the threshold (diffuse vectors): rare
+                    const int kk = __ffsll((long long)amask) - 1;
+                    amask &= amask - 1;
+                    const float xv = fabsf(__ldcg(xrow_f + ((size_t)(kk >> 2) * 128) * 4 + (kk & 3)));
+                    const float4 *row = reinterpret_cast<const float4 *>(tab + kk * WALK_PT_ROW);
+#pragma unroll
+                    for (int q = 0; q < 16; q++) {
+                        const float4 rr = row[q];
+                        acc[4 * q] = fmaf(xv, rr.x, acc[4 * q]); acc[4 * q + 1] = fmaf(xv, rr.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(xv, rr.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(xv, rr.w, acc[4 * q + 3]);
+                    }
+                }
+                mbar_wait(bar_mma, n_mma & 1u, a.err);
                 if (tr) trp[6] = clock64();
-                // the tensor core was the only reader of this ring slot: refill it with the contraction two ahead
-                if (tid == 0 && st.z >= 0) stage_pb(cat, tile, st.z, n_int + 2);
                 tc_fence_after();
 #pragma unroll
                 for (int o = 0; o < 64; o += 16) {
@@ -640,28 +680,26 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
 #pragma unroll
                     for (int k = 0; k < 16; k++) v[o + k] *= ((__uint_as_float(d[k]) + __uint_as_float(d1[k])) + acc[o + k]);
                 }
-                n_int++;
+                n_mma++;
             }
             renorm_f32(v, ex, (flags & STEP_LAST) != 0);
+            n_step++;
             if (flags & STEP_LAST) {
-                // this tile of the parent: conditionals, exponent, (root reduction); epoch flag only if another lane consumes it
+                // this tile of the parent: conditionals and exponent, every word tagged with the node's generation bit
+                // (consumers in other lanes poll the data itself: no flag, no fence, no barrier); root reduction
                 float4 *outp = cond4 + cond_f4(cat, par, tile, 0, tid, a.I, w.T);
 #pragma unroll
-                for (int q = 0; q < 16; q++) __stcg(outp + (size_t)q * 128, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-                __stcg(a.scal + ((size_t)cat * a.I + par) * Sp + s, ex);
+                for (int q = 0; q < 16; q++)
+                    __stcg(reinterpret_cast<uint4 *>(outp + (size_t)q * 128),
+                           make_uint4(__float_as_uint(v[4 * q]) | tagbit, __float_as_uint(v[4 * q + 1]) | tagbit,
+                                      __float_as_uint(v[4 * q + 2]) | tagbit, __float_as_uint(v[4 * q + 3]) | tagbit));
+                __stcg(a.scal + ((size_t)cat * a.I + par) * Sp + s, (int)(((uint32_t)ex << 1) | (tagbit >> 31)));
                 if (par == a.I - 1) {
                     double rr = 0.0;
 #pragma unroll
                     for (int k = 0; k < 64; k++) rr = fma((double)v[k], a.pi[k], rr);
                     a.rootL[(size_t)cat * Sp + s] = rr;
                     a.rootE[(size_t)cat * Sp + s] = ex;
-                }
-                if (flags & STEP_PUBLISH) {
-                    __syncthreads();
-                    if (tid == 96) {
-                        __threadfence();
-                        st_release(w.done + ((size_t)cat * a.I + par) * w.T + tile, w.epoch);
-                    }
                 }
             }
             if (tr) trp[7] = clock64();
@@ -676,5 +714,5 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
     }
 }
 
-}  // namespace hb2
 
+}  // namespace hb2
