@@ -119,6 +119,8 @@ struct hb2_partition {
     bool expm_dfma = false;                   // HB2_EXPM_DFMA=1: previous FFMA-style fp64 expm kernel (A/B testing)
     bool use_walk = false;
     int walk_max_resident = 0;
+    std::vector<char> plan_dirty;       // cached walk plan (h_walk holds its steps): dirty set, lane count, step count
+    int plan_K = 0, plan_steps = 0;
     std::vector<int> walk_gen;          // [C][I] generation bit of each node's resident conditionals (tc walk path)
     bool walk_reset = false;            // a pass was aborted: tags are inconsistent -> wipe and recompute everything
     int *d_walk = nullptr, *h_walk = nullptr;
@@ -311,36 +313,74 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
     const int nslots = (K == 1) ? std::min(CT, p->walk_max_resident) : CT;
     std::vector<char> dirty(I, 0);
     for (auto &lv : levels) for (int n : lv) dirty[n] = 1;
-    std::vector<int> lane_of(I, -1), lane_last(K, -1), lane_total(K, 0);
+    int *buf = p->h_walk;                        // lane_start[K+1] | steps (int2, from int offset 16) | generation bits
+    int ns = p->plan_steps;
+    // the plan depends on the tree, the dirty set and K only: optimisers re-evaluate the same set again and again
+    const bool reuse = p->plan_steps > 0 && p->plan_K == K && p->plan_dirty == dirty;
+    if (!reuse) {
+    // Lane assignment = list scheduling of the dirty subtree on K in-order lanes with a rough cost model (cycles measured
+    // with HB2_WALK_TRACE, profiles/): the pass is bound by the busiest lane or by the deepest root path, so nodes are
+    // handed out longest-remaining-path first to whichever lane is free first, and a node whose internal child was the
+    // lane's previous job continues there (register hand-over: the cheapest kind of step).  Every lane executes its nodes
+    // in the order they were scheduled and a node is scheduled only after its children, so cross-lane waits cannot cycle.
+    const double C_LEAF = 1.8e3, C_CHAIN = 4.7e3, C_INT = 7.0e3, C_NODE = 1.0e3, C_XFER = 1.5e3;
+    std::vector<int> lane_of(I, -1), lane_last(K, -1), chain_child(I, -1);
     std::vector<std::vector<int>> lanes(K);
-    std::vector<int> chain_child(I, -1);
-    for (auto &lv : levels) {
-        if (lv.empty()) continue;
-        std::vector<int> lvl_count(K, 0);
-        const int cap = ((int)lv.size() + K - 1) / K;
-        for (int n : lv) {
-            // preferred lane: the one whose last job is this node's highest dirty internal child (register hand-over)
-            int best = -1, best_h = -1;
+    {
+        std::vector<double> base(I, 0.0), tail(I, 0.0), finish(I, 0.0), lane_time(K, 0.0);
+        std::vector<int> pending(I, 0);          // dirty internal children not yet scheduled
+        std::vector<int> ready;
+        for (int n = 0; n < I; n++) {
+            if (!dirty[n]) continue;
+            base[n] = C_NODE;
             for (int ch : p->children[n]) {
-                if (ch < L) continue;
-                const int ci = ch - L;
-                if (dirty[ci] && lane_of[ci] >= 0 && lane_last[lane_of[ci]] == ci && p->height[ci] > best_h) { best = ci; best_h = p->height[ci]; }
+                base[n] += ch < L ? C_LEAF : C_INT;
+                if (ch >= L && dirty[ch - L]) pending[n]++;
             }
-            int lane = -1;
-            if (best >= 0 && lvl_count[lane_of[best]] < cap) { lane = lane_of[best]; chain_child[n] = best; }
-            if (lane < 0) {
-                for (int r = 0; r < K; r++)
-                    if (lane < 0 || lvl_count[r] < lvl_count[lane] || (lvl_count[r] == lvl_count[lane] && lane_total[r] < lane_total[lane])) lane = r;
+        }
+        for (int h = (int)levels.size() - 1; h >= 0; h--)       // parents before children: remaining path to the root
+            for (int n : levels[h]) {
+                const int64_t par = p->parents[L + n];
+                tail[n] = base[n] + ((par >= 0 && dirty[par]) ? tail[par] : 0.0);
             }
-            lane_of[n] = lane; lane_last[lane] = n; lvl_count[lane]++; lane_total[lane]++;
-            lanes[lane].push_back(n);
+        for (int n = 0; n < I; n++) if (dirty[n] && pending[n] == 0) ready.push_back(n);
+        for (int done = 0; done < total; done++) {
+            // the (node, lane) pair that can START first; ties go to the longer remaining path, then to the lower lane
+            int best = -1, best_r = 0; double best_start = 0.0;
+            for (int n : ready) {
+                for (int r = 0; r < K; r++) {
+                    double est = lane_time[r];
+                    for (int ch : p->children[n]) {
+                        if (ch < L || !dirty[ch - L]) continue;
+                        est = std::max(est, finish[ch - L] + (lane_of[ch - L] == r ? 0.0 : C_XFER));
+                    }
+                    if (best < 0 || est < best_start || (est == best_start && tail[n] > tail[best])) { best = n; best_r = r; best_start = est; }
+                }
+            }
+            const int n = best, r = best_r;
+            double cost = base[n];
+            for (int ch : p->children[n])
+                if (ch >= L && dirty[ch - L] && lane_last[r] == ch - L) { chain_child[n] = ch - L; cost -= C_INT - C_CHAIN; break; }
+            finish[n] = best_start + cost;
+            lane_time[r] = finish[n];
+            lane_of[n] = r; lane_last[r] = n;
+            lanes[r].push_back(n);
+            ready.erase(std::find(ready.begin(), ready.end(), n));
+            const int64_t par = p->parents[L + n];
+            if (par >= 0 && dirty[par] && --pending[par] == 0) ready.push_back((int)par);
+        }
+        if (getenv("HB2_DEBUG")) {
+            double mx = 0; for (double t : lane_time) mx = std::max(mx, t);
+            double deepest = 0; for (int n = 0; n < I; n++) if (dirty[n] && pending[n] == 0) deepest = std::max(deepest, tail[n]);
+            fprintf(stderr, "[hb2] walk schedule: modelled makespan %.0f cycles, deepest root path %.0f, lanes (nodes/cycles):", mx, deepest);
+            for (int r = 0; r < K; r++) fprintf(stderr, " %zu/%.0f", lanes[r].size(), lane_time[r]);
+            fprintf(stderr, "\n");
         }
     }
     // flatten every lane into steps (one per child): chain child first, then leaves, then the other internal children
-    int *buf = p->h_walk;
     int *lane_start = buf;                       // [K+1], steps start at int offset 16 (int2-aligned)
     int *steps = buf + 16;
-    int ns = 0;
+    ns = 0;
     for (int r = 0; r < K; r++) {
         lane_start[r] = ns;
         for (int n : lanes[r]) {
@@ -358,6 +398,8 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
         }
     }
     lane_start[K] = ns;
+    p->plan_steps = ns; p->plan_K = K; p->plan_dirty = dirty;
+    }   // !reuse
     // generation bits: every node re-pruned by this pass flips its bit (per class); the kernel tags what it writes with the
     // new bit and awaits cross-lane children on it.  The table travels behind the steps.
     for (int c = cat0; c < cat0 + ncls; c++)
@@ -404,9 +446,9 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
         cudaFree(d_trace);
         if (FILE *f = fopen(trace_path, "w")) {
             const int r = w.trace_cta % K;
-            fprintf(f, "# cta %d lane %d steps %d..%d ; columns: child_enc parent_flags t_begin bar1 staged/ready tableready|split bar2 bfull mma_done end (cycles rel. to first)\n", w.trace_cta, r, lane_start[r], lane_start[r + 1]);
+            fprintf(f, "# cta %d lane %d steps %d..%d ; columns: child_enc parent_flags t_begin bar1 staged/ready tableready|split bar2 bfull mma_done end (cycles rel. to first)\n", w.trace_cta, r, buf[r], buf[r + 1]);
             const long long t00 = ht[1];
-            for (int i = 0; i < lane_start[r + 1] - lane_start[r]; i++) {
+            for (int i = 0; i < buf[r + 1] - buf[r]; i++) {
                 const long long *q = ht.data() + (size_t)i * 12;
                 fprintf(f, "%d 0x%x 0x%x", i, (unsigned)(q[0] >> 32), (unsigned)(q[0] & 0xffffffff));
                 for (int c = 1; c < 12; c++) fprintf(f, " %lld", q[c] ? q[c] - t00 : -1LL);

@@ -6,7 +6,7 @@ timeout 600 python tools/stress_determinism.py 4 > gpurun_out/${TAG}_stress.log 
 timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/${TAG}_pytest.log
 timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
 timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --emulate-shard 0/8 > gpurun_out/${TAG}_bench_s8.json 2> gpurun_out/${TAG}_bench_s8.err; echo "bench shard rc=$?"
-for c in 2; do timeout 200 python tools/trace_walk.py $c > gpurun_out/trace_$c.log 2>&1; echo "cta $c rc=$?"; cp gpurun_out/walk_trace_cta$c.txt gpurun_out/${TAG}_walk_trace_cta$c.txt; done
+for c in 0 1 2 3; do HB2_DEBUG=1 timeout 200 python tools/trace_walk.py $c > gpurun_out/trace_$c.log 2>&1; echo "cta $c rc=$?"; cp gpurun_out/walk_trace_cta$c.txt gpurun_out/${TAG}_walk_trace_cta$c.txt; done
 python - <<PY
 import json
 for f in ['gpurun_out/${TAG}_bench.json','gpurun_out/${TAG}_bench_s8.json']:
