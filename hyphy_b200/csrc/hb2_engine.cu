@@ -428,19 +428,21 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
     w.lane_start = p->d_walk; w.steps = reinterpret_cast<const int2 *>(p->d_walk + 16);
     w.gen = p->d_walk + gen_off; w.K = K; w.T = T; w.ncls = ncls; w.nslots = nslots;
     if (getenv("HB2_DEBUG")) fprintf(stderr, "[hb2] walk: jobs=%d steps=%d K=%d T=%d ncls=%d nslots=%d grid=%d resident=%d\n", total, ns, K, T, ncls, nslots, nslots * K, p->walk_max_resident);
-    w.trace = nullptr; w.trace_cta = 0;
+    w.trace = nullptr; w.trace_cta = 0; w.trace_cta_times = nullptr;
     const char *trace_path = getenv("HB2_WALK_TRACE");
     long long *d_trace = nullptr;
     if (trace_path) {          // bring-up aid: per-step clock stamps of one CTA -> text file
         const char *tc = getenv("HB2_WALK_TRACE_CTA");
         w.trace_cta = tc ? atoi(tc) : 0;
-        CU(cudaMalloc(&d_trace, (size_t)(ns + 1) * 12 * sizeof(long long)));
-        CU(cudaMemsetAsync(d_trace, 0, (size_t)(ns + 1) * 12 * sizeof(long long), p->stream));
+        const size_t tr_n = (size_t)(ns + 1) * 12 + (size_t)nslots * K * 4;
+        CU(cudaMalloc(&d_trace, tr_n * sizeof(long long)));
+        CU(cudaMemsetAsync(d_trace, 0, tr_n * sizeof(long long), p->stream));
         w.trace = d_trace;
+        w.trace_cta_times = d_trace + (size_t)(ns + 1) * 12;
     }
     hb2::prune64_tc_walk_kernel<<<nslots * K, 128, hb2::WALK_SMEM_BYTES, p->stream>>>(w);
     if (d_trace) {
-        std::vector<long long> ht((size_t)(ns + 1) * 12);
+        std::vector<long long> ht((size_t)(ns + 1) * 12 + (size_t)nslots * K * 4);
         CU(cudaStreamSynchronize(p->stream));
         CU(cudaMemcpy(ht.data(), d_trace, ht.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(d_trace);
@@ -453,6 +455,13 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
                 fprintf(f, "%d 0x%x 0x%x", i, (unsigned)(q[0] >> 32), (unsigned)(q[0] & 0xffffffff));
                 for (int c = 1; c < 12; c++) fprintf(f, " %lld", q[c] ? q[c] - t00 : -1LL);
                 fprintf(f, "\n");
+            }
+            {   // per-CTA residence: "# C <block> <smid> <cycles> <start ns rel. to the earliest CTA>"
+                const long long *ct = ht.data() + (size_t)(ns + 1) * 12;
+                long long g0 = ct[3];
+                for (int b = 0; b < nslots * K; b++) g0 = std::min(g0, ct[(size_t)b * 4 + 3]);
+                for (int b = 0; b < nslots * K; b++)
+                    fprintf(f, "# C %d %lld %lld %lld\n", b, ct[(size_t)b * 4], ct[(size_t)b * 4 + 2] - ct[(size_t)b * 4 + 1], ct[(size_t)b * 4 + 3] - g0);
             }
             fclose(f);
         }

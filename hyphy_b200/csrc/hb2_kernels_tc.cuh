@@ -382,7 +382,8 @@ struct WalkArgs {
     const int2 *steps;
     const int *gen;             // [C][I] generation bit of every node's conditionals AFTER this pass (see "tags" above)
     int K, T, ncls, nslots;
-    long long *trace;           // nullable debug buffer: 8 clock64 stamps per step of CTA `trace_cta` (HB2_WALK_TRACE)
+    long long *trace;           // nullable debug buffer: 12 clock64 stamps per step of CTA `trace_cta` (HB2_WALK_TRACE)
+    long long *trace_cta_times; // nullable: per CTA {smid, clock64 at entry, clock64 at exit, globaltimer at entry}
     int trace_cta;
 };
 
@@ -439,6 +440,13 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
 
     const int r = blockIdx.x % w.K;
     const int i_begin = w.lane_start[r], i_end = w.lane_start[r + 1];
+    if (w.trace_cta_times && tid == 0) {
+        uint32_t smid; unsigned long long gt;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        long long *q = w.trace_cta_times + (size_t)blockIdx.x * 4;
+        q[0] = smid; q[1] = clock64(); q[3] = (long long)gt;
+    }
 
     // thread 0: stage the operands of one step into ring slot (m & 1): two flat bulk copies + one L2 prefetch
     auto stage_step = [&](int cat, int tile, int2 st, uint32_t m) {
@@ -707,6 +715,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
             nx = nx2;
         }
     }
+    if (w.trace_cta_times && tid == 0) w.trace_cta_times[(size_t)blockIdx.x * 4 + 2] = clock64();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
