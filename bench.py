@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fp64", action="store_true", help="force the fp64 pruning kernels (HB2_FLAG_FORCE_FP64)")
+    ap.add_argument("--no-class-groups", action="store_true", help="multi-GPU: shard patterns only (every rank exponentiates every class)")
     ap.add_argument("--emulate-shard", default="", help="debug: R/W -> run rank R's pattern shard of a W-rank job on one GPU, no collectives")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -199,8 +200,12 @@ def main():
 
     w = synth.codon_workload(WORKLOAD["taxa"], WORKLOAD["codons"], WORKLOAD["classes"])
     S = w.S
-    from hyphy_b200.sharding import shard_bounds, exchange_unique_id
-    lo, hi = shard_bounds(S, world, rank)            # contiguous pattern shards, balanced by count
+    from hyphy_b200.sharding import shard_bounds, exchange_unique_id, layout
+    # (pattern shards) x (class groups): classes first (no replicated expm inside a shard), patterns for the rest
+    lay = layout(world, rank, w.C, S)
+    if args.no_class_groups:
+        lay = {"groups": 1, "group": 0, "shards": world, "shard": rank, "patterns": shard_bounds(S, world, rank), "classes": (0, w.C)}
+    lo, hi = lay["patterns"]
     if args.emulate_shard:
         er, ew = (int(x) for x in args.emulate_shard.split("/"))
         lo, hi = shard_bounds(S, ew, er)
@@ -208,6 +213,8 @@ def main():
                             pattern_slice=slice(lo, hi) if (world > 1 or args.emulate_shard) else None)
     if world > 1:
         lf.part.comm_init(world, rank, exchange_unique_id(dist, rank, Partition.comm_unique_id))
+        if lay["groups"] > 1:
+            lf.part.comm_class_groups(lay["groups"])
 
     def barrier():
         if dist is not None:
@@ -320,7 +327,7 @@ def main():
                 "dtype": "tf32x3 (tcgen05, fp32 accumulate) pruning + f64 expm/root" if tc_mode else "f64",
                 "data": "synthetic",
                 "config": {"workload": NAME, "patterns": S, "branches": w.tree.n_branches, "states": w.D, "classes": w.C,
-                           "sharding": f"patterns/{world}", "l2": "inputs larger than L2 (830 MB of conditionals per evaluation)"},
+                           "sharding": f"patterns/{lay['shards']} x classes/{lay['groups']}", "l2": "inputs larger than L2 (830 MB of conditionals per evaluation)"},
                 "e2e": {"value": 1000.0 / e2e_ms, "unit": "evals/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                         "api": "hb2_set_matrices_compiled x C + hb2_evaluate_classes"},
                 "e2e_dense": {"value": 1000.0 / e2e_dense_ms, "unit": "evals/s", "ms_per_step": e2e_dense_ms, "h2d_bytes_per_step": h2d_dense,

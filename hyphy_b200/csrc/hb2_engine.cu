@@ -46,6 +46,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool load() {
@@ -59,9 +60,10 @@ struct NcclApi {
         GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
         CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
         AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+        AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
         CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
         GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
-        return GetUniqueId && CommInitRank && AllReduce && CommDestroy && GetErrorString;
+        return GetUniqueId && CommInitRank && AllReduce && AllGather && CommDestroy && GetErrorString;
     }
 } g_nccl;
 
@@ -129,7 +131,10 @@ struct hb2_partition {
     std::vector<char> evaluated_cat;          // [C] whole tree pruned at least once
     int64_t launches = 0;
     ncclComm_t comm = nullptr;
-    int n_ranks = 1;
+    int n_ranks = 1, rank = 0;
+    // class groups (hb2_comm_class_groups): this rank prunes classes [own0, own0 + ownN) only
+    int cg_G = 1, cg_g = 0, own0 = 0, ownN = 0, xchg_len = 0;
+    double *d_xsend = nullptr, *d_xrecv = nullptr, *d_xfreq = nullptr, *d_xpartial = nullptr;
     int n_partial_blocks = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_staging = nullptr;
@@ -250,6 +255,7 @@ int stage_matrix(hb2_partition *p, int64_t cat, int64_t node, const double *M, i
     if (cat >= p->C) return fail("rate class %lld out of range (C=%lld)", (long long)cat, (long long)p->C);
     if (node < 0 || node >= p->B) return fail("node id %lld has no branch (valid 0..%lld)", (long long)node, (long long)p->B - 1);
     if (kind != HB2_MATRIX_RATE && kind != HB2_MATRIX_TRANS) return fail("unknown matrix kind %d", kind);
+    if (cat < p->own0 || cat >= p->own0 + p->ownN) { p->have_matrix[cat * p->B + node] = 1; return 0; }   // another class group's
     if (p->n_pending == p->q_capacity) {
         cudaSetDevice(p->device);
         if (flush_matrices(p)) return 1;
@@ -521,6 +527,23 @@ int run_root(hb2_partition *p, int c0, int nc, bool use_weights, bool want_sites
     c.partial = p->d_partial; c.flag = p->d_flag; c.siteL = want_sites ? p->d_siteL : nullptr;
     c.siteScale = want_sites ? p->d_siteScale : nullptr;
     c.Sp = (int)p->Sp; c.S = (int)p->S; c.c0 = c0; c.nc = nc;
+    if (p->cg_G > 1) {
+        // class groups: partial over the owned classes into this rank's slot of a buffer that is zero elsewhere; ONE sum
+        // all-reduce then acts as the gather (small-message latency, no second collective: every rank merges every
+        // shard and holds the complete lnL)
+        const int xs = p->xchg_len, N = p->n_ranks;
+        hb2::class_partial_kernel<<<(xs + 255) / 256, 256, 0, p->stream>>>(p->d_rootL, p->d_rootE, p->d_weights, (int)p->Sp, (int)p->S,
+                                                                          p->own0, p->ownN, p->d_xsend + (size_t)p->rank * 2 * xs, xs);
+        ncclResult_t r = g_nccl.AllReduce(p->d_xsend, p->d_xrecv, (size_t)2 * xs * N, ncclDouble, ncclSum, p->comm, p->stream);
+        if (r != ncclSuccess) return fail("ncclAllReduce (class partials): %s", g_nccl.GetErrorString(r));
+        const int nblk = (N / p->cg_G * xs + 255) / 256;
+        hb2::class_merge_kernel<<<nblk, 256, 0, p->stream>>>(p->d_xrecv, p->d_xfreq, xs, N / p->cg_G, p->cg_G, p->rank / p->cg_G, p->d_xpartial,
+                                                             p->d_flag, c.siteL, c.siteScale, (int)p->S);
+        hb2::final_sum_kernel<<<1, 256, 0, p->stream>>>(p->d_xpartial, nblk, p->d_flag, p->d_lnL);
+        p->launches += 3;
+        CU(cudaGetLastError());
+        return 0;
+    }
     hb2::combine_kernel<<<p->n_partial_blocks, 256, 0, p->stream>>>(c);
     hb2::final_sum_kernel<<<1, 256, 0, p->stream>>>(p->d_partial, p->n_partial_blocks, p->d_flag, p->d_lnL);
     p->launches += 2;
@@ -546,6 +569,12 @@ int evaluate_impl(hb2_partition *p, int c0, int nc, const double *weights, int64
     if (!rootFreqs || !lnL) return fail("rootFreqs and lnL must not be null");
     CU(cudaSetDevice(p->device));
     if (check_ready(p, c0, nc)) return 1;
+    if (p->cg_G > 1) {
+        if (!weights || c0 != 0 || nc != (int)p->C) return fail("with class groups only hb2_evaluate_classes is available");
+        c0 = p->own0;                          // prune the owned classes; the weights of all C classes are still uploaded
+    }
+    const int nw = nc;                         // number of class weights the caller passed
+    if (p->cg_G > 1) nc = p->ownN;
     if (flush_matrices(p)) return 1;
     if (p->walk_reset) {                      // an earlier pass was aborted half-way: its tags are inconsistent
         CU(cudaMemsetAsync(p->d_condf, 0, (size_t)p->C * p->I * p->Sp * 64 * sizeof(float), p->stream));
@@ -558,9 +587,9 @@ int evaluate_impl(hb2_partition *p, int c0, int nc, const double *weights, int64
     // small inputs: pi (padded) and class weights
     double *hs = p->h_small;
     for (int k = 0; k < p->Dp; k++) hs[k] = k < p->D ? rootFreqs[k] : 0.0;
-    if (weights) for (int c = 0; c < nc; c++) hs[p->Dp + c] = weights[c];
+    if (weights) for (int c = 0; c < nw; c++) hs[p->Dp + c] = weights[c];
     CU(cudaMemcpyAsync(p->d_pi, hs, p->Dp * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-    if (weights) CU(cudaMemcpyAsync(p->d_weights, hs + p->Dp, nc * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    if (weights) CU(cudaMemcpyAsync(p->d_weights, hs + p->Dp, nw * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     // classes never pruned before need the whole tree regardless of updateNodes (likefunc.cpp:10965-10967)
     bool all = (updateNodes == nullptr || nUpdate < 0);
     for (int c = c0; c < c0 + nc; c++) if (!p->evaluated_cat[c]) all = true;
@@ -765,6 +794,7 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
     p->have_matrix.assign(C * p->B, 0);
     p->is_rate.assign(C * p->B, 0);
     p->evaluated_cat.assign(C, 0);
+    p->own0 = 0; p->ownN = (int)C;
     *out = p;
     return 0;
 }
@@ -794,6 +824,10 @@ int hb2_set_mixture_matrices(hb2_partition *p, int64_t cat, int64_t n, const int
     if (n < 0 || K < 1 || (n > 0 && (!nodeIds || !M || !w))) return fail("bad mixture arguments");
     if (cat < 0) cat = 0;
     if (cat >= p->C) return fail("rate class %lld out of range", (long long)cat);
+    if (cat < p->own0 || cat >= p->own0 + p->ownN) {       // another class group's
+        for (int64_t i = 0; i < n; i++) if (nodeIds && nodeIds[i] >= 0 && nodeIds[i] < p->B) p->have_matrix[cat * p->B + nodeIds[i]] = 1;
+        return 0;
+    }
     if (n > p->q_capacity) return fail("too many nodes");
     CU(cudaSetDevice(p->device));
     if (flush_matrices(p)) return 1;         // keep ordering with plain matrices staged earlier
@@ -859,8 +893,10 @@ int hb2_set_matrices_compiled(hb2_partition *p, int64_t cat, int64_t n, const in
     if (n < 0 || (n > 0 && (!nodeIds || !formulaValues))) return fail("bad compiled matrix list");
     if (cat < 0) cat = 0;
     if (cat >= p->C) return fail("rate class %lld out of range (C=%lld)", (long long)cat, (long long)p->C);
+    const bool owned = cat >= p->own0 && cat < p->own0 + p->ownN;
     for (int64_t k = 0; k < n; k++) {
         if (nodeIds[k] < 0 || nodeIds[k] >= p->B) return fail("node id %lld has no branch", (long long)nodeIds[k]);
+        if (!owned) { p->have_matrix[cat * p->B + nodeIds[k]] = 1; continue; }   // another class group's
         if (p->n_vpending == p->q_capacity) { cudaSetDevice(p->device); if (flush_compiled(p)) return 1; }
         if (p->staging_busy) { CU(cudaEventSynchronize(p->ev_staging)); p->staging_busy = false; }
         memcpy(p->h_V + p->n_vpending * p->t_nF, formulaValues + k * p->t_nF, p->t_nF * sizeof(double));
@@ -945,7 +981,45 @@ int hb2_comm_init(hb2_partition *p, int nRanks, int rank, const void *uniqueId12
     memcpy(&id, uniqueId128, 128);
     ncclResult_t r = g_nccl.CommInitRank(&p->comm, nRanks, id, rank);
     if (r != ncclSuccess) { p->comm = nullptr; return fail("ncclCommInitRank: %s", g_nccl.GetErrorString(r)); }
-    p->n_ranks = nRanks;
+    p->n_ranks = nRanks; p->rank = rank;
+    return 0;
+}
+
+int hb2_comm_class_groups(hb2_partition *p, int nGroups) {
+    if (!p) return fail("null partition");
+    if (!p->comm) return fail("hb2_comm_class_groups needs hb2_comm_init first");
+    if (nGroups < 1 || p->C % nGroups != 0 || p->n_ranks % nGroups != 0)
+        return fail("class groups: %d must divide both the %lld rate classes and the %d ranks", nGroups, (long long)p->C, p->n_ranks);
+    if (p->n_pending || p->n_vpending) return fail("hb2_comm_class_groups must be called before matrices are set");
+    for (char h : p->have_matrix) if (h) return fail("hb2_comm_class_groups must be called before matrices are set");
+    CU(cudaSetDevice(p->device));
+    p->cg_G = nGroups; p->cg_g = p->rank % nGroups;
+    p->ownN = (int)(p->C / nGroups); p->own0 = p->cg_g * p->ownN;
+    if (nGroups == 1) return 0;
+    // exchange length: the longest padded shard among the ranks (shards of the same communicator may differ in size)
+    int *d_len = nullptr;
+    CU(cudaMalloc(&d_len, sizeof(int)));
+    int len = (int)p->Sp;
+    CU(cudaMemcpyAsync(d_len, &len, sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    ncclResult_t r = g_nccl.AllReduce(d_len, d_len, 1, ncclInt32, ncclMax, p->comm, p->stream);
+    if (r != ncclSuccess) { cudaFree(d_len); return fail("ncclAllReduce(max): %s", g_nccl.GetErrorString(r)); }
+    CU(cudaMemcpyAsync(&len, d_len, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    cudaFree(d_len);
+    p->xchg_len = len;
+    for (double **d : {&p->d_xsend, &p->d_xrecv, &p->d_xfreq, &p->d_xpartial}) if (*d) { cudaFree(*d); *d = nullptr; }
+    const size_t tot = (size_t)2 * len * p->n_ranks;
+    CU(cudaMalloc(&p->d_xsend, tot * sizeof(double)));
+    CU(cudaMalloc(&p->d_xrecv, tot * sizeof(double)));
+    CU(cudaMalloc(&p->d_xfreq, (size_t)len * p->n_ranks * sizeof(double)));
+    CU(cudaMalloc(&p->d_xpartial, ((size_t)len * p->n_ranks / 256 + 2) * sizeof(double)));
+    // pattern frequencies of every rank, gathered once with the same zero-elsewhere sum (d_xsend doubles as scratch)
+    CU(cudaMemsetAsync(p->d_xsend, 0, tot * sizeof(double), p->stream));
+    CU(cudaMemcpyAsync(p->d_xsend + (size_t)p->rank * len, p->d_freq, (size_t)std::min<int64_t>(p->Sp, len) * sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    r = g_nccl.AllReduce(p->d_xsend, p->d_xfreq, (size_t)len * p->n_ranks, ncclDouble, ncclSum, p->comm, p->stream);
+    if (r != ncclSuccess) return fail("ncclAllReduce (frequencies): %s", g_nccl.GetErrorString(r));
+    CU(cudaMemsetAsync(p->d_xsend, 0, tot * sizeof(double), p->stream));     // from now on only this rank's slot is written
+    CU(cudaStreamSynchronize(p->stream));
     return 0;
 }
 
@@ -956,7 +1030,7 @@ void hb2_destroy(hb2_partition *p) {
     if (p->comm) g_nccl.CommDestroy(p->comm);
     void *dev[] = {p->d_leaf, p->d_scal, p->d_rootE, p->d_child_start, p->d_child_ids, p->d_jobs, p->d_dst, p->d_flag,
                    p->d_mix_first, p->d_ambig, p->d_freq, p->d_cond, p->d_PT, p->d_Q, p->d_pi, p->d_rootL, p->d_weights,
-                   p->d_partial, p->d_lnL, p->d_siteL, p->d_mix_w, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_walk, p->d_t_index, p->d_t_formula, p->d_vdst, p->d_t_colfreq, p->d_V};
+                   p->d_partial, p->d_lnL, p->d_siteL, p->d_mix_w, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_xsend, p->d_xrecv, p->d_xfreq, p->d_xpartial, p->d_walk, p->d_t_index, p->d_t_formula, p->d_vdst, p->d_t_colfreq, p->d_V};
     for (void *d : dev) if (d) cudaFree(d);
     if (p->h_Q) cudaFreeHost(p->h_Q);
     if (p->h_small) cudaFreeHost(p->h_small);
@@ -982,7 +1056,7 @@ int hb2_time_resident(hb2_partition *p, const double *weights, const double *roo
     if (flush_matrices(p)) return 1;
     // every slot must hold a resident rate matrix so that the expm stage can be replayed
     std::vector<int> dst;
-    for (int64_t k = 0; k < p->C * p->B; k++) {
+    for (int64_t k = (int64_t)p->own0 * p->B; k < (int64_t)(p->own0 + p->ownN) * p->B; k++) {
         if (!p->is_rate[k]) return fail("hb2_time_resident needs HB2_MATRIX_RATE matrices in every slot");
         dst.push_back((int)k);
     }
@@ -998,11 +1072,11 @@ int hb2_time_resident(hb2_partition *p, const double *weights, const double *roo
     double tot = 0, st[3] = {0, 0, 0};
     for (int it = 0; it < iters; it++) {
         CU(cudaEventRecord(p->ev[0], p->stream));
-        if (launch_expm(p, p->d_Qres, p->d_dst, (int)dst.size(), 0, nullptr, nullptr, nullptr)) return 1;
+        if (launch_expm(p, p->d_Qres + (size_t)p->own0 * p->B * p->D * p->D, p->d_dst, (int)dst.size(), 0, nullptr, nullptr, nullptr)) return 1;
         CU(cudaEventRecord(p->ev[1], p->stream));
-        if (run_pruning(p, 0, (int)p->C, levels)) return 1;
+        if (run_pruning(p, p->own0, p->ownN, levels)) return 1;
         CU(cudaEventRecord(p->ev[2], p->stream));
-        if (run_root(p, 0, (int)p->C, true, false)) return 1;
+        if (run_root(p, p->own0, p->ownN, true, false)) return 1;
         CU(cudaEventRecord(p->ev[3], p->stream));
         CU(cudaEventSynchronize(p->ev[3]));
         float a = 0, b = 0, c = 0;

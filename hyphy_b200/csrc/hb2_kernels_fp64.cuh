@@ -925,6 +925,94 @@ __global__ void __launch_bounds__(256) combine_kernel(CombineArgs a) {
     if (threadIdx.x == 0) a.partial[blockIdx.x] = red[0];
 }
 
+// Class-group sharding (hb2_comm_class_groups): this rank's share of sum_c w_c L_{c,s}, as (value, binary exponent) per
+// pattern, written to send[0..xs) | send[xs..2xs) (exponent as a double; NaN value = numerical failure, value 0 = no
+// positive class likelihood).
+__global__ void __launch_bounds__(256) class_partial_kernel(const double *rootL, const int *rootE, const double *weights,
+                                                            int Sp, int S, int c0, int nc, double *send, int xs) {
+    const int s = blockIdx.x * 256 + threadIdx.x;
+    if (s >= xs) return;
+    double sum = 0.0;
+    int emax = 0;
+    if (s < S) {
+        emax = INT_MIN;
+        bool nan_seen = false;
+        for (int c = 0; c < nc; c++) {
+            const double l = rootL[(size_t)(c0 + c) * Sp + s];
+            if (l != l) nan_seen = true;
+            if (l > 0.0) emax = max(emax, rootE[(size_t)(c0 + c) * Sp + s]);
+        }
+        for (int c = 0; c < nc; c++) {
+            const double l = rootL[(size_t)(c0 + c) * Sp + s];
+            if (l > 0.0) {
+                const int de = rootE[(size_t)(c0 + c) * Sp + s] - emax;
+                sum += weights[c0 + c] * l * (de < -1000 ? 0.0 : exp2i(de));
+            }
+        }
+        if (nan_seen) sum = __longlong_as_double(0x7ff8000000000000LL);
+        if (emax == INT_MIN) emax = 0;
+    }
+    send[s] = sum;
+    send[xs + s] = (double)emax;
+}
+
+// Merges the class-group partials of EVERY pattern shard (gath = gathered buffer, rank-major, 2*xs doubles per rank;
+// the G ranks [j*G, j*G+G) hold the class groups of shard j; xfreq = pattern frequencies of every rank, gathered once)
+// and finishes like combine_kernel.  Every rank therefore ends up with the complete lnL -- bit-identical on all ranks --
+// and no second collective is needed; per-pattern outputs are written for the rank's own shard only.
+__global__ void __launch_bounds__(256) class_merge_kernel(const double *gath, const double *xfreq, int xs, int nShards, int G,
+                                                          int myShard, double *partial, int *flag, double *siteL,
+                                                          long long *siteScale, int S) {
+    __shared__ double red[256];
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    double term = 0.0;
+    if (idx < nShards * xs) {
+        const int j = idx / xs, s = idx % xs;
+        const double f = xfreq[(size_t)j * G * xs + s];
+        int emax = INT_MIN;
+        bool nan_seen = false;
+        for (int r = 0; r < G; r++) {
+            const double *q = gath + (size_t)(j * G + r) * 2 * xs;
+            const double m = q[s];
+            if (m != m) nan_seen = true;
+            if (m > 0.0) emax = max(emax, (int)q[xs + s]);
+        }
+        double sum = 0.0;
+        for (int r = 0; r < G; r++) {
+            const double *q = gath + (size_t)(j * G + r) * 2 * xs;
+            const double m = q[s];
+            if (m > 0.0) {
+                const int de = (int)q[xs + s] - emax;
+                sum += m * (de < -1000 ? 0.0 : exp2i(de));
+            }
+        }
+        if (nan_seen) sum = __longlong_as_double(0x7ff8000000000000LL);
+        if (emax == INT_MIN) emax = 0;
+        double lnl;
+        if (sum > 0.0) lnl = log(sum) + (double)emax * 0.693147180559945309417232121458;
+        else if (sum != sum) lnl = sum;
+        else { lnl = -INFINITY; if (f > 0.0) atomicOr(flag, 1); }
+        term = (f > 0.0) ? f * lnl : 0.0;
+        if (siteL && j == myShard && s < S) {
+            long long cnt = 0; double outL = sum;
+            if (sum > 0.0) {
+                const int e2 = emax;
+                cnt = (e2 < 0) ? (long long)((-e2) / 64) : -(long long)((e2 + 63) / 64);
+                const int rem = e2 + (int)(64 * cnt);
+                outL = sum * exp2i(rem);
+            }
+            siteL[s] = outL; siteScale[s] = cnt;
+        }
+    }
+    red[threadIdx.x] = term;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
 __global__ void __launch_bounds__(256) final_sum_kernel(const double *partial, int n, const int *flag, double *out) {
     __shared__ double red[256];
     double s = 0.0;

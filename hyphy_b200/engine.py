@@ -42,6 +42,7 @@ ABI = [
     ("hb2_read_transition", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _dp]),
     ("hb2_comm_unique_id", C.c_int, [C.c_void_p]),
     ("hb2_comm_init", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    ("hb2_comm_class_groups", C.c_int, [C.c_void_p, C.c_int]),
     ("hb2_destroy", None, [C.c_void_p]),
     ("hb2_launch_count", C.c_int64, [C.c_void_p]),
     ("hb2_precision_mode", C.c_int, [C.c_void_p]),
@@ -195,6 +196,10 @@ class Partition:
         assert len(unique_id) == 128
         buf = C.create_string_buffer(unique_id, 128)
         _check(self._lib.hb2_comm_init(self._h, int(n_ranks), int(rank), buf))
+
+    def comm_class_groups(self, n_groups: int):
+        """Second sharding axis (rate classes); see hb2_comm_class_groups in include/hyphy_b200.h."""
+        _check(self._lib.hb2_comm_class_groups(self._h, int(n_groups)))
 
     # -- introspection -----------------------------------------------------------------------------
     @property

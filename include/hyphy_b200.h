@@ -116,6 +116,17 @@ int hb2_read_transition(hb2_partition *p, int64_t cat, int64_t node, double *P);
 int hb2_comm_unique_id(void *uniqueId128);
 int hb2_comm_init(hb2_partition *p, int nRanks, int rank, const void *uniqueId128);
 
+/* Optional second sharding axis for partitions with rate classes (the per-class loop of
+ * ComputeSiteLikelihoodsForABlock, likefunc2.cpp:912, iterates independent ComputeBlock calls): the nRanks ranks are
+ * arranged as (nRanks/nGroups pattern shards) x (nGroups class groups); rank r belongs to class group r % nGroups and
+ * pattern shard r / nGroups, i.e. the nGroups consecutive ranks of one shard are created with the SAME pattern slice.
+ * Group g owns classes [g*C/nGroups, (g+1)*C/nGroups): matrices handed over for other classes are ignored on this
+ * rank (no expm, no pruning), hb2_evaluate_classes prunes the owned classes only, and the per-pattern class partials
+ * (value, binary exponent) of the ranks of a shard are exchanged with one small ncclAllGather before the logarithm;
+ * the ncclAllReduce of the partial lnL follows as usual.  Requires C % nGroups == 0 and nRanks % nGroups == 0;
+ * hb2_evaluate (single class) is refused in this mode.  Call after hb2_comm_init, before the first matrix is set. */
+int hb2_comm_class_groups(hb2_partition *p, int nGroups);
+
 /* Pair of SetupLFCaches in DeleteCaches (likefunc.cpp:10556-10601). */
 void hb2_destroy(hb2_partition *p);
 

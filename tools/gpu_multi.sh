@@ -1,5 +1,20 @@
 #!/bin/bash
+# multi-GPU bench on N GPUs of one box: class groups x pattern shards (default) and patterns only, tight timeouts
 N=${1:-2}
 TAG=${2:-r01m}
 mkdir -p gpurun_out
-HB2_DEBUG=1 NCCL_DEBUG=WARN timeout 100 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29601 bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/${TAG}_bench_n$N.json 2> gpurun_out/${TAG}_bench_n$N.err; echo "n$N rc=$?"; cut -c1-500 gpurun_out/${TAG}_bench_n$N.json; grep -E "EngineError|NCCL WARN|failed" gpurun_out/${TAG}_bench_n$N.err | head -5 | cut -c1-700
+run() {   # name, extra flags
+  HB2_DEBUG=${HB2_DEBUG:-0} NCCL_DEBUG=WARN timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29601 \
+     bench.py --gpus $N --steps 20 --warmup 3 $2 > gpurun_out/${TAG}_bench_n${N}_$1.json 2> gpurun_out/${TAG}_bench_n${N}_$1.err; echo "n$N $1 rc=$?"
+  python - <<PY
+import json
+try:
+    d=[json.loads(l) for l in open('gpurun_out/${TAG}_bench_n${N}_$1.json') if l.startswith('{')][-1]
+    print('$1', d['config']['sharding'], round(d['value'],1), 'evals/s e2e', round(d['e2e']['value'],1), {k:round(v,4) for k,v in d['roofline']['stage_ms'].items()}, 'lnL', repr(d['lnL']), 'resident', repr(d['lnL_resident']))
+except Exception as e:
+    print('$1 ERR', e)
+PY
+  grep -E "EngineError|NCCL WARN|failed|Error" gpurun_out/${TAG}_bench_n${N}_$1.err | head -5 | cut -c1-600
+}
+run cg ""
+run pat "--no-class-groups"
