@@ -896,13 +896,19 @@ int hb2_set_matrices_compiled(hb2_partition *p, int64_t cat, int64_t n, const in
     const bool owned = cat >= p->own0 && cat < p->own0 + p->ownN;
     for (int64_t k = 0; k < n; k++) {
         if (nodeIds[k] < 0 || nodeIds[k] >= p->B) return fail("node id %lld has no branch", (long long)nodeIds[k]);
-        if (!owned) { p->have_matrix[cat * p->B + nodeIds[k]] = 1; continue; }   // another class group's
+        p->have_matrix[cat * p->B + nodeIds[k]] = 1;
+    }
+    if (!owned) return 0;                                   // another class group's matrices
+    // rows are staged in runs as long as the pinned buffer allows: one memcpy per run
+    int64_t k = 0;
+    while (k < n) {
         if (p->n_vpending == p->q_capacity) { cudaSetDevice(p->device); if (flush_compiled(p)) return 1; }
         if (p->staging_busy) { CU(cudaEventSynchronize(p->ev_staging)); p->staging_busy = false; }
-        memcpy(p->h_V + p->n_vpending * p->t_nF, formulaValues + k * p->t_nF, p->t_nF * sizeof(double));
-        p->h_vdst[p->n_vpending] = (int)(cat * p->B + nodeIds[k]);
-        p->have_matrix[cat * p->B + nodeIds[k]] = 1;
-        p->n_vpending++;
+        const int64_t run = std::min<int64_t>(n - k, p->q_capacity - p->n_vpending);
+        memcpy(p->h_V + p->n_vpending * p->t_nF, formulaValues + k * p->t_nF, (size_t)run * p->t_nF * sizeof(double));
+        for (int64_t i = 0; i < run; i++) p->h_vdst[p->n_vpending + i] = (int)(cat * p->B + nodeIds[k + i]);
+        p->n_vpending += run;
+        k += run;
     }
     return 0;
 }

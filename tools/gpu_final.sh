@@ -4,6 +4,7 @@ TAG=${1:-r01z}
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_errors.jsonl
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -4 gpurun_out/${TAG}_smoke.log
+timeout 300 python tools/stress_determinism.py 4 > gpurun_out/${TAG}_stress.log 2>&1; echo "stress rc=$?"; tail -2 gpurun_out/${TAG}_stress.log
 timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/${TAG}_pytest_gpu.log
 cp gpurun_out/parity_errors.jsonl gpurun_out/${TAG}_parity_errors.jsonl 2>/dev/null
 timeout 600 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; cat gpurun_out/${TAG}_bench.json | cut -c1-2500; tail -2 gpurun_out/${TAG}_bench.err
