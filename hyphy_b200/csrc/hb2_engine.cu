@@ -121,6 +121,8 @@ struct hb2_partition {
     bool expm_dfma = false;                   // HB2_EXPM_DFMA=1: previous FFMA-style fp64 expm kernel (A/B testing)
     bool use_walk = false;
     int walk_max_resident = 0;
+    // single-branch shortcut (hb2_branch_cache_*): outside vectors of one branch, all owned classes
+    double *d_bc_out = nullptr; int *d_bc_outE = nullptr, *d_bc_sib = nullptr; int64_t bc_node = -1;
     std::vector<char> plan_dirty;       // cached walk plan (h_walk holds its steps): dirty set, lane count, step count
     int plan_K = 0, plan_steps = 0;
     std::vector<int> walk_gen;          // [C][I] generation bit of each node's resident conditionals (tc walk path)
@@ -573,6 +575,7 @@ int evaluate_impl(hb2_partition *p, int c0, int nc, const double *weights, int64
         if (!weights || c0 != 0 || nc != (int)p->C) return fail("with class groups only hb2_evaluate_classes is available");
         c0 = p->own0;                          // prune the owned classes; the weights of all C classes are still uploaded
     }
+    p->bc_node = -1;                           // conditionals are about to change: the branch cache is stale
     const int nw = nc;                         // number of class weights the caller passed
     if (p->cg_G > 1) nc = p->ownN;
     if (flush_matrices(p)) return 1;
@@ -967,6 +970,94 @@ int hb2_read_transition(hb2_partition *p, int64_t cat, int64_t node, double *P) 
     return 0;
 }
 
+static hb2::BranchCacheArgs bc_args(hb2_partition *p, int c0, int nc) {
+    hb2::BranchCacheArgs a{};
+    a.cv.c64 = p->use_tc ? nullptr : p->d_cond;
+    a.cv.c32 = p->use_tc ? p->d_condf : nullptr;
+    a.cv.scal = p->d_scal; a.cv.I = (int)p->I; a.cv.Sp = (int)p->Sp; a.cv.Dp = p->Dp; a.cv.tagged = (p->use_tc && p->use_walk) ? 1 : 0;
+    a.PT = p->d_PT; a.leaf = p->d_leaf; a.ambig = p->d_ambig; a.pi = p->d_pi; a.out = p->d_bc_out; a.outE = p->d_bc_outE;
+    a.L = (int)p->L; a.B = (int)p->B; a.D = (int)p->D; a.Dp = p->Dp; a.Sp = (int)p->Sp; a.S = (int)p->S; a.cat0 = c0; a.ncls = nc;
+    return a;
+}
+
+int hb2_branch_cache_build(hb2_partition *p, int64_t node, const double *rootFreqs) {
+    if (!p || !rootFreqs) return fail("null argument");
+    if (node < 0 || node >= p->B) return fail("node id %lld has no branch (valid 0..%lld)", (long long)node, (long long)p->B - 1);
+    CU(cudaSetDevice(p->device));
+    for (int c = p->own0; c < p->own0 + p->ownN; c++)
+        if (!p->evaluated_cat[c]) return fail("hb2_branch_cache_build: rate class %d has never been evaluated (no resident conditionals)", c);
+    if (flush_matrices(p)) return 1;
+    if (!p->d_bc_out) {
+        CU(cudaMalloc(&p->d_bc_out, (size_t)p->C * p->Sp * p->Dp * sizeof(double)));
+        CU(cudaMalloc(&p->d_bc_outE, (size_t)p->C * p->Sp * sizeof(int)));
+        CU(cudaMalloc(&p->d_bc_sib, (size_t)(p->L + p->I) * sizeof(int)));
+    }
+    double *hs = p->h_small;
+    for (int k = 0; k < p->Dp; k++) hs[k] = k < p->D ? rootFreqs[k] : 0.0;
+    CU(cudaMemcpyAsync(p->d_pi, hs, p->Dp * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    // root -> parent(node) path (internal indices) and, per path node, its children that are NOT on the path
+    std::vector<int> path;
+    for (int64_t u = p->parents[node]; u >= 0; u = p->parents[p->L + u]) path.push_back((int)u);
+    std::reverse(path.begin(), path.end());
+    std::vector<int> sib, off(path.size() + 1, 0), down(path.size(), -1);
+    for (size_t i = 0; i < path.size(); i++) {
+        const int on_path = (i + 1 < path.size()) ? (int)p->L + path[i + 1] : (int)node;
+        for (int ch : p->children[path[i]]) if (ch != on_path) sib.push_back(ch);
+        off[i + 1] = (int)sib.size();
+        down[i] = (i + 1 < path.size()) ? on_path : -1;
+    }
+    CU(cudaStreamSynchronize(p->stream));            // h_small / sibling upload below are synchronous with respect to earlier work
+    if (!sib.empty()) CU(cudaMemcpy(p->d_bc_sib, sib.data(), sib.size() * sizeof(int), cudaMemcpyHostToDevice));
+    hb2::BranchCacheArgs a = bc_args(p, p->own0, p->ownN);
+    dim3 grid((unsigned)((p->S + 127) / 128), (unsigned)p->ownN);
+    for (size_t i = 0; i < path.size(); i++) {
+        hb2::bc_step_kernel<<<grid, 128, 0, p->stream>>>(a, p->d_bc_sib + off[i], off[i + 1] - off[i], down[i], i == 0 ? 1 : 0);
+        p->launches++;
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(p->stream));
+    p->bc_node = node;
+    return 0;
+}
+
+int hb2_branch_cache_evaluate(hb2_partition *p, int64_t cat, const double *weights, double *lnL, double *siteL, int64_t *siteScale) {
+    if (!p || !lnL) return fail("null argument");
+    if (p->bc_node < 0) return fail("hb2_branch_cache_evaluate: no valid branch cache (build it after the last full evaluation)");
+    CU(cudaSetDevice(p->device));
+    // only the cached branch may have a new matrix: anything else needs a regular evaluation
+    for (int64_t k = 0; k < p->n_pending; k++)
+        if (p->h_dst[k] % p->B != p->bc_node) return fail("branch cache holds node %lld but a matrix of node %lld changed", (long long)p->bc_node, (long long)(p->h_dst[k] % p->B));
+    for (int64_t k = 0; k < p->n_vpending; k++)
+        if (p->h_vdst[k] % p->B != p->bc_node) return fail("branch cache holds node %lld but a matrix of node %lld changed", (long long)p->bc_node, (long long)(p->h_vdst[k] % p->B));
+    if (flush_matrices(p)) return 1;
+    int c0, nc;
+    if (weights) { c0 = p->own0; nc = p->ownN; }
+    else {
+        if (p->cg_G > 1) return fail("with class groups only the all-class form (weights != NULL) is available");
+        if (cat < 0) cat = 0;
+        if (cat >= p->C) return fail("rate class %lld out of range", (long long)cat);
+        c0 = (int)cat; nc = 1;
+    }
+    double *hs = p->h_small;
+    if (weights) {
+        for (int c = 0; c < p->C; c++) hs[p->Dp + c] = weights[c];
+        CU(cudaMemcpyAsync(p->d_weights, hs + p->Dp, p->C * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    }
+    hb2::BranchCacheArgs a = bc_args(p, c0, nc);
+    dim3 grid((unsigned)((p->S + 127) / 128), (unsigned)nc);
+    hb2::bc_eval_kernel<<<grid, 128, 0, p->stream>>>(a, (int)p->bc_node, p->d_rootL, p->d_rootE);
+    p->launches++;
+    CU(cudaGetLastError());
+    const bool want_sites = siteL != nullptr || siteScale != nullptr;
+    if (run_root(p, c0, nc, weights != nullptr, want_sites)) return 1;
+    CU(cudaMemcpyAsync(hs + p->Dp + p->C, p->d_lnL, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (siteL) CU(cudaMemcpyAsync(siteL, p->d_siteL, p->S * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if (siteScale) CU(cudaMemcpyAsync(siteScale, p->d_siteScale, p->S * sizeof(long long), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    *lnL = hs[p->Dp + p->C];
+    return 0;
+}
+
 int hb2_comm_unique_id(void *uniqueId128) {
     if (!uniqueId128) return fail("null id buffer");
     if (!g_nccl.load()) return fail("cannot load libnccl.so.2: %s", dlerror());
@@ -1036,7 +1127,7 @@ void hb2_destroy(hb2_partition *p) {
     if (p->comm) g_nccl.CommDestroy(p->comm);
     void *dev[] = {p->d_leaf, p->d_scal, p->d_rootE, p->d_child_start, p->d_child_ids, p->d_jobs, p->d_dst, p->d_flag,
                    p->d_mix_first, p->d_ambig, p->d_freq, p->d_cond, p->d_PT, p->d_Q, p->d_pi, p->d_rootL, p->d_weights,
-                   p->d_partial, p->d_lnL, p->d_siteL, p->d_mix_w, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_xsend, p->d_xrecv, p->d_xfreq, p->d_xpartial, p->d_walk, p->d_t_index, p->d_t_formula, p->d_vdst, p->d_t_colfreq, p->d_V};
+                   p->d_partial, p->d_lnL, p->d_siteL, p->d_mix_w, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_xsend, p->d_xrecv, p->d_xfreq, p->d_xpartial, p->d_bc_out, p->d_bc_outE, p->d_bc_sib, p->d_walk, p->d_t_index, p->d_t_formula, p->d_vdst, p->d_t_colfreq, p->d_V};
     for (void *d : dev) if (d) cudaFree(d);
     if (p->h_Q) cudaFreeHost(p->h_Q);
     if (p->h_small) cudaFreeHost(p->h_small);
@@ -1060,6 +1151,7 @@ int hb2_time_resident(hb2_partition *p, const double *weights, const double *roo
     CU(cudaSetDevice(p->device));
     if (check_ready(p, 0, (int)p->C)) return 1;
     if (flush_matrices(p)) return 1;
+    p->bc_node = -1;
     // every slot must hold a resident rate matrix so that the expm stage can be replayed
     std::vector<int> dst;
     for (int64_t k = (int64_t)p->own0 * p->B; k < (int64_t)(p->own0 + p->ownN) * p->B; k++) {

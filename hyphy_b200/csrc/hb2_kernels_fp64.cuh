@@ -925,6 +925,131 @@ __global__ void __launch_bounds__(256) combine_kernel(CombineArgs a) {
     if (threadIdx.x == 0) a.partial[blockIdx.x] = red[0];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Single-branch shortcut (reference: ComputeBranchCache tree_evaluator.cpp:4286, ComputeLLWithBranchCache tree.cpp:3383).
+// For a branch b with parent u the likelihood factorises as  L_s = sum_a rest_b[s][a] * (P_b * below_b[s])[a]  where
+// below_b = conditionals of b's subtree (already resident) and rest_b[s][a] = everything else, seen from state a at u:
+//   out_root[a] = pi_a ;  rest_v[a] = out_u[a] * prod_{siblings c of v at u} (P_c L_c)[a] ;  out_v[a'] = sum_a rest_v[a] P_v[a][a'].
+// (No reversibility is needed: the outside vectors are propagated with the transposed matrices instead of re-rooting.)
+// bc_step_kernel does one node of the root->u path; bc_eval_kernel then costs O(S*D^2) per probe of P_b.
+// One thread per (class, pattern), fp64 throughout, matrices read as broadcasts from PT (L1); built once per line search,
+// so simplicity wins over speed here.  CondView abstracts the two conditional layouts (fp64 [I][Sp][Dp]; the walk kernel's
+// tile-wise fp32 with generation tags).
+// ------------------------------------------------------------------------------------------------
+struct CondView {
+    const double *c64;      // fp64 layout or null
+    const float *c32;       // tile-wise fp32 layout ([I][Sp/128][16][128][4], sign bit = tag) or null
+    const int *scal;        // exponents; tagged = 1 -> (value << 1) | tag
+    int I, Sp, Dp, tagged;
+};
+
+__device__ __forceinline__ double cond_at(const CondView &v, int cat, int node, int s, int k) {
+    if (v.c64) return v.c64[(((size_t)cat * v.I + node) * v.Sp + s) * v.Dp + k];
+    const size_t tile = s >> 7, t = s & 127;
+    return (double)fabsf(v.c32[(((((size_t)cat * v.I + node) * (v.Sp >> 7) + tile) * 16 + (k >> 2)) * 128 + t) * 4 + (k & 3)]);
+}
+__device__ __forceinline__ int exp_at(const CondView &v, int cat, int node, int s) {
+    const int e = v.scal[((size_t)cat * v.I + node) * v.Sp + s];
+    return v.tagged ? (e >> 1) : e;
+}
+
+struct BranchCacheArgs {
+    CondView cv;
+    const double *PT;       // [C][B][Dp*Dp] transposed transition matrices
+    const int *leaf;        // [L][Sp]
+    const double *ambig;    // [nAmb][Dp]
+    const double *pi;       // [Dp]
+    double *out;            // [C][Sp][Dp] outside vector of the current path node (in/out)
+    int *outE;              // [C][Sp]
+    int L, B, D, Dp, Sp, S, cat0, ncls;
+};
+
+// message of child `ch` (flat id) towards its parent for one pattern: m[a] = sum_k P_ch[a][k] x[k]  (PT[k][a] = P[a][k])
+__device__ __forceinline__ void bc_message(const BranchCacheArgs &a, int cat, int ch, int s, double *m, int &e) {
+    const double *PTc = a.PT + ((size_t)cat * a.B + ch) * a.Dp * a.Dp;
+    if (ch < a.L) {
+        const int code = a.leaf[(size_t)ch * a.Sp + s];
+        if (code >= 0) {
+            for (int q = 0; q < a.D; q++) m[q] = __ldg(PTc + (size_t)code * a.Dp + q);
+        } else {
+            const double *amb = a.ambig + (size_t)(-code - 1) * a.Dp;
+            for (int q = 0; q < a.D; q++) m[q] = 0.0;
+            for (int k = 0; k < a.D; k++)
+                if (__ldg(amb + k) != 0.0)
+                    for (int q = 0; q < a.D; q++) m[q] += __ldg(PTc + (size_t)k * a.Dp + q);
+        }
+    } else {
+        const int ci = ch - a.L;
+        for (int q = 0; q < a.D; q++) m[q] = 0.0;
+        for (int k = 0; k < a.D; k++) {
+            const double x = cond_at(a.cv, cat, ci, s, k);
+            if (x != 0.0)
+                for (int q = 0; q < a.D; q++) m[q] = fma(x, __ldg(PTc + (size_t)k * a.Dp + q), m[q]);
+        }
+        e += exp_at(a.cv, cat, ci, s);
+    }
+}
+
+__device__ __forceinline__ void bc_renorm(double *v, int D, int &e) {
+    double m = 0.0;
+    for (int q = 0; q < D; q++) m = fmax(m, v[q]);
+    if (m > 0.0 && m < INFINITY) {
+        int ex;
+        frexp(m, &ex);
+        if (ex != 0) {
+            const double sc = exp2i(-ex);
+            for (int q = 0; q < D; q++) v[q] *= sc;
+            e += ex;
+        }
+    }
+}
+
+// One path node u: rest = out_u * prod over `sib` (children of u except the path child); if `down` >= 0 (flat id of the
+// path child, which is not the target branch yet) out <- transpose-propagated through P_down, else out <- rest (= the cache).
+__global__ void __launch_bounds__(128) bc_step_kernel(BranchCacheArgs a, const int *sib, int nsib, int down, int first) {
+    const int s = blockIdx.x * 128 + threadIdx.x;
+    const int cat = a.cat0 + blockIdx.y;
+    if (s >= a.S) return;
+    double r[64], m[64];
+    int e = 0;
+    double *o = a.out + ((size_t)cat * a.Sp + s) * a.Dp;
+    if (first) { for (int q = 0; q < a.D; q++) r[q] = a.pi[q]; }
+    else { for (int q = 0; q < a.D; q++) r[q] = o[q]; e = a.outE[(size_t)cat * a.Sp + s]; }
+    for (int i = 0; i < nsib; i++) {
+        bc_message(a, cat, sib[i], s, m, e);
+        for (int q = 0; q < a.D; q++) r[q] *= m[q];
+        bc_renorm(r, a.D, e);
+    }
+    if (down >= 0) {
+        const double *PTd = a.PT + ((size_t)cat * a.B + down) * a.Dp * a.Dp;     // out'[a'] = sum_a r[a] * PT[a'][a]
+        for (int q = 0; q < a.D; q++) {
+            double acc = 0.0;
+            for (int k = 0; k < a.D; k++) acc = fma(r[k], __ldg(PTd + (size_t)q * a.Dp + k), acc);
+            m[q] = acc;
+        }
+        bc_renorm(m, a.D, e);
+        for (int q = 0; q < a.D; q++) o[q] = m[q];
+    } else {
+        for (int q = 0; q < a.D; q++) o[q] = r[q];
+    }
+    a.outE[(size_t)cat * a.Sp + s] = e;
+}
+
+// Probe: rootL/rootE <- sum_a rest[a] * (P_b * below)[a] with the CURRENT matrix of branch b.
+__global__ void __launch_bounds__(128) bc_eval_kernel(BranchCacheArgs a, int b, double *rootL, int *rootE) {
+    const int s = blockIdx.x * 128 + threadIdx.x;
+    const int cat = a.cat0 + blockIdx.y;
+    if (s >= a.S) return;
+    double m[64];
+    int e = a.outE[(size_t)cat * a.Sp + s];
+    bc_message(a, cat, b, s, m, e);
+    const double *o = a.out + ((size_t)cat * a.Sp + s) * a.Dp;
+    double acc = 0.0;
+    for (int q = 0; q < a.D; q++) acc = fma(o[q], m[q], acc);
+    rootL[(size_t)cat * a.Sp + s] = acc;
+    rootE[(size_t)cat * a.Sp + s] = e;
+}
+
 // Class-group sharding (hb2_comm_class_groups): this rank's share of sum_c w_c L_{c,s}, as (value, binary exponent) per
 // pattern, written to send[0..xs) | send[xs..2xs) (exponent as a double; NaN value = numerical failure, value 0 = no
 // positive class likelihood).

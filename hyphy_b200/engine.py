@@ -41,6 +41,8 @@ ABI = [
     ("hb2_read_conditionals", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _dp, _i32p]),
     ("hb2_read_transition", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _dp]),
     ("hb2_comm_unique_id", C.c_int, [C.c_void_p]),
+    ("hb2_branch_cache_build", C.c_int, [C.c_void_p, C.c_int64, _dp]),
+    ("hb2_branch_cache_evaluate", C.c_int, [C.c_void_p, C.c_int64, _dp, C.POINTER(C.c_double), _dp, _ip]),
     ("hb2_comm_init", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     ("hb2_comm_class_groups", C.c_int, [C.c_void_p, C.c_int]),
     ("hb2_destroy", None, [C.c_void_p]),
@@ -172,6 +174,25 @@ class Partition:
         w, pw = _d(weights)
         assert w.shape == (self.C,)
         return self._eval(self._lib.hb2_evaluate_classes, pw, update_nodes, root_freqs, want_sites)
+
+    # -- single-branch shortcut ----------------------------------------------------------------------
+    def branch_cache_build(self, node, root_freqs):
+        pi, ppi = _d(root_freqs)
+        assert pi.shape == (self.D,)
+        _check(self._lib.hb2_branch_cache_build(self._h, int(node), ppi))
+
+    def branch_cache_evaluate(self, weights=None, cat=0, want_sites=False):
+        """lnL with only the cached branch's matrix changed; weights=None -> single class `cat`."""
+        pw = None
+        if weights is not None:
+            w, pw = _d(weights)
+            assert w.shape == (self.C,)
+        lnl = C.c_double()
+        sl = np.empty(self.S) if want_sites else None
+        ss = np.empty(self.S, dtype=np.int64) if want_sites else None
+        _check(self._lib.hb2_branch_cache_evaluate(self._h, int(cat), pw, C.byref(lnl), sl.ctypes.data_as(_dp) if want_sites else None,
+                                                   ss.ctypes.data_as(_ip) if want_sites else None))
+        return (lnl.value, sl, ss) if want_sites else lnl.value
 
     # -- read-backs --------------------------------------------------------------------------------
     def read_conditionals(self, cat, inode):

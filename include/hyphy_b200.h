@@ -102,6 +102,19 @@ int hb2_evaluate(hb2_partition *p, int64_t cat, int64_t nUpdate, const int64_t *
 int hb2_evaluate_classes(hb2_partition *p, const double *weights, int64_t nUpdate, const int64_t *updateNodes,
                          const double *rootFreqs, double *lnL, double *siteL, int64_t *siteScale);
 
+/* Single-branch shortcut (ComputeBranchCache tree_evaluator.cpp:4286-4845 and ComputeLLWithBranchCache
+ * tree.cpp:3383-3934, entered from ComputeBlock likefunc.cpp:10984-10993 / :11170-11177).  After a regular evaluation,
+ * hb2_branch_cache_build(node) collects, for every owned class and pattern, the likelihood of everything outside the
+ * subtree of `node` as seen from the parent end of its branch (the reference's branchCaches[.][1]; the subtree side is
+ * the resident conditional).  While only THAT branch's matrix changes (set it with hb2_set_matrices*),
+ * hb2_branch_cache_evaluate returns lnL in O(S*D^2) without touching the tree; cat/weights as in hb2_evaluate /
+ * hb2_evaluate_classes (weights != NULL selects the all-class form).  Any regular evaluation invalidates the cache; a
+ * pending matrix of another node makes the call fail.  Unlike the reference this needs no reversible model: the outside
+ * vectors are propagated through transposed transition matrices instead of re-rooting the tree. */
+int hb2_branch_cache_build(hb2_partition *p, int64_t node, const double *rootFreqs);
+int hb2_branch_cache_evaluate(hb2_partition *p, int64_t cat, const double *weights, double *lnL, double *siteL,
+                              int64_t *siteScale);
+
 /* FillInConditionals-style read-back (tree.cpp:3335): conditionals of internal node `inode` (0..I-1), class cat,
  * as S*D doubles (original pattern order) and S binary exponents: true value = cond * 2^exp2. */
 int hb2_read_conditionals(hb2_partition *p, int64_t cat, int64_t inode, double *cond, int32_t *exp2);

@@ -379,3 +379,75 @@ def test_repeated_evaluations_are_bit_identical(mode):
             assert lnl == base[0]
             assert np.array_equal(site, base[1]) and np.array_equal(scc, base[2])
         lf.close()
+
+
+def _branch_nodes(w):
+    """A leaf branch, the deepest internal branch, and a child of the root."""
+    t = w.tree
+    L, I = t.n_leaves, t.n_internal
+    par = np.asarray(t.flat_parents)
+    depth = np.zeros(L + I, dtype=int)
+    for n in range(L + I - 2, -1, -1):               # parents have larger internal index: walk from the root down
+        depth[n] = depth[L + par[n]] + 1
+    internals = [n for n in range(L, L + I - 1)]
+    deepest = max(internals, key=lambda n: depth[n])
+    root_child = next(n for n in range(L + I - 1) if par[n] == I - 1)
+    return sorted({0, int(np.argmax(depth[:L])), deepest, root_child})
+
+
+@pytest.mark.parametrize("name", ["mg94_8x60_c4_ambig", "mg94_30x100_c4_ambig", "mg94_200x64_c4_scaling", "c1_hky85_8x500"])
+def test_branch_cache_equals_full_evaluation(name, mode):
+    """with only one branch's matrix changed, hb2_branch_cache_evaluate must return what a full
+    evaluation with that matrix returns (all classes, per-pattern outputs included)."""
+    w, g = gc.load(name)
+    rtol, atol = tol(w, mode)
+    Qt = w.Qt()
+    lf = LF(w, mode)
+    lf.set_all_matrices(Qt)
+    base = lf.compute()
+    for node in _branch_nodes(w):
+        lf.part.branch_cache_build(node, w.pi)
+        got0 = lf.part.branch_cache_evaluate(w.class_weights)
+        assert abs(got0 - base) <= max(rtol, 1e-12) * abs(base)           # unchanged matrix: the same likelihood
+        for scale in (0.3, 2.5):
+            for c in range(w.C):
+                lf.part.set_matrices(c, [node], (Qt[c, node] * scale)[None])
+            got, sl, ss = lf.part.branch_cache_evaluate(w.class_weights, want_sites=True)
+            Q2 = Qt.copy()
+            Q2[:, node] *= scale
+            ref_lf = LF(w, mode)
+            ref_lf.set_all_matrices(Q2)
+            ref, rl, rs = ref_lf.compute(want_sites=True)
+            ref_lf.close()
+            oracle_lnl, _ = port.lnl(w, Q2)
+            record("branch_cache", f"{name}:node{node}:x{scale}", mode, got, oracle_lnl)
+            assert abs(got - ref) <= max(rtol, 1e-12) * abs(ref), (node, scale, got, ref)
+            assert abs(got - oracle_lnl) <= rtol * abs(oracle_lnl)
+            assert np.abs(_site_lnl(sl, ss) - _site_lnl(rl, rs)).max() <= max(atol, 1e-9)
+        for c in range(w.C):                                              # restore, caches stay consistent
+            lf.part.set_matrices(c, [node], Qt[c, node][None])
+        assert abs(lf.part.branch_cache_evaluate(w.class_weights) - base) <= max(rtol, 1e-12) * abs(base)
+    # single-class form
+    lf.part.branch_cache_build(0, w.pi)
+    one = lf.part.branch_cache_evaluate(None, cat=w.C - 1)
+    assert abs(one - lf.compute_block(w.C - 1)) <= max(rtol, 1e-12) * abs(one)
+    lf.close()
+
+
+def test_branch_cache_guards():
+    w = synth.nucleotide_workload(6, 40, seed=3)
+    lf = LF(w, "fp64")
+    lf.set_all_matrices()
+    with pytest.raises(engine.EngineError, match="never been evaluated"):
+        lf.part.branch_cache_build(0, w.pi)
+    lf.compute()
+    with pytest.raises(engine.EngineError, match="no valid branch cache"):
+        lf.part.branch_cache_evaluate(w.class_weights)
+    lf.part.branch_cache_build(1, w.pi)
+    lf.part.set_matrices(0, [2], w.Qt()[0, 2][None])
+    with pytest.raises(engine.EngineError, match="a matrix of node 2 changed"):
+        lf.part.branch_cache_evaluate(w.class_weights)
+    lf.compute()                                             # a regular evaluation invalidates the cache
+    with pytest.raises(engine.EngineError, match="no valid branch cache"):
+        lf.part.branch_cache_evaluate(w.class_weights)
+    lf.close()
