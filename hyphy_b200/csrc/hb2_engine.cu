@@ -123,6 +123,8 @@ struct hb2_partition {
     int walk_max_resident = 0;
     // single-branch shortcut (hb2_branch_cache_*): outside vectors of one branch, all owned classes
     double *d_bc_out = nullptr; int *d_bc_outE = nullptr, *d_bc_sib = nullptr; int64_t bc_node = -1;
+    std::vector<char> plan_jdirty;      // dirty jobs (nodes + side products) of the cached plan
+    bool walk_split_nodes = true;       // HB2_WALK_SPLIT_NODES=0: no side products (A/B)
     std::vector<char> plan_dirty;       // cached walk plan (h_walk holds its steps): dirty set, lane count, step count
     int plan_K = 0, plan_steps = 0;
     std::vector<int> walk_gen;          // [C][I] generation bit of each node's resident conditionals (tc walk path)
@@ -326,93 +328,125 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
     // the plan depends on the tree, the dirty set and K only: optimisers re-evaluate the same set again and again
     const bool reuse = p->plan_steps > 0 && p->plan_K == K && p->plan_dirty == dirty;
     if (!reuse) {
-    // Lane assignment = list scheduling of the dirty subtree on K in-order lanes with a rough cost model (cycles measured
-    // with HB2_WALK_TRACE, profiles/): the pass is bound by the busiest lane or by the deepest root path, so nodes are
-    // handed out longest-remaining-path first to whichever lane is free first, and a node whose internal child was the
-    // lane's previous job continues there (register hand-over: the cheapest kind of step).  Every lane executes its nodes
-    // in the order they were scheduled and a node is scheduled only after its children, so cross-lane waits cannot cycle.
-    const double C_LEAF = 1.8e3, C_CHAIN = 4.7e3, C_INT = 7.0e3, C_NODE = 1.0e3, C_XFER = 1.5e3;
-    std::vector<int> lane_of(I, -1), lane_last(K, -1), chain_child(I, -1);
-    std::vector<std::vector<int>> lanes(K);
-    {
-        std::vector<double> base(I, 0.0), tail(I, 0.0), finish(I, 0.0), lane_time(K, 0.0);
-        std::vector<int> pending(I, 0);          // dirty internal children not yet scheduled
-        std::vector<int> ready;
-        for (int n = 0; n < I; n++) {
-            if (!dirty[n]) continue;
-            base[n] = C_NODE;
-            for (int ch : p->children[n]) {
-                base[n] += ch < L ? C_LEAF : C_INT;
-                if (ch >= L && dirty[ch - L]) pending[n]++;
-            }
+    // Jobs.  Job j < I is node j; job I + n is the SIDE PRODUCT of node n: a node with two or more internal children is
+    // split into "contract the child with the deepest subtree" (+ multiply the side product in: no matrix, the cheapest
+    // step after a leaf) and a side job that contracts all OTHER children.  Side jobs sit off the root path, so other
+    // lanes do them early and the spine of a deep tree carries one contraction per node instead of two (`split`).
+    // item list of a job: children to contract (flat ids) and, for a split node, the side job to multiply in.
+    const int NJ = 2 * I;
+    const bool split_on = p->walk_split_nodes && K > 1;
+    std::vector<std::vector<int>> jch(NJ);       // children (flat ids, leaves and internals) contracted by the job
+    std::vector<int> jmul(NJ, -1);               // side job multiplied in by the job (real split nodes only)
+    std::vector<char> jdirty(NJ, 0);
+    for (int n = 0; n < I; n++) {
+        if (!dirty[n]) continue;
+        jdirty[n] = 1;
+        int heavy = -1, nint = 0;
+        for (int ch : p->children[n]) if (ch >= L) { nint++; if (heavy < 0 || p->height[ch - L] > p->height[heavy - L]) heavy = ch; }
+        if (split_on && nint >= 2) {
+            jch[n].push_back(heavy);
+            jmul[n] = I + n;
+            jdirty[I + n] = 1;
+            for (int ch : p->children[n]) if (ch != heavy) jch[I + n].push_back(ch);
+        } else {
+            jch[n] = p->children[n];
         }
-        for (int h = (int)levels.size() - 1; h >= 0; h--)       // parents before children: remaining path to the root
-            for (int n : levels[h]) {
-                const int64_t par = p->parents[L + n];
-                tail[n] = base[n] + ((par >= 0 && dirty[par]) ? tail[par] : 0.0);
+    }
+    // Lane assignment = list scheduling of the dirty jobs on K in-order lanes with a rough cost model (cycles measured
+    // with HB2_WALK_TRACE, profiles/): the pass is bound by the busiest lane or by the deepest root path, so the
+    // (job, lane) pair that can start first is scheduled next, ties going to the longer remaining path; a job whose
+    // contracted internal child was the lane's previous job continues there (register hand-over: the cheapest
+    // contraction).  Every lane executes its jobs in the order they were scheduled and a job is scheduled only after
+    // the jobs it consumes, so cross-lane waits cannot cycle.
+    const double C_LEAF = 1.8e3, C_CHAIN = 4.7e3, C_INT = 7.0e3, C_MUL = 2.5e3, C_NODE = 1.0e3, C_XFER = 1.5e3;
+    auto job_of_child = [&](int ch) { return ch - L; };          // internal child (flat id) -> job that produces it
+    std::vector<int> lane_of(NJ, -1), lane_last(K, -1), chain_child(NJ, -1), parent_job(NJ, -1);
+    std::vector<std::vector<int>> lanes(K);
+    int njobs = 0;
+    {
+        std::vector<double> base(NJ, 0.0), tail(NJ, 0.0), finish(NJ, 0.0), lane_time(K, 0.0);
+        std::vector<int> pending(NJ, 0);         // dirty producer jobs not yet scheduled
+        std::vector<int> ready;
+        for (int j = 0; j < NJ; j++) {
+            if (!jdirty[j]) continue;
+            njobs++;
+            base[j] = C_NODE + (jmul[j] >= 0 ? C_MUL : 0.0);
+            for (int ch : jch[j]) {
+                base[j] += ch < L ? C_LEAF : C_INT;
+                if (ch >= L && dirty[ch - L]) { pending[j]++; parent_job[job_of_child(ch)] = j; }
             }
-        for (int n = 0; n < I; n++) if (dirty[n] && pending[n] == 0) ready.push_back(n);
-        for (int done = 0; done < total; done++) {
-            // the (node, lane) pair that can START first; ties go to the longer remaining path, then to the lower lane
+            if (jmul[j] >= 0) { pending[j]++; parent_job[jmul[j]] = j; }
+        }
+        // remaining path to the root, parents before children: real nodes by decreasing height, a side job right after
+        // its node
+        for (int h = (int)levels.size() - 1; h >= 0; h--)
+            for (int n : levels[h]) {
+                tail[n] = base[n] + (parent_job[n] >= 0 ? tail[parent_job[n]] : 0.0);
+                if (jmul[n] >= 0) tail[I + n] = base[I + n] + tail[n];
+            }
+        for (int j = 0; j < NJ; j++) if (jdirty[j] && pending[j] == 0) ready.push_back(j);
+        auto producers = [&](int j, auto &&f) {   // dirty jobs whose output job j consumes
+            for (int ch : jch[j]) if (ch >= L && dirty[ch - L]) f(job_of_child(ch));
+            if (jmul[j] >= 0) f(jmul[j]);
+        };
+        for (int done = 0; done < njobs; done++) {
             int best = -1, best_r = 0; double best_start = 0.0;
-            for (int n : ready) {
+            for (int j : ready) {
                 for (int r = 0; r < K; r++) {
                     double est = lane_time[r];
-                    for (int ch : p->children[n]) {
-                        if (ch < L || !dirty[ch - L]) continue;
-                        est = std::max(est, finish[ch - L] + (lane_of[ch - L] == r ? 0.0 : C_XFER));
-                    }
-                    if (best < 0 || est < best_start || (est == best_start && tail[n] > tail[best])) { best = n; best_r = r; best_start = est; }
+                    producers(j, [&](int q) { est = std::max(est, finish[q] + (lane_of[q] == r ? 0.0 : C_XFER)); });
+                    if (best < 0 || est < best_start || (est == best_start && tail[j] > tail[best])) { best = j; best_r = r; best_start = est; }
                 }
             }
-            const int n = best, r = best_r;
-            double cost = base[n];
-            for (int ch : p->children[n])
-                if (ch >= L && dirty[ch - L] && lane_last[r] == ch - L) { chain_child[n] = ch - L; cost -= C_INT - C_CHAIN; break; }
-            finish[n] = best_start + cost;
-            lane_time[r] = finish[n];
-            lane_of[n] = r; lane_last[r] = n;
-            lanes[r].push_back(n);
-            ready.erase(std::find(ready.begin(), ready.end(), n));
-            const int64_t par = p->parents[L + n];
-            if (par >= 0 && dirty[par] && --pending[par] == 0) ready.push_back((int)par);
+            const int j = best, r = best_r;
+            double cost = base[j];
+            for (int ch : jch[j])
+                if (ch >= L && dirty[ch - L] && lane_last[r] == job_of_child(ch)) { chain_child[j] = ch - L; cost -= C_INT - C_CHAIN; break; }
+            finish[j] = best_start + cost;
+            lane_time[r] = finish[j];
+            lane_of[j] = r; lane_last[r] = j;
+            lanes[r].push_back(j);
+            ready.erase(std::find(ready.begin(), ready.end(), j));
+            if (parent_job[j] >= 0 && --pending[parent_job[j]] == 0) ready.push_back(parent_job[j]);
         }
         if (getenv("HB2_DEBUG")) {
             double mx = 0; for (double t : lane_time) mx = std::max(mx, t);
-            double deepest = 0; for (int n = 0; n < I; n++) if (dirty[n] && pending[n] == 0) deepest = std::max(deepest, tail[n]);
-            fprintf(stderr, "[hb2] walk schedule: modelled makespan %.0f cycles, deepest root path %.0f, lanes (nodes/cycles):", mx, deepest);
+            double deepest = 0; for (int j = 0; j < NJ; j++) if (jdirty[j]) deepest = std::max(deepest, tail[j]);
+            fprintf(stderr, "[hb2] walk schedule: %d jobs, modelled makespan %.0f cycles, deepest root path %.0f, lanes (jobs/cycles):", njobs, mx, deepest);
             for (int r = 0; r < K; r++) fprintf(stderr, " %zu/%.0f", lanes[r].size(), lane_time[r]);
             fprintf(stderr, "\n");
         }
     }
-    // flatten every lane into steps (one per child): chain child first, then leaves, then the other internal children
+    // flatten every lane into steps: chain child first, then leaves, then the other internal children, then the side product
     int *lane_start = buf;                       // [K+1], steps start at int offset 16 (int2-aligned)
     int *steps = buf + 16;
     ns = 0;
     for (int r = 0; r < K; r++) {
         lane_start[r] = ns;
-        for (int n : lanes[r]) {
+        for (int j : lanes[r]) {
             const int first = ns;
-            auto push = [&](int enc) { steps[2 * ns] = enc; steps[2 * ns + 1] = n; ns++; };
-            if (chain_child[n] >= 0) push((chain_child[n] + L) | hb2::WALK_CHAIN);
-            for (int ch : p->children[n]) if (ch < L) push(ch);
-            for (int ch : p->children[n]) {
-                if (ch < L || ch - L == chain_child[n]) continue;
+            auto push = [&](int enc) { steps[2 * ns] = enc; steps[2 * ns + 1] = j; ns++; };
+            if (chain_child[j] >= 0) push((chain_child[j] + L) | hb2::WALK_CHAIN);
+            for (int ch : jch[j]) if (ch < L) push(ch);
+            for (int ch : jch[j]) {
+                if (ch < L || ch - L == chain_child[j]) continue;
                 const int ci = ch - L;
-                push(ch | ((dirty[ci] && lane_of[ci] != lane_of[n]) ? hb2::WALK_WAIT : 0));
+                push(ch | ((dirty[ci] && lane_of[ci] != lane_of[j]) ? hb2::WALK_WAIT : 0));
             }
+            if (jmul[j] >= 0) push((L + jmul[j]) | hb2::WALK_MUL | (lane_of[jmul[j]] != lane_of[j] ? hb2::WALK_WAIT : 0));
             steps[2 * first + 1] |= hb2::STEP_FIRST;
             steps[2 * (ns - 1) + 1] |= hb2::STEP_LAST;
         }
     }
     lane_start[K] = ns;
+    p->plan_jdirty = jdirty;
     p->plan_steps = ns; p->plan_K = K; p->plan_dirty = dirty;
     }   // !reuse
     // generation bits: every node re-pruned by this pass flips its bit (per class); the kernel tags what it writes with the
     // new bit and awaits cross-lane children on it.  The table travels behind the steps.
     for (int c = cat0; c < cat0 + ncls; c++)
-        for (int n = 0; n < I; n++)
-            if (dirty[n]) p->walk_gen[(size_t)c * I + n] ^= 1;
+        for (int j = 0; j < 2 * I; j++)
+            if (p->plan_jdirty[j]) p->walk_gen[(size_t)c * 2 * I + j] ^= 1;
     const int gen_off = 16 + 2 * ns;
     std::copy(p->walk_gen.begin(), p->walk_gen.end(), buf + gen_off);
     const int nints = gen_off + (int)p->walk_gen.size();
@@ -434,7 +468,7 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
     t.rootL = a.rootL; t.rootE = a.rootE; t.tree = a.tree; t.err = p->d_err;
     t.L = a.L; t.I = a.I; t.B = a.B; t.D = a.D; t.Sp = a.Sp; t.cat0 = a.cat0;
     w.lane_start = p->d_walk; w.steps = reinterpret_cast<const int2 *>(p->d_walk + 16);
-    w.gen = p->d_walk + gen_off; w.K = K; w.T = T; w.ncls = ncls; w.nslots = nslots;
+    w.gen = p->d_walk + gen_off; w.NI = 2 * I; w.K = K; w.T = T; w.ncls = ncls; w.nslots = nslots;
     if (getenv("HB2_DEBUG")) fprintf(stderr, "[hb2] walk: jobs=%d steps=%d K=%d T=%d ncls=%d nslots=%d grid=%d resident=%d\n", total, ns, K, T, ncls, nslots, nslots * K, p->walk_max_resident);
     w.trace = nullptr; w.trace_cta = 0; w.trace_cta_times = nullptr;
     const char *trace_path = getenv("HB2_WALK_TRACE");
@@ -580,8 +614,8 @@ int evaluate_impl(hb2_partition *p, int c0, int nc, const double *weights, int64
     if (p->cg_G > 1) nc = p->ownN;
     if (flush_matrices(p)) return 1;
     if (p->walk_reset) {                      // an earlier pass was aborted half-way: its tags are inconsistent
-        CU(cudaMemsetAsync(p->d_condf, 0, (size_t)p->C * p->I * p->Sp * 64 * sizeof(float), p->stream));
-        CU(cudaMemsetAsync(p->d_scal, 0, (size_t)p->C * p->I * p->Sp * sizeof(int), p->stream));
+        CU(cudaMemsetAsync(p->d_condf, 0, (size_t)p->C * 2 * p->I * p->Sp * 64 * sizeof(float), p->stream));
+        CU(cudaMemsetAsync(p->d_scal, 0, (size_t)p->C * 2 * p->I * p->Sp * sizeof(int), p->stream));
         CU(cudaMemsetAsync(p->d_err, 0, sizeof(int), p->stream));
         std::fill(p->walk_gen.begin(), p->walk_gen.end(), 0);
         std::fill(p->evaluated_cat.begin(), p->evaluated_cat.end(), 0);
@@ -687,10 +721,11 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
     CUP(cudaMalloc(&p->d_ambig, std::max<int64_t>(nAmb, 1) * Dp * sizeof(double)));
     CUP(cudaMalloc(&p->d_freq, Sp * sizeof(double)));
     if (p->use_tc) {
-        CUP(cudaMalloc(&p->d_condf, (size_t)C * I * Sp * 64 * sizeof(float)));
+        // 2I node slots per class: I nodes + I side products of the walk kernel (the per-level kernel uses the first I)
+        CUP(cudaMalloc(&p->d_condf, (size_t)C * 2 * I * Sp * 64 * sizeof(float)));
         CUP(cudaMalloc(&p->d_PB, (size_t)C * p->B * hb2::TC_PB_FLOATS * sizeof(float)));
         CUP(cudaMalloc(&p->d_PTf, (size_t)C * p->B * hb2::TC_PTF_FLOATS * sizeof(float)));
-        CUP(cudaMemsetAsync(p->d_condf, 0, (size_t)C * I * Sp * 64 * sizeof(float), p->stream));
+        CUP(cudaMemsetAsync(p->d_condf, 0, (size_t)C * 2 * I * Sp * 64 * sizeof(float), p->stream));
         CUP(cudaMemsetAsync(p->d_PB, 0, (size_t)C * p->B * hb2::TC_PB_FLOATS * sizeof(float), p->stream));
         CUP(cudaMemsetAsync(p->d_PTf, 0, (size_t)C * p->B * hb2::TC_PTF_FLOATS * sizeof(float), p->stream));
         CUP(cudaFuncSetAttribute(hb2::prune64_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::TC_SMEM_BYTES));
@@ -723,8 +758,9 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
             p->walk_max_resident = std::min(per_sm, 2) * sms;          // TMEM: 256 of 512 columns per CTA -> at most 2 per SM
             if (p->walk_max_resident < 1) p->use_walk = false;
             const size_t T = Sp / hb2::TC_TILE_P;
-            p->walk_gen.assign((size_t)C * I, 0);       // matches the zero-filled conditional and exponent buffers
-            const size_t walk_ints = 16 + 2 * (size_t)(L + I) + (size_t)C * I;
+            p->walk_gen.assign((size_t)C * 2 * I, 0);   // matches the zero-filled conditional and exponent buffers
+            const size_t walk_ints = 16 + 2 * (size_t)(L + 2 * I) + (size_t)C * 2 * I;
+            { const char *ev = getenv("HB2_WALK_SPLIT_NODES"); p->walk_split_nodes = !(ev && ev[0] == '0'); }
             CUP(cudaMalloc(&p->d_walk, walk_ints * sizeof(int)));
             CUP(cudaMallocHost(&p->h_walk, walk_ints * sizeof(int)));
         }
@@ -734,7 +770,7 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
     }
     CUP(cudaMalloc(&p->d_err, sizeof(int)));
     CUP(cudaMemsetAsync(p->d_err, 0, sizeof(int), p->stream));
-    CUP(cudaMalloc(&p->d_scal, (size_t)C * I * Sp * sizeof(int)));
+    CUP(cudaMalloc(&p->d_scal, (size_t)C * 2 * I * Sp * sizeof(int)));      // 2I: see d_condf
     CUP(cudaMalloc(&p->d_PT, (size_t)C * p->B * dpdp * sizeof(double)));
     CUP(cudaMalloc(&p->d_Qres, (size_t)C * p->B * dd * sizeof(double)));
     p->q_capacity = C * p->B;
@@ -759,7 +795,7 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
     CUP(cudaMallocHost(&p->h_dst, p->q_capacity * sizeof(int)));
     CUP(cudaMallocHost(&p->h_small, (Dp + C + 8) * sizeof(double)));
     CUP(cudaMallocHost(&p->h_jobs, I * sizeof(int)));
-    CUP(cudaMemsetAsync(p->d_scal, 0, (size_t)C * I * Sp * sizeof(int), p->stream));
+    CUP(cudaMemsetAsync(p->d_scal, 0, (size_t)C * 2 * I * Sp * sizeof(int), p->stream));
     CUP(cudaMemsetAsync(p->d_PT, 0, (size_t)C * p->B * dpdp * sizeof(double), p->stream));
     CUP(cudaMemsetAsync(p->d_rootL, 0, (size_t)C * Sp * sizeof(double), p->stream));
     CUP(cudaMemsetAsync(p->d_rootE, 0, (size_t)C * Sp * sizeof(int), p->stream));
@@ -938,17 +974,18 @@ int hb2_read_conditionals(hb2_partition *p, int64_t cat, int64_t inode, double *
     CU(cudaSetDevice(p->device));
     std::vector<double> tmp((size_t)p->Sp * p->Dp);
     std::vector<int> te(p->Sp);
+    const int64_t nstride = (p->use_tc && p->use_walk) ? 2 * p->I : p->I;     // node slots per class (walk: + side products)
     CU(cudaStreamSynchronize(p->stream));
     if (p->use_tc) {
         std::vector<float> tf(tmp.size());
-        CU(cudaMemcpy(tf.data(), p->d_condf + ((size_t)cat * p->I + inode) * p->Sp * 64, tf.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(tf.data(), p->d_condf + ((size_t)cat * nstride + inode) * p->Sp * 64, tf.size() * sizeof(float), cudaMemcpyDeviceToHost));
         // device layout per tile of 128 patterns: [16 chunks][128 patterns][4 floats]
         for (int64_t s = 0; s < p->Sp; s++)
             for (int k = 0; k < 64; k++)
                 tmp[s * 64 + k] = std::fabs(tf[(((size_t)(s / 128) * 16 + k / 4) * 128 + s % 128) * 4 + k % 4]);   // sign bit = walk tag
     } else
     CU(cudaMemcpy(tmp.data(), p->d_cond + ((size_t)cat * p->I + inode) * p->Sp * p->Dp, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(te.data(), p->d_scal + ((size_t)cat * p->I + inode) * p->Sp, te.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(te.data(), p->d_scal + ((size_t)cat * nstride + inode) * p->Sp, te.size() * sizeof(int), cudaMemcpyDeviceToHost));
     for (int64_t s = 0; s < p->S; s++) {
         for (int64_t k = 0; k < p->D; k++) cond[s * p->D + k] = tmp[s * p->Dp + k];
         exp2[s] = (p->use_tc && p->use_walk) ? (te[s] >> 1) : te[s];      // walk path: bit 0 is the generation tag
@@ -974,7 +1011,7 @@ static hb2::BranchCacheArgs bc_args(hb2_partition *p, int c0, int nc) {
     hb2::BranchCacheArgs a{};
     a.cv.c64 = p->use_tc ? nullptr : p->d_cond;
     a.cv.c32 = p->use_tc ? p->d_condf : nullptr;
-    a.cv.scal = p->d_scal; a.cv.I = (int)p->I; a.cv.Sp = (int)p->Sp; a.cv.Dp = p->Dp; a.cv.tagged = (p->use_tc && p->use_walk) ? 1 : 0;
+    a.cv.scal = p->d_scal; a.cv.I = (int)((p->use_tc && p->use_walk) ? 2 * p->I : p->I); a.cv.Sp = (int)p->Sp; a.cv.Dp = p->Dp; a.cv.tagged = (p->use_tc && p->use_walk) ? 1 : 0;
     a.PT = p->d_PT; a.leaf = p->d_leaf; a.ambig = p->d_ambig; a.pi = p->d_pi; a.out = p->d_bc_out; a.outE = p->d_bc_outE;
     a.L = (int)p->L; a.B = (int)p->B; a.D = (int)p->D; a.Dp = p->Dp; a.Sp = (int)p->Sp; a.S = (int)p->S; a.cat0 = c0; a.ncls = nc;
     return a;

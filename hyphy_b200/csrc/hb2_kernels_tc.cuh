@@ -369,7 +369,8 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_kernel(PruneTcArgs a, const
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int WALK_WAIT = 1 << 30;
 constexpr int WALK_CHAIN = 1 << 29;
-constexpr int WALK_ID_MASK = (1 << 28) - 1;
+constexpr int WALK_MUL = 1 << 28;         // child is a side-product node (index >= I): multiply it in, no contraction
+constexpr int WALK_ID_MASK = (1 << 27) - 1;
 constexpr int STEP_FIRST = 1 << 28;
 constexpr int STEP_LAST = 1 << 29;
 constexpr int WALK_PT_ROW = TC_PTF_ROW;        // same padded rows in shared memory: one flat bulk copy stages the table
@@ -382,6 +383,7 @@ struct WalkArgs {
     const int2 *steps;
     const int *gen;             // [C][I] generation bit of every node's conditionals AFTER this pass (see "tags" above)
     int K, T, ncls, nslots;
+    int NI;                     // node slots per class in cond/scal/gen: I real nodes + I side products
     long long *trace;           // nullable debug buffer: 12 clock64 stamps per step of CTA `trace_cta` (HB2_WALK_TRACE)
     long long *trace_cta_times; // nullable: per CTA {smid, clock64 at entry, clock64 at exit, globaltimer at entry}
     int trace_cta;
@@ -454,13 +456,39 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
         const bool internal = child >= a.L;
         float *dst = stage_base + (m & 1u) * WALK_STAGE_FLOATS;
         uint64_t *bar = bar_full + (m & 1u);
+        if (st.x & WALK_MUL) {               // side product: no matrix involved; the slot's phase still has to complete
+            mbar_expect_tx(bar, 0u);
+            prefetch_l2_bulk(cond4 + cond_f4(cat, child - a.L, tile, 0, 0, w.NI, w.T), 32768u);
+            return;
+        }
         const size_t slot = (size_t)cat * a.B + child;
         mbar_expect_tx(bar, (uint32_t)(TC_PTF_FLOATS * 4) + (internal ? 32768u : 0u));
         bulk_g2s(dst, a.PTf + slot * TC_PTF_FLOATS, (uint32_t)(TC_PTF_FLOATS * 4), bar);
         if (internal) {
             bulk_g2s(dst + 64 * WALK_PT_ROW, a.PB + slot * TC_PB_FLOATS, 32768u, bar);
             if (!(st.x & WALK_CHAIN))      // pull the child's conditional block towards L2 (it may still be in DRAM)
-                prefetch_l2_bulk(cond4 + cond_f4(cat, child - a.L, tile, 0, 0, a.I, w.T), 32768u);
+                prefetch_l2_bulk(cond4 + cond_f4(cat, child - a.L, tile, 0, 0, w.NI, w.T), 32768u);
+        }
+    };
+
+    // This thread's 17 words of another node's tile: 16 x 4 conditionals + the exponent word.  With `await` they are
+    // re-read until every word carries generation bit `want` (sign bit / bit 0), i.e. until the producer lane of THIS
+    // launch has written them; otherwise the tile is resident and its bits are whatever pass produced it.
+    auto load_tile_row = [&](const float4 *xrow, const int *scp, bool await, uint32_t want, uint4 (&x4)[16], uint32_t &sc) {
+#pragma unroll
+        for (int q = 0; q < 16; q++) x4[q] = __ldcg(reinterpret_cast<const uint4 *>(xrow + (size_t)q * 128));
+        sc = (uint32_t)__ldcg(scp);
+        if (await) {
+            for (int it = 0; !bailed; it++) {
+                uint32_t bad = (sc << 31) ^ want;
+#pragma unroll
+                for (int q = 0; q < 16; q++) bad |= (x4[q].x ^ want) | (x4[q].y ^ want) | (x4[q].z ^ want) | (x4[q].w ^ want);
+                if (!(bad >> 31)) break;
+                if (it > (1 << 18)) { atomicExch(a.err, 2); bailed = true; }   // never hang the GPU
+#pragma unroll
+                for (int q = 0; q < 16; q++) x4[q] = ld_relaxed_u4(xrow + (size_t)q * 128);
+                sc = ld_relaxed_u32(scp);
+            }
         }
     };
 
@@ -479,7 +507,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
         auto step_aux = [&](int2 q) -> int {
             const int ch = q.x & WALK_ID_MASK;
             if (ch < a.L) return __ldg(a.leaf + (size_t)ch * Sp + s);
-            return (q.x & WALK_WAIT) ? __ldg(w.gen + (size_t)cat * a.I + (ch - a.L)) : 0;
+            return (q.x & WALK_WAIT) ? __ldg(w.gen + (size_t)cat * w.NI + (ch - a.L)) : 0;
         };
         int next_code = step_aux(st);
         for (int i = i_begin; i < i_end; i++) {
@@ -488,7 +516,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
             const int par = st.y & WALK_ID_MASK;
             const int flags = st.y;
             const int code = next_code;
-            const uint32_t tagbit = (flags & STEP_LAST) ? ((uint32_t)__ldg(w.gen + (size_t)cat * a.I + par) << 31) : 0u;   // used at the end
+            const uint32_t tagbit = (flags & STEP_LAST) ? ((uint32_t)__ldg(w.gen + (size_t)cat * w.NI + par) << 31) : 0u;   // used at the end
             const bool has_next = (i + 1 < i_end);
             const int2 nx2 = (i + 2 < i_end) ? __ldg(w.steps + i + 2) : make_int2(0, 0);   // descriptors run two steps ahead
             const bool tr = w.trace && tid == 0 && (int)blockIdx.x == w.trace_cta;
@@ -534,6 +562,22 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
 #pragma unroll
                     for (int k = 0; k < 64; k++) v[k] *= acc[k];
                 }
+            } else if (enc & WALK_MUL) {
+                // side product of this node (its other children, multiplied up by another lane or earlier in this one):
+                // no matrix, just the element-wise product and the exponent
+                const int cin = child - a.L;
+                const bool await = (enc & WALK_WAIT) != 0;
+                uint4 x4[16];
+                uint32_t sc;
+                load_tile_row(cond4 + cond_f4(cat, cin, tile, 0, tid, w.NI, w.T), a.scal + ((size_t)cat * w.NI + cin) * Sp + s, await,
+                              await ? ((uint32_t)code << 31) : 0u, x4, sc);
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    v[4 * q] *= __uint_as_float(x4[q].x & 0x7fffffffu); v[4 * q + 1] *= __uint_as_float(x4[q].y & 0x7fffffffu);
+                    v[4 * q + 2] *= __uint_as_float(x4[q].z & 0x7fffffffu); v[4 * q + 3] *= __uint_as_float(x4[q].w & 0x7fffffffu);
+                }
+                ex += (int)sc >> 1;
+                if (tr) trp[3] = clock64();
             } else {
                 const int cin = child - a.L;
                 // Anchors without a serial dependency: one independent compare per element builds a 64-bit mask and
@@ -541,7 +585,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                 // values re-read from the child's conditional block in L2 (the row this thread itself loaded or, on a
                 // chain, stored a moment ago), eight loads in flight.
                 uint32_t am0 = 0, am1 = 0, am2 = 0, am3 = 0;
-                const float4 *xrow = cond4 + cond_f4(cat, cin, tile, 0, tid, a.I, w.T);
+                const float4 *xrow = cond4 + cond_f4(cat, cin, tile, 0, tid, w.NI, w.T);
                 {
                     uint32_t hi[64], lo[64];
                     if (enc & WALK_CHAIN) {
@@ -562,24 +606,10 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                         // word).  Other children are resident; their bits are whatever pass produced them and are ignored.
                         const bool await = (enc & WALK_WAIT) != 0;
                         const uint32_t want = await ? ((uint32_t)code << 31) : 0u;
-                        const int *scp = a.scal + ((size_t)cat * a.I + cin) * Sp + s;
+                        const int *scp = a.scal + ((size_t)cat * w.NI + cin) * Sp + s;
                         uint4 x4[16];
                         uint32_t sc;
-#pragma unroll
-                        for (int q = 0; q < 16; q++) x4[q] = __ldcg(reinterpret_cast<const uint4 *>(xrow + (size_t)q * 128));
-                        sc = (uint32_t)__ldcg(scp);
-                        if (await) {
-                            for (int it = 0; !bailed; it++) {
-                                uint32_t bad = (sc << 31) ^ want;
-#pragma unroll
-                                for (int q = 0; q < 16; q++) bad |= (x4[q].x ^ want) | (x4[q].y ^ want) | (x4[q].z ^ want) | (x4[q].w ^ want);
-                                if (!(bad >> 31)) break;
-                                if (it > (1 << 18)) { atomicExch(a.err, 2); bailed = true; }   // never hang the GPU
-#pragma unroll
-                                for (int q = 0; q < 16; q++) x4[q] = ld_relaxed_u4(xrow + (size_t)q * 128);
-                                sc = ld_relaxed_u32(scp);
-                            }
-                        }
+                        load_tile_row(xrow, scp, await, want, x4, sc);
 #pragma unroll
                         for (int q = 0; q < 16; q++) {
                             const uint32_t xs[4] = {x4[q].x, x4[q].y, x4[q].z, x4[q].w};
@@ -695,13 +725,13 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
             if (flags & STEP_LAST) {
                 // this tile of the parent: conditionals and exponent, every word tagged with the node's generation bit
                 // (consumers in other lanes poll the data itself: no flag, no fence, no barrier); root reduction
-                float4 *outp = cond4 + cond_f4(cat, par, tile, 0, tid, a.I, w.T);
+                float4 *outp = cond4 + cond_f4(cat, par, tile, 0, tid, w.NI, w.T);
 #pragma unroll
                 for (int q = 0; q < 16; q++)
                     __stcg(reinterpret_cast<uint4 *>(outp + (size_t)q * 128),
                            make_uint4(__float_as_uint(v[4 * q]) | tagbit, __float_as_uint(v[4 * q + 1]) | tagbit,
                                       __float_as_uint(v[4 * q + 2]) | tagbit, __float_as_uint(v[4 * q + 3]) | tagbit));
-                __stcg(a.scal + ((size_t)cat * a.I + par) * Sp + s, (int)(((uint32_t)ex << 1) | (tagbit >> 31)));
+                __stcg(a.scal + ((size_t)cat * w.NI + par) * Sp + s, (int)(((uint32_t)ex << 1) | (tagbit >> 31)));
                 if (par == a.I - 1) {
                     double rr = 0.0;
 #pragma unroll
