@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fp64", action="store_true", help="force the fp64 pruning kernels (HB2_FLAG_FORCE_FP64)")
+    ap.add_argument("--class-groups", type=int, default=0, help="multi-GPU: force this many class groups (default: as many as divide both)")
     ap.add_argument("--no-class-groups", action="store_true", help="multi-GPU: shard patterns only (every rank exponentiates every class)")
     ap.add_argument("--emulate-shard", default="", help="debug: R/W -> run rank R's pattern shard of a W-rank job on one GPU, no collectives")
     args = ap.parse_args()
@@ -203,6 +204,12 @@ def main():
     from hyphy_b200.sharding import shard_bounds, exchange_unique_id, layout
     # (pattern shards) x (class groups): classes first (no replicated expm inside a shard), patterns for the rest
     lay = layout(world, rank, w.C, S)
+    if args.class_groups > 0:                      # override: G class groups x world/G pattern shards
+        G = args.class_groups
+        assert w.C % G == 0 and world % G == 0, "--class-groups must divide both the classes and the ranks"
+        lo_, hi_ = shard_bounds(S, world // G, rank // G)
+        per = w.C // G
+        lay = {"groups": G, "group": rank % G, "shards": world // G, "shard": rank // G, "patterns": (lo_, hi_), "classes": (rank % G * per, (rank % G + 1) * per)}
     if args.no_class_groups:
         lay = {"groups": 1, "group": 0, "shards": world, "shard": rank, "patterns": shard_bounds(S, world, rank), "classes": (0, w.C)}
     lo, hi = lay["patterns"]

@@ -4,7 +4,7 @@ TAG=${1:-r01z}
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_errors.jsonl
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -4 gpurun_out/${TAG}_smoke.log
-timeout 300 python tools/stress_determinism.py 4 > gpurun_out/${TAG}_stress.log 2>&1; echo "stress rc=$?"; tail -2 gpurun_out/${TAG}_stress.log
+timeout 300 python tools/stress_determinism.py 3 > gpurun_out/${TAG}_stress.log 2>&1; echo "stress rc=$?"; tail -2 gpurun_out/${TAG}_stress.log
 timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/${TAG}_pytest_gpu.log
 cp gpurun_out/parity_errors.jsonl gpurun_out/${TAG}_parity_errors.jsonl 2>/dev/null
 timeout 600 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"; cat gpurun_out/${TAG}_bench.json | cut -c1-2500; tail -2 gpurun_out/${TAG}_bench.err
@@ -13,5 +13,4 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --c
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_bench.log 2>&1; echo "ncu list rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:prune64_tc_walk -s 8 -c 1 -f -o gpurun_out/${TAG}_prof_walk \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:expm64_dmma -s 8 -c 1 -f -o gpurun_out/${TAG}_prof_expm \
-    python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full2.log 2>&1; echo "ncu full2 rc=$?"
+timeout 300 python tools/bench_branch_cache.py 40 > gpurun_out/${TAG}_branch_cache.json 2> gpurun_out/${TAG}_branch_cache.err; echo "branch cache rc=$?"; cut -c1-900 gpurun_out/${TAG}_branch_cache.json

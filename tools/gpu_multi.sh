@@ -17,4 +17,5 @@ PY
   grep -E "EngineError|NCCL WARN|failed|Error" gpurun_out/${TAG}_bench_n${N}_$1.err | head -5 | cut -c1-600
 }
 run cg ""
-run pat "--no-class-groups"
+if [ "$N" -ge 4 ]; then run cg2 "--class-groups 2"; fi
+if [ "${ALSO_PATTERNS_ONLY:-0}" = 1 ]; then run pat "--no-class-groups"; fi
