@@ -309,8 +309,8 @@ hb2::PruneArgs prune_args(hb2_partition *p, int cat0) {
     return a;
 }
 
-// Walk plan: lanes of internal nodes (height-major order inside a lane), children re-ordered and tagged.
-// Layout of the int buffer: lane_start[K+1] | lane_jobs[nJobs] | job_child_start[I+1] | job_child[L+I]
+// Walk plan for prune64_tc_walk_kernel: K lanes of jobs (nodes and side products, in schedule order), flattened into
+// one step per child.  Layout of the int buffer: lane_start[K+1] (16 ints) | steps (int2 each) | generation bits [C][2I]
 int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector<int>> &levels) {
     const int I = (int)p->I, L = (int)p->L;
     const int T = (int)(p->Sp / hb2::TC_TILE_P);

@@ -347,25 +347,27 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_kernel(PruneTcArgs a, const
 // Persistent "walk" kernel: the whole pruning pass of one evaluation in ONE launch.
 //
 // Patterns are independent, so all dependencies are tile-local: tile t of node p needs tile t of p's children only.
-// CTA (c, t, r) owns rate class c, pattern tile t and "lane" r (one of K groups of internal nodes); it executes its
-// lane's STEPS (one per child of every node of the lane, nodes in (height, index) order) back to back.  A child computed
-// by another lane of the same (c, t) is awaited on the DATA ITSELF ("tags"): every node has a generation bit that the
-// host flips each time the node is re-pruned; the producer writes it into the sign bit of every conditional (they are
-// non-negative) and into bit 0 of the exponent word, and the consumer thread -- which needs exactly the 17 words the
-// producer thread of the same pattern wrote -- re-reads them until all carry the new bit.  No flag, no fence, no
-// barrier on either side, and a tile is consumed one L2 round trip after it was written.  A child computed by THIS CTA
-// in the previous job (the spine of deep trees) is taken straight from registers.  All K lanes of a (c,t) must be co-resident (host guarantees grid <= resident capacity); with K == 1 there
-// are no cross-CTA waits at all and a CTA may loop over several (c,t) pairs.
+// CTA (c, t, r) owns rate class c, pattern tile t and "lane" r (one of K in-order queues of JOBS the host planner
+// fills, hb2_engine.cu run_walk: a job is an internal node or the side product of a node -- all its children but the
+// deepest -- kept in node slot I + n); it executes its lane's STEPS (one per child of every job) back to back.
+//   * A child computed by another lane of the same (c, t) is awaited on the DATA ITSELF ("tags"): every job has a
+//     generation bit that the host flips each time the job is re-pruned; the producer writes it into the sign bit of
+//     every conditional (they are non-negative) and into bit 0 of the exponent word, and the consumer thread -- which
+//     needs exactly the 17 words the producer thread of the same pattern wrote -- re-reads them until all carry the new
+//     bit.  No flag, no fence, no barrier on either side; a tile is consumed one L2 round trip after it was written.
+//   * A child computed by THIS CTA in the previous job (the spine of deep trees) is taken straight from registers.
+//   * All K lanes of a (c,t) must be co-resident (the host guarantees grid <= resident capacity); with K == 1 there are
+//     no cross-CTA waits at all and a CTA may loop over several (c,t) pairs.
 //
 // The pass is bound by (tree depth x per-step latency), so every operand of step i+1 is staged while step i runs:
 //   * per step, the branch's fp32 P^T table (64 rows x 256 B, padded to 272 B rows) and -- for a contraction -- its
-//     Ph|Pl UMMA tiles are bulk-copied (TMA engine, mbarrier tx completion) into a 2-stage shared-memory ring by warp 0
+//     Ph|Pl UMMA tiles are bulk-copied (TMA engine, mbarrier tx completion) into a 2-stage shared-memory ring by thread 0
 //     right after the step-begin barrier; leaf column gathers and anchor rows are then shared-memory reads;
 //   * the 32 KB conditional block of the next contraction is prefetched into L2 (cp.async.bulk.prefetch.L2) and the next
-//     leaf's state codes into a register;
+//     leaf's state codes (or the awaited child's generation bit) into a register;
 //   * conditionals are stored tile-wise as [16 chunks][128 patterns][4 floats] (the K-major UMMA core-matrix order), so
-//     thread t's 16-byte accesses are perfectly coalesced for both the producer and the consumer of a tile;
-// Step encoding: x = child id | WALK_WAIT | WALK_CHAIN ; y = parent internal index | STEP_FIRST | STEP_LAST.
+//     thread t's 16-byte accesses are perfectly coalesced for both the producer and the consumer of a tile.
+// Step encoding: x = child id | WALK_WAIT | WALK_CHAIN | WALK_MUL ; y = job's node slot | STEP_FIRST | STEP_LAST.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int WALK_WAIT = 1 << 30;
 constexpr int WALK_CHAIN = 1 << 29;
@@ -381,7 +383,7 @@ struct WalkArgs {
     PruneTcArgs a;
     const int *lane_start;      // [K+1] offsets into steps
     const int2 *steps;
-    const int *gen;             // [C][I] generation bit of every node's conditionals AFTER this pass (see "tags" above)
+    const int *gen;             // [C][NI] generation bit of every job's conditionals AFTER this pass (see "tags" above)
     int K, T, ncls, nslots;
     int NI;                     // node slots per class in cond/scal/gen: I real nodes + I side products
     long long *trace;           // nullable debug buffer: 12 clock64 stamps per step of CTA `trace_cta` (HB2_WALK_TRACE)
