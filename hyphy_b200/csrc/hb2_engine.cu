@@ -309,32 +309,18 @@ hb2::PruneArgs prune_args(hb2_partition *p, int cat0) {
     return a;
 }
 
-// Walk plan for prune64_tc_walk_kernel: K lanes of jobs (nodes and side products, in schedule order), flattened into
-// one step per child.  Layout of the int buffer: lane_start[K+1] (16 ints) | steps (int2 each) | generation bits [C][2I]
-int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector<int>> &levels) {
-    const int I = (int)p->I, L = (int)p->L;
-    const int T = (int)(p->Sp / hb2::TC_TILE_P);
-    const int CT = ncls * T;
-    int K = std::max(1, std::min(p->walk_lane_cap, p->walk_max_resident / std::max(CT, 1)));
-    int total = 0;
-    for (auto &lv : levels) total += (int)lv.size();
-    if (total == 0) return 0;
-    K = std::min(K, total);
-    const int nslots = (K == 1) ? std::min(CT, p->walk_max_resident) : CT;
-    std::vector<char> dirty(I, 0);
-    for (auto &lv : levels) for (int n : lv) dirty[n] = 1;
-    int *buf = p->h_walk;                        // lane_start[K+1] | steps (int2, from int offset 16) | generation bits
-    int ns = p->plan_steps;
-    // the plan depends on the tree, the dirty set and K only: optimisers re-evaluate the same set again and again
-    const bool reuse = p->plan_steps > 0 && p->plan_K == K && p->plan_dirty == dirty;
-    if (!reuse) {
+// Pure host code (no CUDA): the walk plan for a dirty set on K lanes.  lane_start[K+1]; steps = 2 ints per step
+// (child encoding, job's node slot | flags); jdirty[2I] = jobs of the plan.  Returns the number of steps.  Exposed for
+// CPU tests through hb2_plan_walk.
+int plan_walk(const std::vector<std::vector<int>> &children, const std::vector<int> &height, int L, int I,
+              const std::vector<char> &dirty, int K, bool split_nodes, int *lane_start, int *steps, std::vector<char> &jdirty_out) {
     // Jobs.  Job j < I is node j; job I + n is the SIDE PRODUCT of node n: a node with two or more internal children is
     // split into "contract the child with the deepest subtree" (+ multiply the side product in: no matrix, the cheapest
     // step after a leaf) and a side job that contracts all OTHER children.  Side jobs sit off the root path, so other
     // lanes do them early and the spine of a deep tree carries one contraction per node instead of two (`split`).
     // item list of a job: children to contract (flat ids) and, for a split node, the side job to multiply in.
     const int NJ = 2 * I;
-    const bool split_on = p->walk_split_nodes && K > 1;
+    const bool split_on = split_nodes && K > 1;
     std::vector<std::vector<int>> jch(NJ);       // children (flat ids, leaves and internals) contracted by the job
     std::vector<int> jmul(NJ, -1);               // side job multiplied in by the job (real split nodes only)
     std::vector<char> jdirty(NJ, 0);
@@ -342,14 +328,14 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
         if (!dirty[n]) continue;
         jdirty[n] = 1;
         int heavy = -1, nint = 0;
-        for (int ch : p->children[n]) if (ch >= L) { nint++; if (heavy < 0 || p->height[ch - L] > p->height[heavy - L]) heavy = ch; }
+        for (int ch : children[n]) if (ch >= L) { nint++; if (heavy < 0 || height[ch - L] > height[heavy - L]) heavy = ch; }
         if (split_on && nint >= 2) {
             jch[n].push_back(heavy);
             jmul[n] = I + n;
             jdirty[I + n] = 1;
-            for (int ch : p->children[n]) if (ch != heavy) jch[I + n].push_back(ch);
+            for (int ch : children[n]) if (ch != heavy) jch[I + n].push_back(ch);
         } else {
-            jch[n] = p->children[n];
+            jch[n] = children[n];
         }
     }
     // Lane assignment = list scheduling of the dirty jobs on K in-order lanes with a rough cost model (cycles measured
@@ -379,11 +365,13 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
         }
         // remaining path to the root, parents before children: real nodes by decreasing height, a side job right after
         // its node
-        for (int h = (int)levels.size() - 1; h >= 0; h--)
-            for (int n : levels[h]) {
-                tail[n] = base[n] + (parent_job[n] >= 0 ? tail[parent_job[n]] : 0.0);
-                if (jmul[n] >= 0) tail[I + n] = base[I + n] + tail[n];
-            }
+        std::vector<int> by_height;
+        for (int n = 0; n < I; n++) if (dirty[n]) by_height.push_back(n);
+        std::stable_sort(by_height.begin(), by_height.end(), [&](int x, int y) { return height[x] > height[y]; });
+        for (int n : by_height) {
+            tail[n] = base[n] + (parent_job[n] >= 0 ? tail[parent_job[n]] : 0.0);
+            if (jmul[n] >= 0) tail[I + n] = base[I + n] + tail[n];
+        }
         for (int j = 0; j < NJ; j++) if (jdirty[j] && pending[j] == 0) ready.push_back(j);
         auto producers = [&](int j, auto &&f) {   // dirty jobs whose output job j consumes
             for (int ch : jch[j]) if (ch >= L && dirty[ch - L]) f(job_of_child(ch));
@@ -418,9 +406,7 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
         }
     }
     // flatten every lane into steps: chain child first, then leaves, then the other internal children, then the side product
-    int *lane_start = buf;                       // [K+1], steps start at int offset 16 (int2-aligned)
-    int *steps = buf + 16;
-    ns = 0;
+    int ns = 0;
     for (int r = 0; r < K; r++) {
         lane_start[r] = ns;
         for (int j : lanes[r]) {
@@ -439,7 +425,30 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
         }
     }
     lane_start[K] = ns;
-    p->plan_jdirty = jdirty;
+    jdirty_out = jdirty;
+    return ns;
+}
+
+// Walk plan for prune64_tc_walk_kernel: K lanes of jobs (nodes and side products, in schedule order), flattened into
+// one step per child.  Layout of the int buffer: lane_start[K+1] (16 ints) | steps (int2 each) | generation bits [C][2I]
+int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector<int>> &levels) {
+    const int I = (int)p->I, L = (int)p->L;
+    const int T = (int)(p->Sp / hb2::TC_TILE_P);
+    const int CT = ncls * T;
+    int K = std::max(1, std::min(p->walk_lane_cap, p->walk_max_resident / std::max(CT, 1)));
+    int total = 0;
+    for (auto &lv : levels) total += (int)lv.size();
+    if (total == 0) return 0;
+    K = std::min(K, total);
+    const int nslots = (K == 1) ? std::min(CT, p->walk_max_resident) : CT;
+    std::vector<char> dirty(I, 0);
+    for (auto &lv : levels) for (int n : lv) dirty[n] = 1;
+    int *buf = p->h_walk;                        // lane_start[K+1] | steps (int2, from int offset 16) | generation bits
+    int ns = p->plan_steps;
+    // the plan depends on the tree, the dirty set and K only: optimisers re-evaluate the same set again and again
+    const bool reuse = p->plan_steps > 0 && p->plan_K == K && p->plan_dirty == dirty;
+    if (!reuse) {
+    ns = plan_walk(p->children, p->height, L, I, dirty, K, p->walk_split_nodes, buf, buf + 16, p->plan_jdirty);
     p->plan_steps = ns; p->plan_K = K; p->plan_dirty = dirty;
     }   // !reuse
     // generation bits: every node re-pruned by this pass flips its bit (per class); the kernel tags what it writes with the
@@ -1092,6 +1101,43 @@ int hb2_branch_cache_evaluate(hb2_partition *p, int64_t cat, const double *weigh
     if (siteScale) CU(cudaMemcpyAsync(siteScale, p->d_siteScale, p->S * sizeof(long long), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaStreamSynchronize(p->stream));
     *lnL = hs[p->Dp + p->C];
+    return 0;
+}
+
+int hb2_plan_walk(int64_t L, int64_t I, const int64_t *flatParents, int64_t nUpdate, const int64_t *updateNodes, int lanes,
+                  int splitNodes, int32_t *laneStart, int32_t *steps, int64_t stepCapacity, int64_t *nSteps) {
+    if (!flatParents || !laneStart || !steps || !nSteps) return fail("null argument");
+    if (L < 2 || I < 1 || lanes < 1 || lanes > 15) return fail("bad sizes L=%lld I=%lld lanes=%d", (long long)L, (long long)I, lanes);
+    std::vector<std::vector<int>> children(I);
+    for (int64_t n = 0; n < L + I - 1; n++) {
+        const int64_t par = flatParents[n];
+        if (par < 0 || par >= I || (n >= L && par <= n - L)) return fail("flatParents[%lld]=%lld: not a post-ordered tree", (long long)n, (long long)par);
+        children[par].push_back((int)n);
+    }
+    if (flatParents[L + I - 1] != -1) return fail("root must be the last node");
+    std::vector<int> height(I, 0);
+    for (int64_t i = 0; i < I; i++) {
+        if (children[i].empty()) return fail("internal node %lld has no children", (long long)i);
+        for (int ch : children[i]) if (ch >= L) height[i] = std::max(height[i], height[ch - L] + 1);
+    }
+    std::vector<char> dirty(I, 0);
+    if (!updateNodes || nUpdate < 0) std::fill(dirty.begin(), dirty.end(), 1);
+    else
+        for (int64_t k = 0; k < nUpdate; k++) {                       // same closure as hb2_evaluate: parents and ancestors
+            if (updateNodes[k] < 0 || updateNodes[k] >= L + I) return fail("updateNodes[%lld] out of range", (long long)k);
+            for (int64_t par = flatParents[updateNodes[k]]; par >= 0 && !dirty[par]; par = flatParents[L + par]) dirty[par] = 1;
+        }
+    int total = 0;
+    for (char d : dirty) total += d;
+    if (total == 0) { *nSteps = 0; for (int r = 0; r <= lanes; r++) laneStart[r] = 0; return 0; }
+    const int K = std::min(lanes, total);
+    if (stepCapacity < L + 2 * I) return fail("steps needs room for %lld entries", (long long)(L + 2 * I));
+    std::vector<int> ls(K + 1), st(2 * (size_t)(L + 2 * I));
+    std::vector<char> jdirty;
+    const int ns = plan_walk(children, height, (int)L, (int)I, dirty, K, splitNodes != 0, ls.data(), st.data(), jdirty);
+    for (int r = 0; r <= lanes; r++) laneStart[r] = ls[std::min(r, K)];
+    for (int i = 0; i < 2 * ns; i++) steps[i] = st[i];
+    *nSteps = ns;
     return 0;
 }
 

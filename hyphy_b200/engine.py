@@ -43,6 +43,7 @@ ABI = [
     ("hb2_comm_unique_id", C.c_int, [C.c_void_p]),
     ("hb2_branch_cache_build", C.c_int, [C.c_void_p, C.c_int64, _dp]),
     ("hb2_branch_cache_evaluate", C.c_int, [C.c_void_p, C.c_int64, _dp, C.POINTER(C.c_double), _dp, _ip]),
+    ("hb2_plan_walk", C.c_int, [C.c_int64, C.c_int64, _ip, C.c_int64, _ip, C.c_int, C.c_int, _i32p, _i32p, C.c_int64, _ip]),
     ("hb2_comm_init", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     ("hb2_comm_class_groups", C.c_int, [C.c_void_p, C.c_int]),
     ("hb2_destroy", None, [C.c_void_p]),
@@ -73,6 +74,29 @@ def load_library():
             fn.argtypes = args
         _lib = lib
     return _lib
+
+
+STEP_WAIT, STEP_CHAIN, STEP_MUL, STEP_ID_MASK = 1 << 30, 1 << 29, 1 << 28, (1 << 27) - 1
+STEP_FIRST, STEP_LAST = 1 << 28, 1 << 29
+
+
+def plan_walk(flat_parents, n_leaves, update_nodes=None, lanes=4, split_nodes=True):
+    """The walk kernel's plan for a tree and a dirty set (host code only: works without a GPU).
+    Returns (lane_start[lanes+1], steps[n, 2])."""
+    fp, pfp = _i(flat_parents)
+    L = int(n_leaves)
+    I = len(fp) - L
+    ls = np.zeros(lanes + 1, dtype=np.int32)
+    st = np.zeros(2 * (L + 2 * I), dtype=np.int32)
+    n = C.c_int64()
+    if update_nodes is None:
+        nu, pu = -1, None
+    else:
+        u, pu = _i(update_nodes)
+        nu = len(u)
+    _check(load_library().hb2_plan_walk(L, I, pfp, nu, pu, int(lanes), int(bool(split_nodes)), ls.ctypes.data_as(_i32p),
+                                        st.ctypes.data_as(_i32p), len(st) // 2, C.byref(n)))
+    return ls, st[:2 * n.value].reshape(-1, 2).copy()
 
 
 def device_count() -> int:

@@ -143,6 +143,16 @@ int hb2_comm_class_groups(hb2_partition *p, int nGroups);
 /* Pair of SetupLFCaches in DeleteCaches (likefunc.cpp:10556-10601). */
 void hb2_destroy(hb2_partition *p);
 
+/* Host-side planner of the tcgen05 pruning pass, callable WITHOUT a GPU (tests/test_planner.py): for a tree (same
+ * flatParents as hb2_create), a dirty set given as hb2_evaluate's updateNodes (NULL or nUpdate < 0 = whole tree) and a
+ * number of lanes (1..15), returns the lanes' step lists exactly as the kernel receives them: laneStart[lanes+1] and
+ * 2 ints per step -- child id | HB2_STEP_WAIT (1<<30: produced by another lane) | HB2_STEP_CHAIN (1<<29: produced by
+ * the lane's previous job, taken from registers) | HB2_STEP_MUL (1<<28: side product, multiply without a matrix); job's
+ * node slot (>= I: side product of node slot-I) | HB2_STEP_FIRST (1<<28) | HB2_STEP_LAST (1<<29).  `steps` must hold
+ * 2*(L+2I) ints. */
+int hb2_plan_walk(int64_t L, int64_t I, const int64_t *flatParents, int64_t nUpdate, const int64_t *updateNodes, int lanes,
+                  int splitNodes, int32_t *laneStart, int32_t *steps, int64_t stepCapacity, int64_t *nSteps);
+
 /* Introspection for tests/bench: kernel launches issued so far by this partition, and device pointers/timing. */
 int64_t hb2_launch_count(const hb2_partition *p);
 /* 0: fp64 pruning kernels (4/20-state register kernels, or HB2_FLAG_FORCE_FP64);
