@@ -69,3 +69,60 @@ def test_oracle_reproduces_reference_own_golden_smallcodon():
     lnl, _ = port.lnl(w, Qt=Qt)
     assert abs(lnl - g["lnL_reference_run"]) <= 1e-11 * abs(lnl)
     assert abs(lnl - g["lnL_golden"]) < 0.002
+
+
+def test_single_branch_factorisation_identity():
+    """The algebra behind hb2_branch_cache_* (DESIGN 4.6), on the CPU with the oracle's matrices: for every branch b,
+    L_s = sum_a rest_b[s][a] * (P_b below_b[s])[a] with rest propagated from the root through TRANSPOSED matrices
+    (no re-rooting, no reversibility).  Plain numpy restatement; small cases only."""
+    import numpy as np
+    from tests import golden_cases as gc
+    from oracle import port
+    for name in ("mg94_8x60_c4_ambig", "c1_hky85_8x500"):
+        w, _ = gc.load(name)
+        t = w.tree
+        L, I, D, S = t.n_leaves, t.n_internal, w.D, min(w.S, 40)
+        par = np.asarray(t.flat_parents)
+        Qt = w.Qt()
+        c = Qt.shape[0] - 1
+        P = np.stack([port.expm(Qt[c, b]) for b in range(L + I - 1)])          # P[b][parent state][child state]
+        children = [[] for _ in range(I)]
+        for n in range(L + I - 1):
+            children[par[n]].append(n)
+
+        def leafvec(n):
+            v = np.zeros((S, D))
+            for s in range(S):
+                code = w.leaf_states[n, s]
+                if code >= 0:
+                    v[s, code] = 1.0
+                else:
+                    v[s] = w.ambig[-code - 1]
+            return v
+
+        cond = [None] * I
+        below = lambda n: leafvec(n) if n < L else cond[n - L]
+        for i in range(I):
+            v = np.ones((S, D))
+            for ch in children[i]:
+                v *= below(ch) @ P[ch].T
+            cond[i] = v
+        full = cond[I - 1] @ w.pi
+        for b in range(L + I - 1):
+            path = []
+            u = par[b]
+            while u >= 0:
+                path.append(u)
+                u = par[L + u]
+            out = np.tile(w.pi, (S, 1))
+            rest = None
+            for i, u in enumerate(reversed(path)):
+                on_path = L + path[len(path) - 2 - i] if i + 1 < len(path) else b
+                rest = out.copy()
+                for ch in children[u]:
+                    if ch != on_path:
+                        rest *= below(ch) @ P[ch].T
+                if i + 1 < len(path):
+                    out = rest @ P[on_path]                                   # out'[a'] = sum_a rest[a] P[a][a']
+            got = np.sum(rest * (below(b) @ P[b].T), axis=1)
+            assert np.abs(got / full - 1.0).max() < 1e-12, (name, b)
