@@ -193,9 +193,8 @@ def main():
     dist = None
     if world > 1:
         # control plane (barriers, id exchange, max-over-ranks of the timings) over gloo; the DATA path -- the per-evaluation
-        # sum of partial log-likelihoods -- is the engine's own NCCL communicator (hb2_comm_init) on the engine's stream.
-        # (A second, torch-owned NCCL communicator in the same process made cudaMemcpyAsync on the engine's stream fail with
-        # "invalid argument" right after torch's first MAX all-reduce on this box: gpurun r01n/r01p.)
+        # exchange of class partials / partial log-likelihoods -- is the engine's own NCCL communicator (hb2_comm_init) on
+        # the engine's stream, so no torch-owned NCCL communicator is needed in this process.
         import torch.distributed as dist
         dist.init_process_group("gloo")
 
