@@ -12,7 +12,9 @@ the whole tree pruned for all patterns and classes, root reduction, one fp64 lnL
           every class + hb2_evaluate_classes) with HOST buffers: the H2D copy of that step's formula values and the D2H
           read of lnL are inside the timed region.  e2e_dense is the same with dense D*D rate matrices
           (hb2_set_matrices_packed), i.e. without the compiled-template hand-over.
-Multi-GPU: patterns are sharded across ranks (strong scaling of one alignment); one fp64 ncclAllReduce per evaluation.
+Multi-GPU (strong scaling of one alignment): ranks form (pattern shards) x (class groups) -- rate classes first, so no
+rank exponentiates another group's matrices, patterns for the remaining factor (hyphy_b200/sharding.py); one exchange
+per evaluation on the engine's own NCCL communicator.
 The oracle / reference binary under oracle/ is used only for cpu_baseline and --impl reference.
 """
 from __future__ import annotations
@@ -109,60 +111,70 @@ def algorithmic_work(w, S, word=8):
     B = L + I - 1
     flops = C * ((I - 1) * S * 2 * D * D + (L + B) * S * D + 2 * S * D)
     byts = C * ((2 * I - 1) * S * D * word + B * D * D * 8 + L * S)
-    expm_flops = C * B * 7 * 2 * D ** 3          # this engine: 6 products + ~1 squaring per matrix
+    expm_flops = C * B * 5 * 2 * 64 ** 3         # this engine: ~5.0 products of 64^3 per matrix on this stream
     return flops, byts, expm_flops
 
 
-def cpu_baseline_sample(steps, warmup, threads):
-    """Reference HYPHYMP (oracle/_ref/hyphy) on a bounded sample: same tree/model/classes, 1/8 of the codons.
-    Pruning + per-pattern work scale linearly in patterns, expm does not: full-size evals/s are reported as
-    sample evals/s * (S_sample/S_full), which flatters the CPU slightly (its expm share is counted 1/8)."""
+def cpu_baseline_full(steps, warmup, threads, probe=True):
+    """Reference HYPHYMP (oracle/_ref/hyphy) on the FULL stated workload (200 x 2000 x 4 classes): `steps` timed full
+    evaluations after `warmup`, each perturbing one global parameter so every matrix is re-exponentiated.
+    No sub-sampling and no extrapolation: the number is evaluations/s of the same config the GPU arm runs."""
     from hyphy_b200 import synth
     from oracle import ref_harness as rh, port
-    frac = 8
-    ws = synth.codon_workload(WORKLOAD["taxa"], WORKLOAD["codons"] // frac, WORKLOAD["classes"])
+    w = synth.codon_workload(WORKLOAD["taxa"], WORKLOAD["codons"], WORKLOAD["classes"])
     if rh.have_reference():
         # the reference tunes its own thread count (BenchmarkThreads, likefunc.cpp:219); give it the same courtesy:
-        # a short probe over a few counts, then the timed run at the best one
-        cands = sorted({t for t in (8, 16, 32, 64, threads) if t <= threads})
-        best, best_rate = cands[0], 0.0
-        for t in cands:
-            pr = rh.run_reference(ws, n_evals=2, threads=t, per_site=False, n_warm=1)
-            if 2 / pr["loop_seconds"] > best_rate:
-                best, best_rate = t, 2 / pr["loop_seconds"]
-        r = rh.run_reference(ws, n_evals=steps, threads=best, per_site=False, n_warm=warmup)
-        rate_sample = steps / r["loop_seconds"]
-        kind, cores = "reference", best
-        lnl = r["lnL"]
+        # a short probe over a few counts (2 full-size evaluations each), then the timed run at the best one
+        best = threads
+        probe_rates = {}
+        if probe:
+            cands = sorted({t for t in (8, 16, 32, 64, threads) if t <= threads})
+            best, best_rate = cands[0], 0.0
+            for t in cands:
+                pr = rh.run_reference(w, n_evals=2, threads=t, per_site=False, n_warm=1)
+                probe_rates[t] = 2 / pr["loop_seconds"]
+                if probe_rates[t] > best_rate:
+                    best, best_rate = t, probe_rates[t]
+        r = rh.run_reference(w, n_evals=steps, threads=best, per_site=False, n_warm=warmup)
+        rate = steps / r["loop_seconds"]
+        kind, cores, lnl = "reference", best, r["lnL"]
     else:
-        port.lnl(ws)
+        port.lnl(w)
+        n = max(1, min(steps, 2))
         t0 = time.perf_counter()
-        for _ in range(max(1, steps // 4)):
-            lnl, _ = port.lnl(ws)
-        rate_sample = max(1, steps // 4) / (time.perf_counter() - t0)
-        kind, cores = "port", 1
-    return dict(kind=kind, cores=cores, rate_sample=rate_sample, S_sample=ws.S, lnl_sample=lnl,
-                sample=f"{WORKLOAD['taxa']} taxa x {WORKLOAD['codons'] // frac} codons x {WORKLOAD['classes']} classes "
-                       f"(1/{frac} of the codons, S={ws.S} patterns), {steps} full evaluations after {warmup} warm-up; "
-                       f"value = sample evals/s x S_sample/S_full")
+        for _ in range(n):
+            lnl, _ = port.lnl(w)
+        rate = n / (time.perf_counter() - t0)
+        kind, cores, probe_rates = "port", 1, {}
+    return dict(kind=kind, cores=cores, rate=rate, S=w.S, lnl=lnl, probe=probe_rates,
+                sample=f"full workload: {WORKLOAD['taxa']} taxa x {WORKLOAD['codons']} codons x {WORKLOAD['classes']} classes "
+                       f"(S={w.S} patterns), {steps} full evaluations after {warmup} warm-up, no extrapolation")
+
+
+def config_dict(S, B, D, C):
+    """Identical for both arms (the driver compares them): the workload and nothing implementation-specific."""
+    return {"workload": NAME, "taxa": WORKLOAD["taxa"], "codons": WORKLOAD["codons"], "patterns": S, "branches": B, "states": D,
+            "classes": C, "l2": "inputs larger than L2 (830 MB of conditionals per evaluation)"}
 
 
 def run_reference_arm(args, rank):
+    """--impl reference: the unmodified reference binary (HYPHYMP, OpenMP + AVX2) on the box's host cores, same config."""
     if rank != 0:
         return
-    from hyphy_b200 import synth
     threads = os.cpu_count() or 1
-    w_full_S = synth.codon_workload(WORKLOAD["taxa"], WORKLOAD["codons"], WORKLOAD["classes"]).S
     t0 = time.time()
-    cb = cpu_baseline_sample(args.steps, args.warmup, threads)
-    value = cb["rate_sample"] * cb["S_sample"] / w_full_S
+    cb = cpu_baseline_full(args.steps, args.warmup, threads)
+    value = cb["rate"]
+    L = WORKLOAD["taxa"]
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": NAME, "patterns": w_full_S, "l2": "inputs larger than L2 (n/a on CPU)"},
-            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]},
+            "config": config_dict(cb["S"], 2 * L - 3, 61, WORKLOAD["classes"]),
+            "layout": "host cores (OpenMP), no GPU",
+            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"],
+                             "thread_probe_evals_per_s": cb["probe"]},
             "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "wall_s": time.time() - t0}
+            "gpu_launches": 0, "lnL": cb["lnl"], "wall_s": time.time() - t0}
     print(json.dumps(line), flush=True)
 
 
@@ -301,6 +313,8 @@ def main():
         lf.part.time_resident(w.class_weights, w.pi, iters=args.steps)
     clocks = sampler.stop()
     tc_mode = lf.part.precision_mode == 1
+    prune_kernel = lf.part.pruning_kernel
+    stage_launches = [int(x) for x in lf.part.stage_launches]
     ms = max_over_ranks(ms)
     stage = [max_over_ranks(float(s)) for s in stage]
     lf.close()
@@ -308,14 +322,14 @@ def main():
     if rank == 0:
         pk, pk_kind = peaks()
         flops, byts, expm_flops = algorithmic_work(w, S, 4 if tc_mode else 8)
-        # dominant kernel: the fused pruning update (one launch per tree level); per-launch = per-evaluation / levels
-        prune_launches = (launches // args.steps) - 3     # minus expm (packs the tensor operands itself), combine, final_sum
+        # dominant kernel: the fused pruning pass; name and launches per evaluation come from the engine itself
+        prune_launches = stage_launches[1]
         prune_ms = stage[1]
         achieved_gbs = (byts / world) / (prune_ms * 1e-3) / 1e9
         single_launch = prune_launches == 1
-        kname = ("prune64_tc_walk_kernel (tcgen05 3xTF32 fused pruning pass, whole tree in one launch)" if (tc_mode and single_launch)
-                 else "prune64_tc_kernel (tcgen05 3xTF32 fused pruning update, one launch per tree level)" if tc_mode
-                 else "prune64_kernel (fp64 fused pruning update, one launch per tree level)")
+        kname = {"prune64_tc_walk_kernel": "prune64_tc_walk_kernel (tcgen05 3xTF32 fused pruning pass, whole tree in one launch)",
+                 "prune64_tc_kernel": "prune64_tc_kernel (tcgen05 3xTF32 fused pruning update, one launch per tree level)",
+                 "prune64_kernel": "prune64_kernel (fp64 fused pruning update, one launch per tree level)"}.get(prune_kernel, prune_kernel)
         # DRAM traffic of that kernel from the committed `ncu --set full` capture of this same command (profiles/)
         traffic, traffic_src = None, None
         try:
@@ -329,7 +343,7 @@ def main():
         roofline = {"kernel": kname, "bound": "hbm",
                     "achieved": achieved_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / pk["hbm_gbs"],
                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": f"MEASURED_PEAKS.json ({pk_kind})",
-                    "launches_per_eval": prune_launches, "avg_launch_ms": prune_ms / max(prune_launches, 1),
+                    "launches_per_eval": prune_launches, "stage_launches_per_eval": {"expm": stage_launches[0], "pruning": stage_launches[1], "root": stage_launches[2]}, "avg_launch_ms": prune_ms / max(prune_launches, 1),
                     "algorithmic_bytes_per_eval": byts, "algorithmic_flops_per_eval": flops,
                     "tflops_pruning": (flops / world) / (prune_ms * 1e-3) / 1e12,
                     "tensor_frac_of_tf32_peak": ((flops / world) / (prune_ms * 1e-3) / 1e12) / (pk["bf16_tflops"] / 2) if tc_mode else None,
@@ -342,8 +356,8 @@ def main():
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "tf32x3 (tcgen05, fp32 accumulate) pruning + f64 expm/root" if tc_mode else "f64",
                 "data": "synthetic",
-                "config": {"workload": NAME, "patterns": S, "branches": w.tree.n_branches, "states": w.D, "classes": w.C,
-                           "sharding": f"patterns/{lay['shards']} x classes/{lay['groups']}", "l2": "inputs larger than L2 (830 MB of conditionals per evaluation)"},
+                "config": config_dict(S, w.tree.n_branches, w.D, w.C),
+                "layout": f"patterns/{lay['shards']} x classes/{lay['groups']}",
                 "e2e": {"value": 1000.0 / e2e_ms, "unit": "evals/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                         "api": "hb2_set_matrices_compiled x C + hb2_evaluate_classes", "host_split": e2e_split},
                 "e2e_dense": {"value": 1000.0 / e2e_dense_ms, "unit": "evals/s", "ms_per_step": e2e_dense_ms, "h2d_bytes_per_step": h2d_dense,
@@ -352,9 +366,9 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             try:
                 threads = os.cpu_count() or 1
-                cb = cpu_baseline_sample(6, 1, threads)
-                v = cb["rate_sample"] * cb["S_sample"] / S
-                line["cpu_baseline"] = {"value": v, "unit": "evals/s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"]}
+                cb = cpu_baseline_full(6, 1, threads)
+                line["cpu_baseline"] = {"value": cb["rate"], "unit": "evals/s", "cores": cb["cores"], "kind": cb["kind"], "sample": cb["sample"],
+                                        "lnL": cb["lnl"]}
             except Exception as e:                   # the baseline is a report, never a reason to lose the bench line
                 line["cpu_baseline"] = {"value": None, "unit": "evals/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
         print(json.dumps(line), flush=True)

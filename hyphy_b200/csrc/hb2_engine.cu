@@ -91,9 +91,9 @@ struct hb2_partition {
     int max_height = 0;
     // device
     int *d_leaf = nullptr, *d_scal = nullptr, *d_rootE = nullptr, *d_child_start = nullptr, *d_child_ids = nullptr;
-    int *d_jobs = nullptr, *d_dst = nullptr, *d_flag = nullptr, *d_mix_first = nullptr;
+    int *d_jobs = nullptr, *d_dst = nullptr, *d_flag = nullptr;
     double *d_ambig = nullptr, *d_freq = nullptr, *d_cond = nullptr, *d_PT = nullptr, *d_Q = nullptr, *d_pi = nullptr;
-    double *d_rootL = nullptr, *d_weights = nullptr, *d_partial = nullptr, *d_lnL = nullptr, *d_siteL = nullptr, *d_mix_w = nullptr;
+    double *d_rootL = nullptr, *d_weights = nullptr, *d_partial = nullptr, *d_lnL = nullptr, *d_siteL = nullptr;
     long long *d_siteScale = nullptr;
     // pinned host staging
     double *h_Q = nullptr, *h_small = nullptr;   // h_small: pi (Dp) + weights (C) + lnL (1)
@@ -101,11 +101,22 @@ struct hb2_partition {
     // pending matrices: entries [0, n_pending) of h_Q / h_dst, with kinds
     int64_t n_pending = 0;
     std::vector<int> pending_kind;
+    // one pending entry per (class, node) slot across BOTH queues: >= 0 index into the dense queue, <= -2 -> index
+    // -(v+2) into the compiled queue, -1 none.  A slot handed over twice before an evaluation overwrites / retires its
+    // earlier entry (last one wins, like the reference's SetCompExp, calcnode.cpp:714), so one expm launch never holds
+    // two CTAs with the same destination and the flush order of the two queues cannot matter.
+    std::vector<int> pend_pos;
     int64_t q_capacity = 0;                   // in matrices
     std::vector<char> have_matrix;            // [C*B]
     std::vector<char> is_rate;                // [C*B] slot holds a rate matrix resident in d_Qres (for hb2_time_resident)
     double *d_Qres = nullptr;                 // [C][B][D*D] last rate matrices, resident copy
-    double *d_mix_scratch = nullptr;          // [capacity][4096] expm scratch for mixture components (allocated on first use)
+    // explicit-form mixtures (hb2_set_mixture_matrices): own staging so that nothing is shared with the plain queues
+    double *d_mix_scratch = nullptr, *d_mix_Q = nullptr, *h_mix = nullptr;   // [cap][Dp*Dp], [cap][D*D], pinned [cap][D*D + 1]
+    int *d_mix_dst = nullptr;
+    int64_t mix_capacity = 0;
+    cudaEvent_t ev_mix = nullptr;
+    bool mix_busy = false;
+    int64_t stage_launches[3] = {0, 0, 0};    // launches per evaluation of the last hb2_time_resident {expm, pruning, root}
     // compiled rate-matrix template (hb2_set_rate_template) and its per-evaluation formula values
     int64_t t_nnz = 0, t_nF = 0;
     bool t_has_colfreq = false;
@@ -123,6 +134,7 @@ struct hb2_partition {
     int walk_max_resident = 0;
     // single-branch shortcut (hb2_branch_cache_*): outside vectors of one branch, all owned classes
     double *d_bc_out = nullptr; int *d_bc_outE = nullptr, *d_bc_sib = nullptr; int64_t bc_node = -1;
+    int64_t bc_dirty_node = -1;               // first node other than bc_node whose matrix changed since the build
     std::vector<char> plan_jdirty;      // dirty jobs (nodes + side products) of the cached plan
     bool walk_split_nodes = true;       // HB2_WALK_SPLIT_NODES=0: no side products (A/B)
     std::vector<char> plan_dirty;       // cached walk plan (h_walk holds its steps): dirty set, lane count, step count
@@ -147,25 +159,28 @@ struct hb2_partition {
 
 namespace {
 
-int launch_expm(hb2_partition *p, const double *dQ, const int *d_dst, int n, int is_trans, const double *mix_w,
-                const int *mix_first, double *qres, bool pack_tc = true) {
+// One CTA per listed matrix.  is_trans: 0 rate matrices (exponentiated), 1 transition matrices (transposed/padded only),
+// 2 compiled template (dQ = formula values).  pt_override: write the results there instead of the P cache (mixture
+// components go to a scratch area first); pack_tc: also emit the tensor-path operands of the slot.
+int launch_expm(hb2_partition *p, const double *dQ, const int *d_dst, int n, int is_trans, double *qres, bool pack_tc = true,
+                double *pt_override = nullptr) {
     if (n <= 0) return 0;
     hb2::ExpmArgs a{};
-    a.Q = dQ; a.dst = d_dst; a.mix_w = mix_w; a.mix_first = mix_first; a.PT = p->d_PT; a.Qres = qres; a.D = (int)p->D;
+    a.Q = dQ; a.dst = d_dst; a.PT = pt_override ? pt_override : p->d_PT; a.Qres = qres; a.D = (int)p->D;
     a.is_trans = is_trans;
-    a.park = mix_w ? p->d_mix_scratch : nullptr;
     if (is_trans == 2) {                       // compiled template: dQ points at the formula values [n][nF]
         a.is_trans = 0; a.Q = nullptr; a.V = dQ; a.tmpl_index = p->d_t_index; a.tmpl_formula = p->d_t_formula;
         a.tmpl_colfreq = p->t_has_colfreq ? p->d_t_colfreq : nullptr; a.tmpl_nnz = (int)p->t_nnz; a.nF = (int)p->t_nF;
     }
     bool packed = false;
+    pack_tc = pack_tc && p->use_tc && !pt_override;
     switch (p->Dp) {
         case 64:
             if (p->expm_dfma) {
                 hb2::expm64_kernel<<<n, 256, 5 * 64 * hb2::LD64 * sizeof(double), p->stream>>>(a);
             } else {
                 hb2::ExpmTcOut tco{nullptr, nullptr};
-                if (p->use_tc && pack_tc && !mix_w) { tco.PB = p->d_PB; tco.PTf = p->d_PTf; packed = true; }
+                if (pack_tc) { tco.PB = p->d_PB; tco.PTf = p->d_PTf; packed = true; }
                 hb2::expm64_dmma_kernel<<<n, 256, 3 * 64 * hb2::LD64 * sizeof(double), p->stream>>>(a, tco);
             }
             break;
@@ -178,7 +193,7 @@ int launch_expm(hb2_partition *p, const double *dQ, const int *d_dst, int n, int
     }
     p->launches++;
     CU(cudaGetLastError());
-    if (p->use_tc && pack_tc && !packed) {
+    if (pack_tc && !packed) {
         hb2::pack_tc_kernel<<<n, 256, 0, p->stream>>>(p->d_PT, d_dst, p->d_PB, p->d_PTf);
         p->launches++;
         CU(cudaGetLastError());
@@ -214,7 +229,17 @@ int launch_prune(hb2_partition *p, const hb2::PruneArgs &a, const int *d_jobs, i
     return 0;
 }
 
-// Flush matrices handed over since the last evaluation: one H2D copy + one (or two) expm launches.
+// The pinned staging buffers (both queues, h_dst/h_vdst included) may still be read by the H2D copies of the last flush.
+int wait_staging(hb2_partition *p) {
+    if (p->staging_busy) {
+        CU(cudaEventSynchronize(p->ev_staging));
+        p->staging_busy = false;
+    }
+    return 0;
+}
+
+// Flush matrices handed over since the last evaluation: one H2D copy + one (or two) expm launches per queue.  Retired
+// entries (destination -1: the slot was handed over again later) are skipped by the kernels.
 int flush_compiled(hb2_partition *p) {
     const int64_t n = p->n_vpending;
     if (n == 0) return 0;
@@ -222,8 +247,9 @@ int flush_compiled(hb2_partition *p) {
     CU(cudaMemcpyAsync(p->d_vdst, p->h_vdst, n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
     CU(cudaEventRecord(p->ev_staging, p->stream));
     p->staging_busy = true;
-    if (launch_expm(p, p->d_V, p->d_vdst, (int)n, 2, nullptr, nullptr, p->d_Qres)) return 1;
-    for (int64_t k = 0; k < n; k++) p->is_rate[p->h_vdst[k]] = 1;
+    if (launch_expm(p, p->d_V, p->d_vdst, (int)n, 2, p->d_Qres)) return 1;
+    for (int64_t k = 0; k < n; k++)
+        if (p->h_vdst[k] >= 0) { p->is_rate[p->h_vdst[k]] = 1; p->pend_pos[p->h_vdst[k]] = -1; }
     p->n_vpending = 0;
     return 0;
 }
@@ -245,13 +271,35 @@ int flush_matrices(hb2_partition *p) {
         int64_t j = i;
         while (j < n && p->pending_kind[j] == p->pending_kind[i]) j++;
         const int is_trans = p->pending_kind[i] == HB2_MATRIX_TRANS;
-        if (launch_expm(p, p->d_Q + i * dd, p->d_dst + i, (int)(j - i), is_trans, nullptr, nullptr, is_trans ? nullptr : p->d_Qres)) return 1;
+        if (launch_expm(p, p->d_Q + i * dd, p->d_dst + i, (int)(j - i), is_trans, is_trans ? nullptr : p->d_Qres)) return 1;
         i = j;
     }
-    for (int64_t k = 0; k < n; k++) p->is_rate[p->h_dst[k]] = (p->pending_kind[k] == HB2_MATRIX_RATE);
+    for (int64_t k = 0; k < n; k++)
+        if (p->h_dst[k] >= 0) { p->is_rate[p->h_dst[k]] = (p->pending_kind[k] == HB2_MATRIX_RATE); p->pend_pos[p->h_dst[k]] = -1; }
     p->n_pending = 0;
     p->pending_kind.clear();
     return 0;
+}
+
+// A matrix of `node` is about to change: the single-branch cache (if any) only survives changes of ITS branch.
+inline void note_matrix_change(hb2_partition *p, int64_t node) {
+    if (p->bc_node >= 0 && node != p->bc_node && p->bc_dirty_node < 0) p->bc_dirty_node = node;
+}
+
+// Retire the pending entry of `slot` that sits in the OTHER queue (compiled = true: we are about to add it to the
+// compiled queue).  Returns the index of an entry of the SAME queue that can be overwritten in place, or -1.
+int64_t claim_slot(hb2_partition *p, int64_t slot, bool compiled) {
+    const int pos = p->pend_pos[slot];
+    if (pos == -1) return -1;
+    if (pos >= 0) {                            // pending in the dense queue
+        if (!compiled) return pos;
+        p->h_dst[pos] = -1;
+    } else {                                   // pending in the compiled queue
+        if (compiled) return -(int64_t)pos - 2;
+        p->h_vdst[-(int64_t)pos - 2] = -1;
+    }
+    p->pend_pos[slot] = -1;
+    return -1;
 }
 
 int stage_matrix(hb2_partition *p, int64_t cat, int64_t node, const double *M, int kind) {
@@ -259,21 +307,25 @@ int stage_matrix(hb2_partition *p, int64_t cat, int64_t node, const double *M, i
     if (cat >= p->C) return fail("rate class %lld out of range (C=%lld)", (long long)cat, (long long)p->C);
     if (node < 0 || node >= p->B) return fail("node id %lld has no branch (valid 0..%lld)", (long long)node, (long long)p->B - 1);
     if (kind != HB2_MATRIX_RATE && kind != HB2_MATRIX_TRANS) return fail("unknown matrix kind %d", kind);
+    note_matrix_change(p, node);
     if (cat < p->own0 || cat >= p->own0 + p->ownN) { p->have_matrix[cat * p->B + node] = 1; return 0; }   // another class group's
-    if (p->n_pending == p->q_capacity) {
-        cudaSetDevice(p->device);
-        if (flush_matrices(p)) return 1;
-    }
-    if (p->staging_busy) {                    // previous flush's H2D copies must have left the pinned buffers
-        CU(cudaEventSynchronize(p->ev_staging));
-        p->staging_busy = false;
+    if (wait_staging(p)) return 1;            // previous flush's H2D copies must have left the pinned buffers
+    const int64_t slot = cat * p->B + node;
+    int64_t at = claim_slot(p, slot, false);
+    if (at < 0) {
+        if (p->n_pending == p->q_capacity) {
+            cudaSetDevice(p->device);
+            if (flush_matrices(p) || wait_staging(p)) return 1;
+        }
+        at = p->n_pending++;
+        p->pending_kind.push_back(kind);
+        p->pend_pos[slot] = (int)at;
     }
     const size_t dd = (size_t)p->D * p->D;
-    memcpy(p->h_Q + p->n_pending * dd, M, dd * sizeof(double));
-    p->h_dst[p->n_pending] = (int)(cat * p->B + node);
-    p->pending_kind.push_back(kind);
-    p->have_matrix[cat * p->B + node] = 1;
-    p->n_pending++;
+    memcpy(p->h_Q + at * dd, M, dd * sizeof(double));
+    p->h_dst[at] = (int)slot;
+    p->pending_kind[at] = kind;
+    p->have_matrix[slot] = 1;
     return 0;
 }
 
@@ -618,7 +670,7 @@ int evaluate_impl(hb2_partition *p, int c0, int nc, const double *weights, int64
         if (!weights || c0 != 0 || nc != (int)p->C) return fail("with class groups only hb2_evaluate_classes is available");
         c0 = p->own0;                          // prune the owned classes; the weights of all C classes are still uploaded
     }
-    p->bc_node = -1;                           // conditionals are about to change: the branch cache is stale
+    p->bc_node = -1; p->bc_dirty_node = -1;     // conditionals are about to change: the branch cache is stale
     const int nw = nc;                         // number of class weights the caller passed
     if (p->cg_G > 1) nc = p->ownN;
     if (flush_matrices(p)) return 1;
@@ -654,8 +706,12 @@ int evaluate_impl(hb2_partition *p, int c0, int nc, const double *weights, int64
     if (siteL) CU(cudaMemcpyAsync(siteL, p->d_siteL, p->S * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
     if (siteScale) CU(cudaMemcpyAsync(siteScale, p->d_siteScale, p->S * sizeof(long long), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaStreamSynchronize(p->stream));
-    if (*reinterpret_cast<int *>(hs + p->Dp + p->C + 1) != 0) p->walk_reset = p->use_tc && p->use_walk;
-    if (*reinterpret_cast<int *>(hs + p->Dp + p->C + 1) != 0) return fail("device-side wait timed out in the tcgen05 pruning kernel (code %d)", *reinterpret_cast<int *>(hs + p->Dp + p->C + 1));
+    if (const int code = *reinterpret_cast<int *>(hs + p->Dp + p->C + 1)) {
+        p->walk_reset = p->use_tc && p->use_walk;          // tags are inconsistent: the next pass starts from scratch
+        cudaMemsetAsync(p->d_err, 0, sizeof(int), p->stream);   // on every path, or each later evaluation would fail too
+        std::fill(p->evaluated_cat.begin(), p->evaluated_cat.end(), 0);
+        return fail("device-side wait timed out in the tcgen05 pruning kernel (code %d)", code);
+    }
     *lnL = hs[p->Dp + p->C];
     for (int c = c0; c < c0 + nc; c++) p->evaluated_cat[c] = 1;
     return 0;
@@ -725,6 +781,7 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
     CUP(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     for (auto &e : p->ev) CUP(cudaEventCreate(&e));
     CUP(cudaEventCreateWithFlags(&p->ev_staging, cudaEventDisableTiming));
+    CUP(cudaEventCreateWithFlags(&p->ev_mix, cudaEventDisableTiming));
     const size_t Sp = p->Sp, dpdp = (size_t)Dp * Dp, dd = (size_t)D * D;
     CUP(cudaMalloc(&p->d_leaf, L * Sp * sizeof(int)));
     CUP(cudaMalloc(&p->d_ambig, std::max<int64_t>(nAmb, 1) * Dp * sizeof(double)));
@@ -785,8 +842,6 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
     p->q_capacity = C * p->B;
     CUP(cudaMalloc(&p->d_Q, (size_t)p->q_capacity * dd * sizeof(double)));
     CUP(cudaMalloc(&p->d_dst, p->q_capacity * sizeof(int)));
-    CUP(cudaMalloc(&p->d_mix_w, p->q_capacity * sizeof(double)));
-    CUP(cudaMalloc(&p->d_mix_first, p->q_capacity * sizeof(int)));
     CUP(cudaMalloc(&p->d_pi, Dp * sizeof(double)));
     CUP(cudaMalloc(&p->d_rootL, (size_t)C * Sp * sizeof(double)));
     CUP(cudaMalloc(&p->d_rootE, (size_t)C * Sp * sizeof(int)));
@@ -841,6 +896,7 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
     { const char *env = getenv("HB2_SMALL_WALK"); p->small_walk = !(env && env[0] == '0'); }
     p->have_matrix.assign(C * p->B, 0);
     p->is_rate.assign(C * p->B, 0);
+    p->pend_pos.assign(C * p->B, -1);
     p->evaluated_cat.assign(C, 0);
     p->own0 = 0; p->ownN = (int)C;
     *out = p;
@@ -872,32 +928,48 @@ int hb2_set_mixture_matrices(hb2_partition *p, int64_t cat, int64_t n, const int
     if (n < 0 || K < 1 || (n > 0 && (!nodeIds || !M || !w))) return fail("bad mixture arguments");
     if (cat < 0) cat = 0;
     if (cat >= p->C) return fail("rate class %lld out of range", (long long)cat);
+    for (int64_t i = 0; i < n; i++) {
+        if (nodeIds[i] < 0 || nodeIds[i] >= p->B) return fail("node id %lld has no branch", (long long)nodeIds[i]);
+        note_matrix_change(p, nodeIds[i]);
+    }
     if (cat < p->own0 || cat >= p->own0 + p->ownN) {       // another class group's
-        for (int64_t i = 0; i < n; i++) if (nodeIds && nodeIds[i] >= 0 && nodeIds[i] < p->B) p->have_matrix[cat * p->B + nodeIds[i]] = 1;
+        for (int64_t i = 0; i < n; i++) p->have_matrix[cat * p->B + nodeIds[i]] = 1;
         return 0;
     }
-    if (n > p->q_capacity) return fail("too many nodes");
+    if (n == 0) return 0;
     CU(cudaSetDevice(p->device));
-    if (flush_matrices(p)) return 1;         // keep ordering with plain matrices staged earlier
-    if (!p->d_mix_scratch && p->Dp == 64) CU(cudaMalloc(&p->d_mix_scratch, (size_t)p->q_capacity * 4096 * sizeof(double)));
-    const size_t dd = (size_t)p->D * p->D;
-    std::vector<double> hw(n);
-    std::vector<int> hf(n);
-    for (int64_t k = 0; k < K; k++) {        // one launch per component: components of a node accumulate in order
-        for (int64_t i = 0; i < n; i++) {
-            if (nodeIds[i] < 0 || nodeIds[i] >= p->B) return fail("node id %lld has no branch", (long long)nodeIds[i]);
-            memcpy(p->h_Q + i * dd, M + (i * K + k) * dd, dd * sizeof(double));
-            p->h_dst[i] = (int)(cat * p->B + nodeIds[i]);
-            hw[i] = w[i * K + k];
-            hf[i] = (k == 0);
-        }
-        CU(cudaMemcpyAsync(p->d_Q, p->h_Q, n * dd * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-        CU(cudaMemcpyAsync(p->d_dst, p->h_dst, n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
-        CU(cudaMemcpyAsync(p->d_mix_w, hw.data(), n * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-        CU(cudaMemcpyAsync(p->d_mix_first, hf.data(), n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
-        if (launch_expm(p, p->d_Q, p->d_dst, (int)n, 0, p->d_mix_w, p->d_mix_first, nullptr, k == K - 1)) return 1;
+    if (flush_matrices(p)) return 1;         // keep ordering with plain matrices staged earlier (same stream)
+    // Two launches, no host synchronisation: all n*K components are exponentiated side by side into a scratch area
+    // (one CTA each), then one CTA per node forms sum_k w_k Exp(Q_k) in component order (deterministic) and emits the
+    // tensor-path operands.  Own pinned staging: [n*K matrices | n*K weights], then the n destination slots as ints.
+    const size_t dd = (size_t)p->D * p->D, dpdp = (size_t)p->Dp * p->Dp;
+    const int64_t nk = n * K;
+    if (p->mix_busy) { CU(cudaEventSynchronize(p->ev_mix)); p->mix_busy = false; }
+    if (nk > p->mix_capacity) {
         CU(cudaStreamSynchronize(p->stream));
+        for (void *d : {(void *)p->d_mix_scratch, (void *)p->d_mix_Q, (void *)p->d_mix_dst}) if (d) cudaFree(d);
+        if (p->h_mix) cudaFreeHost(p->h_mix);
+        p->d_mix_scratch = p->d_mix_Q = nullptr; p->d_mix_dst = nullptr; p->h_mix = nullptr; p->mix_capacity = 0;
+        CU(cudaMalloc(&p->d_mix_scratch, (size_t)nk * dpdp * sizeof(double)));
+        CU(cudaMalloc(&p->d_mix_Q, (size_t)nk * (dd + 1) * sizeof(double)));
+        CU(cudaMalloc(&p->d_mix_dst, (size_t)2 * nk * sizeof(int)));
+        CU(cudaMallocHost(&p->h_mix, (size_t)nk * (dd + 1) * sizeof(double) + (size_t)2 * nk * sizeof(int)));
+        p->mix_capacity = nk;
     }
+    memcpy(p->h_mix, M, (size_t)nk * dd * sizeof(double));
+    memcpy(p->h_mix + (size_t)nk * dd, w, (size_t)nk * sizeof(double));
+    int *h_idx = reinterpret_cast<int *>(p->h_mix + (size_t)nk * (dd + 1));      // [nk] scratch slots 0..nk-1 | [n] P-cache slots
+    for (int64_t k = 0; k < nk; k++) h_idx[k] = (int)k;
+    for (int64_t i = 0; i < n; i++) h_idx[nk + i] = (int)(cat * p->B + nodeIds[i]);
+    CU(cudaMemcpyAsync(p->d_mix_Q, p->h_mix, (size_t)nk * (dd + 1) * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CU(cudaMemcpyAsync(p->d_mix_dst, h_idx, (size_t)(nk + n) * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    CU(cudaEventRecord(p->ev_mix, p->stream));
+    p->mix_busy = true;
+    if (launch_expm(p, p->d_mix_Q, p->d_mix_dst, (int)nk, 0, nullptr, false, p->d_mix_scratch)) return 1;
+    hb2::mix_reduce_kernel<<<(unsigned)n, 256, 0, p->stream>>>(p->d_mix_scratch, p->d_mix_Q + (size_t)nk * dd, p->d_mix_dst + nk, (int)K, p->Dp,
+                                                              p->d_PT, p->use_tc ? p->d_PB : nullptr, p->d_PTf);
+    p->launches++;
+    CU(cudaGetLastError());
     for (int64_t i = 0; i < n; i++) { p->have_matrix[cat * p->B + nodeIds[i]] = 1; p->is_rate[cat * p->B + nodeIds[i]] = 0; }
     return 0;
 }
@@ -909,6 +981,7 @@ int hb2_set_rate_template(hb2_partition *p, int64_t nnz, const int64_t *entryInd
     CU(cudaSetDevice(p->device));
     if (flush_matrices(p)) return 1;
     CU(cudaStreamSynchronize(p->stream));
+    p->staging_busy = false;
     std::vector<int> idx(nnz), frm(nnz);
     for (int64_t e = 0; e < nnz; e++) {
         if (entryIndex[e] < 0 || entryIndex[e] >= p->D * p->D) return fail("template entry %lld: index %lld out of range", (long long)e, (long long)entryIndex[e]);
@@ -945,18 +1018,21 @@ int hb2_set_matrices_compiled(hb2_partition *p, int64_t cat, int64_t n, const in
     for (int64_t k = 0; k < n; k++) {
         if (nodeIds[k] < 0 || nodeIds[k] >= p->B) return fail("node id %lld has no branch", (long long)nodeIds[k]);
         p->have_matrix[cat * p->B + nodeIds[k]] = 1;
+        note_matrix_change(p, nodeIds[k]);
     }
     if (!owned) return 0;                                   // another class group's matrices
-    // rows are staged in runs as long as the pinned buffer allows: one memcpy per run
-    int64_t k = 0;
-    while (k < n) {
-        if (p->n_vpending == p->q_capacity) { cudaSetDevice(p->device); if (flush_compiled(p)) return 1; }
-        if (p->staging_busy) { CU(cudaEventSynchronize(p->ev_staging)); p->staging_busy = false; }
-        const int64_t run = std::min<int64_t>(n - k, p->q_capacity - p->n_vpending);
-        memcpy(p->h_V + p->n_vpending * p->t_nF, formulaValues + k * p->t_nF, (size_t)run * p->t_nF * sizeof(double));
-        for (int64_t i = 0; i < run; i++) p->h_vdst[p->n_vpending + i] = (int)(cat * p->B + nodeIds[k + i]);
-        p->n_vpending += run;
-        k += run;
+    if (wait_staging(p)) return 1;
+    const size_t row = (size_t)p->t_nF * sizeof(double);
+    for (int64_t k = 0; k < n; k++) {
+        const int64_t slot = cat * p->B + nodeIds[k];
+        int64_t at = claim_slot(p, slot, true);
+        if (at < 0) {
+            if (p->n_vpending == p->q_capacity) { cudaSetDevice(p->device); if (flush_compiled(p) || wait_staging(p)) return 1; }
+            at = p->n_vpending++;
+            p->pend_pos[slot] = (int)(-at - 2);
+        }
+        memcpy(p->h_V + at * p->t_nF, formulaValues + k * p->t_nF, row);
+        p->h_vdst[at] = (int)slot;
     }
     return 0;
 }
@@ -1063,6 +1139,7 @@ int hb2_branch_cache_build(hb2_partition *p, int64_t node, const double *rootFre
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(p->stream));
     p->bc_node = node;
+    p->bc_dirty_node = -1;
     return 0;
 }
 
@@ -1070,11 +1147,10 @@ int hb2_branch_cache_evaluate(hb2_partition *p, int64_t cat, const double *weigh
     if (!p || !lnL) return fail("null argument");
     if (p->bc_node < 0) return fail("hb2_branch_cache_evaluate: no valid branch cache (build it after the last full evaluation)");
     CU(cudaSetDevice(p->device));
-    // only the cached branch may have a new matrix: anything else needs a regular evaluation
-    for (int64_t k = 0; k < p->n_pending; k++)
-        if (p->h_dst[k] % p->B != p->bc_node) return fail("branch cache holds node %lld but a matrix of node %lld changed", (long long)p->bc_node, (long long)(p->h_dst[k] % p->B));
-    for (int64_t k = 0; k < p->n_vpending; k++)
-        if (p->h_vdst[k] % p->B != p->bc_node) return fail("branch cache holds node %lld but a matrix of node %lld changed", (long long)p->bc_node, (long long)(p->h_vdst[k] % p->B));
+    // only the cached branch may have a new matrix (flushed or not, plain, compiled or mixture): anything else needs a
+    // regular evaluation
+    if (p->bc_dirty_node >= 0)
+        return fail("branch cache holds node %lld but a matrix of node %lld changed", (long long)p->bc_node, (long long)p->bc_dirty_node);
     if (flush_matrices(p)) return 1;
     int c0, nc;
     if (weights) { c0 = p->own0; nc = p->ownN; }
@@ -1157,6 +1233,7 @@ int hb2_comm_init(hb2_partition *p, int nRanks, int rank, const void *uniqueId12
     if (nRanks < 1 || rank < 0 || rank >= nRanks) return fail("bad rank %d of %d", rank, nRanks);
     if (!g_nccl.load()) return fail("cannot load libnccl.so.2: %s", dlerror());
     CU(cudaSetDevice(p->device));
+    if (p->comm) { g_nccl.CommDestroy(p->comm); p->comm = nullptr; }      // re-initialisation replaces the communicator
     ncclUniqueId id;
     memcpy(&id, uniqueId128, 128);
     ncclResult_t r = g_nccl.CommInitRank(&p->comm, nRanks, id, rank);
@@ -1209,8 +1286,8 @@ void hb2_destroy(hb2_partition *p) {
     if (p->stream) cudaStreamSynchronize(p->stream);
     if (p->comm) g_nccl.CommDestroy(p->comm);
     void *dev[] = {p->d_leaf, p->d_scal, p->d_rootE, p->d_child_start, p->d_child_ids, p->d_jobs, p->d_dst, p->d_flag,
-                   p->d_mix_first, p->d_ambig, p->d_freq, p->d_cond, p->d_PT, p->d_Q, p->d_pi, p->d_rootL, p->d_weights,
-                   p->d_partial, p->d_lnL, p->d_siteL, p->d_mix_w, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_xsend, p->d_xrecv, p->d_xfreq, p->d_xpartial, p->d_bc_out, p->d_bc_outE, p->d_bc_sib, p->d_walk, p->d_t_index, p->d_t_formula, p->d_vdst, p->d_t_colfreq, p->d_V};
+                   p->d_mix_dst, p->d_mix_Q, p->d_ambig, p->d_freq, p->d_cond, p->d_PT, p->d_Q, p->d_pi, p->d_rootL, p->d_weights,
+                   p->d_partial, p->d_lnL, p->d_siteL, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_xsend, p->d_xrecv, p->d_xfreq, p->d_xpartial, p->d_bc_out, p->d_bc_outE, p->d_bc_sib, p->d_walk, p->d_t_index, p->d_t_formula, p->d_vdst, p->d_t_colfreq, p->d_V};
     for (void *d : dev) if (d) cudaFree(d);
     if (p->h_Q) cudaFreeHost(p->h_Q);
     if (p->h_small) cudaFreeHost(p->h_small);
@@ -1218,6 +1295,9 @@ void hb2_destroy(hb2_partition *p) {
     if (p->h_dst) cudaFreeHost(p->h_dst);
     if (p->h_V) cudaFreeHost(p->h_V);
     if (p->h_vdst) cudaFreeHost(p->h_vdst);
+    if (p->h_walk) cudaFreeHost(p->h_walk);
+    if (p->h_mix) cudaFreeHost(p->h_mix);
+    if (p->ev_mix) cudaEventDestroy(p->ev_mix);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
     if (p->ev_staging) cudaEventDestroy(p->ev_staging);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -1226,6 +1306,17 @@ void hb2_destroy(hb2_partition *p) {
 
 int64_t hb2_launch_count(const hb2_partition *p) { return p ? p->launches : 0; }
 int hb2_precision_mode(const hb2_partition *p) { return (p && p->use_tc) ? 1 : 0; }
+int hb2_stage_launches(const hb2_partition *p, int64_t *out3) {
+    if (!p || !out3) return fail("null argument");
+    for (int k = 0; k < 3; k++) out3[k] = p->stage_launches[k];
+    return 0;
+}
+const char *hb2_pruning_kernel(const hb2_partition *p) {
+    if (!p) return "";
+    if (p->use_tc) return p->use_walk ? "prune64_tc_walk_kernel" : "prune64_tc_kernel";
+    if (p->Dp == 64) return "prune64_kernel";
+    return p->small_walk ? "prune_small_walk_kernel" : "prune_small_kernel";
+}
 
 int hb2_time_resident(hb2_partition *p, const double *weights, const double *rootFreqs, int iters, double *msPerEval,
                       double *stageMs, double *lnL) {
@@ -1234,15 +1325,18 @@ int hb2_time_resident(hb2_partition *p, const double *weights, const double *roo
     CU(cudaSetDevice(p->device));
     if (check_ready(p, 0, (int)p->C)) return 1;
     if (flush_matrices(p)) return 1;
-    p->bc_node = -1;
+    p->bc_node = -1; p->bc_dirty_node = -1;
     // every slot must hold a resident rate matrix so that the expm stage can be replayed
     std::vector<int> dst;
     for (int64_t k = (int64_t)p->own0 * p->B; k < (int64_t)(p->own0 + p->ownN) * p->B; k++) {
         if (!p->is_rate[k]) return fail("hb2_time_resident needs HB2_MATRIX_RATE matrices in every slot");
         dst.push_back((int)k);
     }
+    if (wait_staging(p)) return 1;           // the flush above may still be reading the pinned queues
     memcpy(p->h_dst, dst.data(), dst.size() * sizeof(int));
     CU(cudaMemcpyAsync(p->d_dst, p->h_dst, dst.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    CU(cudaEventRecord(p->ev_staging, p->stream));
+    p->staging_busy = true;
     double *hs = p->h_small;
     for (int k = 0; k < p->Dp; k++) hs[k] = k < p->D ? rootFreqs[k] : 0.0;
     for (int c = 0; c < p->C; c++) hs[p->Dp + c] = weights[c];
@@ -1253,11 +1347,15 @@ int hb2_time_resident(hb2_partition *p, const double *weights, const double *roo
     double tot = 0, st[3] = {0, 0, 0};
     for (int it = 0; it < iters; it++) {
         CU(cudaEventRecord(p->ev[0], p->stream));
-        if (launch_expm(p, p->d_Qres + (size_t)p->own0 * p->B * p->D * p->D, p->d_dst, (int)dst.size(), 0, nullptr, nullptr, nullptr)) return 1;
+        const int64_t l0 = p->launches;
+        if (launch_expm(p, p->d_Qres + (size_t)p->own0 * p->B * p->D * p->D, p->d_dst, (int)dst.size(), 0, nullptr)) return 1;
+        const int64_t l1 = p->launches;
         CU(cudaEventRecord(p->ev[1], p->stream));
         if (run_pruning(p, p->own0, p->ownN, levels)) return 1;
         CU(cudaEventRecord(p->ev[2], p->stream));
+        const int64_t l2 = p->launches;
         if (run_root(p, p->own0, p->ownN, true, false)) return 1;
+        p->stage_launches[0] = l1 - l0; p->stage_launches[1] = l2 - l1; p->stage_launches[2] = p->launches - l2;
         CU(cudaEventRecord(p->ev[3], p->stream));
         CU(cudaEventSynchronize(p->ev[3]));
         float a = 0, b = 0, c = 0;

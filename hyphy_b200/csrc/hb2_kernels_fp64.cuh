@@ -94,9 +94,7 @@ __device__ __forceinline__ void tile_mm64(const double *__restrict__ A, const do
 // ------------------------------------------------------------------------------------------------
 struct ExpmArgs {
     const double *Q;        // [n][D*D]
-    const int *dst;         // [n]
-    const double *mix_w;    // nullable [n]
-    const int *mix_first;   // nullable [n]: 1 => overwrite, 0 => accumulate
+    const int *dst;         // [n] destination slot; < 0: retired entry (the slot was handed over again), skipped
     double *PT;
     double *Qres;           // nullable [slots][D*D]: resident copy of the rate matrices, written while loading
     int D;
@@ -108,7 +106,6 @@ struct ExpmArgs {
     const int *tmpl_formula;// [nnz]
     const double *tmpl_colfreq;  // nullable [D]
     int tmpl_nnz, nF;
-    double *park;           // nullable [n][4096] scratch for expm64_dmma_kernel (needed when PT[slot] must not be clobbered: mixtures)
 };
 
 // Builds A1[j][i] = Q[i][j] (transposed, zero padded, leading dimension LD) from dense or compiled input and leaves a
@@ -160,6 +157,7 @@ __global__ void __launch_bounds__(256, 1) expm64_kernel(ExpmArgs a) {
     __shared__ int s_shift;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int D = a.D;
+    if (a.dst[blockIdx.x] < 0) return;
     double *out = a.PT + (size_t)a.dst[blockIdx.x] * 4096;
 
     load_rate_matrix<64, LD64, 256>(a, A1, tid);
@@ -259,16 +257,7 @@ __global__ void __launch_bounds__(256, 1) expm64_kernel(ExpmArgs a) {
         if (tid < D) R[tid * LD64 + tid] = fmax(1.0 - s, 0.0);
     }
     __syncthreads();
-    if (a.mix_w) {
-        const double w = a.mix_w[blockIdx.x];
-        const bool first = a.mix_first[blockIdx.x] != 0;
-        for (int idx = tid; idx < 4096; idx += 256) {
-            double v = w * R[(idx >> 6) * LD64 + (idx & 63)];
-            out[idx] = first ? v : out[idx] + v;
-        }
-    } else {
-        for (int idx = tid; idx < 4096; idx += 256) out[idx] = R[(idx >> 6) * LD64 + (idx & 63)];
-    }
+    for (int idx = tid; idx < 4096; idx += 256) out[idx] = R[(idx >> 6) * LD64 + (idx & 63)];
 }
 
 
@@ -330,9 +319,10 @@ __global__ void __launch_bounds__(256, 2) expm64_dmma_kernel(ExpmArgs a, ExpmTcO
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wr = warp >> 1, wc = warp & 1, g = lane >> 2, q4 = lane & 3;
     const int D = a.D;
+    if (a.dst[blockIdx.x] < 0) return;
     const size_t slot = a.dst[blockIdx.x];
     double *out = a.PT + slot * 4096;
-    double *park = a.park ? a.park + (size_t)blockIdx.x * 4096 : out;
+    double *park = out;
     double *R = X0;
 
     load_rate_matrix<64, LD64, 256>(a, X0, tid);
@@ -452,14 +442,7 @@ __global__ void __launch_bounds__(256, 2) expm64_dmma_kernel(ExpmArgs a, ExpmTcO
         if (tid < D) R[tid * LD64 + tid] = fmax(1.0 - (X1[tid] + X1[64 + tid] + X1[128 + tid] + X1[192 + tid]), 0.0);
         __syncthreads();
     }
-    if (a.mix_w) {
-        const double w = a.mix_w[blockIdx.x];
-        const bool first = a.mix_first[blockIdx.x] != 0;
-        for (int idx = tid; idx < 4096; idx += 256) {
-            double v = w * R[(idx >> 6) * LD64 + (idx & 63)];
-            out[idx] = first ? v : out[idx] + v;
-        }
-    } else {
+    {
         for (int idx = tid; idx < 4096; idx += 256) out[idx] = R[(idx >> 6) * LD64 + (idx & 63)];
         if (tc.PB) {
             float *pb = tc.PB + slot * 8192;
@@ -486,6 +469,7 @@ __global__ void __launch_bounds__(128) expm_small_kernel(ExpmArgs a) {
     __shared__ double red[DP];
     __shared__ int s_shift;
     const int tid = threadIdx.x, D = a.D;
+    if (a.dst[blockIdx.x] < 0) return;
     double *out = a.PT + (size_t)a.dst[blockIdx.x] * DP * DP;
     load_rate_matrix<DP, LD, 128>(a, A1, tid);
     if (a.is_trans) {
@@ -558,16 +542,7 @@ __global__ void __launch_bounds__(128) expm_small_kernel(ExpmArgs a) {
         if (tid < D) R[tid * LD + tid] = fmax(1.0 - s, 0.0);
     }
     __syncthreads();
-    if (a.mix_w) {
-        const double w = a.mix_w[blockIdx.x];
-        const bool first = a.mix_first[blockIdx.x] != 0;
-        for (int idx = tid; idx < DP * DP; idx += 128) {
-            double v = w * R[(idx / DP) * LD + idx % DP];
-            out[idx] = first ? v : out[idx] + v;
-        }
-    } else {
-        for (int idx = tid; idx < DP * DP; idx += 128) out[idx] = R[(idx / DP) * LD + idx % DP];
-    }
+    for (int idx = tid; idx < DP * DP; idx += 128) out[idx] = R[(idx / DP) * LD + idx % DP];
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -67,10 +67,19 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Bounded wait: a protocol bug must surface as an error flag (host returns an error), never as a hung GPU.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Device-side waits are bounded by TIME (4 s of globaltimer), not by an iteration count: a slow producer (another
+// partition or process sharing the GPU, fewer co-resident CTAs than planned) only makes the pass slower; a protocol bug
+// still surfaces as an error flag (the host returns an error), never as a hung GPU.
+constexpr unsigned long long HB2_WAIT_LIMIT_NS = 4000000000ull;
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int *err_flag) {
     const uint32_t addr = smem_u32(bar);
-    for (int it = 0; it < (1 << 22); it++) {
+    unsigned long long t0 = 0;
+    for (int it = 0;; it++) {
         uint32_t ok;
         asm volatile(
             "{\n\t"
@@ -79,6 +88,11 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int *e
             "selp.u32 %0, 1, 0, P1;\n\t"
             "}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
         if (ok) return true;
+        if ((it & 1023) == 1023) {
+            const unsigned long long now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > HB2_WAIT_LIMIT_NS) break;
+        }
     }
     atomicExch(err_flag, 1);
     return false;
@@ -130,6 +144,7 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) <
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pack_tc_kernel(const double *__restrict__ PT, const int *__restrict__ slots,
                                                        float *__restrict__ PB, float *__restrict__ PTf) {
+    if (slots[blockIdx.x] < 0) return;
     const size_t slot = slots[blockIdx.x];
     const double *src = PT + slot * 4096;
     float *pb = PB + slot * TC_PB_FLOATS;
@@ -142,6 +157,37 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const double *__restrict__
         pb[o] = hi;
         pb[4096 + o] = lo;
         pf[(o >> 6) * TC_PTF_ROW + (o & 63)] = (float)src[o];
+    }
+}
+
+// Explicit-form mixtures (BS-REL, reference tree.cpp:3047-3089): PT[slot_i] = sum_k w[i][k] * comp[i*K + k], components
+// added in order k = 0..K-1 (deterministic); 64-state tensor partitions also get the split tiles and the fp32 table.
+// One CTA per node; comp = scratch matrices [n*K][Dp*Dp] in the PT layout (transposed).
+__global__ void __launch_bounds__(256) mix_reduce_kernel(const double *__restrict__ comp, const double *__restrict__ w,
+                                                          const int *__restrict__ slots, int K, int Dp, double *__restrict__ PT,
+                                                          float *__restrict__ PB, float *__restrict__ PTf) {
+    const size_t slot = slots[blockIdx.x];
+    const int dpdp = Dp * Dp;
+    double *dst = PT + slot * dpdp;
+    const double *src = comp + (size_t)blockIdx.x * K * dpdp;
+    const double *wk = w + (size_t)blockIdx.x * K;
+    for (int o = threadIdx.x; o < dpdp; o += 256) {
+        double s = 0.0;
+        for (int k = 0; k < K; k++) s += wk[k] * src[(size_t)k * dpdp + o];
+        dst[o] = s;
+    }
+    if (PB && Dp == 64) {
+        __syncthreads();                         // this CTA's own global writes are visible to it after the barrier
+        float *pb = PB + slot * TC_PB_FLOATS;
+        float *pf = PTf + slot * TC_PTF_FLOATS;
+        for (int o = threadIdx.x; o < 4096; o += 256) {
+            const int chunk = o >> 8, n = (o >> 2) & 63, kk = chunk * 4 + (o & 3);
+            const double p = dst[kk * 64 + n];
+            const float hi = tf32_rn((float)p);
+            pb[o] = hi;
+            pb[4096 + o] = tf32_rn((float)(p - (double)hi));
+            pf[(o >> 6) * TC_PTF_ROW + (o & 63)] = (float)dst[o];
+        }
     }
 }
 
@@ -481,12 +527,17 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
         for (int q = 0; q < 16; q++) x4[q] = __ldcg(reinterpret_cast<const uint4 *>(xrow + (size_t)q * 128));
         sc = (uint32_t)__ldcg(scp);
         if (await) {
+            unsigned long long t0 = 0;
             for (int it = 0; !bailed; it++) {
                 uint32_t bad = (sc << 31) ^ want;
 #pragma unroll
                 for (int q = 0; q < 16; q++) bad |= (x4[q].x ^ want) | (x4[q].y ^ want) | (x4[q].z ^ want) | (x4[q].w ^ want);
                 if (!(bad >> 31)) break;
-                if (it > (1 << 18)) { atomicExch(a.err, 2); bailed = true; }   // never hang the GPU
+                if ((it & 255) == 255) {                                       // never hang the GPU: time-bounded
+                    const unsigned long long now = globaltimer_ns();
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > HB2_WAIT_LIMIT_NS) { atomicExch(a.err, 2); bailed = true; }
+                }
 #pragma unroll
                 for (int q = 0; q < 16; q++) x4[q] = ld_relaxed_u4(xrow + (size_t)q * 128);
                 sc = ld_relaxed_u32(scp);

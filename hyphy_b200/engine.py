@@ -49,6 +49,8 @@ ABI = [
     ("hb2_destroy", None, [C.c_void_p]),
     ("hb2_launch_count", C.c_int64, [C.c_void_p]),
     ("hb2_precision_mode", C.c_int, [C.c_void_p]),
+    ("hb2_pruning_kernel", C.c_char_p, [C.c_void_p]),
+    ("hb2_stage_launches", C.c_int, [C.c_void_p, _ip]),
     ("hb2_time_resident", C.c_int, [C.c_void_p, _dp, _dp, C.c_int, _dp, _dp, _dp]),
 ]
 
@@ -254,6 +256,16 @@ class Partition:
     @property
     def precision_mode(self) -> int:
         return int(self._lib.hb2_precision_mode(self._h))
+
+    @property
+    def pruning_kernel(self) -> str:
+        return self._lib.hb2_pruning_kernel(self._h).decode()
+
+    @property
+    def stage_launches(self):
+        out = np.zeros(3, dtype=np.int64)
+        _check(self._lib.hb2_stage_launches(self._h, out.ctypes.data_as(_ip)))
+        return out
 
     def time_resident(self, weights, root_freqs, iters=10):
         w, pw = _d(weights)

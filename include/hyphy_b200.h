@@ -84,7 +84,8 @@ int hb2_set_matrices_compiled(hb2_partition *p, int64_t cat, int64_t n, const in
                               const double *formulaValues);
 
 /* Explicit-form mixtures P = sum_k w_k Exp(Q_k) per branch (BS-REL; tree.cpp:3047-3089):
- * K components for each listed node, M packed [n][K][D*D], w packed [n][K]. */
+ * K components for each listed node, M packed [n][K][D*D], w packed [n][K].  Asynchronous like the other hand-overs
+ * (two kernel launches on the partition's stream, no host synchronisation); M and w are copied before the call returns. */
 int hb2_set_mixture_matrices(hb2_partition *p, int64_t cat, int64_t n, const int64_t *nodeIds, int64_t K,
                              const double *M, const double *w);
 
@@ -135,9 +136,11 @@ int hb2_comm_init(hb2_partition *p, int nRanks, int rank, const void *uniqueId12
  * pattern shard r / nGroups, i.e. the nGroups consecutive ranks of one shard are created with the SAME pattern slice.
  * Group g owns classes [g*C/nGroups, (g+1)*C/nGroups): matrices handed over for other classes are ignored on this
  * rank (no expm, no pruning), hb2_evaluate_classes prunes the owned classes only, and the per-pattern class partials
- * (value, binary exponent) of the ranks of a shard are exchanged with one small ncclAllGather before the logarithm;
- * the ncclAllReduce of the partial lnL follows as usual.  Requires C % nGroups == 0 and nRanks % nGroups == 0;
- * hb2_evaluate (single class) is refused in this mode.  Call after hb2_comm_init, before the first matrix is set. */
+ * (value, binary exponent) of all ranks are exchanged before the logarithm with ONE collective per evaluation: every
+ * rank writes its partials into its own slot of a buffer that is zero elsewhere and a sum ncclAllReduce acts as the
+ * gather; every rank then merges every shard and holds the complete, bit-identical lnL (no second collective).
+ * Requires C % nGroups == 0 and nRanks % nGroups == 0; hb2_evaluate (single class) is refused in this mode.  Call after
+ * hb2_comm_init, before the first matrix is set. */
 int hb2_comm_class_groups(hb2_partition *p, int nGroups);
 
 /* Pair of SetupLFCaches in DeleteCaches (likefunc.cpp:10556-10601). */
@@ -158,6 +161,10 @@ int64_t hb2_launch_count(const hb2_partition *p);
 /* 0: fp64 pruning kernels (4/20-state register kernels, or HB2_FLAG_FORCE_FP64);
  * 1: tcgen05 tensor-core pruning, error-compensated 3xTF32 split with fp32 conditionals (33..64 states). */
 int hb2_precision_mode(const hb2_partition *p);
+/* Name of the pruning kernel this partition launches, and the kernel launches per evaluation of the three stages
+ * {expm, pruning, root reduction} as counted during the last hb2_time_resident (bench.py's roofline object). */
+const char *hb2_pruning_kernel(const hb2_partition *p);
+int hb2_stage_launches(const hb2_partition *p, int64_t *out3);
 /* Runs the same work as hb2_evaluate_classes `iters` times with inputs already resident on the device
  * (re-exponentiating every cached rate matrix and re-pruning the whole tree each time) and returns the mean
  * device time per evaluation in milliseconds (CUDA events on the partition's stream).  stageMs (nullable, 3 doubles)
