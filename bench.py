@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-host", action="store_true", help="skip the patched-HyPhy end-to-end leg")
     ap.add_argument("--fp64", action="store_true", help="force the fp64 pruning kernels (HB2_FLAG_FORCE_FP64)")
     ap.add_argument("--class-groups", type=int, default=0, help="multi-GPU: force this many class groups (default: as many as divide both)")
     ap.add_argument("--no-class-groups", action="store_true", help="multi-GPU: shard patterns only (every rank exponentiates every class)")
@@ -363,6 +364,20 @@ def main():
                 "e2e_dense": {"value": 1000.0 / e2e_dense_ms, "unit": "evals/s", "ms_per_step": e2e_dense_ms, "h2d_bytes_per_step": h2d_dense,
                               "d2h_bytes_per_step": 12, "api": "hb2_set_matrices_packed x C + hb2_evaluate_classes", "lnL": lnl_dense},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "lnL": lnl0, "lnL_resident": lnl_res}
+        # the same evaluation stream through the PATCHED HyPhy binary (host/_build/hyphy: the reference's HBL interpreter,
+        # formula evaluation and DetermineNodesForUpdate on the host, everything below ComputeBlock on the engine):
+        # wall-clock evaluations/s of `LFCompute` as a user of the reference would see them
+        host_bin = os.path.join(ROOT, "host", "_build", "hyphy")
+        if world == 1 and not args.no_host and os.path.isfile(host_bin):
+            try:
+                from oracle import ref_harness as rh
+                hr = rh.run_reference(w, n_evals=max(args.steps, 10), n_warm=args.warmup, per_site=False, binary=host_bin,
+                                      env_extra={"HYPHY_B200_VERBOSE": "1", "HYPHY_B200_DEVICE": str(local_rank)})
+                line["host_e2e"] = {"value": max(args.steps, 10) / hr["loop_seconds"], "unit": "evals/s", "lnL": hr["lnL"],
+                                    "api": "patched HyPhy binary: HBL LFCompute -> _LikelihoodFunction::ComputeBlock -> hb2_hooks -> C ABI (dense Q*t hand-over)",
+                                    "engine": hr["engine"][-2:]}
+            except Exception as e:
+                line["host_e2e"] = {"value": None, "error": repr(e)}
         if not args.no_cpu_baseline and world == 1:
             try:
                 threads = os.cpu_count() or 1

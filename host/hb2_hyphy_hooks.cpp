@@ -1,0 +1,184 @@
+// hb2_hyphy_hooks.cpp -- see hb2_hyphy_hooks.h.  Compiled with the HyPhy build copy's headers.
+#include "hb2_hyphy_hooks.h"
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "calcnode.h"
+#include "dataset_filter.h"
+#include "global_things.h"
+#include "likefunc.h"
+#include "matrix.h"
+#include "tree.h"
+#include "vector.h"
+
+#include "hyphy_b200.h"
+
+static_assert(sizeof(long) == sizeof(int64_t), "HyPhy's long arrays are passed to the engine as int64_t (LP64)");
+
+// friend of _TheTree (one inserted line in tree.h): the flat parent table is protected there
+struct hb2_hooks_access {
+    static long const *flat_parents(_TheTree const *t) { return t->flatParents.list_data; }
+    static unsigned long flat_parents_length(_TheTree const *t) { return t->flatParents.lLength; }
+};
+
+namespace hb2_hooks {
+
+namespace {
+
+struct Part {
+    hb2_partition *h = nullptr;
+    _TheTree *tree = nullptr;
+    long S = 0, D = 0, L = 0, I = 0, C = 0;
+    std::unordered_map<_CalcNode const *, long> node_id;    // tree node -> flat id (leaves, then internal nodes)
+    std::mutex lock;                                         // SetCompExp is called from ExponentiateMatrices' OpenMP loop
+    unsigned long n_eval = 0, n_rate = 0, n_trans = 0;
+};
+
+struct State {
+    std::vector<Part *> parts;
+};
+
+Part *g_current = nullptr;          // ComputeBlock is entered from the single interpreter thread
+
+bool env_true(char const *name) {
+    char const *v = getenv(name);
+    return v && v[0] && v[0] != '0';
+}
+
+bool engine_enabled() {
+    char const *v = getenv("HYPHY_B200");
+    if (v && v[0] == '0') return false;
+    return true;
+}
+
+[[noreturn]] void fatal(char const *what) {
+    // no CPU fallback exists once a partition is on the engine: every failure is fatal for the host
+    hy_global::HandleApplicationError(_String("hyphy_b200 engine: ") & what & " -- " & hb2_last_error(), true);
+    abort();
+}
+
+}  // namespace
+
+void create(void *&state, unsigned long n_trees, unsigned long index, _TheTree *tree, _DataSetFilter const *filter,
+            long const *leaf_flags, _Vector const *ambiguities, long n_ambiguities) {
+    if (!engine_enabled()) return;
+    State *st = static_cast<State *>(state);
+    if (!st) { st = new State(); state = st; }
+    if (st->parts.size() < n_trees) st->parts.resize(n_trees, nullptr);
+    if (st->parts[index]) { hb2_destroy(st->parts[index]->h); delete st->parts[index]; st->parts[index] = nullptr; }
+    if (hb2_device_count() <= 0) fatal("no CUDA device is visible (set HYPHY_B200=0 to run the CPU path)");
+
+    Part *p = new Part();
+    p->tree = tree;
+    p->S = (long)filter->GetPatternCount();
+    p->D = (long)filter->GetDimension();
+    p->L = tree->GetLeafCount();
+    p->I = tree->GetINodeCount();
+    p->C = tree->categoryCount > 0 ? tree->categoryCount : 1;
+    if ((long)hb2_hooks_access::flat_parents_length(tree) != p->L + p->I) fatal("tree has not been flattened (SetUp)");
+    for (long k = 0; k < p->L; k++) p->node_id[(_CalcNode const *)tree->flatCLeaves.GetItem(k)] = k;
+    for (long k = 0; k < p->I; k++) p->node_id[(_CalcNode const *)tree->flatTree.GetItem(k)] = p->L + k;
+
+    int device = 0;
+    if (char const *dv = getenv("HYPHY_B200_DEVICE")) device = atoi(dv);
+#ifdef __HYPHYMPI__
+    else device = hy_mpi_node_rank % hb2_device_count();
+#endif
+    // pattern multiplicities: theFrequencies is a _SimpleList of long (dataset_filter.h), original pattern order
+    if (hb2_create(&p->h, p->S, p->D, p->L, p->I, p->C, (int64_t const *)hb2_hooks_access::flat_parents(tree),
+                   (int64_t const *)leaf_flags, n_ambiguities > 0 ? ambiguities->theData : nullptr, n_ambiguities,
+                   (int64_t const *)filter->theFrequencies.list_data, device,
+                   env_true("HYPHY_B200_FP64") ? HB2_FLAG_FORCE_FP64 : HB2_FLAG_DEFAULT)) {
+        delete p;
+        fatal("hb2_create failed");
+    }
+    st->parts[index] = p;
+    if (env_true("HYPHY_B200_VERBOSE"))
+        fprintf(stderr, "[hyphy_b200] partition %lu on device %d: %ld patterns x %ld states, %ld leaves, %ld internal nodes, %ld rate classes, %s pruning\n",
+                index, device, p->S, p->D, p->L, p->I, p->C, hb2_pruning_kernel(p->h));
+}
+
+void *partition(void *state, unsigned long index) {
+    State *st = static_cast<State *>(state);
+    return (st && index < st->parts.size()) ? st->parts[index] : nullptr;
+}
+
+void destroy_all(void *&state) {
+    State *st = static_cast<State *>(state);
+    if (!st) return;
+    for (Part *p : st->parts) {
+        if (!p) continue;
+        if (env_true("HYPHY_B200_VERBOSE"))
+            fprintf(stderr, "[hyphy_b200] partition destroyed after %lu evaluations, %lu rate matrices exponentiated on the device, %lu host transition matrices, %lld kernel launches\n",
+                    p->n_eval, p->n_rate, p->n_trans, (long long)hb2_launch_count(p->h));
+        if (g_current == p) g_current = nullptr;
+        hb2_destroy(p->h);
+        delete p;
+    }
+    delete st;
+    state = nullptr;
+}
+
+Scope::Scope(void *part) : part_(part), prev_(g_current) { g_current = static_cast<Part *>(part); }
+Scope::~Scope() { g_current = static_cast<Part *>(prev_); }
+
+_Matrix *intercept(_CalcNode *node, _Matrix *m, long catID, bool do_exponentiation, _Matrix *existing) {
+    Part *p = g_current;
+    if (!p || !m) return nullptr;
+    auto it = p->node_id.find(node);
+    if (it == p->node_id.end()) return nullptr;                       // a node of some other tree
+    if ((long)m->GetHDim() != p->D || (long)m->GetVDim() != p->D) return nullptr;
+    int64_t const id = it->second;
+    double const *data = m->is_dense() ? m->theData : nullptr;
+    if (!data) {                                                      // compressed-sparse rate matrix (codon models)
+        thread_local std::vector<double> dense;
+        dense.assign((size_t)p->D * p->D, 0.0);
+        double *d = dense.data();
+        m->ForEachCellNumeric([d](hyFloat v, long idx, long, long) -> void { d[idx] = v; });
+        data = d;
+    }
+    {
+        std::lock_guard<std::mutex> guard(p->lock);                   // one host thread per partition handle at a time
+        if (hb2_set_matrices(p->h, catID, 1, &id, &data, do_exponentiation ? HB2_MATRIX_RATE : HB2_MATRIX_TRANS))
+            fatal("hb2_set_matrices failed");
+        if (do_exponentiation) p->n_rate++; else p->n_trans++;
+    }
+    if (!do_exponentiation) return m;                                 // host-computed P (explicit-form models): kept as is
+    // exp(Qt) now lives on the device only.  The node keeps a matrix object of the right shape so that the host's
+    // "has this node ever been exponentiated" bookkeeping (NeedNewCategoryExponential, calcnode.cpp:480-523) works; its
+    // entries are NaN so that any host code path that still tried to READ a transition matrix would fail loudly
+    // instead of computing with stale numbers.
+    if (existing && existing != m && (long)existing->GetHDim() == p->D && (long)existing->GetVDim() == p->D && existing->is_dense())
+        return existing;
+    _Matrix *ph = new _Matrix(p->D, p->D, false, true);
+    for (long k = 0; k < p->D * p->D; k++) ph->theData[k] = NAN;
+    return ph;
+}
+
+double compute_block(void *part, _TheTree *tree, long catID, _SimpleList const &branches, double *siteRes, long *scc,
+                     long branchIndex, _SimpleList *branchValues) {
+    Part *p = static_cast<Part *>(part);
+    static int64_t const none = 0;
+    int64_t const *upd = branches.lLength ? (int64_t const *)branches.list_data : &none;
+    double lnl = 0.0;
+    int rc;
+    if (branchIndex >= 0) {
+        // reference convention (tree_evaluator.cpp:3624,173): internal index, or I + leaf index -> flat node id
+        int64_t const forced = branchIndex < p->I ? branchIndex + p->L : branchIndex - p->I;
+        rc = hb2_evaluate_forced(p->h, catID, (int64_t)branches.lLength, upd, tree->GetProbs(), forced,
+                                 (int64_t const *)branchValues->list_data, &lnl, siteRes, (int64_t *)scc);
+    } else {
+        rc = hb2_evaluate(p->h, catID, (int64_t)branches.lLength, upd, tree->GetProbs(), &lnl, siteRes, (int64_t *)scc);
+    }
+    if (rc) fatal("evaluation failed");
+    p->n_eval++;
+    return lnl;
+}
+
+}  // namespace hb2_hooks

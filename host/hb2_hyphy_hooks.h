@@ -1,0 +1,57 @@
+// hb2_hyphy_hooks.h -- glue between a build copy of HyPhy (veg/hyphy) and libhyphy_b200.so.
+//
+// The reference has no evaluator plugin interface, so the binding is a handful of ONE-LINE insertions
+// into a build copy of its sources (host/apply_hooks.py lists them with their anchors) that call the functions below;
+// everything else -- the logic of the binding -- lives in hb2_hyphy_hooks.cpp, which is compiled with HyPhy's headers
+// and linked against the engine's C ABI (include/hyphy_b200.h).  Nothing here is reference code.
+//
+//   _LikelihoodFunction::SetupLFCaches   (likefunc.cpp:4163)  -> hb2_hooks::create      one engine partition per tree
+//   _LikelihoodFunction::ComputeBlock    (likefunc.cpp:10783) -> hb2_hooks::Scope + hb2_hooks::compute_block
+//   _CalcNode::SetCompExp                (calcnode.cpp:714)   -> hb2_hooks::intercept   matrices go to the GPU instead of
+//                                                                                       _Matrix::Exponentiate
+//                                                                                       (called from the OpenMP loop of
+//                                                                                       ExponentiateMatrices, tree.cpp:2995:
+//                                                                                       the hand-over is serialised inside)
+//   _LikelihoodFunction::DeleteCaches    (likefunc.cpp:10556) -> hb2_hooks::destroy_all
+//
+// Environment: HYPHY_B200=0 disables the engine (the unmodified CPU path runs); HYPHY_B200_FP64=1 forces the fp64
+// kernels; HYPHY_B200_DEVICE=n selects the CUDA device (default: MPI rank modulo visible devices, or 0);
+// HYPHY_B200_VERBOSE=1 prints one line per partition created / destroyed with evaluation counts.
+#pragma once
+
+class _CalcNode;
+class _Matrix;
+class _TheTree;
+class _SimpleList;
+class _DataSetFilter;
+class _Vector;
+
+namespace hb2_hooks {
+
+// SetupLFCaches: create the engine partition of tree `index` (state = the likelihood function's opaque slot).
+void create(void *&state, unsigned long n_trees, unsigned long index, _TheTree *tree, _DataSetFilter const *filter,
+            long const *leaf_flags, _Vector const *ambiguities, long n_ambiguities);
+// the partition of tree `index`, or nullptr when the engine does not run it (disabled, 2-sequence / numeric filters)
+void *partition(void *state, unsigned long index);
+// DeleteCaches
+void destroy_all(void *&state);
+
+// ComputeBlock: while a Scope is alive, _CalcNode::SetCompExp calls of nodes of its tree are diverted to the engine.
+class Scope {
+  public:
+    explicit Scope(void *part);
+    ~Scope();
+    void *part() const { return part_; }
+  private:
+    void *part_, *prev_;
+};
+
+// SetCompExp(m, catID, do_exponentiation): returns the matrix to keep as compExp (a placeholder of the right shape for
+// rate matrices, `m` itself for host-computed transition matrices) or nullptr when the call is not diverted.
+_Matrix *intercept(_CalcNode *node, _Matrix *m, long catID, bool do_exponentiation, _Matrix *existing);
+
+// ComputeBlock after DetermineNodesForUpdate + ExponentiateMatrices: pruning, root reduction, scaling correction.
+double compute_block(void *part, _TheTree *tree, long catID, _SimpleList const &branches, double *siteRes, long *scc,
+                     long branchIndex, _SimpleList *branchValues);
+
+}  // namespace hb2_hooks

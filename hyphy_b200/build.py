@@ -31,7 +31,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         subprocess.check_call(cmd)
         objs.append(obj)
-    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ldl"])
+    # soname: hosts that link the library (host/Makefile) find it through their rpath, not through the build-time path
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xlinker", "-soname,libhyphy_b200.so",
+                           "-o", LIB] + objs + ["-ldl"])
     return LIB
 
 

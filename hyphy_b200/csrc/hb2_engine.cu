@@ -127,6 +127,8 @@ struct hb2_partition {
     bool use_tc = false;
     float *d_condf = nullptr, *d_PB = nullptr, *d_PTf = nullptr;
     int *d_err = nullptr;
+    int *d_forced = nullptr, *h_forced = nullptr;   // forced states of the current evaluation (hb2_evaluate_forced)
+    int forced_node = -1;
     // persistent walk kernel (one launch per evaluation): plan buffers, generation bits of the tagged hand-over, residency
     bool small_walk = true;                   // HB2_SMALL_WALK=0: per-level launches of prune_small_kernel (A/B testing)
     bool expm_dfma = false;                   // HB2_EXPM_DFMA=1: previous FFMA-style fp64 expm kernel (A/B testing)
@@ -208,6 +210,7 @@ int launch_prune(hb2_partition *p, const hb2::PruneArgs &a, const int *d_jobs, i
         t.PB = p->d_PB; t.PTf = p->d_PTf; t.cond = p->d_condf; t.scal = a.scal; t.leaf = a.leaf; t.ambig = a.ambig; t.pi = a.pi;
         t.rootL = a.rootL; t.rootE = a.rootE; t.tree = a.tree; t.err = p->d_err;
         t.L = a.L; t.I = a.I; t.B = a.B; t.D = a.D; t.Sp = a.Sp; t.cat0 = a.cat0;
+        t.forced = a.forced; t.forced_node = a.forced_node;
         dim3 grid((unsigned)(p->Sp / hb2::TC_TILE_P), (unsigned)njobs, (unsigned)ncls);
         hb2::prune64_tc_kernel<<<grid, 128, hb2::TC_SMEM_BYTES, p->stream>>>(t, d_jobs);
     } else if (p->Dp == 64) {
@@ -358,6 +361,7 @@ hb2::PruneArgs prune_args(hb2_partition *p, int cat0) {
     a.rootL = p->d_rootL; a.rootE = p->d_rootE;
     a.tree.child_start = p->d_child_start; a.tree.child_ids = p->d_child_ids;
     a.L = (int)p->L; a.I = (int)p->I; a.B = (int)p->B; a.D = (int)p->D; a.Sp = (int)p->Sp; a.cat0 = cat0;
+    a.forced = p->d_forced; a.forced_node = p->forced_node;
     return a;
 }
 
@@ -528,6 +532,7 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
     t.PB = p->d_PB; t.PTf = p->d_PTf; t.cond = p->d_condf; t.scal = a.scal; t.leaf = a.leaf; t.ambig = a.ambig; t.pi = a.pi;
     t.rootL = a.rootL; t.rootE = a.rootE; t.tree = a.tree; t.err = p->d_err;
     t.L = a.L; t.I = a.I; t.B = a.B; t.D = a.D; t.Sp = a.Sp; t.cat0 = a.cat0;
+    t.forced = a.forced; t.forced_node = a.forced_node;
     w.lane_start = p->d_walk; w.steps = reinterpret_cast<const int2 *>(p->d_walk + 16);
     w.gen = p->d_walk + gen_off; w.NI = 2 * I; w.K = K; w.T = T; w.ncls = ncls; w.nslots = nslots;
     if (getenv("HB2_DEBUG")) fprintf(stderr, "[hb2] walk: jobs=%d steps=%d K=%d T=%d ncls=%d nslots=%d grid=%d resident=%d\n", total, ns, K, T, ncls, nslots, nslots * K, p->walk_max_resident);
@@ -661,10 +666,28 @@ int check_ready(hb2_partition *p, int c0, int nc) {
 }
 
 int evaluate_impl(hb2_partition *p, int c0, int nc, const double *weights, int64_t nUpdate, const int64_t *updateNodes,
-                  const double *rootFreqs, double *lnL, double *siteL, int64_t *siteScale) {
+                  const double *rootFreqs, double *lnL, double *siteL, int64_t *siteScale, int64_t forcedNode = -1,
+                  const int64_t *forcedStates = nullptr) {
     if (!p) return fail("null partition");
     if (!rootFreqs || !lnL) return fail("rootFreqs and lnL must not be null");
     CU(cudaSetDevice(p->device));
+    p->forced_node = -1;
+    if (forcedNode >= 0) {
+        if (forcedNode >= p->L + p->I) return fail("forced node %lld out of range", (long long)forcedNode);
+        if (!forcedStates) return fail("forced states are null");
+        if (!p->d_forced) {
+            CU(cudaMalloc(&p->d_forced, p->Sp * sizeof(int)));
+            CU(cudaMallocHost(&p->h_forced, p->Sp * sizeof(int)));
+        }
+        CU(cudaStreamSynchronize(p->stream));         // h_forced may still be in flight from the previous forced evaluation
+        for (int64_t s = 0; s < p->Sp; s++) {
+            const int64_t f = s < p->S ? forcedStates[s] : 0;
+            if (f < 0 || f >= p->D) return fail("forced state %lld of pattern %lld out of range", (long long)f, (long long)s);
+            p->h_forced[s] = (int)f;
+        }
+        CU(cudaMemcpyAsync(p->d_forced, p->h_forced, p->Sp * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+        p->forced_node = (int)forcedNode;
+    }
     if (check_ready(p, c0, nc)) return 1;
     if (p->cg_G > 1) {
         if (!weights || c0 != 0 || nc != (int)p->C) return fail("with class groups only hb2_evaluate_classes is available");
@@ -949,6 +972,7 @@ int hb2_set_mixture_matrices(hb2_partition *p, int64_t cat, int64_t n, const int
         CU(cudaStreamSynchronize(p->stream));
         for (void *d : {(void *)p->d_mix_scratch, (void *)p->d_mix_Q, (void *)p->d_mix_dst}) if (d) cudaFree(d);
         if (p->h_mix) cudaFreeHost(p->h_mix);
+    if (p->h_forced) cudaFreeHost(p->h_forced);
         p->d_mix_scratch = p->d_mix_Q = nullptr; p->d_mix_dst = nullptr; p->h_mix = nullptr; p->mix_capacity = 0;
         CU(cudaMalloc(&p->d_mix_scratch, (size_t)nk * dpdp * sizeof(double)));
         CU(cudaMalloc(&p->d_mix_Q, (size_t)nk * (dd + 1) * sizeof(double)));
@@ -1043,6 +1067,15 @@ int hb2_evaluate(hb2_partition *p, int64_t cat, int64_t nUpdate, const int64_t *
     if (cat < 0) cat = 0;
     if (cat >= p->C) return fail("rate class %lld out of range", (long long)cat);
     return evaluate_impl(p, (int)cat, 1, nullptr, nUpdate, updateNodes, rootFreqs, lnL, siteL, siteScale);
+}
+
+int hb2_evaluate_forced(hb2_partition *p, int64_t cat, int64_t nUpdate, const int64_t *updateNodes, const double *rootFreqs,
+                        int64_t forcedNode, const int64_t *forcedStates, double *lnL, double *siteL, int64_t *siteScale) {
+    if (!p) return fail("null partition");
+    if (cat < 0) cat = 0;
+    if (cat >= p->C) return fail("rate class %lld out of range", (long long)cat);
+    if (p->cg_G > 1) return fail("forced states are not available with class groups");
+    return evaluate_impl(p, (int)cat, 1, nullptr, nUpdate, updateNodes, rootFreqs, lnL, siteL, siteScale, forcedNode, forcedStates);
 }
 
 int hb2_evaluate_classes(hb2_partition *p, const double *weights, int64_t nUpdate, const int64_t *updateNodes,
@@ -1287,7 +1320,7 @@ void hb2_destroy(hb2_partition *p) {
     if (p->comm) g_nccl.CommDestroy(p->comm);
     void *dev[] = {p->d_leaf, p->d_scal, p->d_rootE, p->d_child_start, p->d_child_ids, p->d_jobs, p->d_dst, p->d_flag,
                    p->d_mix_dst, p->d_mix_Q, p->d_ambig, p->d_freq, p->d_cond, p->d_PT, p->d_Q, p->d_pi, p->d_rootL, p->d_weights,
-                   p->d_partial, p->d_lnL, p->d_siteL, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_xsend, p->d_xrecv, p->d_xfreq, p->d_xpartial, p->d_bc_out, p->d_bc_outE, p->d_bc_sib, p->d_walk, p->d_t_index, p->d_t_formula, p->d_vdst, p->d_t_colfreq, p->d_V};
+                   p->d_partial, p->d_lnL, p->d_siteL, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_xsend, p->d_xrecv, p->d_xfreq, p->d_xpartial, p->d_bc_out, p->d_bc_outE, p->d_bc_sib, p->d_walk, p->d_t_index, p->d_t_formula, p->d_vdst, p->d_t_colfreq, p->d_V, p->d_forced};
     for (void *d : dev) if (d) cudaFree(d);
     if (p->h_Q) cudaFreeHost(p->h_Q);
     if (p->h_small) cudaFreeHost(p->h_small);
@@ -1297,6 +1330,7 @@ void hb2_destroy(hb2_partition *p) {
     if (p->h_vdst) cudaFreeHost(p->h_vdst);
     if (p->h_walk) cudaFreeHost(p->h_walk);
     if (p->h_mix) cudaFreeHost(p->h_mix);
+    if (p->h_forced) cudaFreeHost(p->h_forced);
     if (p->ev_mix) cudaEventDestroy(p->ev_mix);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
     if (p->ev_staging) cudaEventDestroy(p->ev_staging);

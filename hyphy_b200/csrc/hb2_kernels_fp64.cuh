@@ -43,6 +43,11 @@ struct PruneArgs {
     int *rootE;                     // [C][Sp]
     TreeDev tree;
     int L, I, B, D, Sp, cat0;
+    // forced states (reference setBranch / setBranchTo, tree_evaluator.cpp:3624,173-181,4059): flat id of ONE node whose
+    // state is pinned per pattern to forced[s] (a leaf: its observed state is replaced; an internal node or the root: its
+    // conditional vector is masked to that state), or -1
+    const int *forced;
+    int forced_node;
 };
 
 __device__ __forceinline__ double exp2i(int e) {   // exact 2^e for |e| < 1022
@@ -575,7 +580,7 @@ __global__ void __launch_bounds__(256, 2) prune64_kernel(PruneArgs a, const int 
             // leaf: column gather PT[state][k]; ambiguous: sum_j amb[j] PT[j][k]
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const int code = a.leaf[(size_t)child * Sp + s0 + 4 * ty + i];
+                const int code = (child == a.forced_node) ? a.forced[s0 + 4 * ty + i] : a.leaf[(size_t)child * Sp + s0 + 4 * ty + i];
                 double m0, m1, m2, m3;
                 if (code >= 0) {
                     const double2 *p = reinterpret_cast<const double2 *>(PT + (size_t)code * 64 + 2 * tx);
@@ -618,6 +623,14 @@ __global__ void __launch_bounds__(256, 2) prune64_kernel(PruneArgs a, const int 
 #pragma unroll
                 for (int j = 0; j < 4; j++) v[i][j] *= acc[i][j];
             }
+        }
+    }
+    if (a.L + par == a.forced_node) {            // pinned internal node: only the forced state survives
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int f = a.forced[s0 + 4 * ty + i];
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (col_of(tx, j) != f) v[i][j] = 0.0;
         }
     }
     // per-pattern renormalisation: exact power of two so that max_k lands in [0.5, 1)
@@ -676,7 +689,7 @@ __global__ void __launch_bounds__(128) prune_small_kernel(PruneArgs a, const int
         for (int idx = tid; idx < DP * DP; idx += 128) Ps[idx] = __ldg(PT + idx);
         __syncthreads();
         if (child < a.L) {
-            const int code = a.leaf[(size_t)child * Sp + s];
+            const int code = (child == a.forced_node) ? a.forced[s] : a.leaf[(size_t)child * Sp + s];
             if (code >= 0) {
 #pragma unroll
                 for (int k = 0; k < DP; k++) v[k] *= Ps[code * DP + k];
@@ -711,6 +724,11 @@ __global__ void __launch_bounds__(128) prune_small_kernel(PruneArgs a, const int
             for (int k = 0; k < DP; k++) v[k] *= acc[k];
             ex += a.scal[((size_t)cat * a.I + cin) * Sp + s];
         }
+    }
+    if (a.L + par == a.forced_node) {
+        const int f = a.forced[s];
+#pragma unroll
+        for (int k = 0; k < DP; k++) if (k != f) v[k] = 0.0;
     }
     double m = 0.0;
 #pragma unroll
@@ -774,7 +792,7 @@ __global__ void __launch_bounds__(128) prune_small_walk_kernel(PruneArgs a, cons
                 PT = Ps;
             }
             if (child < a.L) {
-                const int code = __ldg(a.leaf + (size_t)child * Sp + s);
+                const int code = (child == a.forced_node) ? __ldg(a.forced + s) : __ldg(a.leaf + (size_t)child * Sp + s);
                 if (code >= 0) {
                     const double2 *row = reinterpret_cast<const double2 *>(PT + (size_t)code * DP);
 #pragma unroll
@@ -812,6 +830,11 @@ __global__ void __launch_bounds__(128) prune_small_walk_kernel(PruneArgs a, cons
                 for (int k = 0; k < DP; k++) v[k] *= acc[k];
                 ex += a.scal[((size_t)cat * a.I + cin) * Sp + s];
             }
+        }
+        if (a.L + par == a.forced_node) {
+            const int f = __ldg(a.forced + s);
+#pragma unroll
+            for (int k = 0; k < DP; k++) if (k != f) v[k] = 0.0;
         }
         double m = 0.0;
 #pragma unroll

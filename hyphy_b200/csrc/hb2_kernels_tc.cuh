@@ -56,6 +56,8 @@ struct PruneTcArgs {
     TreeDev tree;
     int *err;                       // device error flag (mbarrier timeout)
     int L, I, B, D, Sp, cat0;
+    const int *forced;              // forced states of ONE node (see PruneArgs), or unused when forced_node < 0
+    int forced_node;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_kernel(PruneTcArgs a, const
         const int child = a.tree.child_ids[ci];
         const size_t slot = (size_t)cat * a.B + child;
         if (child < a.L) {
-            const int code = a.leaf[(size_t)child * Sp + s];
+            const int code = (child == a.forced_node) ? a.forced[s] : a.leaf[(size_t)child * Sp + s];
             const float *PTf = a.PTf + slot * TC_PTF_FLOATS;
             if (code >= 0) {
                 const float4 *row = reinterpret_cast<const float4 *>(PTf + (size_t)code * TC_PTF_ROW);
@@ -364,6 +366,11 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_kernel(PruneTcArgs a, const
                 for (int k = 0; k < 16; k++) v[o + k] *= (__uint_as_float(d[k]) + acc[o + k]);
             }
             phase ^= 1u;
+        }
+        if (ci == c_end - 1 && a.L + par == a.forced_node) {     // pinned internal node: only the forced state survives
+            const int f = a.forced[s];
+#pragma unroll
+            for (int k = 0; k < 64; k++) if (k != f) v[k] = 0.f;
         }
         renorm_f32(v, ex);
     }
@@ -559,7 +566,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
         // fetched one step ahead: a leaf's state code, or (contractions) the generation bit the child's words must carry
         auto step_aux = [&](int2 q) -> int {
             const int ch = q.x & WALK_ID_MASK;
-            if (ch < a.L) return __ldg(a.leaf + (size_t)ch * Sp + s);
+            if (ch < a.L) return (ch == a.forced_node) ? __ldg(a.forced + s) : __ldg(a.leaf + (size_t)ch * Sp + s);
             return (q.x & WALK_WAIT) ? __ldg(w.gen + (size_t)cat * w.NI + (ch - a.L)) : 0;
         };
         int next_code = step_aux(st);
@@ -772,6 +779,11 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                     for (int k = 0; k < 16; k++) v[o + k] *= ((__uint_as_float(d[k]) + __uint_as_float(d1[k])) + acc[o + k]);
                 }
                 n_mma++;
+            }
+            if ((flags & STEP_LAST) && a.L + par == a.forced_node) {   // pinned internal node (never a side-product slot)
+                const int f = __ldg(a.forced + s);
+#pragma unroll
+                for (int k = 0; k < 64; k++) if (k != f) v[k] = 0.f;
             }
             renorm_f32(v, ex, (flags & STEP_LAST) != 0);
             n_step++;

@@ -37,6 +37,7 @@ ABI = [
     ("hb2_set_matrices_compiled", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _ip, _dp]),
     ("hb2_set_mixture_matrices", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _ip, C.c_int64, _dp, _dp]),
     ("hb2_evaluate", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _ip, _dp, _dp, _dp, _ip]),
+    ("hb2_evaluate_forced", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _ip, _dp, C.c_int64, _ip, _dp, _dp, _ip]),
     ("hb2_evaluate_classes", C.c_int, [C.c_void_p, _dp, C.c_int64, _ip, _dp, _dp, _dp, _ip]),
     ("hb2_read_conditionals", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _dp, _i32p]),
     ("hb2_read_transition", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _dp]),
@@ -195,6 +196,23 @@ class Partition:
 
     def evaluate(self, cat, root_freqs, update_nodes=None, want_sites=False):
         return self._eval(self._lib.hb2_evaluate, C.c_int64(int(cat)), update_nodes, root_freqs, want_sites)
+
+    def evaluate_forced(self, cat, root_freqs, forced_node, forced_states, update_nodes=None, want_sites=True):
+        """ComputeBlock(index, siteRes, cat, branchIndex, branchValues): one node pinned to a state per pattern."""
+        pi, ppi = _d(root_freqs)
+        fs, pfs = _i(forced_states)
+        assert fs.shape == (self.S,)
+        if update_nodes is None:
+            n, pu = -1, None
+        else:
+            u, pu = _i(update_nodes)
+            n = len(u)
+        lnl = C.c_double()
+        sl = np.empty(self.S) if want_sites else None
+        ss = np.empty(self.S, dtype=np.int64) if want_sites else None
+        _check(self._lib.hb2_evaluate_forced(self._h, int(cat), n, pu, ppi, int(forced_node), pfs, C.byref(lnl),
+                                             sl.ctypes.data_as(_dp) if want_sites else None, ss.ctypes.data_as(_ip) if want_sites else None))
+        return (lnl.value, sl, ss) if want_sites else lnl.value
 
     def evaluate_classes(self, weights, root_freqs, update_nodes=None, want_sites=False):
         w, pw = _d(weights)

@@ -232,6 +232,10 @@ class Workload:
     site_chars: list | None = None  # per leaf, the character string (for FASTA export to the reference)
     meta: dict = dataclasses.field(default_factory=dict)
     _tmpl: tuple | None = None
+    # explicit-form mixture (BS-REL / BUSTED shape, reference tree.cpp:3047-3089): every branch's transition matrix is
+    # sum_k mix_weights[k] * Exp(mix_Q[k] * t_b); None for ordinary models
+    mix_Q: list | None = None
+    mix_weights: np.ndarray | None = None
 
     @property
     def S(self):
@@ -288,6 +292,14 @@ class Workload:
         _, _, base, _ = self._formulas()
         nb = self.tree.n_branches
         return base[:, None, :] * (self.tree.t[:nb, None] * (1.0 + perturb))[None, :, :]
+
+    def mixture_Qt(self, perturb: float = 0.0):
+        """Explicit-form mixture inputs: (M [B, K, D, D] component rate matrices Q_k * t_b, weights [B, K])."""
+        assert self.mix_Q is not None
+        nb = self.tree.n_branches
+        t = self.tree.t[:nb] * (1.0 + perturb)
+        M = np.stack([np.stack([Qk * tb for Qk in self.mix_Q]) for tb in t])
+        return M, np.tile(np.asarray(self.mix_weights, dtype=np.float64), (nb, 1))
 
     def Qt(self, perturb: float = 0.0) -> np.ndarray:
         """Dense Q*t for every (class, branch node): float64 [C, L+I-1, D, D].  `perturb` scales all
@@ -394,6 +406,20 @@ def codon_workload(n_taxa: int, n_codons: int, n_classes: int = 1, seed: int = 2
                     ["".join(r) for r in chars],
                     {"kind": "codon", "theta": DEFAULT_THETA.tolist(), "posfreq": DEFAULT_POSFREQ.tolist(),
                      "omegas": (DEFAULT_OMEGAS.tolist() if n_classes == 4 else [0.3]), "seed": seed})
+
+
+def bsrel_workload(n_taxa: int, n_codons: int, omegas=(0.1, 1.0, 4.0), weights=(0.6, 0.3, 0.1), seed: int = 20260924,
+                   mean_t: float = 0.05, name: str | None = None) -> Workload:
+    """BUSTED / BS-REL shaped model (config c3): ONE rate class whose per-branch transition matrix is the explicit-form
+    mixture sum_k w_k Exp(Q(omega_k) t_b) (random-effects over omega on every branch).  The alignment is the codon_workload
+    alignment of the same size and seed; only the MODEL differs."""
+    w = codon_workload(n_taxa, n_codons, 1, seed=seed, mean_t=mean_t)
+    w.name = name or f"bsrel_{n_taxa}x{n_codons}_k{len(omegas)}"
+    w.mix_Q = [mg94_rev_Q(om) for om in omegas]
+    w.mix_weights = np.asarray(weights, dtype=np.float64)
+    w.Q_classes = [sum(wt * Q for wt, Q in zip(weights, w.mix_Q))]     # placeholder (never used for likelihoods of this model)
+    w.meta = dict(w.meta, mixture={"omegas": list(map(float, omegas)), "weights": list(map(float, weights))})
+    return w
 
 
 _IUPAC = {"A": "A", "C": "C", "G": "G", "T": "T", "R": "AG", "Y": "CT", "N": "ACGT", "-": "ACGT", "?": "ACGT"}

@@ -97,6 +97,20 @@ int hb2_set_mixture_matrices(hb2_partition *p, int64_t cat, int64_t n, const int
 int hb2_evaluate(hb2_partition *p, int64_t cat, int64_t nUpdate, const int64_t *updateNodes,
                  const double *rootFreqs, double *lnL, double *siteL, int64_t *siteScale);
 
+/* hb2_evaluate with ONE node pinned to a per-pattern state -- the reference's `branchIndex` / `branchValues` arguments of
+ * ComputeBlock (likefunc.cpp:10783), i.e. setBranch / setBranchTo of ComputeTreeBlockByBranch (tree_evaluator.cpp:3624:
+ * a pinned leaf has its observed state replaced :173-181, a pinned internal node starts from the indicator vector of its
+ * state :585-605, a pinned root contributes only that state :4059-4063).  forcedNode is a FLAT node id (0..L-1 leaves,
+ * L..L+I-1 internal nodes; the reference's branchIndex b maps to b + L for b < I and to b - I otherwise), forcedStates[S]
+ * in original pattern order, each in 0..D-1.  The caller lists the pinned node (a leaf) or its children (an internal
+ * node) in updateNodes exactly as DetermineNodesForUpdate does with `addOne` (tree.cpp:3117,3262), and schedules the
+ * recomputation of the affected conditionals afterwards (AddBranchToForcedRecomputeList, likefunc2.cpp:979-1041).
+ * Everything PopulateConditionalProbabilities builds on per-class ComputeBlock calls -- ConstructCategoryMatrix run
+ * modes, HMM / constant-on-partition categories, ancestral sampling -- only needs this entry point. */
+int hb2_evaluate_forced(hb2_partition *p, int64_t cat, int64_t nUpdate, const int64_t *updateNodes,
+                        const double *rootFreqs, int64_t forcedNode, const int64_t *forcedStates,
+                        double *lnL, double *siteL, int64_t *siteScale);
+
 /* Fused replacement for the whole category loop PopulateConditionalProbabilities(WeightedSum) +
  * SumUpSiteLikelihoods (likefunc2.cpp:484-908, 1446-1506): all C classes pruned in one pass,
  * L_s = sum_c weights[c]*L_{c,s} combined on device, one lnL comes back.  Same outputs as hb2_evaluate. */

@@ -173,9 +173,10 @@ static void handle_scaling(double sum, double *parent, int D, double *adj, int64
  * leafState [L*S] original pattern order, >=0 state, <0 -> ambig row -(code+1).  P: [(L+I-1)][D*D] row=parent state.
  * Outputs: siteL[S] (root likelihood incl. pi), siteScale[S] with L_true = L * 2^(-64*count).
  * cond (nullable): caller buffer [I*S*D] receiving the internal-node conditionals. */
-int hb2o_prune(int64_t S, int D, int64_t L, int64_t I, const int64_t *flatParents, const int64_t *leafState,
+static int prune_impl(int64_t S, int D, int64_t L, int64_t I, const int64_t *flatParents, const int64_t *leafState,
                const double *ambig, int64_t nAmb, const double *P, const double *pi,
-               double *siteL, int64_t *siteScale, double *cond_out) {
+               double *siteL, int64_t *siteScale, double *cond_out, int64_t setBranch, const int64_t *setBranchTo) {
+    /* setBranch follows the reference: internal index 0..I-1, or I + leaf index; -1 none (tree_evaluator.cpp:3624,173) */
     size_t nc = (size_t)I * S * D;
     double *cond = cond_out ? cond_out : (double *)malloc(nc * sizeof(double));
     double *adj = (double *)malloc((size_t)I * S * sizeof(double));
@@ -191,6 +192,10 @@ int hb2o_prune(int64_t S, int D, int64_t L, int64_t I, const int64_t *flatParent
             touched[par] = 1;
             for (int64_t s = 0; s < S; s++) {
                 double *pc = cond + ((size_t)par * S + s) * D;
+                if (par == setBranch) {                              /* __ll_loop_handle_leaf_case, matchSet :585-592 */
+                    for (int k = 0; k < D; k++) pc[k] = 0.0;
+                    pc[setBranchTo[s]] = adj[(size_t)par * S + s];
+                } else
                 for (int k = 0; k < D; k++) pc[k] = adj[(size_t)par * S + s];
             }
         }
@@ -199,7 +204,7 @@ int hb2o_prune(int64_t S, int D, int64_t L, int64_t I, const int64_t *flatParent
             const double *child = NULL;
             double sum = 0.0;
             if (node < L) {
-                int64_t st = leafState[(size_t)node * S + s];
+                int64_t st = (setBranch == node + I) ? setBranchTo[s] : leafState[(size_t)node * S + s];   /* :173-181 */
                 if (st >= 0) {                                       /* column gather tree_evaluator.cpp:171-235 */
                     for (int k = 0; k < D; k++) { pc[k] *= Pn[(size_t)k * D + st]; sum += pc[k]; }
                     handle_scaling(sum, pc, D, &adj[(size_t)par * S + s], &siteScale[s]);
@@ -223,12 +228,27 @@ int hb2o_prune(int64_t S, int D, int64_t L, int64_t I, const int64_t *flatParent
     const double *root = cond + (size_t)(I - 1) * S * D;            /* tree_evaluator.cpp:4048-4067 */
     for (int64_t s = 0; s < S; s++) {
         double acc = 0.0;
+        if (setBranch + 1 == I) acc = root[(size_t)s * D + setBranchTo[s]] * pi[setBranchTo[s]];     /* :4059-4063 */
+        else
         for (int p = 0; p < D; p++) acc += root[(size_t)s * D + p] * pi[p];
         siteL[s] = acc;
     }
     if (!cond_out) free(cond);
     free(adj); free(touched); free(mvs);
     return 0;
+}
+
+int hb2o_prune(int64_t S, int D, int64_t L, int64_t I, const int64_t *flatParents, const int64_t *leafState,
+               const double *ambig, int64_t nAmb, const double *P, const double *pi,
+               double *siteL, int64_t *siteScale, double *cond_out) {
+    return prune_impl(S, D, L, I, flatParents, leafState, ambig, nAmb, P, pi, siteL, siteScale, cond_out, -1, NULL);
+}
+
+/* ComputeTreeBlockByBranch with setBranch / setBranchTo (forced states of one node, reference convention for setBranch) */
+int hb2o_prune_forced(int64_t S, int D, int64_t L, int64_t I, const int64_t *flatParents, const int64_t *leafState,
+               const double *ambig, int64_t nAmb, const double *P, const double *pi,
+               double *siteL, int64_t *siteScale, int64_t setBranch, const int64_t *setBranchTo) {
+    return prune_impl(S, D, L, I, flatParents, leafState, ambig, nAmb, P, pi, siteL, siteScale, NULL, setBranch, setBranchTo);
 }
 
 /* ---------------------------------------------------------------------------------------------------- */

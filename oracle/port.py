@@ -33,6 +33,8 @@ def lib():
         _lib.hb2o_expm.argtypes = [_dp, C.c_int, C.c_int, _dp]
         _lib.hb2o_prune.restype = C.c_int
         _lib.hb2o_prune.argtypes = [C.c_int64, C.c_int, C.c_int64, C.c_int64, _ip, _ip, _dp, C.c_int64, _dp, _dp, _dp, _ip, _dp]
+        _lib.hb2o_prune_forced.restype = C.c_int
+        _lib.hb2o_prune_forced.argtypes = [C.c_int64, C.c_int, C.c_int64, C.c_int64, _ip, _ip, _dp, C.c_int64, _dp, _dp, _dp, _ip, C.c_int64, _ip]
         _lib.hb2o_combine.restype = None
         _lib.hb2o_combine.argtypes = [C.c_int64, C.c_int64, _dp, _dp, _ip, _dp, _ip]
         _lib.hb2o_sum.restype = C.c_double
@@ -83,6 +85,26 @@ def prune(w, P: np.ndarray, want_cond: bool = False):
     return (sl, ss, cond) if want_cond else (sl, ss)
 
 
+def prune_forced(w, P: np.ndarray, forced_node: int, forced_states):
+    """One rate class with ONE node pinned (flat node id: leaves 0..L-1, internals L..).  Returns (siteL[S], siteScale[S])."""
+    t = w.tree
+    S, D = w.S, w.D
+    fp, pfp = _i(t.flat_parents)
+    ls, pls = _i(w.leaf_states)
+    am, pam = _d(w.ambig if len(w.ambig) else np.zeros((1, D)))
+    Pm, pP = _d(P)
+    pi, ppi = _d(w.pi)
+    fs, pfs = _i(forced_states)
+    set_branch = forced_node - t.n_leaves if forced_node >= t.n_leaves else t.n_internal + forced_node   # reference convention
+    sl = np.empty(S)
+    ss = np.empty(S, dtype=np.int64)
+    rc = lib().hb2o_prune_forced(S, D, t.n_leaves, t.n_internal, pfp, pls, pam, len(w.ambig), pP, ppi,
+                                 sl.ctypes.data_as(_dp), ss.ctypes.data_as(_ip), set_branch, pfs)
+    if rc:
+        raise RuntimeError(f"hb2o_prune_forced failed rc={rc}")
+    return sl, ss
+
+
 def lnl(w, Qt: np.ndarray | None = None, weights=None, sparse_storage: bool | None = None):
     """Full likelihood of workload `w` (all rate classes).  Returns (lnL, per-pattern lnL[S])."""
     t = w.tree
@@ -102,3 +124,17 @@ def lnl(w, Qt: np.ndarray | None = None, weights=None, sparse_storage: bool | No
     v = lib().hb2o_lnl(S, D, t.n_leaves, t.n_internal, Q.shape[0], pfp, pls, pam, len(w.ambig), pfr, pQ,
                        int(sparse_storage), pwt, ppi, site.ctypes.data_as(_dp))
     return float(v), site
+
+
+def mixture_P(w, perturb: float = 0.0) -> np.ndarray:
+    """Explicit-form mixture transition matrices [B, D, D]: sum_k w_k Exp(Q_k t_b), each Exp by the reference's algorithm
+    (tree.cpp:3047-3089 evaluates the formula on the exponentiated components)."""
+    M, wk = w.mixture_Qt(perturb)
+    return np.stack([sum(wk[b, k] * expm(M[b, k], True) for k in range(M.shape[1])) for b in range(M.shape[0])])
+
+
+def lnl_mixture(w, perturb: float = 0.0):
+    """(lnL, per-pattern log-likelihoods) of an explicit-form mixture workload (one rate class)."""
+    sl, ss = prune(w, mixture_P(w, perturb))
+    site = np.log(sl) - 64.0 * np.log(2.0) * ss
+    return float((w.pattern_freq * site).sum()), site

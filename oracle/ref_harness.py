@@ -55,18 +55,43 @@ def write_hbl(w: synth.Workload, path_bf: str, path_fas: str, n_evals: int = 0, 
         th = dict(zip(["AC", "AG", "AT", "CG", "CT", "GT"], w.meta["theta"]))
         for nm in ["AC", "AT", "CG", "CT", "GT"]:
             o.append(f"global {nm} = {_fmt(th[nm])};")
+        mix = w.meta.get("mixture")
         omegas = w.meta["omegas"]
-        if len(omegas) == 1:
-            o.append(f"global omega = {_fmt(omegas[0])};")
+        if mix:
+            # explicit-form model: P_b = sum_k bw_k * Exp(Q_k), Q_k = MG94 with omega_k (BranchSiteREL.bf:272-277 builds its
+            # models the same way); rates carry the frequencies, the diagonal is filled by the evaluator (matrix.cpp:3296)
+            K = len(mix["omegas"])
+            for k in range(K):
+                o.append(f"global omega{k + 1} = {_fmt(mix['omegas'][k])};")
+                o.append(f"global bw{k + 1} = {_fmt(mix['weights'][k])};")
+            entries = synth.mg94_entries(w.meta["theta"], np.array(w.meta["posfreq"]))
+            for k in range(K):
+                o.append(f"Q{k + 1} = {{61,61}};")
+                for i, j, pf, nonsyn, nm in entries:
+                    terms = ["t"]
+                    if nm != "AG":
+                        terms.append(nm)
+                    if nonsyn:
+                        terms.append(f"omega{k + 1}")
+                    terms.append(_fmt(pf))
+                    o.append(f"Q{k + 1}[{i}][{j}] := {'*'.join(terms)};")
+            o.append("freqs = {61,1};")
+            for k, p in enumerate(w.pi):
+                o.append(f"freqs[{k}][0] = {_fmt(p)};")
+            expr = "+".join(f"Exp(Q{k + 1})*bw{k + 1}" for k in range(K))
+            o.append(f'Model M = ("{expr}", freqs, EXPLICIT_FORM_MATRIX_EXPONENTIAL);')
         else:
+          if len(omegas) == 1:
+            o.append(f"global omega = {_fmt(omegas[0])};")
+          else:
             wts = ",".join(_fmt(x) for x in w.class_weights)
             rts = ",".join(_fmt(x) for x in omegas)
             o.append(f"catW = {{{{{wts}}}}};")
             o.append(f"catR = {{{{{rts}}}}};")
             o.append(f"category omega = ({len(omegas)}, catW, MEAN, , catR, 0, 1e25);")
-        o.append("Q = {61,61};")
-        assert abs(th["AG"] - 1.0) < 1e-15
-        for i, j, pf, nonsyn, nm in synth.mg94_entries(w.meta["theta"], np.array(w.meta["posfreq"])):
+          o.append("Q = {61,61};")
+          assert abs(th["AG"] - 1.0) < 1e-15
+          for i, j, pf, nonsyn, nm in synth.mg94_entries(w.meta["theta"], np.array(w.meta["posfreq"])):
             terms = ["t"]
             if nm != "AG":
                 terms.append(nm)
@@ -74,10 +99,10 @@ def write_hbl(w: synth.Workload, path_bf: str, path_fas: str, n_evals: int = 0, 
                 terms.append("omega")
             terms.append(_fmt(pf))
             o.append(f"Q[{i}][{j}] := {'*'.join(terms)};")
-        o.append("freqs = {61,1};")
-        for k, p in enumerate(w.pi):
+          o.append("freqs = {61,1};")
+          for k, p in enumerate(w.pi):
             o.append(f"freqs[{k}][0] = {_fmt(p)};")
-        o.append("Model M = (Q, freqs, 0);")
+          o.append("Model M = (Q, freqs, 0);")
         perturb_name, perturb_base = "AC", th["AC"]
     elif kind == "nuc":
         o.append("DataSetFilter flt = CreateFilter (ds,1);")
@@ -101,7 +126,7 @@ def write_hbl(w: synth.Workload, path_bf: str, path_fas: str, n_evals: int = 0, 
         if kind == "codon":
             for nm in ["AC", "AT", "CG", "CT", "GT"]:
                 o.append(f"{nm} = {_fmt(th[nm])};")
-            if len(w.meta["omegas"]) == 1:
+            if len(w.meta["omegas"]) == 1 and not w.meta.get("mixture"):
                 o.append(f"omega = {_fmt(w.meta['omegas'][0])};")
         else:
             o.append(f"kappa = {_fmt(w.meta['kappa'])};")
@@ -124,25 +149,30 @@ def write_hbl(w: synth.Workload, path_bf: str, path_fas: str, n_evals: int = 0, 
 
 
 def run_reference(w: synth.Workload, n_evals: int = 0, threads: int = 0, per_site: bool = True,
-                  timeout: float = 3600.0, workdir: str | None = None, n_warm: int = 0) -> dict:
+                  timeout: float = 3600.0, workdir: str | None = None, n_warm: int = 0, binary: str | None = None,
+                  env_extra: dict | None = None) -> dict:
     """Run the reference binary on `w`.  Returns {"lnL", "site_lnL" (np array, alignment order) or None,
-    "loop_seconds" (wall time between LOOP_BEGIN and LOOP_END, measured on this side of the pipe), "wall"}."""
-    if not have_reference():
+    "loop_seconds" (wall time between LOOP_BEGIN and LOOP_END, measured on this side of the pipe), "wall"}.
+    binary: another HyPhy executable fed the same script -- the PATCHED host (host/_build/hyphy) in tests/test_host_binding.py."""
+    if binary is None and not have_reference():
         raise RuntimeError(f"reference binary missing: {REF_BIN} (build with make -f oracle/Makefile.ref)")
     tmp = workdir or tempfile.mkdtemp(prefix="hb2ref_")
     bf, fas = os.path.join(tmp, "job.bf"), os.path.join(tmp, "job.fas")
     write_hbl(w, bf, fas, n_evals, threads, per_site, n_warm)
     env = dict(os.environ)
+    env.update(env_extra or {})
     if threads > 0:
         env["OMP_NUM_THREADS"] = str(threads)
     t0 = time.time()
-    proc = subprocess.Popen([REF_BIN, f"CPU={max(threads, 1)}", bf], cwd=tmp, stdin=subprocess.DEVNULL,
+    proc = subprocess.Popen([binary or REF_BIN, f"CPU={max(threads, 1)}", bf], cwd=tmp, stdin=subprocess.DEVNULL,
                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
-    lnL, sites, t_begin, t_end, loop_lnl, tail = None, {}, None, None, None, []
+    lnL, sites, t_begin, t_end, loop_lnl, tail, engine_lines = None, {}, None, None, None, [], []
     try:
         for line in proc.stdout:
             tail.append(line)
             tail = tail[-30:]
+            if line.startswith("[hyphy_b200]"):
+                engine_lines.append(line.strip())
             if line.startswith("LNL="):
                 lnL = float(line[4:])
             elif line.startswith("LOOP_BEGIN"):
@@ -165,5 +195,5 @@ def run_reference(w: synth.Workload, n_evals: int = 0, threads: int = 0, per_sit
     site_arr = None
     if sites:
         site_arr = np.array([sites[k] for k in range(len(sites))])
-    return {"lnL": lnL, "site_lnL": site_arr, "loop_lnL": loop_lnl,
+    return {"lnL": lnL, "site_lnL": site_arr, "loop_lnL": loop_lnl, "engine": engine_lines,
             "loop_seconds": (t_end - t_begin) if (t_begin and t_end) else None, "wall": time.time() - t0}

@@ -26,6 +26,12 @@ SMALL = ["c1_hky85_8x500", "nuc_300x200_scaling", "mg94_8x60_c1", "mg94_8x60_c4_
          "mg94_200x64_c4_scaling"]
 MEDIUM = ["c2_mg94_50x1000_c1"]
 FULL = ["ns_mg94_200x2000_c4"]
+# explicit-form mixtures (BS-REL / BUSTED shape; the workload carries mix_Q / mix_weights): config c3 and a small sibling
+MIXTURE_SMALL = ["bsrel_12x80_k3"]
+MIXTURE_FULL = ["c3_bsrel_100x1500_k3"]
+# config c5 (aBSREL size: 500 taxa x 5000 codons x 4 classes, 5.2 GB of conditionals): GPU against the reference's output
+# directly -- the scalar oracle would need minutes for it, so the CPU suite pins the oracle on the smaller cases only
+HUGE = ["c5_mg94_500x5000_c4"]
 
 
 def load_smallcodon():

@@ -245,6 +245,47 @@ def test_mixture_matrices_bsrel(mode):
     assert abs(got - ref) <= tol(w, mode)[0] * abs(ref)
 
 
+@pytest.mark.parametrize("name", gc.MIXTURE_SMALL + gc.MIXTURE_FULL)
+def test_mixture_model_matches_reference_golden(name, mode):
+    """BASELINE.json configs[2] (c3: BUSTED shape, 100 taxa x 1500 codons, K = 3 explicit-form mixture on every branch)
+    and a small sibling, through hb2_set_mixture_matrices, against the unmodified reference binary's output."""
+    w, g = gc.load(name)
+    rtol, atol = tol(w, mode)
+    M, wk = w.mixture_Qt()
+    lf = LF(w, mode)
+    lf.part.set_mixture_matrices(0, np.arange(w.tree.n_branches), M, wk)
+    lnl, sl, ss = lf.compute(want_sites=True)
+    err = float(np.abs(_site_lnl(sl, ss)[w.site_to_pattern] - g["site_lnL"]).max())
+    record("golden_mixture", name, mode, lnl, g["lnL"], err)
+    # second evaluation with every component changed, then back: the mixture path is re-entrant and leaves no residue
+    M2, _ = w.mixture_Qt(perturb=0.25)
+    lf.part.set_mixture_matrices(0, np.arange(w.tree.n_branches), M2, wk)
+    other = lf.compute()
+    lf.part.set_mixture_matrices(0, np.arange(w.tree.n_branches), M, wk)
+    again = lf.compute()
+    lf.close()
+    assert abs(lnl - g["lnL"]) <= rtol * abs(g["lnL"])
+    assert err <= atol
+    assert other != lnl and again == lnl
+
+
+@pytest.mark.parametrize("name", gc.HUGE)
+def test_c5_absrel_size_matches_reference_golden(name, mode):
+    """BASELINE.json configs[4] (c5: 500 taxa x 5000 codons x 4 classes; 5.2 GB of fp32 conditionals, 10.4 GB in fp64)
+    on ONE GPU against the unmodified reference binary's lnL and per-site log-likelihoods."""
+    w, g = gc.load(name)
+    rtol, atol = tol(w, mode)
+    lf = LF(w, mode)
+    lf.set_template()
+    lf.set_all_compiled()
+    lnl, sl, ss = lf.compute(want_sites=True)
+    err = float(np.abs(_site_lnl(sl, ss)[w.site_to_pattern] - g["site_lnL"]).max())
+    record("golden_c5", name, mode, lnl, g["lnL"], err)
+    lf.close()
+    assert abs(lnl - g["lnL"]) <= rtol * abs(g["lnL"])
+    assert err <= atol
+
+
 def test_plain_matrices_then_mixtures_before_first_evaluate(mode):
     """The usual BS-REL sequence: plain matrices for most branches, mixtures for a few, no evaluation in between.  The
     mixture hand-over must not disturb plain matrices whose H2D copy is still in flight (staging race)."""
@@ -318,6 +359,50 @@ def test_other_state_counts(D, taxa, sites, C, mode):
     ref, _ = port.lnl(w, sparse_storage=False)
     record("states", w.name, mode, got, ref)
     assert abs(got - ref) <= tol(w, mode)[0] * abs(ref)
+
+
+@pytest.mark.parametrize("name", ["mg94_8x60_c4_ambig", "mg94_200x64_c4_scaling", "c1_hky85_8x500"])
+def test_forced_states_match_oracle(name, mode):
+    """ComputeBlock(..., branchIndex, branchValues) -- one node pinned to a per-pattern state (tree_evaluator.cpp:3624,
+    173-181, 585-592, 4059): leaf, internal node, root; full and partial (children-of-the-node) update lists; the
+    caches must be usable again after the host-style recomputation of the touched path."""
+    w, g = gc.load(name)
+    rtol, atol = tol(w, mode)
+    rng = np.random.default_rng(7)
+    L, I = w.tree.n_leaves, w.tree.n_internal
+    Qt = w.Qt()
+    lf = LF(w, mode)
+    lf.set_all_matrices(Qt)
+    c = w.C - 1
+    base, bl, bs = lf.compute_block(c, want_sites=True)
+    P = np.stack([port.expm(q, w.D > 20) for q in Qt[c]])
+    children = w.tree.children()
+    for node in sorted({0, L - 1, L, L + I // 2, L + I - 1}):
+        fs = rng.integers(0, w.D, size=w.S)
+        oL, oS = port.prune_forced(w, P, node, fs)
+        ref_site = _site_lnl(np.maximum(oL, 1e-300), oS)
+        for upd in (None, [node] if node < L else children[node - L]):
+            lnl, sl, ss = lf.part.evaluate_forced(c, w.pi, node, fs, update_nodes=upd)
+            got_site = _site_lnl(np.maximum(sl, 1e-300), ss)
+            ok = oL > 0
+            assert np.array_equal(sl > 0, ok)
+            assert np.abs(got_site[ok] - ref_site[ok]).max() <= max(atol, 1e-9), (node, upd is None)
+            if ok.all():
+                ref = (w.pattern_freq * ref_site).sum()
+                assert abs(lnl - ref) <= rtol * abs(ref)
+            else:
+                assert lnl == -np.inf
+        # what the host does next (AddBranchToForcedRecomputeList): recompute the touched path without forcing
+        again, al, as_ = lf.compute_block(c, update_nodes=[node] if node < L else children[node - L], want_sites=True)
+        assert again == base and np.array_equal(al, bl) and np.array_equal(as_, bs)
+    # marginalisation identity on an internal node: sum over its states of the pinned likelihoods = the likelihood
+    node = L + I // 3
+    tot = np.zeros(w.S)
+    for st in range(w.D):
+        _, sl, ss = lf.part.evaluate_forced(c, w.pi, node, np.full(w.S, st), update_nodes=children[node - L])
+        tot += sl * 2.0 ** (-64.0 * (ss - bs))
+    lf.close()
+    np.testing.assert_allclose(tot, bl, rtol=max(atol, 1e-9))
 
 
 def test_conditionals_readback_matches_oracle(mode):

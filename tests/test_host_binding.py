@@ -1,0 +1,72 @@
+"""GPU suite, part 2: the REAL boundary.  host/_build/hyphy is a build copy of the reference with the hook calls of
+host/apply_hooks.py inserted and host/hb2_hyphy_hooks.cpp linked against libhyphy_b200.so (built here by
+__graft_entry__.build(); the binary travels to the GPU box).  The same HBL scripts that produced the golden fixtures with
+the UNMODIFIED reference binary are fed to the patched binary: `LFCompute`, `ConstructCategoryMatrix`, `Optimize` now run
+on the engine, behind `_LikelihoodFunction::ComputeBlock`, with no change to the batch files."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import ref_harness as rh
+from tests import golden_cases as gc
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST_BIN = os.path.join(ROOT, "host", "_build", "hyphy")
+MODES = {"fp64": ({"HYPHY_B200_FP64": "1"}, 1e-10, 1e-8), "tc": ({}, 1e-7, 1e-5)}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_host():
+    assert os.path.isfile(HOST_BIN), f"{HOST_BIN} is missing: run __graft_entry__.build() where /root/reference exists"
+
+
+def _tol(w, mode):
+    if mode == "tc" and w.D > 32:
+        return MODES["tc"][1:]
+    return MODES["fp64"][1:]
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+@pytest.mark.parametrize("name", gc.SMALL + gc.MEDIUM)
+def test_patched_host_reproduces_reference_fixture(name, mode):
+    """lnL (LFCompute) and per-site log-likelihoods (ConstructCategoryMatrix SITE_LOG_LIKELIHOODS, i.e. the per-class
+    ComputeBlock path with siteRes / scaler counts combined by the HOST) of the patched binary against the fixture the
+    unmodified binary produced from the same script."""
+    w, g = gc.load(name)
+    env = dict(MODES[mode][0], HYPHY_B200_VERBOSE="1")
+    r = rh.run_reference(w, binary=HOST_BIN, env_extra=env)
+    rtol, atol = _tol(w, mode)
+    assert any("partition 0 on device" in l for l in r["engine"]), "the engine did not run this likelihood function"
+    assert abs(r["lnL"] - g["lnL"]) <= rtol * abs(g["lnL"]), (r["lnL"], g["lnL"])
+    assert np.abs(r["site_lnL"] - g["site_lnL"]).max() <= max(atol, 1e-9)
+
+
+def test_patched_host_evaluation_stream_and_partial_updates():
+    """The bench's evaluation stream (one global parameter perturbed per evaluation -> every matrix re-exponentiated on the
+    device) through the patched binary: final lnL of the loop equals the unmodified binary's to 1e-7 relative."""
+    w, g = gc.load("mg94_30x100_c4_ambig")
+    a = rh.run_reference(w, n_evals=5, n_warm=1, per_site=False)
+    b = rh.run_reference(w, n_evals=5, n_warm=1, per_site=False, binary=HOST_BIN, env_extra={"HYPHY_B200_VERBOSE": "1"})
+    assert abs(b["loop_lnL"] - a["loop_lnL"]) <= 1e-7 * abs(a["loop_lnL"])
+    assert abs(b["lnL"] - g["lnL"]) <= 1e-7 * abs(g["lnL"])
+
+
+def test_patched_host_runs_reference_regression_batch_files():
+    """The reference's own regression batch files (tests/hbltests: optimisations, category variables, HMM, explicit-form
+    mixtures, ancestral reconstruction, per-site likelihoods) through the patched binary, UNMODIFIED: same verdict and the
+    same fitted log-likelihoods as the unmodified reference binary recorded in tests/golden/hbltests_expected.json."""
+    pr = subprocess.run([sys.executable, os.path.join(ROOT, "host", "regress.py"), "check"], stdout=subprocess.PIPE, text=True)
+    rows = [json.loads(l) for l in pr.stdout.splitlines() if l.startswith("{")]
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "host_regression.jsonl"), "w") as f:
+        for r in rows:
+            f.write(json.dumps(r) + "\n")
+    assert rows, pr.stdout[-2000:]
+    bad = [r["test"] for r in rows if not r["ok"]]
+    assert not bad, bad

@@ -15,6 +15,40 @@ def test_oracle_matches_reference_golden(name):
     np.testing.assert_allclose(site[w.site_to_pattern], g["site_lnL"], rtol=0, atol=1e-10)
 
 
+@pytest.mark.parametrize("name", gc.MIXTURE_SMALL + gc.MIXTURE_FULL)
+def test_oracle_mixture_matches_reference_golden(name):
+    """Explicit-form models (P_b = sum_k w_k Exp(Q_k t_b), reference tree.cpp:3047-3089): the fixture was produced by the
+    unmodified binary from `Model M = ("Exp(Q1)*bw1+...", freqs, EXPLICIT_FORM_MATRIX_EXPONENTIAL)`."""
+    w, g = gc.load(name)
+    lnl, site = port.lnl_mixture(w)
+    assert abs(lnl - g["lnL"]) <= 1e-11 * abs(g["lnL"])
+    np.testing.assert_allclose(site[w.site_to_pattern], g["site_lnL"], rtol=0, atol=1e-10)
+
+
+def test_oracle_forced_states_marginalise():
+    """setBranch / setBranchTo restatement (tree_evaluator.cpp:3624,173-181,585-592,4059): pinning a node to each state in
+    turn and summing recovers the unpinned likelihood -- for a leaf with an ambiguous observation, an internal node and
+    the root; pinning a leaf to its observed state changes nothing."""
+    w, _ = gc.load("mg94_8x60_c4_ambig")
+    L, I = w.tree.n_leaves, w.tree.n_internal
+    P = np.stack([port.expm(q, True) for q in w.Qt()[1]])
+    sl, ss = port.prune(w, P)
+    base = sl * 2.0 ** (-64.0 * ss)
+    for node in (L + 1, L + I - 1):
+        tot = np.zeros(w.S)
+        for st in range(w.D):
+            a, b = port.prune_forced(w, P, node, np.full(w.S, st))
+            tot += a * 2.0 ** (-64.0 * b)
+        np.testing.assert_allclose(tot, base, rtol=1e-12)
+    leaf = int(np.argmax((w.leaf_states < 0).sum(axis=1)))             # the leaf with most ambiguities
+    tot = np.zeros(w.S)
+    for st in range(w.D):
+        a, b = port.prune_forced(w, P, leaf, np.full(w.S, st))
+        allowed = np.array([w.ambig[-c - 1][st] if c < 0 else float(c == st) for c in w.leaf_states[leaf]])
+        tot += allowed * a * 2.0 ** (-64.0 * b)
+    np.testing.assert_allclose(tot, base, rtol=1e-12)
+
+
 def test_oracle_expm_is_a_transition_matrix_and_semigroup():
     Q = synth.mg94_rev_Q(0.7)
     P1 = port.expm(Q * 0.05, sparse_storage=True)

@@ -26,6 +26,10 @@ CASES = {
     "c2_mg94_50x1000_c1":    lambda: synth.codon_workload(50, 1000, 1),
     "mg94_200x64_c4_scaling": lambda: synth.codon_workload(200, 64, 4),
     "ns_mg94_200x2000_c4":   lambda: synth.codon_workload(200, 2000, 4),
+    # BASELINE.json configs[2] (c3, BUSTED shape: K=3 explicit-form mixture on every branch) and configs[4] (c5)
+    "bsrel_12x80_k3":        lambda: synth.bsrel_workload(12, 80),
+    "c3_bsrel_100x1500_k3":  lambda: synth.bsrel_workload(100, 1500),
+    "c5_mg94_500x5000_c4":   lambda: synth.codon_workload(500, 5000, 4),
 }
 
 
