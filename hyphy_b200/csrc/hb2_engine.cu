@@ -116,6 +116,15 @@ struct hb2_partition {
     int64_t mix_capacity = 0;
     cudaEvent_t ev_mix = nullptr;
     bool mix_busy = false;
+    // shared-powers expm (64 padded states, hb2_kernels_fp64.cuh "Shared powers"): group = rate class (plain batches) or
+    // C + mixture component; per-entry arrays are indexed like the batch
+    int ex_G = 0, ex_stride = 0;              // groups, doubles per cached reference direction
+    int *d_ex_int = nullptr, *h_ex_int = nullptr, *d_ex_flag = nullptr;     // [group cap | ref cap | refs G]
+    double *d_ex_weight = nullptr, *d_ex_pow = nullptr, *d_ex_refvec = nullptr, *d_Vres = nullptr;
+    void *d_ex_groups = nullptr;
+    std::vector<int> ex_kind;                 // host mirror: kind of the reference direction each group holds (0 none)
+    int64_t ex_cap = 0;
+    bool ex_enabled = true;                   // HB2_EXPM_SHARED=0 switches the path off (A/B testing)
     int64_t stage_launches[3] = {0, 0, 0};    // launches per evaluation of the last hb2_time_resident {expm, pruning, root}
     // compiled rate-matrix template (hb2_set_rate_template) and its per-evaluation formula values
     int64_t t_nnz = 0, t_nF = 0;
@@ -161,11 +170,50 @@ struct hb2_partition {
 
 namespace {
 
+// Host half of the shared-powers path for one batch: groups and references of the n entries (h_dst = their slots, < 0
+// retired; kind 1 = compiled hand-over, 2 = dense).  A group whose batch holds at least EX_MIN_GROUP live entries gets its
+// power table rebuilt from the first of them; smaller groups are compared with the direction the table was last built
+// from.  Fills the pinned arrays and enqueues their upload: call BEFORE ev_staging is recorded.
+struct SharedPlan {
+    bool use = false;
+    int kind = 0, n_refs = 0;
+    int64_t cap_off = 0;
+};
+constexpr int EX_MIN_GROUP = 24;
+
+int plan_shared(hb2_partition *p, const int *h_dst, int64_t n, int kind, const int *group_override, SharedPlan &sp) {
+    sp = SharedPlan();
+    if (p->Dp != 64 || p->expm_dfma || !p->ex_enabled || !p->d_ex_int || n <= 0 || n > p->ex_cap) return 0;
+    if (kind == 1 && !p->d_Vres) return 0;
+    int *grp = p->h_ex_int, *ref = p->h_ex_int + p->ex_cap, *refs = p->h_ex_int + 2 * p->ex_cap;
+    std::vector<int> count(p->ex_G, 0), first(p->ex_G, -1);
+    for (int64_t k = 0; k < n; k++) {
+        int g = -1;
+        if (h_dst[k] >= 0) g = group_override ? group_override[k] : (int)(h_dst[k] / p->B);
+        if (g >= p->ex_G) g = -1;
+        grp[k] = g;
+        if (g >= 0) { if (first[g] < 0) first[g] = (int)k; count[g]++; }
+    }
+    bool any = false;
+    int nr = 0;
+    for (int g = 0; g < p->ex_G; g++) {
+        if (count[g] >= EX_MIN_GROUP) { refs[nr++] = first[g]; any = true; }
+        else { first[g] = -1; if (count[g] > 0 && p->ex_kind[g] == kind) any = true; }
+    }
+    if (!any) return 0;
+    for (int64_t k = 0; k < n; k++) ref[k] = grp[k] >= 0 ? first[grp[k]] : -1;
+    for (int r = 0; r < nr; r++) p->ex_kind[grp[refs[r]]] = kind;
+    CU(cudaMemcpyAsync(p->d_ex_int, p->h_ex_int, (size_t)(2 * p->ex_cap + p->ex_G) * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    sp.use = true; sp.kind = kind; sp.n_refs = nr;
+    return 0;
+}
+
 // One CTA per listed matrix.  is_trans: 0 rate matrices (exponentiated), 1 transition matrices (transposed/padded only),
 // 2 compiled template (dQ = formula values).  pt_override: write the results there instead of the P cache (mixture
-// components go to a scratch area first); pack_tc: also emit the tensor-path operands of the slot.
+// components go to a scratch area first); pack_tc: also emit the tensor-path operands of the slot.  sp: shared-powers plan
+// of the WHOLE batch this run [off, off + n) belongs to (dQ / d_dst already point at the run).
 int launch_expm(hb2_partition *p, const double *dQ, const int *d_dst, int n, int is_trans, double *qres, bool pack_tc = true,
-                double *pt_override = nullptr) {
+                double *pt_override = nullptr, const SharedPlan *sp = nullptr, int64_t off = 0) {
     if (n <= 0) return 0;
     hb2::ExpmArgs a{};
     a.Q = dQ; a.dst = d_dst; a.PT = pt_override ? pt_override : p->d_PT; a.Qres = qres; a.D = (int)p->D;
@@ -181,9 +229,35 @@ int launch_expm(hb2_partition *p, const double *dQ, const int *d_dst, int n, int
             if (p->expm_dfma) {
                 hb2::expm64_kernel<<<n, 256, 5 * 64 * hb2::LD64 * sizeof(double), p->stream>>>(a);
             } else {
+                const size_t smem = 3 * 64 * hb2::LD64 * sizeof(double);
+                if (sp && sp->use && is_trans != 1) {
+                    const int nV = sp->kind == 1 ? (int)p->t_nF : (int)(p->D * p->D);
+                    const hb2::ExpmGroup *groups = static_cast<const hb2::ExpmGroup *>(p->d_ex_groups);
+                    hb2::ExpmClassifyArgs ca{};
+                    ca.V = dQ; ca.nV = nV; ca.kind = sp->kind; ca.dst = d_dst; ca.group = p->d_ex_int + off;
+                    ca.ref = p->d_ex_int + p->ex_cap + off; ca.groups = groups; ca.refvec = p->d_ex_refvec; ca.refvec_stride = p->ex_stride;
+                    ca.weight = p->d_ex_weight + off; ca.flag = p->d_ex_flag + off;
+                    ca.res = sp->kind == 1 ? p->d_Vres : qres;
+                    // references index the whole batch: classification has to see it in one piece (off == 0 for compiled batches
+                    // and for dense batches that consist of a single run; mixed dense batches fall back below)
+                    hb2::expm_classify_kernel<<<n, 128, 0, p->stream>>>(ca);
+                    a.group = ca.group; a.flag = ca.flag; a.weight = ca.weight; a.groups = groups; a.pow = p->d_ex_pow;
+                    a.Qres = nullptr;                    // the classification stage keeps the resident copy
+                    if (sp->n_refs > 0) {
+                        hb2::ExpmPowersArgs pa{};
+                        pa.a = a; pa.refs = p->d_ex_int + 2 * p->ex_cap; pa.groups = static_cast<hb2::ExpmGroup *>(p->d_ex_groups);
+                        pa.pow = p->d_ex_pow; pa.refvec = p->d_ex_refvec; pa.refvec_stride = p->ex_stride; pa.nV = nV; pa.kind = sp->kind; pa.Vin = dQ;
+                        hb2::expm_powers_kernel<<<sp->n_refs, 256, smem, p->stream>>>(pa);
+                        p->launches++;
+                    }
+                    const int chunks = std::max(1, std::min(n, 18));
+                    const int per_chunk = (n + chunks - 1) / chunks;
+                    hb2::expm_poly_kernel<<<dim3(16, (unsigned)((n + per_chunk - 1) / per_chunk)), 256, 0, p->stream>>>(a, n, per_chunk);
+                    p->launches += 2;
+                }
                 hb2::ExpmTcOut tco{nullptr, nullptr};
                 if (pack_tc) { tco.PB = p->d_PB; tco.PTf = p->d_PTf; packed = true; }
-                hb2::expm64_dmma_kernel<<<n, 256, 3 * 64 * hb2::LD64 * sizeof(double), p->stream>>>(a, tco);
+                hb2::expm64_dmma_kernel<<<n, 256, smem, p->stream>>>(a, tco);
             }
             break;
         case 4: hb2::expm_small_kernel<4><<<n, 128, hb2::expm_small_smem_bytes(4), p->stream>>>(a); break;
@@ -248,11 +322,13 @@ int flush_compiled(hb2_partition *p) {
     if (n == 0) return 0;
     CU(cudaMemcpyAsync(p->d_V, p->h_V, n * p->t_nF * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     CU(cudaMemcpyAsync(p->d_vdst, p->h_vdst, n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    SharedPlan sp;
+    if (plan_shared(p, p->h_vdst, n, 1, nullptr, sp)) return 1;
     CU(cudaEventRecord(p->ev_staging, p->stream));
     p->staging_busy = true;
-    if (launch_expm(p, p->d_V, p->d_vdst, (int)n, 2, p->d_Qres)) return 1;
+    if (launch_expm(p, p->d_V, p->d_vdst, (int)n, 2, sp.use ? nullptr : p->d_Qres, true, nullptr, &sp)) return 1;
     for (int64_t k = 0; k < n; k++)
-        if (p->h_vdst[k] >= 0) { p->is_rate[p->h_vdst[k]] = 1; p->pend_pos[p->h_vdst[k]] = -1; }
+        if (p->h_vdst[k] >= 0) { p->is_rate[p->h_vdst[k]] = sp.use ? 2 : 1; p->pend_pos[p->h_vdst[k]] = -1; }
     p->n_vpending = 0;
     return 0;
 }
@@ -264,6 +340,12 @@ int flush_matrices(hb2_partition *p) {
     const size_t dd = (size_t)p->D * p->D;
     CU(cudaMemcpyAsync(p->d_Q, p->h_Q, n * dd * sizeof(double), cudaMemcpyHostToDevice, p->stream));
     CU(cudaMemcpyAsync(p->d_dst, p->h_dst, n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    SharedPlan sp;                           // shared powers only for batches that are one run of rate matrices
+    {
+        bool all_rate = true;
+        for (int64_t k = 0; k < n; k++) all_rate = all_rate && p->pending_kind[k] == HB2_MATRIX_RATE;
+        if (all_rate && plan_shared(p, p->h_dst, n, 2, nullptr, sp)) return 1;
+    }
     // the pinned staging buffers are reused by the next hb2_set_matrices: it waits on this event (copies only)
     CU(cudaEventRecord(p->ev_staging, p->stream));
     p->staging_busy = true;
@@ -274,7 +356,7 @@ int flush_matrices(hb2_partition *p) {
         int64_t j = i;
         while (j < n && p->pending_kind[j] == p->pending_kind[i]) j++;
         const int is_trans = p->pending_kind[i] == HB2_MATRIX_TRANS;
-        if (launch_expm(p, p->d_Q + i * dd, p->d_dst + i, (int)(j - i), is_trans, is_trans ? nullptr : p->d_Qres)) return 1;
+        if (launch_expm(p, p->d_Q + i * dd, p->d_dst + i, (int)(j - i), is_trans, is_trans ? nullptr : p->d_Qres, true, nullptr, &sp, i)) return 1;
         i = j;
     }
     for (int64_t k = 0; k < n; k++)
@@ -907,6 +989,18 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
     }
     if (Dp == 32) CUP(cudaFuncSetAttribute(hb2::expm_small_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hb2::expm_small_smem_bytes(32)));
     if (Dp == 64) {
+        { const char *env = getenv("HB2_EXPM_SHARED"); p->ex_enabled = !(env && env[0] == '0'); }
+        p->ex_G = (int)C + 8; p->ex_cap = (int64_t)(C + 8) * p->B; p->ex_stride = 4096;
+        p->ex_kind.assign(p->ex_G, 0);
+        CUP(cudaMalloc(&p->d_ex_int, (size_t)(2 * p->ex_cap + p->ex_G) * sizeof(int)));
+        CUP(cudaMallocHost(&p->h_ex_int, (size_t)(2 * p->ex_cap + p->ex_G) * sizeof(int)));
+        CUP(cudaMalloc(&p->d_ex_flag, (size_t)p->ex_cap * sizeof(int)));
+        CUP(cudaMalloc(&p->d_ex_weight, (size_t)p->ex_cap * sizeof(double)));
+        CUP(cudaMalloc(&p->d_ex_groups, (size_t)p->ex_G * sizeof(hb2::ExpmGroup)));
+        CUP(cudaMemsetAsync(p->d_ex_groups, 0, (size_t)p->ex_G * sizeof(hb2::ExpmGroup), p->stream));
+        CUP(cudaMalloc(&p->d_ex_pow, (size_t)p->ex_G * hb2::EXPM_POW_TERMS * 4096 * sizeof(double)));
+        CUP(cudaMalloc(&p->d_ex_refvec, (size_t)p->ex_G * p->ex_stride * sizeof(double)));
+        CUP(cudaFuncSetAttribute(hb2::expm_powers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * 64 * hb2::LD64 * sizeof(double))));
         CUP(cudaFuncSetAttribute(hb2::expm64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(5 * 64 * hb2::LD64 * sizeof(double))));
         CUP(cudaFuncSetAttribute(hb2::expm64_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * 64 * hb2::LD64 * sizeof(double))));
         CUP(cudaFuncSetAttribute(hb2::expm64_dmma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -973,6 +1067,7 @@ int hb2_set_mixture_matrices(hb2_partition *p, int64_t cat, int64_t n, const int
         for (void *d : {(void *)p->d_mix_scratch, (void *)p->d_mix_Q, (void *)p->d_mix_dst}) if (d) cudaFree(d);
         if (p->h_mix) cudaFreeHost(p->h_mix);
     if (p->h_forced) cudaFreeHost(p->h_forced);
+    if (p->h_ex_int) cudaFreeHost(p->h_ex_int);
         p->d_mix_scratch = p->d_mix_Q = nullptr; p->d_mix_dst = nullptr; p->h_mix = nullptr; p->mix_capacity = 0;
         CU(cudaMalloc(&p->d_mix_scratch, (size_t)nk * dpdp * sizeof(double)));
         CU(cudaMalloc(&p->d_mix_Q, (size_t)nk * (dd + 1) * sizeof(double)));
@@ -989,7 +1084,18 @@ int hb2_set_mixture_matrices(hb2_partition *p, int64_t cat, int64_t n, const int
     CU(cudaMemcpyAsync(p->d_mix_dst, h_idx, (size_t)(nk + n) * sizeof(int), cudaMemcpyHostToDevice, p->stream));
     CU(cudaEventRecord(p->ev_mix, p->stream));
     p->mix_busy = true;
-    if (launch_expm(p, p->d_mix_Q, p->d_mix_dst, (int)nk, 0, nullptr, false, p->d_mix_scratch)) return 1;
+    // component k of every node is (in BS-REL / BUSTED models) the same rate matrix up to the branch length: the components
+    // form shared-powers groups C + k
+    SharedPlan sp;
+    if (K <= 8) {
+        if (wait_staging(p)) return 1;
+        std::vector<int> grp(nk);
+        for (int64_t k = 0; k < nk; k++) grp[k] = (int)(p->C + k % K);
+        if (plan_shared(p, h_idx, nk, 2, grp.data(), sp)) return 1;
+        CU(cudaEventRecord(p->ev_staging, p->stream));
+        p->staging_busy = true;
+    }
+    if (launch_expm(p, p->d_mix_Q, p->d_mix_dst, (int)nk, 0, nullptr, false, p->d_mix_scratch, &sp)) return 1;
     hb2::mix_reduce_kernel<<<(unsigned)n, 256, 0, p->stream>>>(p->d_mix_scratch, p->d_mix_Q + (size_t)nk * dd, p->d_mix_dst + nk, (int)K, p->Dp,
                                                               p->d_PT, p->use_tc ? p->d_PB : nullptr, p->d_PTf);
     p->launches++;
@@ -1012,7 +1118,8 @@ int hb2_set_rate_template(hb2_partition *p, int64_t nnz, const int64_t *entryInd
         if (entryFormula[e] < 0 || entryFormula[e] >= nFormulas) return fail("template entry %lld: formula %lld out of range", (long long)e, (long long)entryFormula[e]);
         idx[e] = (int)entryIndex[e]; frm[e] = (int)entryFormula[e];
     }
-    void *old[] = {p->d_t_index, p->d_t_formula, p->d_t_colfreq, p->d_V, p->d_vdst};
+    void *old[] = {p->d_t_index, p->d_t_formula, p->d_t_colfreq, p->d_V, p->d_vdst, p->d_Vres};
+    p->d_Vres = nullptr;
     for (void *d : old) if (d) cudaFree(d);
     if (p->h_V) cudaFreeHost(p->h_V);
     if (p->h_vdst) cudaFreeHost(p->h_vdst);
@@ -1022,6 +1129,12 @@ int hb2_set_rate_template(hb2_partition *p, int64_t nnz, const int64_t *entryInd
     CU(cudaMalloc(&p->d_t_colfreq, p->D * sizeof(double)));
     CU(cudaMalloc(&p->d_V, (size_t)p->q_capacity * nFormulas * sizeof(double)));
     CU(cudaMalloc(&p->d_vdst, p->q_capacity * sizeof(int)));
+    if (p->d_ex_groups) {                      // resident formula values of every slot + cached directions of the old template are void
+        CU(cudaMalloc(&p->d_Vres, (size_t)p->C * p->B * nFormulas * sizeof(double)));
+        CU(cudaMemset(p->d_ex_groups, 0, (size_t)p->ex_G * sizeof(hb2::ExpmGroup)));
+        std::fill(p->ex_kind.begin(), p->ex_kind.end(), 0);
+        for (auto &r : p->is_rate) if (r == 2) r = 0;
+    }
     CU(cudaMallocHost(&p->h_V, (size_t)p->q_capacity * nFormulas * sizeof(double)));
     CU(cudaMallocHost(&p->h_vdst, p->q_capacity * sizeof(int)));
     CU(cudaMemcpy(p->d_t_index, idx.data(), nnz * sizeof(int), cudaMemcpyHostToDevice));
@@ -1320,7 +1433,7 @@ void hb2_destroy(hb2_partition *p) {
     if (p->comm) g_nccl.CommDestroy(p->comm);
     void *dev[] = {p->d_leaf, p->d_scal, p->d_rootE, p->d_child_start, p->d_child_ids, p->d_jobs, p->d_dst, p->d_flag,
                    p->d_mix_dst, p->d_mix_Q, p->d_ambig, p->d_freq, p->d_cond, p->d_PT, p->d_Q, p->d_pi, p->d_rootL, p->d_weights,
-                   p->d_partial, p->d_lnL, p->d_siteL, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_xsend, p->d_xrecv, p->d_xfreq, p->d_xpartial, p->d_bc_out, p->d_bc_outE, p->d_bc_sib, p->d_walk, p->d_t_index, p->d_t_formula, p->d_vdst, p->d_t_colfreq, p->d_V, p->d_forced};
+                   p->d_partial, p->d_lnL, p->d_siteL, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_xsend, p->d_xrecv, p->d_xfreq, p->d_xpartial, p->d_bc_out, p->d_bc_outE, p->d_bc_sib, p->d_walk, p->d_t_index, p->d_t_formula, p->d_vdst, p->d_t_colfreq, p->d_V, p->d_forced, p->d_ex_int, p->d_ex_flag, p->d_ex_weight, p->d_ex_groups, p->d_ex_pow, p->d_ex_refvec, p->d_Vres};
     for (void *d : dev) if (d) cudaFree(d);
     if (p->h_Q) cudaFreeHost(p->h_Q);
     if (p->h_small) cudaFreeHost(p->h_small);
@@ -1331,6 +1444,7 @@ void hb2_destroy(hb2_partition *p) {
     if (p->h_walk) cudaFreeHost(p->h_walk);
     if (p->h_mix) cudaFreeHost(p->h_mix);
     if (p->h_forced) cudaFreeHost(p->h_forced);
+    if (p->h_ex_int) cudaFreeHost(p->h_ex_int);
     if (p->ev_mix) cudaEventDestroy(p->ev_mix);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
     if (p->ev_staging) cudaEventDestroy(p->ev_staging);
@@ -1360,15 +1474,22 @@ int hb2_time_resident(hb2_partition *p, const double *weights, const double *roo
     if (check_ready(p, 0, (int)p->C)) return 1;
     if (flush_matrices(p)) return 1;
     p->bc_node = -1; p->bc_dirty_node = -1;
-    // every slot must hold a resident rate matrix so that the expm stage can be replayed
+    // every slot must hold a resident copy of its rate matrix (dense, or the formula values of a compiled hand-over) so
+    // that the expm stage can be replayed
     std::vector<int> dst;
+    int res_kind = 0;
     for (int64_t k = (int64_t)p->own0 * p->B; k < (int64_t)(p->own0 + p->ownN) * p->B; k++) {
         if (!p->is_rate[k]) return fail("hb2_time_resident needs HB2_MATRIX_RATE matrices in every slot");
+        if (res_kind && res_kind != p->is_rate[k]) return fail("hb2_time_resident: hand all matrices over the same way (dense or compiled) before timing");
+        res_kind = p->is_rate[k];
         dst.push_back((int)k);
     }
     if (wait_staging(p)) return 1;           // the flush above may still be reading the pinned queues
     memcpy(p->h_dst, dst.data(), dst.size() * sizeof(int));
     CU(cudaMemcpyAsync(p->d_dst, p->h_dst, dst.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    SharedPlan sp;
+    if (plan_shared(p, p->h_dst, (int64_t)dst.size(), res_kind == 2 ? 1 : 2, nullptr, sp)) return 1;
+    if (res_kind == 2 && !sp.use) return fail("hb2_time_resident: compiled resident copies need the shared-powers path");
     CU(cudaEventRecord(p->ev_staging, p->stream));
     p->staging_busy = true;
     double *hs = p->h_small;
@@ -1382,7 +1503,9 @@ int hb2_time_resident(hb2_partition *p, const double *weights, const double *roo
     for (int it = 0; it < iters; it++) {
         CU(cudaEventRecord(p->ev[0], p->stream));
         const int64_t l0 = p->launches;
-        if (launch_expm(p, p->d_Qres + (size_t)p->own0 * p->B * p->D * p->D, p->d_dst, (int)dst.size(), 0, nullptr)) return 1;
+        if (res_kind == 2) {
+            if (launch_expm(p, p->d_Vres + (size_t)p->own0 * p->B * p->t_nF, p->d_dst, (int)dst.size(), 2, nullptr, true, nullptr, &sp)) return 1;
+        } else if (launch_expm(p, p->d_Qres + (size_t)p->own0 * p->B * p->D * p->D, p->d_dst, (int)dst.size(), 0, nullptr, true, nullptr, &sp)) return 1;
         const int64_t l1 = p->launches;
         CU(cudaEventRecord(p->ev[1], p->stream));
         if (run_pruning(p, p->own0, p->ownN, levels)) return 1;

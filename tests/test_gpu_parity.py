@@ -141,6 +141,69 @@ def test_expm_large_rates_and_zero():
     lf.close()
 
 
+def test_expm_shared_powers_and_fallbacks():
+    """The shared-powers path (one power table per rate class, a scalar polynomial per branch) against the oracle, together
+    with everything that must NOT take it: a branch whose matrix is not a multiple of the class's reference direction,
+    very long branches (squarings), later single-matrix batches judged against the CACHED direction, and both hand-over
+    forms.  HB2_EXPM_SHARED=0 (the product kernel for every matrix) must give the same matrices to rounding."""
+    w, _ = gc.load("mg94_30x100_c4_ambig")
+    nb = w.tree.n_branches
+    Qt = w.Qt()
+    odd = synth.mg94_rev_Q(7.5) * 0.11                      # a different direction (another omega)
+    Qt[1, 5] = odd
+    Qt[2, 9] *= 60.0                                         # rho ~ 10: several squarings after the polynomial
+    Qt[3, 11] *= 1e-7                                        # tiny rho
+    Qt[0, 3] *= 0.0                                          # zero matrix -> identity
+
+    def check(part, c, b, M, tol=3e-14):
+        P = part.read_transition(c, b)
+        Po = port.expm(M, True)
+        np.testing.assert_allclose(P, Po, rtol=0, atol=tol)
+        assert np.all(P >= 0) and np.abs(P.sum(axis=1) - 1.0).max() <= 1e-14
+
+    lf = LF(w, "fp64")
+    lf.set_all_matrices(Qt)
+    for c in range(w.C):
+        for b in (0, 3, 5, 9, 11, nb - 1):
+            check(lf.part, c, b, Qt[c, b], 5e-13 if (c, b) == (2, 9) else 3e-14)
+    np.testing.assert_array_equal(lf.part.read_transition(0, 3), np.eye(61))
+    # single-matrix batches: proportional to the cached direction (polynomial, no products) and not proportional (products)
+    lf.part.set_matrices(0, [7], Qt[0, 7][None] * 1.75)
+    lf.part.set_matrices(1, [7], odd[None] * 0.5)
+    check(lf.part, 0, 7, Qt[0, 7] * 1.75)
+    check(lf.part, 1, 7, odd * 0.5)
+    lnl_shared = lf.compute()
+    # compiled hand-over: same matrices assembled on the device, class 2 moved to another direction afterwards
+    lf.set_template()
+    vals = w.compiled_values()
+    lf.set_all_compiled(vals)
+    for c in (0, 3):
+        for b in (1, nb - 2):
+            check(lf.part, c, b, w.Qt()[c, b])
+    lf.part.set_matrices_compiled(2, [4], vals[2, 4][None] * 3.0)
+    check(lf.part, 2, 4, w.Qt()[2, 4] * 3.0)
+    skew = vals[2, 6].copy()
+    skew[::3] *= 1.3                                         # not a multiple any more
+    lf.part.set_matrices_compiled(2, [6], skew[None])
+    ei, ef, nf, cf = w.compiled_template()
+    M = np.zeros((61, 61))
+    M.flat[ei] = skew[ef]
+    M[np.diag_indices(61)] = -M.sum(axis=1)
+    check(lf.part, 2, 6, M)
+    lf.close()
+    os.environ["HB2_EXPM_SHARED"] = "0"
+    try:
+        lf = LF(w, "fp64")
+        lf.set_all_matrices(Qt)
+        lf.part.set_matrices(0, [7], Qt[0, 7][None] * 1.75)
+        lf.part.set_matrices(1, [7], odd[None] * 0.5)
+        lnl_products = lf.compute()
+        lf.close()
+    finally:
+        del os.environ["HB2_EXPM_SHARED"]
+    assert abs(lnl_shared - lnl_products) <= 1e-12 * abs(lnl_products)
+
+
 def test_host_transition_matrices_path(mode):
     """HB2_MATRIX_TRANS: host-exponentiated P (GetCompExp()->theData) gives the same lnL."""
     w, g = gc.load("mg94_8x60_c1")
@@ -394,7 +457,10 @@ def test_forced_states_match_oracle(name, mode):
                 assert lnl == -np.inf
         # what the host does next (AddBranchToForcedRecomputeList): recompute the touched path without forcing
         again, al, as_ = lf.compute_block(c, update_nodes=[node] if node < L else children[node - L], want_sites=True)
-        assert again == base and np.array_equal(al, bl) and np.array_equal(as_, bs)
+        if mode == "fp64" or w.D <= 32:
+            assert again == base and np.array_equal(al, bl) and np.array_equal(as_, bs)
+        else:           # tensor path: a partial plan multiplies the children in another order (fp32 rounding); no residue otherwise
+            assert abs(again - base) <= 1e-8 * abs(base) and np.array_equal(as_, bs)
     # marginalisation identity on an internal node: sum over its states of the pinned likelihoods = the likelihood
     node = L + I // 3
     tot = np.zeros(w.S)
@@ -402,7 +468,7 @@ def test_forced_states_match_oracle(name, mode):
         _, sl, ss = lf.part.evaluate_forced(c, w.pi, node, np.full(w.S, st), update_nodes=children[node - L])
         tot += sl * 2.0 ** (-64.0 * (ss - bs))
     lf.close()
-    np.testing.assert_allclose(tot, bl, rtol=max(atol, 1e-9))
+    np.testing.assert_allclose(tot, bl, rtol=max(10 * atol, 1e-9))
 
 
 def test_conditionals_readback_matches_oracle(mode):
