@@ -372,7 +372,7 @@ def main():
             try:
                 from oracle import ref_harness as rh
                 hr = rh.run_reference(w, n_evals=max(args.steps, 10), n_warm=args.warmup, per_site=False, binary=host_bin,
-                                      env_extra={"HYPHY_B200_VERBOSE": "1", "HYPHY_B200_DEVICE": str(local_rank)})
+                                      env_extra={"HYPHY_B200_VERBOSE": "1", "HYPHY_B200_DEVICE": str(local_rank), "HYPHY_B200_TC": "1"})
                 line["host_e2e"] = {"value": max(args.steps, 10) / hr["loop_seconds"], "unit": "evals/s", "lnL": hr["lnL"],
                                     "api": "patched HyPhy binary: HBL LFCompute -> _LikelihoodFunction::ComputeBlock -> hb2_hooks -> C ABI (dense Q*t hand-over)",
                                     "engine": hr["engine"][-2:]}

@@ -94,7 +94,7 @@ void create(void *&state, unsigned long n_trees, unsigned long index, _TheTree *
     if (hb2_create(&p->h, p->S, p->D, p->L, p->I, p->C, (int64_t const *)hb2_hooks_access::flat_parents(tree),
                    (int64_t const *)leaf_flags, n_ambiguities > 0 ? ambiguities->theData : nullptr, n_ambiguities,
                    (int64_t const *)filter->theFrequencies.list_data, device,
-                   env_true("HYPHY_B200_FP64") ? HB2_FLAG_FORCE_FP64 : HB2_FLAG_DEFAULT)) {
+                   env_true("HYPHY_B200_TC") ? HB2_FLAG_DEFAULT : HB2_FLAG_FORCE_FP64)) {
         delete p;
         fatal("hb2_create failed");
     }

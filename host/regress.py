@@ -5,7 +5,8 @@ test's PASSED / FAILED verdict.
 
     python host/regress.py expect   # here (container with /root/reference): run the UNMODIFIED reference binary
                                     # (oracle/_ref/hyphy) and write tests/golden/hbltests_expected.json
-    python host/regress.py check    # GPU box: run the PATCHED binary (host/_build/hyphy, engine on) and compare
+    python host/regress.py check    # GPU box: run the PATCHED binary (host/_build/hyphy, engine on, its default fp64
+                                    # kernels) and compare;  `tc` = the same with HYPHY_B200_TC=1, `cpu` = engine off
 
 TEST INFRASTRUCTURE (it drives the unmodified reference as the checker); the product is the patched binary it checks.
 """
@@ -73,7 +74,7 @@ def run(binary, test, env_extra=None, timeout=900, threads=0):
     verdict = "passed" if "[TEST PASSED]" in out else "failed" if "[TEST FAILED]" in out else "error" if rc != 0 else "none"
     if os.environ.get("HB2_REGRESS_KEEP"):          # debugging aid: full transcript next to the other gpurun outputs
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        tag = "fp64" if (env_extra or {}).get("HYPHY_B200_FP64") else "cpu" if (env_extra or {}).get("HYPHY_B200") == "0" else "tc"
+        tag = "tc" if (env_extra or {}).get("HYPHY_B200_TC") else "cpu" if (env_extra or {}).get("HYPHY_B200") == "0" else "fp64"
         with open(os.path.join(ROOT, "gpurun_out", "regress_" + test.replace("/", "_") + "." + tag + ".txt"), "w") as f:
             f.write(out)
     return {"lnL": [float(x) for x in LL.findall(out)], "verdict": verdict, "rc": rc, "seconds": round(time.time() - t0, 2),
@@ -100,8 +101,8 @@ def main():
         extra = {"HYPHY_B200_VERBOSE": "1"}
         if mode == "cpu":
             extra["HYPHY_B200"] = "0"
-        if mode == "fp64":
-            extra["HYPHY_B200_FP64"] = "1"
+        if mode == "tc":
+            extra["HYPHY_B200_TC"] = "1"
         r = run(HOST_BIN, t, extra)
         e = exp[t]
         # fitted log-likelihoods: optimiser end points, printed with 2 decimals by the workflows -> 0.05 absolute

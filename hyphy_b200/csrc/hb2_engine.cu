@@ -170,6 +170,15 @@ struct hb2_partition {
 
 namespace {
 
+// The pinned staging buffers (both queues, h_dst/h_vdst included) may still be read by the H2D copies of the last flush.
+int wait_staging(hb2_partition *p) {
+    if (p->staging_busy) {
+        CU(cudaEventSynchronize(p->ev_staging));
+        p->staging_busy = false;
+    }
+    return 0;
+}
+
 // Host half of the shared-powers path for one batch: groups and references of the n entries (h_dst = their slots, < 0
 // retired; kind 1 = compiled hand-over, 2 = dense).  A group whose batch holds at least EX_MIN_GROUP live entries gets its
 // power table rebuilt from the first of them; smaller groups are compared with the direction the table was last built
@@ -185,6 +194,7 @@ int plan_shared(hb2_partition *p, const int *h_dst, int64_t n, int kind, const i
     sp = SharedPlan();
     if (p->Dp != 64 || p->expm_dfma || !p->ex_enabled || !p->d_ex_int || n <= 0 || n > p->ex_cap) return 0;
     if (kind == 1 && !p->d_Vres) return 0;
+    if (wait_staging(p)) return 1;            // an earlier plan's upload may still be reading the pinned arrays
     int *grp = p->h_ex_int, *ref = p->h_ex_int + p->ex_cap, *refs = p->h_ex_int + 2 * p->ex_cap;
     std::vector<int> count(p->ex_G, 0), first(p->ex_G, -1);
     for (int64_t k = 0; k < n; k++) {
@@ -303,15 +313,6 @@ int launch_prune(hb2_partition *p, const hb2::PruneArgs &a, const int *d_jobs, i
     }
     p->launches++;
     CU(cudaGetLastError());
-    return 0;
-}
-
-// The pinned staging buffers (both queues, h_dst/h_vdst included) may still be read by the H2D copies of the last flush.
-int wait_staging(hb2_partition *p) {
-    if (p->staging_busy) {
-        CU(cudaEventSynchronize(p->ev_staging));
-        p->staging_busy = false;
-    }
     return 0;
 }
 

@@ -603,6 +603,7 @@ __global__ void __launch_bounds__(256, 1) expm_powers_kernel(ExpmPowersArgs pa) 
     const int wr = warp >> 1, wc = warp & 1, g = lane >> 2, q4 = lane & 3;
     const int entry = pa.refs[blockIdx.x];
     const int grp = pa.a.group[entry];
+    if (grp < 0 || pa.a.dst[entry] < 0) return;                       // (cannot happen: the host lists live references only)
     load_rate_matrix<64, LD64, 256>(pa.a, X0, tid, entry);          // X0 = A_ref^T, zero padded
     if (tid < 64) {
         double s = 0.0;

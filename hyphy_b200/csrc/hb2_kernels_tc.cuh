@@ -38,7 +38,7 @@ constexpr int TC_PB_FLOATS = 2 * 4096;         // per (class, branch): Ph tile +
 constexpr int TC_PTF_ROW = 68;                 // floats per row of the fp32 P^T table (64 + 4 padding: 272-byte rows)
 constexpr int TC_PTF_FLOATS = 64 * TC_PTF_ROW; // per (class, branch)
 constexpr int TC_SMEM_BYTES = 2 * 32768 + 1024; // two B stages (one used for now; also caps residency at 2 CTAs/SM) + barriers
-constexpr uint32_t TC_TMEM_COLS = 256;         // D: 0..63, Xh: 64..127, Xl: 128..191
+constexpr uint32_t TC_TMEM_COLS = 256;         // D: 0..63, Xh: 64..127, Xl: 128..191 (allocations are powers of two)
 constexpr int TC_MAX_ANCHORS = 8;              // per pattern and child (list capacity of the per-level and split-row kernels)
 constexpr int WALK_FAST_ANCHORS = 4;           // anchors handled by the unrolled fast path of the walk kernel; more go to a loop
 constexpr float TC_ANCHOR_THR = 0.015625f;     // 2^-6 (rows are normalised to max in [0.5,1))
@@ -116,6 +116,15 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem,
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
         "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// One lane of a converged warp (the CUTLASS issue idiom).  tcgen05.mma wants its operands in UNIFORM registers: issued
+// from a divergent `if (lane == 0)` ptxas wraps every UTCHMMA in an ELECT / R2UR.BROADCAST waterfall loop (~190 cycles per
+// instruction, profiles/r01j_mma_issue_timing.txt); issued by an elected lane inside a warp-uniform branch, with operands
+// that were broadcast by __shfl_sync, the instructions go out back to back (profiles/r02_mma_issue_uniform.txt).
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred;
 }
 // round-to-nearest (ties away from zero) to tf32, i.e. what cvt.rna.tf32.f32 computes, but with two full-rate integer
 // instructions: the conversion instruction issues at a quarter of the ALU rate and dominated the operand-split phase
@@ -222,7 +231,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_kernel(PruneTcArgs a, const
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_b + 2);
     int *s_ak = reinterpret_cast<int *>(smem + 32768);                   // [TC_MAX_ANCHORS][128] anchor state
     float *s_av = reinterpret_cast<float *>(smem + 32768 + TC_MAX_ANCHORS * 128 * 4);   // [TC_MAX_ANCHORS][128] anchor value
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int par = jobs[blockIdx.y];
     const int cat = a.cat0 + blockIdx.z;
     const size_t Sp = a.Sp;
@@ -240,10 +249,10 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_kernel(PruneTcArgs a, const
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);      // this warp's TMEM lane quarter
-    const uint64_t bdesc_hi = make_b_desc(smem_u32(Bs));
-    const uint64_t bdesc_lo = make_b_desc(smem_u32(Bs + 4096));
+    const uint64_t bdesc_hi = make_b_desc(__shfl_sync(0xffffffffu, smem_u32(Bs), 0));
+    const uint64_t bdesc_lo = make_b_desc(__shfl_sync(0xffffffffu, smem_u32(Bs + 4096), 0));
 
     float v[64];
 #pragma unroll
@@ -321,20 +330,22 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_kernel(PruneTcArgs a, const
             ex += a.scal[((size_t)cat * a.I + cin) * Sp + s];
             tc_fence_before();
             __syncthreads();                 // A operand complete in TMEM; every thread is done reading the previous D
-            if (tid == 0) {
+            if (warp == 0) {
                 tc_fence_after();
                 mbar_wait(bar_b, phase, a.err);
-                // small terms first: Xl*Ph, Xh*Pl, then Xh*Ph (8 K-steps of 8 each)
+                if (elect_one()) {
+                    // small terms first: Xl*Ph, Xh*Pl, then Xh*Ph (8 K-steps of 8 each)
 #pragma unroll
-                for (int kk = 0; kk < 8; kk++)
-                    tc_mma_tf32_ts(tmem_base, tmem_base + 128 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, kk > 0);
+                    for (int kk = 0; kk < 8; kk++)
+                        tc_mma_tf32_ts(tmem_base, tmem_base + 128 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, kk > 0);
 #pragma unroll
-                for (int kk = 0; kk < 8; kk++)
-                    tc_mma_tf32_ts(tmem_base, tmem_base + 64 + kk * 8, bdesc_lo + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u);
+                    for (int kk = 0; kk < 8; kk++)
+                        tc_mma_tf32_ts(tmem_base, tmem_base + 64 + kk * 8, bdesc_lo + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u);
 #pragma unroll
-                for (int kk = 0; kk < 8; kk++)
-                    tc_mma_tf32_ts(tmem_base, tmem_base + 64 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u);
-                tc_commit(bar_mma);
+                    for (int kk = 0; kk < 8; kk++)
+                        tc_mma_tf32_ts(tmem_base, tmem_base + 64 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u);
+                    tc_commit(bar_mma);
+                }
             }
             __syncwarp();
             // anchors on the CUDA cores while the tensor core works: acc[n] = sum_a x[k_a] * P[n][k_a], fp32 RN
@@ -473,14 +484,14 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
     uint64_t *bar_full = reinterpret_cast<uint64_t *>(s_av + TC_MAX_ANCHORS * 128); // [2]
     uint64_t *bar_mma = bar_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_mma + 1);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const size_t Sp = a.Sp;
     float4 *cond4 = reinterpret_cast<float4 *>(a.cond);
 
     if (tid == 0) {
         mbar_init(bar_full, 1);
         mbar_init(bar_full + 1, 1);
-        mbar_init(bar_mma, 2);               // one tcgen05.commit per issuing thread (warps 0 and 1)
+        mbar_init(bar_mma, 1);               // one tcgen05.commit per contraction (elected lane of warp 0)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -490,7 +501,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     uint32_t n_step = 0, n_mma = 0;          // running counters: select ring stage / barrier parities
     bool bailed = false;                     // a dependency wait timed out: stop waiting, the host reports the error
@@ -715,25 +726,25 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                 tc_fence_before();
                 __syncthreads();             // (2) A operand complete in TMEM; every thread is done reading the previous D
                 if (tr) trp[4] = clock64();
-                if (lane == 0 && warp < 2) {
-                    // One thread issues a tcgen05.mma only every ~100-190 cycles (tools/tc_mma_timing.cu: 24 MMAs take 4770
-                    // cycles from one thread, 2560 from two, 1460 from four).  Two threads issue here, each into its OWN
-                    // accumulator (warp 0: even K-steps -> D0 = columns 0..63, warp 1: odd K-steps -> D1 = columns
-                    // 192..255) in a fixed order (small terms first), so the result is bit-reproducible; D0 + D1 is formed
-                    // in registers after the read-back.
+                if (warp == 0) {
+                    // 24 tcgen05.mma (small terms first: Xl*Ph, Xh*Pl, Xh*Ph; 8 K-steps of 8 each) into ONE accumulator
+                    // (TMEM columns 0..63), issued back to back by the elected lane of warp 0 with uniform operands: the
+                    // chain is bound by the tensor pipe (32 cycles per M128 N64 K8 instruction), not by the issue.
                     tc_fence_after();
                     mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
                     if (tr) trp[5] = clock64();
-                    const uint64_t bdesc_hi = make_b_desc(smem_u32(tab + 64 * WALK_PT_ROW));
-                    const uint64_t bdesc_lo = make_b_desc(smem_u32(tab + 64 * WALK_PT_ROW + 4096));
-                    const uint32_t dcol = warp ? 192u : 0u;
+                    const uint32_t baddr = __shfl_sync(0xffffffffu, smem_u32(tab + 64 * WALK_PT_ROW), 0);
+                    const uint64_t bdesc_hi = make_b_desc(baddr);
+                    const uint64_t bdesc_lo = make_b_desc(baddr + 4096 * 4);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int j = 0; j < 4; j++) { const int kk = 2 * j + warp; tc_mma_tf32_ts(tmem_base + dcol, tmem_base + 128 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, j > 0); }
+                        for (int kk = 0; kk < 8; kk++) tc_mma_tf32_ts(tmem_base, tmem_base + 128 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, kk > 0);
 #pragma unroll
-                    for (int j = 0; j < 4; j++) { const int kk = 2 * j + warp; tc_mma_tf32_ts(tmem_base + dcol, tmem_base + 64 + kk * 8, bdesc_lo + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u); }
+                        for (int kk = 0; kk < 8; kk++) tc_mma_tf32_ts(tmem_base, tmem_base + 64 + kk * 8, bdesc_lo + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u);
 #pragma unroll
-                    for (int j = 0; j < 4; j++) { const int kk = 2 * j + warp; tc_mma_tf32_ts(tmem_base + dcol, tmem_base + 64 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u); }
-                    tc_commit(bar_mma);
+                        for (int kk = 0; kk < 8; kk++) tc_mma_tf32_ts(tmem_base, tmem_base + 64 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u);
+                        tc_commit(bar_mma);
+                    }
                 }
                 __syncwarp();
                 // anchors on the CUDA cores while the tensor core works (rows of the P^T table in shared memory)
@@ -771,12 +782,11 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                 tc_fence_after();
 #pragma unroll
                 for (int o = 0; o < 64; o += 16) {
-                    uint32_t d[16], d1[16];
+                    uint32_t d[16];
                     HB2_TMEM_LD16(lane_addr + o, d, 0);
-                    HB2_TMEM_LD16(lane_addr + 192 + o, d1, 0);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int k = 0; k < 16; k++) v[o + k] *= ((__uint_as_float(d[k]) + __uint_as_float(d1[k])) + acc[o + k]);
+                    for (int k = 0; k < 16; k++) v[o + k] *= (__uint_as_float(d[k]) + acc[o + k]);
                 }
                 n_mma++;
             }

@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOST_BIN = os.path.join(ROOT, "host", "_build", "hyphy")
-MODES = {"fp64": ({"HYPHY_B200_FP64": "1"}, 1e-10, 1e-8), "tc": ({}, 1e-7, 1e-5)}
+MODES = {"fp64": ({}, 1e-10, 1e-8), "tc": ({"HYPHY_B200_TC": "1"}, 1e-7, 1e-5)}     # the host's default is fp64 (see hb2_hyphy_hooks.h)
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -52,7 +52,7 @@ def test_patched_host_evaluation_stream_and_partial_updates():
     device) through the patched binary: final lnL of the loop equals the unmodified binary's to 1e-7 relative."""
     w, g = gc.load("mg94_30x100_c4_ambig")
     a = rh.run_reference(w, n_evals=5, n_warm=1, per_site=False)
-    b = rh.run_reference(w, n_evals=5, n_warm=1, per_site=False, binary=HOST_BIN, env_extra={"HYPHY_B200_VERBOSE": "1"})
+    b = rh.run_reference(w, n_evals=5, n_warm=1, per_site=False, binary=HOST_BIN, env_extra={"HYPHY_B200_VERBOSE": "1", "HYPHY_B200_TC": "1"})
     assert abs(b["loop_lnL"] - a["loop_lnL"]) <= 1e-7 * abs(a["loop_lnL"])
     assert abs(b["lnL"] - g["lnL"]) <= 1e-7 * abs(g["lnL"])
 
