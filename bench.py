@@ -186,6 +186,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-host", action="store_true", help="skip the patched-HyPhy end-to-end leg")
+    ap.add_argument("--no-c5", action="store_true", help="skip the extra 500 x 5000 x 4 line")
     ap.add_argument("--fp64", action="store_true", help="force the fp64 pruning kernels (HB2_FLAG_FORCE_FP64)")
     ap.add_argument("--class-groups", type=int, default=0, help="multi-GPU: force this many class groups (default: as many as divide both)")
     ap.add_argument("--no-class-groups", action="store_true", help="multi-GPU: shard patterns only (every rank exponentiates every class)")
@@ -315,10 +316,41 @@ def main():
     clocks = sampler.stop()
     tc_mode = lf.part.precision_mode == 1
     prune_kernel = lf.part.pruning_kernel
+    root_path = "peer" if os.environ.get("HB2_PEER_XCHG", "1") != "0" else "nccl"
     stage_launches = [int(x) for x in lf.part.stage_launches]
     ms = max_over_ranks(ms)
     stage = [max_over_ranks(float(s)) for s in stage]
     lf.close()
+
+    # ---- extra line: BASELINE.json configs[4] (c5: 500 taxa x 5000 codons x 4 classes, 5.2 GB of conditionals), the size at
+    #      which sharding one alignment over the box pays; same measurement as `value` (resident, device time, max over ranks)
+    c5 = None
+    if not args.no_c5:
+        w5 = synth.codon_workload(500, 5000, 4)
+        lay5 = layout(world, rank, w5.C, w5.S)
+        if args.no_class_groups:
+            lay5 = {"groups": 1, "group": 0, "shards": world, "shard": rank, "patterns": shard_bounds(w5.S, world, rank), "classes": (0, w5.C)}
+        lo5, hi5 = lay5["patterns"]
+        lf5 = LikelihoodFunction(w5, device=local_rank, flags=1 if args.fp64 else 0, pattern_slice=slice(lo5, hi5) if world > 1 else None)
+        if world > 1:
+            lf5.part.comm_init(world, rank, exchange_unique_id(dist, rank, Partition.comm_unique_id))
+            if lay5["groups"] > 1:
+                lf5.part.comm_class_groups(lay5["groups"])
+        lf5.set_template()
+        lf5.set_all_compiled()
+        lnl5 = lf5.compute()
+        lf5.part.time_resident(w5.class_weights, w5.pi, iters=3)
+        barrier()
+        ms5, stage5, lnl5r = lf5.part.time_resident(w5.class_weights, w5.pi, iters=max(5, args.steps // 2))
+        barrier()
+        ms5 = max_over_ranks(ms5)
+        stage5 = [max_over_ranks(float(x)) for x in stage5]
+        lf5.close()
+        golden5 = -1160063.8295306289                 # unmodified reference binary (tests/golden/c5_mg94_500x5000_c4.npz)
+        c5 = {"workload": "MG94xREV 500 taxa x 5000 codons, 4 omega classes (BASELINE.json configs[4])", "patterns": w5.S,
+              "value": 1000.0 / ms5, "unit": "evals/s", "ms_per_step": ms5, "stage_ms": {"expm": stage5[0], "pruning": stage5[1], "root": stage5[2]},
+              "layout": f"patterns/{lay5['shards']} x classes/{lay5['groups']}", "lnL": lnl5, "lnL_reference": golden5,
+              "rel_err": abs(lnl5 - golden5) / abs(golden5)}
 
     if rank == 0:
         pk, pk_kind = peaks()
@@ -363,7 +395,8 @@ def main():
                         "api": "hb2_set_matrices_compiled x C + hb2_evaluate_classes", "host_split": e2e_split},
                 "e2e_dense": {"value": 1000.0 / e2e_dense_ms, "unit": "evals/s", "ms_per_step": e2e_dense_ms, "h2d_bytes_per_step": h2d_dense,
                               "d2h_bytes_per_step": 12, "api": "hb2_set_matrices_packed x C + hb2_evaluate_classes", "lnL": lnl_dense},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "lnL": lnl0, "lnL_resident": lnl_res}
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "lnL": lnl0, "lnL_resident": lnl_res,
+                "lnL_reference": -205416.12461664603, "root_exchange": root_path if world > 1 else None, "c5": c5}
         # the same evaluation stream through the PATCHED HyPhy binary (host/_build/hyphy: the reference's HBL interpreter,
         # formula evaluation and DetermineNodesForUpdate on the host, everything below ComputeBlock on the engine):
         # wall-clock evaluations/s of `LFCompute` as a user of the reference would see them

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -38,7 +39,13 @@ struct Part {
     std::unordered_map<_CalcNode const *, long> node_id;    // tree node -> flat id (leaves, then internal nodes)
     std::mutex lock;                                         // SetCompExp is called from ExponentiateMatrices' OpenMP loop
     unsigned long n_eval = 0, n_rate = 0, n_trans = 0;
+    double t_handover = 0.0, t_evaluate = 0.0;               // seconds inside hb2_set_matrices* / hb2_evaluate* (HYPHY_B200_VERBOSE)
+    std::chrono::steady_clock::time_point t_created;
 };
+
+inline double seconds_since(std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
 
 struct State {
     std::vector<Part *> parts;
@@ -99,6 +106,7 @@ void create(void *&state, unsigned long n_trees, unsigned long index, _TheTree *
         fatal("hb2_create failed");
     }
     st->parts[index] = p;
+    p->t_created = std::chrono::steady_clock::now();
     if (env_true("HYPHY_B200_VERBOSE"))
         fprintf(stderr, "[hyphy_b200] partition %lu on device %d: %ld patterns x %ld states, %ld leaves, %ld internal nodes, %ld rate classes, %s pruning\n",
                 index, device, p->S, p->D, p->L, p->I, p->C, hb2_pruning_kernel(p->h));
@@ -115,8 +123,9 @@ void destroy_all(void *&state) {
     for (Part *p : st->parts) {
         if (!p) continue;
         if (env_true("HYPHY_B200_VERBOSE"))
-            fprintf(stderr, "[hyphy_b200] partition destroyed after %lu evaluations, %lu rate matrices exponentiated on the device, %lu host transition matrices, %lld kernel launches\n",
-                    p->n_eval, p->n_rate, p->n_trans, (long long)hb2_launch_count(p->h));
+            fprintf(stderr, "[hyphy_b200] partition destroyed after %lu evaluations, %lu rate matrices exponentiated on the device, %lu host transition matrices, %lld kernel launches; "
+                            "lifetime %.3f s of which %.3f s in matrix hand-over (densify + hb2_set_matrices) and %.3f s in hb2_evaluate (rest = HyPhy host code)\n",
+                    p->n_eval, p->n_rate, p->n_trans, (long long)hb2_launch_count(p->h), seconds_since(p->t_created), p->t_handover, p->t_evaluate);
         if (g_current == p) g_current = nullptr;
         hb2_destroy(p->h);
         delete p;
@@ -135,6 +144,7 @@ _Matrix *intercept(_CalcNode *node, _Matrix *m, long catID, bool do_exponentiati
     if (it == p->node_id.end()) return nullptr;                       // a node of some other tree
     if ((long)m->GetHDim() != p->D || (long)m->GetVDim() != p->D) return nullptr;
     int64_t const id = it->second;
+    auto const t0 = std::chrono::steady_clock::now();
     double const *data = m->is_dense() ? m->theData : nullptr;
     if (!data) {                                                      // compressed-sparse rate matrix (codon models)
         thread_local std::vector<double> dense;
@@ -148,6 +158,7 @@ _Matrix *intercept(_CalcNode *node, _Matrix *m, long catID, bool do_exponentiati
         if (hb2_set_matrices(p->h, catID, 1, &id, &data, do_exponentiation ? HB2_MATRIX_RATE : HB2_MATRIX_TRANS))
             fatal("hb2_set_matrices failed");
         if (do_exponentiation) p->n_rate++; else p->n_trans++;
+        p->t_handover += seconds_since(t0);
     }
     if (!do_exponentiation) return m;                                 // host-computed P (explicit-form models): kept as is
     // exp(Qt) now lives on the device only.  The node keeps a matrix object of the right shape so that the host's
@@ -168,6 +179,7 @@ double compute_block(void *part, _TheTree *tree, long catID, _SimpleList const &
     int64_t const *upd = branches.lLength ? (int64_t const *)branches.list_data : &none;
     double lnl = 0.0;
     int rc;
+    auto const t0 = std::chrono::steady_clock::now();
     if (branchIndex >= 0) {
         // reference convention (tree_evaluator.cpp:3624,173): internal index, or I + leaf index -> flat node id
         int64_t const forced = branchIndex < p->I ? branchIndex + p->L : branchIndex - p->I;
@@ -178,6 +190,7 @@ double compute_block(void *part, _TheTree *tree, long catID, _SimpleList const &
     }
     if (rc) fatal("evaluation failed");
     p->n_eval++;
+    p->t_evaluate += seconds_since(t0);
     return lnl;
 }
 

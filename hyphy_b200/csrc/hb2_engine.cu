@@ -122,6 +122,7 @@ struct hb2_partition {
     int *d_ex_int = nullptr, *h_ex_int = nullptr, *d_ex_flag = nullptr;     // [group cap | ref cap | refs G]
     double *d_ex_weight = nullptr, *d_ex_pow = nullptr, *d_ex_refvec = nullptr, *d_Vres = nullptr;
     void *d_ex_groups = nullptr;
+    unsigned long long *d_ex_flags = nullptr, ex_gen = 0;   // generation flags of the coefficient matrices [G][EXPM_POW_TERMS]
     std::vector<int> ex_kind;                 // host mirror: kind of the reference direction each group holds (0 none)
     int64_t ex_cap = 0;
     bool ex_enabled = true;                   // HB2_EXPM_SHARED=0 switches the path off (A/B testing)
@@ -163,6 +164,15 @@ struct hb2_partition {
     int cg_G = 1, cg_g = 0, own0 = 0, ownN = 0, xchg_len = 0;
     double *d_xsend = nullptr, *d_xrecv = nullptr, *d_xfreq = nullptr, *d_xpartial = nullptr;
     int n_partial_blocks = 0;
+    // peer exchange (hb2_kernels_fp64.cuh "Peer exchange"): IPC-mapped buffers of all ranks; falls back to NCCL when the
+    // mapping cannot be established (px_ok false)
+    bool px_ok = false, px_enabled = true;
+    int px_payload = 0;
+    unsigned long long px_gen = 0;
+    double *px_local = nullptr;
+    std::vector<double *> px_peer;            // host copy of the mapped pointers (entry rank = px_local)
+    double **d_px_peer = nullptr;
+    unsigned int *d_px_counter = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_staging = nullptr;
     bool staging_busy = false;
@@ -257,12 +267,11 @@ int launch_expm(hb2_partition *p, const double *dQ, const int *d_dst, int n, int
                         hb2::ExpmPowersArgs pa{};
                         pa.a = a; pa.refs = p->d_ex_int + 2 * p->ex_cap; pa.groups = static_cast<hb2::ExpmGroup *>(p->d_ex_groups);
                         pa.pow = p->d_ex_pow; pa.refvec = p->d_ex_refvec; pa.refvec_stride = p->ex_stride; pa.nV = nV; pa.kind = sp->kind; pa.Vin = dQ;
-                        hb2::expm_powers_kernel<<<sp->n_refs, 256, smem, p->stream>>>(pa);
+                        pa.flags = p->d_ex_flags; pa.gen = ++p->ex_gen; pa.err = p->d_err;
+                        hb2::expm_powers_kernel<<<dim3(hb2::EXPM_POW_TERMS - 1, (unsigned)sp->n_refs), 256, smem, p->stream>>>(pa);
                         p->launches++;
                     }
-                    const int chunks = std::max(1, std::min(n, 18));
-                    const int per_chunk = (n + chunks - 1) / chunks;
-                    hb2::expm_poly_kernel<<<dim3(16, (unsigned)((n + per_chunk - 1) / per_chunk)), 256, 0, p->stream>>>(a, n, per_chunk);
+                    hb2::expm_poly_kernel<<<dim3(16, (unsigned)((n + hb2::EXPM_POLY_CHUNK - 1) / hb2::EXPM_POLY_CHUNK)), 256, 0, p->stream>>>(a, n);
                     p->launches += 2;
                 }
                 hb2::ExpmTcOut tco{nullptr, nullptr};
@@ -705,6 +714,90 @@ int run_pruning(hb2_partition *p, int cat0, int ncls, const std::vector<std::vec
     return 0;
 }
 
+// (Re)creates the peer-exchange buffers with room for `payload` doubles per rank and maps every other rank's buffer through
+// CUDA IPC; the 64-byte handles travel over the partition's NCCL communicator.  Collective: every rank calls it with the
+// same payload.  On any failure (IPC not permitted in this container, no peer access) ALL ranks fall back to NCCL.
+void peer_teardown(hb2_partition *p) {
+    for (size_t r = 0; r < p->px_peer.size(); r++)
+        if ((int)r != p->rank && p->px_peer[r]) cudaIpcCloseMemHandle(p->px_peer[r]);
+    p->px_peer.clear();
+    if (p->px_local) cudaFree(p->px_local);
+    if (p->d_px_peer) cudaFree(p->d_px_peer);
+    if (p->d_px_counter) cudaFree(p->d_px_counter);
+    p->px_local = nullptr; p->d_px_peer = nullptr; p->d_px_counter = nullptr; p->px_ok = false;
+}
+
+int peer_setup(hb2_partition *p, int payload) {
+    peer_teardown(p);
+    { const char *env = getenv("HB2_PEER_XCHG"); p->px_enabled = !(env && env[0] == '0'); }
+    if (!p->comm || p->n_ranks < 2 || p->n_ranks > 64) return 0;
+    const int R = p->n_ranks;
+    const size_t doubles = (size_t)2 * R * payload + (size_t)2 * R;          // data + flags (uint64 = double sized)
+    int ok = p->px_enabled ? 1 : 0;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof mine);
+    if (ok && cudaMalloc(&p->px_local, doubles * sizeof(double)) != cudaSuccess) { cudaGetLastError(); p->px_local = nullptr; ok = 0; }
+    if (ok) {
+        CU(cudaMemsetAsync(p->px_local, 0, doubles * sizeof(double), p->stream));
+        if (cudaIpcGetMemHandle(&mine, p->px_local) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    }
+    // exchange {ok, handle} of every rank: one all-gather of 72 bytes per rank
+    const size_t rec = 8 + sizeof(cudaIpcMemHandle_t);
+    std::vector<unsigned char> sendrec(rec, 0), all(rec * R, 0);
+    memcpy(sendrec.data(), &ok, sizeof(int));
+    memcpy(sendrec.data() + 8, &mine, sizeof mine);
+    unsigned char *d_send = nullptr, *d_all = nullptr;
+    CU(cudaMalloc(&d_send, rec));
+    CU(cudaMalloc(&d_all, rec * R));
+    CU(cudaMemcpyAsync(d_send, sendrec.data(), rec, cudaMemcpyHostToDevice, p->stream));
+    ncclResult_t nr = g_nccl.AllGather(d_send, d_all, rec, ncclChar, p->comm, p->stream);
+    if (nr != ncclSuccess) { cudaFree(d_send); cudaFree(d_all); return fail("ncclAllGather (IPC handles): %s", g_nccl.GetErrorString(nr)); }
+    CU(cudaMemcpyAsync(all.data(), d_all, rec * R, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    cudaFree(d_send); cudaFree(d_all);
+    int all_ok = 1;
+    for (int r = 0; r < R; r++) { int o; memcpy(&o, all.data() + rec * r, sizeof(int)); all_ok = all_ok && o; }
+    p->px_peer.assign(R, nullptr);
+    if (all_ok) {
+        for (int r = 0; r < R && all_ok; r++) {
+            if (r == p->rank) { p->px_peer[r] = p->px_local; continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, all.data() + rec * r + 8, sizeof h);
+            void *ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); all_ok = 0; }
+            p->px_peer[r] = static_cast<double *>(ptr);
+        }
+    }
+    // the mapping must have worked on EVERY rank: agree with a max-reduce of "failed"
+    int *d_flag2 = nullptr;
+    CU(cudaMalloc(&d_flag2, sizeof(int)));
+    int failed = all_ok ? 0 : 1;
+    CU(cudaMemcpyAsync(d_flag2, &failed, sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    nr = g_nccl.AllReduce(d_flag2, d_flag2, 1, ncclInt32, ncclMax, p->comm, p->stream);
+    if (nr != ncclSuccess) { cudaFree(d_flag2); return fail("ncclAllReduce (IPC agreement): %s", g_nccl.GetErrorString(nr)); }
+    CU(cudaMemcpyAsync(&failed, d_flag2, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    cudaFree(d_flag2);
+    if (failed) {
+        const bool wanted = p->px_enabled;
+        peer_teardown(p);
+        if (wanted && getenv("HB2_DEBUG")) fprintf(stderr, "[hb2] rank %d: peer exchange unavailable (CUDA IPC), using NCCL collectives\n", p->rank);
+        return 0;
+    }
+    CU(cudaMalloc(&p->d_px_peer, R * sizeof(double *)));
+    CU(cudaMemcpy(p->d_px_peer, p->px_peer.data(), R * sizeof(double *), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&p->d_px_counter, sizeof(unsigned int)));
+    CU(cudaMemset(p->d_px_counter, 0, sizeof(unsigned int)));
+    p->px_payload = payload; p->px_gen = 0; p->px_ok = true;
+    return 0;
+}
+
+hb2::PeerBuf peer_buf(hb2_partition *p) {
+    hb2::PeerBuf b;
+    b.peer = p->d_px_peer; b.R = p->n_ranks; b.rank = p->rank; b.payload = p->px_payload; b.gen = ++p->px_gen; b.err = p->d_err;
+    return b;
+}
+
 int run_root(hb2_partition *p, int c0, int nc, bool use_weights, bool want_sites) {
     CU(cudaMemsetAsync(p->d_flag, 0, sizeof(int), p->stream));
     hb2::CombineArgs c;
@@ -712,10 +805,22 @@ int run_root(hb2_partition *p, int c0, int nc, bool use_weights, bool want_sites
     c.partial = p->d_partial; c.flag = p->d_flag; c.siteL = want_sites ? p->d_siteL : nullptr;
     c.siteScale = want_sites ? p->d_siteScale : nullptr;
     c.Sp = (int)p->Sp; c.S = (int)p->S; c.c0 = c0; c.nc = nc;
+    if (p->cg_G > 1 && p->px_ok) {
+        // class groups over NVLink peer memory: ONE kernel computes this rank's class partials, stores them into every
+        // rank's exchange buffer, and (its last block) merges all shards and classes into the complete lnL
+        hb2::ClassXchgArgs x;
+        x.rootL = p->d_rootL; x.rootE = p->d_rootE; x.weights = p->d_weights; x.Sp = (int)p->Sp; x.S = (int)p->S; x.c0 = p->own0; x.nc = p->ownN;
+        x.xs = p->xchg_len; x.pb = peer_buf(p); x.xfreq = p->d_xfreq; x.nShards = p->n_ranks / p->cg_G; x.G = p->cg_G; x.myShard = p->rank / p->cg_G;
+        x.lnL = p->d_lnL; x.siteL = c.siteL; x.siteScale = c.siteScale; x.counter = p->d_px_counter;
+        const int nblk = std::max(1, std::min(16, (p->xchg_len + 255) / 256));
+        hb2::class_exchange_kernel<<<nblk, 256, 0, p->stream>>>(x);
+        p->launches++;
+        CU(cudaGetLastError());
+        return 0;
+    }
     if (p->cg_G > 1) {
-        // class groups: partial over the owned classes into this rank's slot of a buffer that is zero elsewhere; ONE sum
-        // all-reduce then acts as the gather (small-message latency, no second collective: every rank merges every
-        // shard and holds the complete lnL)
+        // class groups without peer mapping: partial over the owned classes into this rank's slot of a buffer that is zero
+        // elsewhere; ONE sum all-reduce then acts as the gather (every rank merges every shard and holds the complete lnL)
         const int xs = p->xchg_len, N = p->n_ranks;
         hb2::class_partial_kernel<<<(xs + 255) / 256, 256, 0, p->stream>>>(p->d_rootL, p->d_rootE, p->d_weights, (int)p->Sp, (int)p->S,
                                                                           p->own0, p->ownN, p->d_xsend + (size_t)p->rank * 2 * xs, xs);
@@ -733,7 +838,11 @@ int run_root(hb2_partition *p, int c0, int nc, bool use_weights, bool want_sites
     hb2::final_sum_kernel<<<1, 256, 0, p->stream>>>(p->d_partial, p->n_partial_blocks, p->d_flag, p->d_lnL);
     p->launches += 2;
     CU(cudaGetLastError());
-    if (p->comm) {
+    if (p->comm && p->px_ok) {                // pattern shards: R partial lnL over peer memory, summed in rank order
+        hb2::peer_sum_kernel<<<1, 64, 0, p->stream>>>(peer_buf(p), p->d_lnL);
+        p->launches++;
+        CU(cudaGetLastError());
+    } else if (p->comm) {
         ncclResult_t r = g_nccl.AllReduce(p->d_lnL, p->d_lnL, 1, ncclDouble, ncclSum, p->comm, p->stream);
         if (r != ncclSuccess) return fail("ncclAllReduce: %s", g_nccl.GetErrorString(r));
     }
@@ -816,7 +925,8 @@ int evaluate_impl(hb2_partition *p, int c0, int nc, const double *weights, int64
         p->walk_reset = p->use_tc && p->use_walk;          // tags are inconsistent: the next pass starts from scratch
         cudaMemsetAsync(p->d_err, 0, sizeof(int), p->stream);   // on every path, or each later evaluation would fail too
         std::fill(p->evaluated_cat.begin(), p->evaluated_cat.end(), 0);
-        return fail("device-side wait timed out in the tcgen05 pruning kernel (code %d)", code);
+        return fail("a device-side wait timed out (code %d: 1 = operand staging / tensor pipe, 2 = another lane's conditionals, 3 = a peer "
+                    "rank's partials, 4 = a coefficient matrix of the shared-powers exponential)", code);
     }
     *lnL = hs[p->Dp + p->C];
     for (int c = c0; c < c0 + nc; c++) p->evaluated_cat[c] = 1;
@@ -1000,6 +1110,8 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
         CUP(cudaMalloc(&p->d_ex_groups, (size_t)p->ex_G * sizeof(hb2::ExpmGroup)));
         CUP(cudaMemsetAsync(p->d_ex_groups, 0, (size_t)p->ex_G * sizeof(hb2::ExpmGroup), p->stream));
         CUP(cudaMalloc(&p->d_ex_pow, (size_t)p->ex_G * hb2::EXPM_POW_TERMS * 4096 * sizeof(double)));
+        CUP(cudaMalloc(&p->d_ex_flags, (size_t)p->ex_G * hb2::EXPM_POW_TERMS * sizeof(unsigned long long)));
+        CUP(cudaMemsetAsync(p->d_ex_flags, 0, (size_t)p->ex_G * hb2::EXPM_POW_TERMS * sizeof(unsigned long long), p->stream));
         CUP(cudaMalloc(&p->d_ex_refvec, (size_t)p->ex_G * p->ex_stride * sizeof(double)));
         CUP(cudaFuncSetAttribute(hb2::expm_powers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * 64 * hb2::LD64 * sizeof(double))));
         CUP(cudaFuncSetAttribute(hb2::expm64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(5 * 64 * hb2::LD64 * sizeof(double))));
@@ -1386,7 +1498,7 @@ int hb2_comm_init(hb2_partition *p, int nRanks, int rank, const void *uniqueId12
     ncclResult_t r = g_nccl.CommInitRank(&p->comm, nRanks, id, rank);
     if (r != ncclSuccess) { p->comm = nullptr; return fail("ncclCommInitRank: %s", g_nccl.GetErrorString(r)); }
     p->n_ranks = nRanks; p->rank = rank;
-    return 0;
+    return peer_setup(p, 2);
 }
 
 int hb2_comm_class_groups(hb2_partition *p, int nGroups) {
@@ -1424,17 +1536,18 @@ int hb2_comm_class_groups(hb2_partition *p, int nGroups) {
     if (r != ncclSuccess) return fail("ncclAllReduce (frequencies): %s", g_nccl.GetErrorString(r));
     CU(cudaMemsetAsync(p->d_xsend, 0, tot * sizeof(double), p->stream));     // from now on only this rank's slot is written
     CU(cudaStreamSynchronize(p->stream));
-    return 0;
+    return peer_setup(p, 2 * len);
 }
 
 void hb2_destroy(hb2_partition *p) {
     if (!p) return;
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
+    peer_teardown(p);
     if (p->comm) g_nccl.CommDestroy(p->comm);
     void *dev[] = {p->d_leaf, p->d_scal, p->d_rootE, p->d_child_start, p->d_child_ids, p->d_jobs, p->d_dst, p->d_flag,
                    p->d_mix_dst, p->d_mix_Q, p->d_ambig, p->d_freq, p->d_cond, p->d_PT, p->d_Q, p->d_pi, p->d_rootL, p->d_weights,
-                   p->d_partial, p->d_lnL, p->d_siteL, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_xsend, p->d_xrecv, p->d_xfreq, p->d_xpartial, p->d_bc_out, p->d_bc_outE, p->d_bc_sib, p->d_walk, p->d_t_index, p->d_t_formula, p->d_vdst, p->d_t_colfreq, p->d_V, p->d_forced, p->d_ex_int, p->d_ex_flag, p->d_ex_weight, p->d_ex_groups, p->d_ex_pow, p->d_ex_refvec, p->d_Vres};
+                   p->d_partial, p->d_lnL, p->d_siteL, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_xsend, p->d_xrecv, p->d_xfreq, p->d_xpartial, p->d_bc_out, p->d_bc_outE, p->d_bc_sib, p->d_walk, p->d_t_index, p->d_t_formula, p->d_vdst, p->d_t_colfreq, p->d_V, p->d_forced, p->d_ex_int, p->d_ex_flag, p->d_ex_weight, p->d_ex_groups, p->d_ex_pow, p->d_ex_refvec, p->d_Vres, p->d_ex_flags};
     for (void *d : dev) if (d) cudaFree(d);
     if (p->h_Q) cudaFreeHost(p->h_Q);
     if (p->h_small) cudaFreeHost(p->h_small);

@@ -123,13 +123,14 @@ struct ExpmArgs {
 // to the branch length: A_b = rho_b * R with ||R||_inf = 1 (VERDICT r1 "what's weak" 4).  Then
 //     exp(A_b) = sum_m (R^m / m!) * rho_b^m
 // is, element by element, a scalar polynomial in rho_b whose coefficient matrices S_m = R^m/m! are the same for every
-// branch of the group: they are built ONCE per group and evaluation (expm_powers_kernel, EXPM_POW_TERMS-2 dependent 64^3
-// products), after which a branch costs 17 FMAs per matrix element (expm_poly_kernel) instead of ~5 matrix products;
-// only matrices with rho_b > 0.975 still need squarings (s of them, x = rho_b / 2^s <= 0.975; degree 17 truncates below
-// 1e-16 there, the same bound the product kernel uses).  Proportionality is CHECKED on the device for every matrix
+// branch of the group: they are built ONCE per group and evaluation (expm_powers_kernel: 23 products of 64^3 arranged as
+// a 5-level tree S_{a+b} = S_a S_b / C(a+b,a), one CTA per product, dependencies resolved through generation flags),
+// after which a branch costs 24 FMAs per matrix element (expm_poly_kernel) instead of ~5 matrix products; only matrices
+// with rho_b > 2.3 still need squarings (s of them, x = rho_b / 2^s <= 2.3; degree 24 truncates below 1e-16 there).  Proportionality is CHECKED on the device for every matrix
 // (expm_classify_kernel), never assumed: anything that is not a multiple of its group's reference direction to 1e-13
 // takes the general scaling-and-squaring path inside the same launch.
-constexpr int EXPM_POW_TERMS = 18;        // S_0 = I (not stored, slot unused) .. S_17
+constexpr int EXPM_POW_TERMS = 25;        // S_0 = I (not stored, slot unused) .. S_24
+constexpr double EXPM_POLY_THETA = 2.3;   // x^25/25! < 1e-16 for x <= 2.33: degree 24 needs no squaring up to here
 struct ExpmGroup {
     double nu;        // ||A_ref||_inf of the reference matrix the powers were built from
     double weight;    // its L1 weight (same measure as ExpmArgs::weight)
@@ -429,7 +430,7 @@ __global__ void __launch_bounds__(256, 2) expm64_dmma_kernel(ExpmArgs a, ExpmTcO
         const ExpmGroup gi = a.groups[a.group[blockIdx.x]];
         const double rho = gi.nu * (a.weight[blockIdx.x] / gi.weight);
         int shift = 0;
-        if (rho > 0.975) { int e = 0; frexp(rho / 0.975, &e); shift = max(e, 0); }
+        if (rho > EXPM_POLY_THETA) { int e = 0; frexp(rho / EXPM_POLY_THETA, &e); shift = max(e, 0); }
         if (!(rho == rho) || shift > 900) {
             for (int idx = tid; idx < 4096; idx += 256) out[idx] = __longlong_as_double(0x7ff8000000000000LL);
             if (tc.PB) {
@@ -580,125 +581,172 @@ __global__ void __launch_bounds__(256, 2) expm64_dmma_kernel(ExpmArgs a, ExpmTcO
 }
 
 // ------------------------------------------------------------------------------------------------
-// Shared-powers path, stage 2: S_m = R^m / m! (PT layout, i.e. powers of the TRANSPOSED reference matrix) for m = 1..17,
-// one CTA per group whose reference is (re)established in this batch.  refs[blockIdx.x] = batch index of the reference
-// entry.  Also records the group's reference direction (refvec) and measures (nu, weight) for later batches.
+// Shared-powers path, stage 2: S_m = R^m / m! (PT layout, i.e. powers of the TRANSPOSED reference matrix), m = 1..24, for
+// every group whose reference is (re)established in this batch.  grid = (24, number of such groups); CTA (j, g) produces
+// S_{j+1}:  j = 0 assembles the reference matrix, normalises it (R = A_ref / ||A_ref||_inf -> S_1) and records the
+// group's measures and direction; CTA j >= 1 multiplies two EARLIER coefficient matrices,
+//     S_m = S_a S_b / C(m, a),   (a, b) = (1,1) (2,1) (2,2) (4,1..4) (8,1..8) (16,1..8),
+// which it awaits on generation flags (flag[group][m] == gen once S_m is complete; the producer fences before it
+// publishes).  Blocks are dispatched in index order and only wait for lower indices of their own column, so the scheme
+// cannot deadlock even if not all of them are co-resident; waits are time-bounded like every device-side wait here.
+// Critical path: 5 products instead of 23.
 // ------------------------------------------------------------------------------------------------
 struct ExpmPowersArgs {
     ExpmArgs a;               // input description (dense or compiled); a.Qres must be null
-    const int *refs;          // [gridDim.x] batch indices of the reference entries
+    const int *refs;          // [gridDim.y] batch indices of the reference entries
     ExpmGroup *groups;        // out
     double *pow;              // out [G][EXPM_POW_TERMS][4096]
     double *refvec;           // out [G][refvec_stride]
     int refvec_stride, nV, kind;
     const double *Vin;        // the raw input vectors [n][nV] (formula values or dense entries)
+    unsigned long long *flags;   // [G][EXPM_POW_TERMS] generation of each coefficient matrix
+    unsigned long long gen;
+    int *err;
 };
+
+__device__ __forceinline__ bool expm_await_flag(const unsigned long long *f, unsigned long long gen, int *err) {
+    unsigned long long t0 = 0;
+    for (int it = 0;; it++) {
+        unsigned long long v;
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+        if (v == gen) return true;
+        if ((it & 255) == 255) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) { atomicExch(err, 4); return false; }
+        }
+    }
+}
 
 __global__ void __launch_bounds__(256, 1) expm_powers_kernel(ExpmPowersArgs pa) {
     extern __shared__ __align__(16) double sm[];
-    double *X0 = sm, *X1 = X0 + 64 * LD64, *X2 = X1 + 64 * LD64;
+    double *X0 = sm, *X1 = X0 + 64 * LD64;
     __shared__ double red[64];
     __shared__ double s_nu;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wr = warp >> 1, wc = warp & 1, g = lane >> 2, q4 = lane & 3;
-    const int entry = pa.refs[blockIdx.x];
+    const int entry = pa.refs[blockIdx.y];
     const int grp = pa.a.group[entry];
     if (grp < 0 || pa.a.dst[entry] < 0) return;                       // (cannot happen: the host lists live references only)
-    load_rate_matrix<64, LD64, 256>(pa.a, X0, tid, entry);          // X0 = A_ref^T, zero padded
-    if (tid < 64) {
-        double s = 0.0;
-        for (int j = 0; j < 64; j++) s += fabs(X0[j * LD64 + tid]);   // column sums of A^T = row sums of A
-        red[tid] = s;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        double m = 0.0;
-        bool bad = false;
-        for (int i = 0; i < 64; i++) { if (!(red[i] == red[i]) || isinf(red[i])) bad = true; m = fmax(m, red[i]); }
-        s_nu = (bad || !(m > 0.0)) ? 0.0 : m;
-    }
-    __syncthreads();
-    const double nu = s_nu;
-    if (tid == 0) {
-        ExpmGroup gi;
-        gi.nu = nu; gi.weight = pa.a.weight[entry]; gi.kind = nu > 0.0 ? pa.kind : 0; gi.pad = 0;
-        pa.groups[grp] = gi;
-    }
-    for (int f = tid; f < pa.nV; f += 256) pa.refvec[(size_t)grp * pa.refvec_stride + f] = pa.Vin[(size_t)entry * pa.nV + f];
-    if (!(nu > 0.0)) return;                                         // (no entry can have been flagged against this reference)
+    const int m = blockIdx.x + 1;                                      // this CTA produces S_m
     double *pw = pa.pow + (size_t)grp * EXPM_POW_TERMS * 4096;
-    {
-        const double inv = 1.0 / nu;
-        for (int idx = tid; idx < 4096; idx += 256) {
-            const int o = (idx >> 6) * LD64 + (idx & 63);
-            const double v = X0[o] * inv;
-            X0[o] = v;
-            pw[4096 + idx] = v;                                       // S_1 = R
+    unsigned long long *flags = pa.flags + (size_t)grp * EXPM_POW_TERMS;
+    if (m == 1) {
+        load_rate_matrix<64, LD64, 256>(pa.a, X0, tid, entry);        // X0 = A_ref^T, zero padded
+        if (tid < 64) {
+            double s = 0.0;
+            for (int j = 0; j < 64; j++) s += fabs(X0[j * LD64 + tid]);   // column sums of A^T = row sums of A
+            red[tid] = s;
         }
+        __syncthreads();
+        if (tid == 0) {
+            double mx = 0.0;
+            bool bad = false;
+            for (int i = 0; i < 64; i++) { if (!(red[i] == red[i]) || isinf(red[i])) bad = true; mx = fmax(mx, red[i]); }
+            s_nu = (bad || !(mx > 0.0)) ? 0.0 : mx;
+        }
+        __syncthreads();
+        const double nu = s_nu;
+        if (tid == 0) {
+            ExpmGroup gi;
+            gi.nu = nu; gi.weight = pa.a.weight[entry]; gi.kind = nu > 0.0 ? pa.kind : 0; gi.pad = 0;
+            pa.groups[grp] = gi;
+        }
+        for (int f = tid; f < pa.nV; f += 256) pa.refvec[(size_t)grp * pa.refvec_stride + f] = pa.Vin[(size_t)entry * pa.nV + f];
+        // (no entry can have been flagged against a reference with nu == 0; the other CTAs of the column still need S_1)
+        const double inv = nu > 0.0 ? 1.0 / nu : 0.0;
+        for (int idx = tid; idx < 4096; idx += 256) pw[4096 + idx] = X0[(idx >> 6) * LD64 + (idx & 63)] * inv;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(flags + 1), "l"(pa.gen) : "memory");
+        return;
+    }
+    const int a = m <= 2 ? 1 : m <= 4 ? 2 : m <= 8 ? 4 : m <= 16 ? 8 : 16, b = m - a;
+    if (tid == 0) expm_await_flag(flags + a, pa.gen, pa.err);
+    if (tid == 32) expm_await_flag(flags + b, pa.gen, pa.err);
+    __syncthreads();
+    for (int idx = tid; idx < 2048; idx += 256) {                     // both operands as double2, coalesced
+        const int r = idx >> 5, c2 = (idx & 31) * 2;
+        *reinterpret_cast<double2 *>(X0 + r * LD64 + c2) = __ldcg(reinterpret_cast<const double2 *>(pw + (size_t)a * 4096 + r * 64 + c2));
+        *reinterpret_cast<double2 *>(X1 + r * LD64 + c2) = __ldcg(reinterpret_cast<const double2 *>(pw + (size_t)b * 4096 + r * 64 + c2));
     }
     __syncthreads();
     double acc[2][4][2];
-    const double *prev = X0;
-    for (int m = 2; m < EXPM_POW_TERMS; m++) {
-        double *next = (m & 1) ? X2 : X1;
 #pragma unroll
-        for (int i = 0; i < 2; i++)
+    for (int i = 0; i < 2; i++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-        tile_mm64_dmma(prev, X0, wr, wc, g, q4, acc);                 // S_{m-1} * R (powers of one matrix commute)
-        const double inv = 1.0 / (double)m;
+        for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    tile_mm64_dmma(X0, X1, wr, wc, g, q4, acc);                       // S_a * S_b (powers of one matrix commute)
+    double binom = 1.0;                                                // C(m, a), exact in fp64 for m <= 24
+    for (int i = 1; i <= a; i++) binom = binom * (double)(m - a + i) / (double)i;
+    const double inv = 1.0 / binom;
 #pragma unroll
-        for (int i = 0; i < 2; i++)
+    for (int i = 0; i < 2; i++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int r = 16 * wr + 8 * i + g, c = 32 * wc + 8 * j + 2 * q4;
-                const double2 v = make_double2(acc[i][j][0] * inv, acc[i][j][1] * inv);
-                *reinterpret_cast<double2 *>(next + r * LD64 + c) = v;
-                *reinterpret_cast<double2 *>(pw + (size_t)m * 4096 + r * 64 + c) = v;
-            }
-        __syncthreads();
-        prev = next;
-    }
+        for (int j = 0; j < 4; j++) {
+            const int r = 16 * wr + 8 * i + g, c = 32 * wc + 8 * j + 2 * q4;
+            __stcg(reinterpret_cast<double2 *>(pw + (size_t)m * 4096 + r * 64 + c), make_double2(acc[i][j][0] * inv, acc[i][j][1] * inv));
+        }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(flags + m), "l"(pa.gen) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------
-// Shared-powers path, stage 3: PT[slot] <- sum_m S_m x^m with x = rho / 2^shift <= 0.975 for every flagged entry.
-// grid = (16 element slices, chunks of the batch); thread t of slice sl owns element (row 4 sl + t/64, column t%64) of
-// the PT layout and keeps that element's 17 coefficients in registers while it walks its chunk of entries (they are
-// reloaded only when the group changes: batches are class-major).  Writes are 2 KB contiguous per (entry, slice).
+// Shared-powers path, stage 3: PT[slot] <- sum_m S_m x^m with x = rho / 2^shift <= EXPM_POLY_THETA for every flagged
+// entry.  grid = (16 element slices, chunks of EXPM_POLY_CHUNK entries); thread t of slice sl owns element
+// (row 4 sl + t/64, column t%64) of the PT layout and keeps that element's 24 coefficients in registers while it walks
+// its chunk (reloaded only when the group changes: batches are class-major).  The chunk's metadata is fetched up front
+// so that the loop carries no dependent global loads.  Writes are 2 KB contiguous per (entry, slice).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) expm_poly_kernel(ExpmArgs a, int n, int per_chunk) {
+constexpr int EXPM_POLY_CHUNK = 8;
+__global__ void __launch_bounds__(256) expm_poly_kernel(ExpmArgs a, int n) {
     const int tid = threadIdx.x;
     const int e = blockIdx.x * 256 + tid;                             // element index in the 64x64 PT layout
-    const bool diag = (e >> 6) == (e & 63);
-    const int k0 = blockIdx.y * per_chunk, k1 = min(n, k0 + per_chunk);
+    const double unit = ((e >> 6) == (e & 63)) ? 1.0 : 0.0;
+    const int k0 = blockIdx.y * EXPM_POLY_CHUNK;
+    int slot[EXPM_POLY_CHUNK], grp[EXPM_POLY_CHUNK];
+    double wgt[EXPM_POLY_CHUNK];
+#pragma unroll
+    for (int i = 0; i < EXPM_POLY_CHUNK; i++) {
+        const int k = k0 + i;
+        const bool live = k < n;
+        slot[i] = live ? a.dst[k] : -1;
+        if (live && slot[i] >= 0 && !a.flag[k]) slot[i] = -1;
+        grp[i] = live ? a.group[k] : -1;
+        wgt[i] = live ? a.weight[k] : 0.0;
+    }
     double c[EXPM_POW_TERMS];
     int cur = -1;
     double nu = 0.0, wref = 1.0;
-    for (int k = k0; k < k1; k++) {
-        const int slot = a.dst[k];
-        if (slot < 0 || !a.flag[k]) continue;
-        const int grp = a.group[k];
-        if (grp != cur) {
-            cur = grp;
-            const double *pw = a.pow + (size_t)grp * EXPM_POW_TERMS * 4096 + e;
 #pragma unroll
-            for (int m = 1; m < EXPM_POW_TERMS; m++) c[m] = __ldg(pw + (size_t)m * 4096);
-            nu = a.groups[grp].nu; wref = a.groups[grp].weight;
+    for (int i = 0; i < EXPM_POLY_CHUNK; i++) {
+        if (slot[i] < 0) continue;
+        if (grp[i] != cur) {
+            cur = grp[i];
+            const double *pw = a.pow + (size_t)cur * EXPM_POW_TERMS * 4096 + e;
+#pragma unroll
+            for (int m = 1; m < EXPM_POW_TERMS; m++) c[m] = __ldcg(pw + (size_t)m * 4096);
+            nu = a.groups[cur].nu; wref = a.groups[cur].weight;
         }
-        const double rho = nu * (a.weight[k] / wref);
+        const double rho = nu * (wgt[i] / wref);
         double x = rho;
-        if (rho > 0.975) {
+        if (rho > EXPM_POLY_THETA) {
             int ex = 0;
-            frexp(rho / 0.975, &ex);
+            frexp(rho / EXPM_POLY_THETA, &ex);
             if (ex > 900) continue;                                   // the finishing kernel writes NaN for absurd rates
             x = ldexp(rho, -max(ex, 0));
         }
-        double v = c[EXPM_POW_TERMS - 1];
+        // p(x) = 1 + x (c1 + c3 x^2 + .. + c23 x^22) + x^2 (c2 + c4 x^2 + .. + c24 x^22): two interleaved Horner chains in
+        // x^2 halve the dependent-FMA depth
+        static_assert(EXPM_POW_TERMS == 25, "the even/odd split below assumes degree 24");
+        const double x2 = x * x;
+        double ve = c[24], vo = c[23];
 #pragma unroll
-        for (int m = EXPM_POW_TERMS - 2; m >= 1; m--) v = fma(v, x, c[m]);
-        v = fma(v, x, diag ? 1.0 : 0.0);
-        __stcg(a.PT + (size_t)slot * 4096 + e, v);
+        for (int m = 22; m >= 2; m -= 2) { ve = fma(ve, x2, c[m]); vo = fma(vo, x2, c[m - 1]); }
+        const double v = fma(vo, x, fma(ve, x2, unit));
+        __stcg(a.PT + (size_t)slot[i] * 4096 + e, v);
     }
 }
 
@@ -1372,6 +1420,166 @@ __global__ void __launch_bounds__(256) class_merge_kernel(const double *gath, co
         __syncthreads();
     }
     if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Peer exchange over NVLink (one process per GPU; every rank maps every other rank's exchange buffer through CUDA IPC).
+// Buffer of a rank:  data[2 parities][R source ranks][payload doubles]  followed by  flags[2][R] (uint64 generation).
+// A writer stores its payload into slot `rank` of EVERY rank's buffer (its own included), fences system-wide and then
+// publishes the generation number in the matching flag; a reader spins (time-bounded) on its LOCAL flags.  Two
+// parities suffice: a rank can run at most one evaluation ahead of the slowest one (it needs that rank's flag to finish).
+// ------------------------------------------------------------------------------------------------
+struct PeerBuf {
+    double *const *peer;        // [R] device pointers to the ranks' buffers (entry `rank` = the local one)
+    int R, rank, payload;
+    unsigned long long gen;     // generation of THIS exchange (1, 2, 3, ...)
+    int *err;
+};
+__device__ __forceinline__ double *peer_data(const PeerBuf &b, int dst_rank, int src_rank) {
+    return b.peer[dst_rank] + ((size_t)(b.gen & 1ull) * b.R + src_rank) * b.payload;
+}
+__device__ __forceinline__ unsigned long long *peer_flag(const PeerBuf &b, int dst_rank, int src_rank) {
+    return reinterpret_cast<unsigned long long *>(b.peer[dst_rank] + (size_t)2 * b.R * b.payload) + (b.gen & 1ull) * b.R + src_rank;
+}
+__device__ __forceinline__ void peer_publish(const PeerBuf &b, int dst_rank) {       // after __threadfence_system()
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flag(b, dst_rank, b.rank)), "l"(b.gen) : "memory");
+}
+__device__ __forceinline__ bool peer_await(const PeerBuf &b, int src_rank) {
+    const unsigned long long *f = peer_flag(b, b.rank, src_rank);
+    unsigned long long t0 = 0;
+    for (int it = 0;; it++) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+        if (v == b.gen) return true;
+        if ((it & 255) == 255) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 20000000000ull) { atomicExch(b.err, 3); return false; }      // 20 s: a rank is gone
+        }
+    }
+}
+
+// Pattern shards only: every rank contributes its partial lnL; all ranks add the R partials in rank order, so the
+// result is bit-identical everywhere.  One block, launched after final_sum_kernel.  payload >= 1.
+__global__ void __launch_bounds__(64) peer_sum_kernel(PeerBuf b, double *lnL) {
+    const int t = threadIdx.x;
+    if (t < b.R) *peer_data(b, t, b.rank) = *lnL;
+    __threadfence_system();
+    __syncthreads();
+    if (t < b.R) peer_publish(b, t);
+    if (t < b.R) peer_await(b, t);
+    __syncthreads();
+    if (t == 0) {
+        double s = 0.0;
+        for (int r = 0; r < b.R; r++) s += __ldcg(peer_data(b, b.rank, r));
+        *lnL = s;
+    }
+}
+
+// Class groups: fused class-partial computation + exchange + merge + final sum (replaces class_partial_kernel, the
+// zero-padded all-reduce used as a gather, class_merge_kernel and final_sum_kernel).  payload = 2*xs doubles per rank:
+// [0,xs) partial values, [xs,2xs) binary exponents.  The block that finishes its stores LAST publishes the flags, waits
+// for the other ranks' and merges every shard (fixed order: bit-identical lnL on all ranks).
+struct ClassXchgArgs {
+    const double *rootL; const int *rootE; const double *weights;
+    int Sp, S, c0, nc, xs;
+    PeerBuf pb;
+    const double *xfreq;        // [nShards*G][xs] pattern frequencies of every rank (gathered once)
+    int nShards, G, myShard;
+    double *lnL; double *siteL; long long *siteScale;
+    unsigned int *counter;
+};
+
+__global__ void __launch_bounds__(256) class_exchange_kernel(ClassXchgArgs a) {
+    __shared__ double red[256];
+    __shared__ int s_last, s_bad;
+    const int tid = threadIdx.x;
+    const PeerBuf &b = a.pb;
+    const int xs = a.xs;
+    for (int s = blockIdx.x * 256 + tid; s < xs; s += gridDim.x * 256) {
+        double sum = 0.0;
+        int emax = 0;
+        if (s < a.S) {
+            emax = INT_MIN;
+            bool nan_seen = false;
+            for (int c = 0; c < a.nc; c++) {
+                const double l = a.rootL[(size_t)(a.c0 + c) * a.Sp + s];
+                if (l != l) nan_seen = true;
+                if (l > 0.0) emax = max(emax, a.rootE[(size_t)(a.c0 + c) * a.Sp + s]);
+            }
+            for (int c = 0; c < a.nc; c++) {
+                const double l = a.rootL[(size_t)(a.c0 + c) * a.Sp + s];
+                if (l > 0.0) {
+                    const int de = a.rootE[(size_t)(a.c0 + c) * a.Sp + s] - emax;
+                    sum += a.weights[a.c0 + c] * l * (de < -1000 ? 0.0 : exp2i(de));
+                }
+            }
+            if (nan_seen) sum = __longlong_as_double(0x7ff8000000000000LL);
+            if (emax == INT_MIN) emax = 0;
+        }
+        for (int r = 0; r < b.R; r++) {
+            double *d = peer_data(b, r, b.rank);
+            d[s] = sum;
+            d[xs + s] = (double)emax;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    if (tid == 0) { *a.counter = 0u; s_bad = 0; }
+    __threadfence_system();
+    if (tid < b.R) peer_publish(b, tid);
+    if (tid < b.R) peer_await(b, tid);
+    __syncthreads();
+    double term = 0.0;
+    for (int idx = tid; idx < a.nShards * xs; idx += 256) {
+        const int j = idx / xs, s = idx - j * xs;
+        const double f = a.xfreq[(size_t)j * a.G * xs + s];
+        int emax = INT_MIN;
+        bool nan_seen = false;
+        for (int r = 0; r < a.G; r++) {
+            const double *q = peer_data(b, b.rank, j * a.G + r);
+            const double m = __ldcg(q + s);
+            if (m != m) nan_seen = true;
+            if (m > 0.0) emax = max(emax, (int)__ldcg(q + xs + s));
+        }
+        double sum = 0.0;
+        for (int r = 0; r < a.G; r++) {
+            const double *q = peer_data(b, b.rank, j * a.G + r);
+            const double m = __ldcg(q + s);
+            if (m > 0.0) {
+                const int de = (int)__ldcg(q + xs + s) - emax;
+                sum += m * (de < -1000 ? 0.0 : exp2i(de));
+            }
+        }
+        if (nan_seen) sum = __longlong_as_double(0x7ff8000000000000LL);
+        if (emax == INT_MIN) emax = 0;
+        double lnl;
+        if (sum > 0.0) lnl = log(sum) + (double)emax * 0.693147180559945309417232121458;
+        else if (sum != sum) lnl = sum;
+        else { lnl = -INFINITY; if (f > 0.0) s_bad = 1; }
+        if (f > 0.0) term += f * lnl;
+        if (a.siteL && j == a.myShard && s < a.S) {
+            long long cnt = 0; double outL = sum;
+            if (sum > 0.0) {
+                const int e2 = emax;
+                cnt = (e2 < 0) ? (long long)((-e2) / 64) : -(long long)((e2 + 63) / 64);
+                const int rem = e2 + (int)(64 * cnt);
+                outL = sum * exp2i(rem);
+            }
+            a.siteL[s] = outL; a.siteScale[s] = cnt;
+        }
+    }
+    red[tid] = term;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) red[tid] += red[tid + o];
+        __syncthreads();
+    }
+    if (tid == 0) *a.lnL = s_bad ? -INFINITY : red[0];
 }
 
 __global__ void __launch_bounds__(256) final_sum_kernel(const double *partial, int n, const int *flag, double *out) {

@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
         q[0] = smid; q[1] = clock64(); q[3] = (long long)gt;
     }
 
-    // thread 0: stage the operands of one step into ring slot (m & 1): two flat bulk copies + one L2 prefetch
+    // one lane of warp 3: stage the operands of one step into ring slot (m & 1): two flat bulk copies + one L2 prefetch
     auto stage_step = [&](int cat, int tile, int2 st, uint32_t m) {
         const int child = st.x & WALK_ID_MASK;
         const bool internal = child >= a.L;
@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
         int2 st = __ldg(w.steps + i_begin);
         int2 nx = (i_begin + 1 < i_end) ? __ldg(w.steps + i_begin + 1) : make_int2(0, 0);
         __syncthreads();                      // previous (class, tile): every read of the ring is complete
-        if (tid == 0) stage_step(cat, tile, st, n_step);
+        if (warp == 3 && elect_one()) stage_step(cat, tile, st, n_step);     // warp 3 stages: warp 0 issues the MMAs
         // fetched one step ahead: a leaf's state code, or (contractions) the generation bit the child's words must carry
         auto step_aux = [&](int2 q) -> int {
             const int ch = q.x & WALK_ID_MASK;
@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
             if (tr) { trp[0] = ((long long)st.x << 32) | (unsigned)st.y; trp[1] = clock64(); }
             __syncthreads();                  // (1) everyone is done with step i-1: ring slot (n_step+1)&1 is free
             if (has_next) {
-                if (tid == 0) stage_step(cat, tile, nx, n_step + 1);
+                if (warp == 3 && elect_one()) stage_step(cat, tile, nx, n_step + 1);
                 next_code = step_aux(nx);
             }
             if ((flags & STEP_FIRST) && !(enc & WALK_CHAIN)) {
