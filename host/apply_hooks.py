@@ -27,6 +27,10 @@ HOOKS = [
     ("core/include/tree.h", "class _TheTree : public _TreeTopology {", "after",
      "  friend struct hb2_hooks_access;   // hyphy_b200: read access to flatParents\n",
      "friend declaration"),
+    # ---- matrix.h: the compiled form of a model matrix (cmd, theIndex, lDim) is private -------------------------------
+    ("core/include/matrix.h", "class _Matrix : public _MathObject {", "after",
+     "  friend struct hb2_hooks_access;   // hyphy_b200: read access to the compiled formula data\n",
+     "friend declaration"),
     # ---- likefunc.h: one opaque slot per likelihood function ---------------------------------------------------------
     ("core/include/likefunc.h", "  hyFloat **conditionalInternalNodeLikelihoodCaches, **siteScalingFactors,", ("after", 1),
      "  void *hb2_state = nullptr;   // hyphy_b200: engine partitions, parallel to theTrees\n",
@@ -54,6 +58,22 @@ HOOKS = [
     ("core/calcnode.cpp", "void _CalcNode::SetCompExp(_Matrix *m, long catID, bool do_exponentiation) {", "after",
      "  long const hb2_cat = catID;   // hyphy_b200: the rate class as ComputeBlock numbers it (before the category remap)\n",
      "remember the global class index"),
+    ("core/calcnode.cpp", "        temp = (_Matrix *)myModelMatrix->MultByFreqs(theModel, true);", ("before", -3),
+     "      // hyphy_b200: compiled hand-over -- the formula VALUES go to the engine, which scatters, multiplies by the\n"
+     "      // frequencies, fills the diagonal and exponentiates; the if below makes the host's own assembly conditional\n"
+     "      _Matrix *hb2_ph = (!isExplicitForm && queue && tags && !storeRateMatrix)\n"
+     "                            ? hb2_hooks::compiled(this, myModelMatrix, theModel, categID, GetCompExp(totalCategs > 1 ? categID : -1))\n"
+     "                            : nil;\n"
+     "      if (!hb2_ph)\n",
+     "RecomputeMatrix: skip EvaluateSimple's scatter + MultByFreqs (calcnode.cpp:620-625)"),
+    ("core/calcnode.cpp", "      if (storeRateMatrix) {", "before",
+     "      if (hb2_ph) {   // hyphy_b200: nothing to queue for ExponentiateMatrices; the node keeps a shape-only matrix\n"
+     "        hb2_hooks::Bypass hb2_bypass;\n"
+     "        SetCompExp(hb2_ph, totalCategs > 1 ? categID : -1);\n"
+     "        reuse_exponentials();\n"
+     "        return false;\n"
+     "      }\n",
+     "RecomputeMatrix: after the parameter write-back block (calcnode.cpp:667)"),
     ("core/calcnode.cpp", "    compExp = m->Exponentiate(1., true, *store_exp_here);", ("before", -1),
      "  if (_Matrix *hb2_keep = hb2_hooks::intercept(this, m, hb2_cat, do_exponentiation, *store_exp_here)) {   // hyphy_b200\n"
      "    compExp = hb2_keep;\n"

@@ -10,7 +10,9 @@
 #include <unordered_map>
 #include <vector>
 
+#include "batchlan.h"
 #include "calcnode.h"
+#include "formula.h"
 #include "dataset_filter.h"
 #include "global_things.h"
 #include "likefunc.h"
@@ -22,10 +24,14 @@
 
 static_assert(sizeof(long) == sizeof(int64_t), "HyPhy's long arrays are passed to the engine as int64_t (LP64)");
 
-// friend of _TheTree (one inserted line in tree.h): the flat parent table is protected there
+// friend of _TheTree and _Matrix (one inserted line each): the flat parent table and the compiled form of a model matrix
+// are not public there
 struct hb2_hooks_access {
     static long const *flat_parents(_TheTree const *t) { return t->flatParents.list_data; }
     static unsigned long flat_parents_length(_TheTree const *t) { return t->flatParents.lLength; }
+    static _CompiledMatrixData *compiled(_Matrix const *m) { return m->cmd; }
+    static long const *stored_index(_Matrix const *m) { return m->theIndex; }
+    static long stored_count(_Matrix const *m) { return m->lDim; }
 };
 
 namespace hb2_hooks {
@@ -38,6 +44,16 @@ struct Part {
     long S = 0, D = 0, L = 0, I = 0, C = 0;
     std::unordered_map<_CalcNode const *, long> node_id;    // tree node -> flat id (leaves, then internal nodes)
     std::mutex lock;                                         // SetCompExp is called from ExponentiateMatrices' OpenMP loop
+    // compiled route: one engine template per model matrix seen on this tree
+    struct Template {
+        int id = -1;
+        _CompiledMatrixData const *cmd = nullptr;
+        long stored = 0, n_formulas = 0, freq_var = -1;
+        unsigned long checked_epoch = 0;
+        std::vector<double> freqs;
+    };
+    std::unordered_map<_Matrix const *, Template> templates;
+    unsigned long epoch = 0, n_compiled = 0;                 // epoch: one per ComputeBlock scope (frequencies are re-read once per epoch)
     unsigned long n_eval = 0, n_rate = 0, n_trans = 0;
     double t_handover = 0.0, t_evaluate = 0.0;               // seconds inside hb2_set_matrices* / hb2_evaluate* (HYPHY_B200_VERBOSE)
     std::chrono::steady_clock::time_point t_created;
@@ -52,6 +68,7 @@ struct State {
 };
 
 Part *g_current = nullptr;          // ComputeBlock is entered from the single interpreter thread
+int g_bypass = 0;
 
 bool env_true(char const *name) {
     char const *v = getenv(name);
@@ -124,8 +141,8 @@ void destroy_all(void *&state) {
         if (!p) continue;
         if (env_true("HYPHY_B200_VERBOSE"))
             fprintf(stderr, "[hyphy_b200] partition destroyed after %lu evaluations, %lu rate matrices exponentiated on the device, %lu host transition matrices, %lld kernel launches; "
-                            "lifetime %.3f s of which %.3f s in matrix hand-over (densify + hb2_set_matrices) and %.3f s in hb2_evaluate (rest = HyPhy host code)\n",
-                    p->n_eval, p->n_rate, p->n_trans, (long long)hb2_launch_count(p->h), seconds_since(p->t_created), p->t_handover, p->t_evaluate);
+                            "%lu of them handed over as formula values through %zu template(s); lifetime %.3f s of which %.3f s in matrix hand-over and %.3f s in hb2_evaluate (rest = HyPhy host code)\n",
+                    p->n_eval, p->n_rate, p->n_trans, (long long)hb2_launch_count(p->h), p->n_compiled, p->templates.size(), seconds_since(p->t_created), p->t_handover, p->t_evaluate);
         if (g_current == p) g_current = nullptr;
         hb2_destroy(p->h);
         delete p;
@@ -134,12 +151,104 @@ void destroy_all(void *&state) {
     state = nullptr;
 }
 
-Scope::Scope(void *part) : part_(part), prev_(g_current) { g_current = static_cast<Part *>(part); }
+Scope::Scope(void *part) : part_(part), prev_(g_current) {
+    g_current = static_cast<Part *>(part);
+    if (g_current) g_current->epoch++;
+}
+Bypass::Bypass() { g_bypass++; }
+Bypass::~Bypass() { g_bypass--; }
 Scope::~Scope() { g_current = static_cast<Part *>(prev_); }
+
+namespace {
+
+_Matrix *placeholder(Part *p, _Matrix *existing, _Matrix const *not_this) {
+    // exp(Qt) lives on the device only.  The node keeps a matrix object of the right shape so that the host's "has this
+    // node ever been exponentiated" bookkeeping (NeedNewCategoryExponential, calcnode.cpp:480-523) works; its entries are
+    // NaN so that any host code path that still tried to READ a transition matrix would fail loudly instead of computing
+    // with stale numbers.
+    if (existing && existing != not_this && (long)existing->GetHDim() == p->D && (long)existing->GetVDim() == p->D && existing->is_dense())
+        return existing;
+    _Matrix *ph = new _Matrix(p->D, p->D, false, true);
+    for (long k = 0; k < p->D * p->D; k++) ph->theData[k] = NAN;
+    return ph;
+}
+
+// equilibrium frequencies MultByFreqs would multiply the columns by (matrix.cpp:1550-1563), or nullptr
+double const *model_frequencies(long model_index, long D) {
+    if (model_index < 0 || model_index >= (long)modelFrequenciesIndices.lLength) return nullptr;
+    long const fv = modelFrequenciesIndices.list_data[model_index];
+    if (fv < 0) return nullptr;
+    _Matrix *fm = (_Matrix *)LocateVar(fv)->GetValue();
+    if (!fm) return nullptr;
+    fm = (_Matrix *)fm->ComputeNumeric();
+    if (!fm || !fm->is_dense() || (long)(fm->GetHDim() * fm->GetVDim()) != D) return nullptr;
+    return fm->theData;
+}
+
+}  // namespace
+
+_Matrix *compiled(_CalcNode *node, _Matrix *mm, long model_index, long catID, _Matrix *existing) {
+    Part *p = g_current;
+    static bool const dense_only = env_true("HYPHY_B200_DENSE");
+    if (!p || !mm || dense_only) return nullptr;
+    auto it = p->node_id.find(node);
+    if (it == p->node_id.end()) return nullptr;
+    _CompiledMatrixData *cmd = hb2_hooks_access::compiled(mm);
+    if (!cmd || (long)mm->GetHDim() != p->D || (long)mm->GetVDim() != p->D) return nullptr;
+    auto const t0 = std::chrono::steady_clock::now();
+    long const stored = hb2_hooks_access::stored_count(mm), n_formulas = (long)cmd->formulasToEval.lLength;
+    Part::Template &T = p->templates[mm];
+    bool const wants_freqs = model_index >= 0 && model_index < (long)modelFrequenciesIndices.lLength && modelFrequenciesIndices.list_data[model_index] >= 0;
+    if (T.id < 0 || T.cmd != cmd || T.stored != stored || T.n_formulas != n_formulas) {
+        // (re)register the static half: which stored off-diagonal entry takes which formula
+        if (T.id < 0) {
+            if ((long)p->templates.size() > HB2_MAX_TEMPLATES) { p->templates.erase(mm); return nullptr; }   // dense route for the rest
+            T.id = (int)p->templates.size() - 1;
+        }
+        long const *index = hb2_hooks_access::stored_index(mm);
+        std::vector<int64_t> ei, ef;
+        for (long e = 0; e < stored; e++) {
+            long const flat = index ? index[e] : e, f = cmd->formulaRefs[e];
+            if (flat < 0 || f < 0) continue;
+            if (flat / p->D == flat % p->D) continue;                      // the diagonal is -(row sum) on the device too
+            ei.push_back(flat); ef.push_back(f);
+        }
+        double const *fr = wants_freqs ? model_frequencies(model_index, p->D) : nullptr;
+        if (ei.empty() || (wants_freqs && !fr)) { p->templates.erase(mm); return nullptr; }
+        if (hb2_set_rate_template_id(p->h, T.id, (int64_t)ei.size(), ei.data(), ef.data(), n_formulas, fr)) fatal("hb2_set_rate_template_id failed");
+        T.cmd = cmd; T.stored = stored; T.n_formulas = n_formulas;
+        T.freq_var = wants_freqs ? modelFrequenciesIndices.list_data[model_index] : -1;
+        T.freqs.assign(fr ? fr : nullptr, fr ? fr + p->D : nullptr);
+        T.checked_epoch = p->epoch;
+    } else if (T.freq_var >= 0 && T.checked_epoch != p->epoch) {
+        // estimated equilibrium frequencies can move between evaluations: one comparison per ComputeBlock
+        T.checked_epoch = p->epoch;
+        double const *fr = model_frequencies(model_index, p->D);
+        if (!fr) fatal("model frequencies became unavailable");
+        if (memcmp(fr, T.freqs.data(), sizeof(double) * p->D) != 0) {
+            if (hb2_set_template_frequencies(p->h, T.id, fr)) fatal("hb2_set_template_frequencies failed");
+            T.freqs.assign(fr, fr + p->D);
+        }
+    }
+    // this node's parameter values are already in the model's variables (RecomputeMatrix copied them): refresh the
+    // compiled formulas' inputs and evaluate the unique formulas
+    for (unsigned long i = 0; i < cmd->varIndex.lLength; i++) {
+        _Variable *v = LocateVar(cmd->varIndex.list_data[i]);
+        if (v->ObjectClass() == MATRIX) cmd->varValues[i].reference = (hyPointer)((_Matrix *)v->Compute())->theData;
+        else cmd->varValues[i].value = v->IsIndependent() ? v->Value() : v->Compute()->Value();
+    }
+    for (long f = 0; f < n_formulas; f++)
+        cmd->formulaValues[f] = ((_Formula *)cmd->formulasToEval.list_data[f])->ComputeSimple(cmd->theStack, cmd->varValues);
+    int64_t const id = it->second;
+    if (hb2_set_matrices_compiled_id(p->h, T.id, catID, 1, &id, cmd->formulaValues)) fatal("hb2_set_matrices_compiled_id failed");
+    p->n_rate++; p->n_compiled++;
+    p->t_handover += seconds_since(t0);
+    return placeholder(p, existing, nullptr);
+}
 
 _Matrix *intercept(_CalcNode *node, _Matrix *m, long catID, bool do_exponentiation, _Matrix *existing) {
     Part *p = g_current;
-    if (!p || !m) return nullptr;
+    if (!p || !m || g_bypass) return nullptr;
     auto it = p->node_id.find(node);
     if (it == p->node_id.end()) return nullptr;                       // a node of some other tree
     if ((long)m->GetHDim() != p->D || (long)m->GetVDim() != p->D) return nullptr;
@@ -161,15 +270,7 @@ _Matrix *intercept(_CalcNode *node, _Matrix *m, long catID, bool do_exponentiati
         p->t_handover += seconds_since(t0);
     }
     if (!do_exponentiation) return m;                                 // host-computed P (explicit-form models): kept as is
-    // exp(Qt) now lives on the device only.  The node keeps a matrix object of the right shape so that the host's
-    // "has this node ever been exponentiated" bookkeeping (NeedNewCategoryExponential, calcnode.cpp:480-523) works; its
-    // entries are NaN so that any host code path that still tried to READ a transition matrix would fail loudly
-    // instead of computing with stale numbers.
-    if (existing && existing != m && (long)existing->GetHDim() == p->D && (long)existing->GetVDim() == p->D && existing->is_dense())
-        return existing;
-    _Matrix *ph = new _Matrix(p->D, p->D, false, true);
-    for (long k = 0; k < p->D * p->D; k++) ph->theData[k] = NAN;
-    return ph;
+    return placeholder(p, existing, m);
 }
 
 double compute_block(void *part, _TheTree *tree, long catID, _SimpleList const &branches, double *siteRes, long *scc,

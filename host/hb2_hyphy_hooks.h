@@ -12,6 +12,8 @@
 //                                                                                       (called from the OpenMP loop of
 //                                                                                       ExponentiateMatrices, tree.cpp:2995:
 //                                                                                       the hand-over is serialised inside)
+//   _CalcNode::RecomputeMatrix           (calcnode.cpp:526)   -> hb2_hooks::compiled    formula VALUES go to the GPU instead
+//                                                                                       of a numeric rate matrix
 //   _LikelihoodFunction::DeleteCaches    (likefunc.cpp:10556) -> hb2_hooks::destroy_all
 //
 // Environment: HYPHY_B200=0 disables the engine (the unmodified CPU path runs); HYPHY_B200_TC=1 selects the tcgen05
@@ -52,6 +54,21 @@ class Scope {
 // SetCompExp(m, catID, do_exponentiation): returns the matrix to keep as compExp (a placeholder of the right shape for
 // rate matrices, `m` itself for host-computed transition matrices) or nullptr when the call is not diverted.
 _Matrix *intercept(_CalcNode *node, _Matrix *m, long catID, bool do_exponentiation, _Matrix *existing);
+
+// _CalcNode::RecomputeMatrix (calcnode.cpp:526), queue mode, ordinary (not explicit-form) models whose rate matrix has been
+// compiled (_CompiledMatrixData, matrix.h:69-80): evaluates the model's unique formulas with this node's parameters --
+// the first half of _Matrix::EvaluateSimple (matrix.cpp:3112-3133) -- and hands the ~50 VALUES to the engine; the scatter
+// into the matrix (matrix.cpp:3135-3321), the multiplication by the equilibrium frequencies and the diagonal
+// (MultByFreqs, matrix.cpp:1546) and the exponential all happen on the device.  Returns the matrix the node keeps as
+// compExp (shape only, NaN filled), or nullptr when the node takes the dense route (SetCompExp interception).
+// HYPHY_B200_DENSE=1 disables this route (A/B).
+_Matrix *compiled(_CalcNode *node, _Matrix *model_matrix, long model_index, long catID, _Matrix *existing);
+// while alive, SetCompExp is NOT intercepted (the node stores the placeholder the call above returned)
+class Bypass {
+  public:
+    Bypass();
+    ~Bypass();
+};
 
 // ComputeBlock after DetermineNodesForUpdate + ExponentiateMatrices: pruning, root reduction, scaling correction.
 double compute_block(void *part, _TheTree *tree, long catID, _SimpleList const &branches, double *siteRes, long *scc,

@@ -120,19 +120,25 @@ struct hb2_partition {
     // C + mixture component; per-entry arrays are indexed like the batch
     int ex_G = 0, ex_stride = 0;              // groups, doubles per cached reference direction
     int *d_ex_int = nullptr, *h_ex_int = nullptr, *d_ex_flag = nullptr;     // [group cap | ref cap | refs G]
-    double *d_ex_weight = nullptr, *d_ex_pow = nullptr, *d_ex_refvec = nullptr, *d_Vres = nullptr;
+    double *d_ex_weight = nullptr, *d_ex_pow = nullptr, *d_ex_refvec = nullptr;
     void *d_ex_groups = nullptr;
     unsigned long long *d_ex_flags = nullptr, ex_gen = 0;   // generation flags of the coefficient matrices [G][EXPM_POW_TERMS]
     std::vector<int> ex_kind;                 // host mirror: kind of the reference direction each group holds (0 none)
     int64_t ex_cap = 0;
     bool ex_enabled = true;                   // HB2_EXPM_SHARED=0 switches the path off (A/B testing)
     int64_t stage_launches[3] = {0, 0, 0};    // launches per evaluation of the last hb2_time_resident {expm, pruning, root}
-    // compiled rate-matrix template (hb2_set_rate_template) and its per-evaluation formula values
-    int64_t t_nnz = 0, t_nF = 0;
-    bool t_has_colfreq = false;
-    int *d_t_index = nullptr, *d_t_formula = nullptr, *d_vdst = nullptr, *h_vdst = nullptr;
-    double *d_t_colfreq = nullptr, *d_V = nullptr, *h_V = nullptr;
-    int64_t n_vpending = 0;
+    // compiled rate-matrix templates (hb2_set_rate_template*): static scatter map + own queue of per-evaluation formula
+    // values.  A tree may carry several models (foreground / background branches, per-branch models of aBSREL): one
+    // template each, up to HB2_MAX_TEMPLATES.
+    struct Tmpl {
+        int64_t nnz = 0, nF = 0, n_pending = 0;
+        bool has_colfreq = false;
+        int *d_index = nullptr, *d_formula = nullptr, *d_vdst = nullptr, *h_vdst = nullptr;
+        double *d_colfreq = nullptr, *h_colfreq = nullptr, *d_V = nullptr, *h_V = nullptr, *d_Vres = nullptr;
+    };
+    std::vector<Tmpl> tmpls;
+    std::vector<signed char> pend_tmpl;       // [C*B] template of the slot's pending compiled entry
+    std::vector<signed char> res_tmpl;        // [C*B] template of the slot's resident formula values (is_rate == 2)
     // tensor-core path (33..64 states unless HB2_FLAG_FORCE_FP64): fp32 conditionals + split/tiled P operands
     bool use_tc = false;
     float *d_condf = nullptr, *d_PB = nullptr, *d_PTf = nullptr;
@@ -195,21 +201,20 @@ int wait_staging(hb2_partition *p) {
 // from.  Fills the pinned arrays and enqueues their upload: call BEFORE ev_staging is recorded.
 struct SharedPlan {
     bool use = false;
-    int kind = 0, n_refs = 0;
-    int64_t cap_off = 0;
+    int kind = 0, n_refs = 0, tmpl = 0;
 };
 constexpr int EX_MIN_GROUP = 24;
 
-int plan_shared(hb2_partition *p, const int *h_dst, int64_t n, int kind, const int *group_override, SharedPlan &sp) {
+int plan_shared(hb2_partition *p, const int *h_dst, int64_t n, int kind, const int *group_override, SharedPlan &sp, int tmpl = 0) {
     sp = SharedPlan();
     if (p->Dp != 64 || p->expm_dfma || !p->ex_enabled || !p->d_ex_int || n <= 0 || n > p->ex_cap) return 0;
-    if (kind == 1 && !p->d_Vres) return 0;
+    if (kind == 1 && !p->tmpls[tmpl].d_Vres) return 0;
     if (wait_staging(p)) return 1;            // an earlier plan's upload may still be reading the pinned arrays
     int *grp = p->h_ex_int, *ref = p->h_ex_int + p->ex_cap, *refs = p->h_ex_int + 2 * p->ex_cap;
     std::vector<int> count(p->ex_G, 0), first(p->ex_G, -1);
     for (int64_t k = 0; k < n; k++) {
         int g = -1;
-        if (h_dst[k] >= 0) g = group_override ? group_override[k] : (int)(h_dst[k] / p->B);
+        if (h_dst[k] >= 0) g = group_override ? group_override[k] : (int)(h_dst[k] / p->B) + tmpl * (int)p->C;   // (template, class)
         if (g >= p->ex_G) g = -1;
         grp[k] = g;
         if (g >= 0) { if (first[g] < 0) first[g] = (int)k; count[g]++; }
@@ -224,7 +229,7 @@ int plan_shared(hb2_partition *p, const int *h_dst, int64_t n, int kind, const i
     for (int64_t k = 0; k < n; k++) ref[k] = grp[k] >= 0 ? first[grp[k]] : -1;
     for (int r = 0; r < nr; r++) p->ex_kind[grp[refs[r]]] = kind;
     CU(cudaMemcpyAsync(p->d_ex_int, p->h_ex_int, (size_t)(2 * p->ex_cap + p->ex_G) * sizeof(int), cudaMemcpyHostToDevice, p->stream));
-    sp.use = true; sp.kind = kind; sp.n_refs = nr;
+    sp.use = true; sp.kind = kind; sp.n_refs = nr; sp.tmpl = tmpl;
     return 0;
 }
 
@@ -233,14 +238,15 @@ int plan_shared(hb2_partition *p, const int *h_dst, int64_t n, int kind, const i
 // components go to a scratch area first); pack_tc: also emit the tensor-path operands of the slot.  sp: shared-powers plan
 // of the WHOLE batch this run [off, off + n) belongs to (dQ / d_dst already point at the run).
 int launch_expm(hb2_partition *p, const double *dQ, const int *d_dst, int n, int is_trans, double *qres, bool pack_tc = true,
-                double *pt_override = nullptr, const SharedPlan *sp = nullptr, int64_t off = 0) {
+                double *pt_override = nullptr, const SharedPlan *sp = nullptr, int64_t off = 0, int tmpl = 0) {
     if (n <= 0) return 0;
     hb2::ExpmArgs a{};
     a.Q = dQ; a.dst = d_dst; a.PT = pt_override ? pt_override : p->d_PT; a.Qres = qres; a.D = (int)p->D;
     a.is_trans = is_trans;
     if (is_trans == 2) {                       // compiled template: dQ points at the formula values [n][nF]
-        a.is_trans = 0; a.Q = nullptr; a.V = dQ; a.tmpl_index = p->d_t_index; a.tmpl_formula = p->d_t_formula;
-        a.tmpl_colfreq = p->t_has_colfreq ? p->d_t_colfreq : nullptr; a.tmpl_nnz = (int)p->t_nnz; a.nF = (int)p->t_nF;
+        const hb2_partition::Tmpl &t = p->tmpls[tmpl];
+        a.is_trans = 0; a.Q = nullptr; a.V = dQ; a.tmpl_index = t.d_index; a.tmpl_formula = t.d_formula;
+        a.tmpl_colfreq = t.has_colfreq ? t.d_colfreq : nullptr; a.tmpl_nnz = (int)t.nnz; a.nF = (int)t.nF;
     }
     bool packed = false;
     pack_tc = pack_tc && p->use_tc && !pt_override;
@@ -251,13 +257,13 @@ int launch_expm(hb2_partition *p, const double *dQ, const int *d_dst, int n, int
             } else {
                 const size_t smem = 3 * 64 * hb2::LD64 * sizeof(double);
                 if (sp && sp->use && is_trans != 1) {
-                    const int nV = sp->kind == 1 ? (int)p->t_nF : (int)(p->D * p->D);
+                    const int nV = sp->kind == 1 ? (int)p->tmpls[tmpl].nF : (int)(p->D * p->D);
                     const hb2::ExpmGroup *groups = static_cast<const hb2::ExpmGroup *>(p->d_ex_groups);
                     hb2::ExpmClassifyArgs ca{};
                     ca.V = dQ; ca.nV = nV; ca.kind = sp->kind; ca.dst = d_dst; ca.group = p->d_ex_int + off;
                     ca.ref = p->d_ex_int + p->ex_cap + off; ca.groups = groups; ca.refvec = p->d_ex_refvec; ca.refvec_stride = p->ex_stride;
                     ca.weight = p->d_ex_weight + off; ca.flag = p->d_ex_flag + off;
-                    ca.res = sp->kind == 1 ? p->d_Vres : qres;
+                    ca.res = sp->kind == 1 ? p->tmpls[tmpl].d_Vres : qres;
                     // references index the whole batch: classification has to see it in one piece (off == 0 for compiled batches
                     // and for dense batches that consist of a single run; mixed dense batches fall back below)
                     hb2::expm_classify_kernel<<<n, 128, 0, p->stream>>>(ca);
@@ -328,18 +334,21 @@ int launch_prune(hb2_partition *p, const hb2::PruneArgs &a, const int *d_jobs, i
 // Flush matrices handed over since the last evaluation: one H2D copy + one (or two) expm launches per queue.  Retired
 // entries (destination -1: the slot was handed over again later) are skipped by the kernels.
 int flush_compiled(hb2_partition *p) {
-    const int64_t n = p->n_vpending;
-    if (n == 0) return 0;
-    CU(cudaMemcpyAsync(p->d_V, p->h_V, n * p->t_nF * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-    CU(cudaMemcpyAsync(p->d_vdst, p->h_vdst, n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
-    SharedPlan sp;
-    if (plan_shared(p, p->h_vdst, n, 1, nullptr, sp)) return 1;
-    CU(cudaEventRecord(p->ev_staging, p->stream));
-    p->staging_busy = true;
-    if (launch_expm(p, p->d_V, p->d_vdst, (int)n, 2, sp.use ? nullptr : p->d_Qres, true, nullptr, &sp)) return 1;
-    for (int64_t k = 0; k < n; k++)
-        if (p->h_vdst[k] >= 0) { p->is_rate[p->h_vdst[k]] = sp.use ? 2 : 1; p->pend_pos[p->h_vdst[k]] = -1; }
-    p->n_vpending = 0;
+    for (size_t ti = 0; ti < p->tmpls.size(); ti++) {
+        hb2_partition::Tmpl &t = p->tmpls[ti];
+        const int64_t n = t.n_pending;
+        if (n == 0) continue;
+        CU(cudaMemcpyAsync(t.d_V, t.h_V, n * t.nF * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        CU(cudaMemcpyAsync(t.d_vdst, t.h_vdst, n * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+        SharedPlan sp;
+        if (plan_shared(p, t.h_vdst, n, 1, nullptr, sp, (int)ti)) return 1;
+        CU(cudaEventRecord(p->ev_staging, p->stream));
+        p->staging_busy = true;
+        if (launch_expm(p, t.d_V, t.d_vdst, (int)n, 2, sp.use ? nullptr : p->d_Qres, true, nullptr, &sp, 0, (int)ti)) return 1;
+        for (int64_t k = 0; k < n; k++)
+            if (t.h_vdst[k] >= 0) { p->is_rate[t.h_vdst[k]] = sp.use ? 2 : 1; p->res_tmpl[t.h_vdst[k]] = (signed char)ti; p->pend_pos[t.h_vdst[k]] = -1; }
+        t.n_pending = 0;
+    }
     return 0;
 }
 
@@ -381,17 +390,19 @@ inline void note_matrix_change(hb2_partition *p, int64_t node) {
     if (p->bc_node >= 0 && node != p->bc_node && p->bc_dirty_node < 0) p->bc_dirty_node = node;
 }
 
-// Retire the pending entry of `slot` that sits in the OTHER queue (compiled = true: we are about to add it to the
-// compiled queue).  Returns the index of an entry of the SAME queue that can be overwritten in place, or -1.
-int64_t claim_slot(hb2_partition *p, int64_t slot, bool compiled) {
+// Retire the pending entry of `slot` if it sits in ANOTHER queue than the one it is about to join (tmpl < 0: the dense
+// queue; >= 0: that template's compiled queue).  Returns the index of an entry of the SAME queue that can be overwritten
+// in place, or -1.
+int64_t claim_slot(hb2_partition *p, int64_t slot, int tmpl) {
     const int pos = p->pend_pos[slot];
     if (pos == -1) return -1;
     if (pos >= 0) {                            // pending in the dense queue
-        if (!compiled) return pos;
+        if (tmpl < 0) return pos;
         p->h_dst[pos] = -1;
-    } else {                                   // pending in the compiled queue
-        if (compiled) return -(int64_t)pos - 2;
-        p->h_vdst[-(int64_t)pos - 2] = -1;
+    } else {                                   // pending in a compiled queue
+        const int pt = p->pend_tmpl[slot];
+        if (pt == tmpl) return -(int64_t)pos - 2;
+        p->tmpls[pt].h_vdst[-(int64_t)pos - 2] = -1;
     }
     p->pend_pos[slot] = -1;
     return -1;
@@ -406,7 +417,7 @@ int stage_matrix(hb2_partition *p, int64_t cat, int64_t node, const double *M, i
     if (cat < p->own0 || cat >= p->own0 + p->ownN) { p->have_matrix[cat * p->B + node] = 1; return 0; }   // another class group's
     if (wait_staging(p)) return 1;            // previous flush's H2D copies must have left the pinned buffers
     const int64_t slot = cat * p->B + node;
-    int64_t at = claim_slot(p, slot, false);
+    int64_t at = claim_slot(p, slot, -1);
     if (at < 0) {
         if (p->n_pending == p->q_capacity) {
             cudaSetDevice(p->device);
@@ -1101,7 +1112,7 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
     if (Dp == 32) CUP(cudaFuncSetAttribute(hb2::expm_small_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hb2::expm_small_smem_bytes(32)));
     if (Dp == 64) {
         { const char *env = getenv("HB2_EXPM_SHARED"); p->ex_enabled = !(env && env[0] == '0'); }
-        p->ex_G = (int)C + 8; p->ex_cap = (int64_t)(C + 8) * p->B; p->ex_stride = 4096;
+        p->ex_G = std::max((int)C + 8, HB2_MAX_TEMPLATES * (int)C); p->ex_cap = (int64_t)(C + 8) * p->B; p->ex_stride = 4096;
         p->ex_kind.assign(p->ex_G, 0);
         CUP(cudaMalloc(&p->d_ex_int, (size_t)(2 * p->ex_cap + p->ex_G) * sizeof(int)));
         CUP(cudaMallocHost(&p->h_ex_int, (size_t)(2 * p->ex_cap + p->ex_G) * sizeof(int)));
@@ -1127,6 +1138,8 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
     p->have_matrix.assign(C * p->B, 0);
     p->is_rate.assign(C * p->B, 0);
     p->pend_pos.assign(C * p->B, -1);
+    p->pend_tmpl.assign(C * p->B, 0);
+    p->res_tmpl.assign(C * p->B, 0);
     p->evaluated_cat.assign(C, 0);
     p->own0 = 0; p->ownN = (int)C;
     *out = p;
@@ -1179,8 +1192,6 @@ int hb2_set_mixture_matrices(hb2_partition *p, int64_t cat, int64_t n, const int
         CU(cudaStreamSynchronize(p->stream));
         for (void *d : {(void *)p->d_mix_scratch, (void *)p->d_mix_Q, (void *)p->d_mix_dst}) if (d) cudaFree(d);
         if (p->h_mix) cudaFreeHost(p->h_mix);
-    if (p->h_forced) cudaFreeHost(p->h_forced);
-    if (p->h_ex_int) cudaFreeHost(p->h_ex_int);
         p->d_mix_scratch = p->d_mix_Q = nullptr; p->d_mix_dst = nullptr; p->h_mix = nullptr; p->mix_capacity = 0;
         CU(cudaMalloc(&p->d_mix_scratch, (size_t)nk * dpdp * sizeof(double)));
         CU(cudaMalloc(&p->d_mix_Q, (size_t)nk * (dd + 1) * sizeof(double)));
@@ -1217,9 +1228,16 @@ int hb2_set_mixture_matrices(hb2_partition *p, int64_t cat, int64_t n, const int
     return 0;
 }
 
-int hb2_set_rate_template(hb2_partition *p, int64_t nnz, const int64_t *entryIndex, const int64_t *entryFormula,
-                          int64_t nFormulas, const double *colFreq) {
+static void free_template(hb2_partition::Tmpl &t) {
+    for (void *d : {(void *)t.d_index, (void *)t.d_formula, (void *)t.d_vdst, (void *)t.d_colfreq, (void *)t.d_V, (void *)t.d_Vres}) if (d) cudaFree(d);
+    for (void *h : {(void *)t.h_vdst, (void *)t.h_colfreq, (void *)t.h_V}) if (h) cudaFreeHost(h);
+    t = hb2_partition::Tmpl();
+}
+
+int hb2_set_rate_template_id(hb2_partition *p, int64_t templateId, int64_t nnz, const int64_t *entryIndex, const int64_t *entryFormula,
+                             int64_t nFormulas, const double *colFreq) {
     if (!p) return fail("null partition");
+    if (templateId < 0 || templateId >= HB2_MAX_TEMPLATES) return fail("template id %lld out of range (0..%d)", (long long)templateId, HB2_MAX_TEMPLATES - 1);
     if (nnz < 1 || nFormulas < 1 || !entryIndex || !entryFormula) return fail("bad template arguments");
     CU(cudaSetDevice(p->device));
     if (flush_matrices(p)) return 1;
@@ -1231,39 +1249,65 @@ int hb2_set_rate_template(hb2_partition *p, int64_t nnz, const int64_t *entryInd
         if (entryFormula[e] < 0 || entryFormula[e] >= nFormulas) return fail("template entry %lld: formula %lld out of range", (long long)e, (long long)entryFormula[e]);
         idx[e] = (int)entryIndex[e]; frm[e] = (int)entryFormula[e];
     }
-    void *old[] = {p->d_t_index, p->d_t_formula, p->d_t_colfreq, p->d_V, p->d_vdst, p->d_Vres};
-    p->d_Vres = nullptr;
-    for (void *d : old) if (d) cudaFree(d);
-    if (p->h_V) cudaFreeHost(p->h_V);
-    if (p->h_vdst) cudaFreeHost(p->h_vdst);
-    p->d_t_index = p->d_t_formula = p->d_vdst = nullptr; p->d_t_colfreq = p->d_V = nullptr; p->h_V = nullptr; p->h_vdst = nullptr;
-    CU(cudaMalloc(&p->d_t_index, nnz * sizeof(int)));
-    CU(cudaMalloc(&p->d_t_formula, nnz * sizeof(int)));
-    CU(cudaMalloc(&p->d_t_colfreq, p->D * sizeof(double)));
-    CU(cudaMalloc(&p->d_V, (size_t)p->q_capacity * nFormulas * sizeof(double)));
-    CU(cudaMalloc(&p->d_vdst, p->q_capacity * sizeof(int)));
-    if (p->d_ex_groups) {                      // resident formula values of every slot + cached directions of the old template are void
-        CU(cudaMalloc(&p->d_Vres, (size_t)p->C * p->B * nFormulas * sizeof(double)));
-        CU(cudaMemset(p->d_ex_groups, 0, (size_t)p->ex_G * sizeof(hb2::ExpmGroup)));
-        std::fill(p->ex_kind.begin(), p->ex_kind.end(), 0);
-        for (auto &r : p->is_rate) if (r == 2) r = 0;
+    if ((int64_t)p->tmpls.size() <= templateId) p->tmpls.resize(templateId + 1);
+    hb2_partition::Tmpl &t = p->tmpls[templateId];
+    free_template(t);
+    CU(cudaMalloc(&t.d_index, nnz * sizeof(int)));
+    CU(cudaMalloc(&t.d_formula, nnz * sizeof(int)));
+    CU(cudaMalloc(&t.d_colfreq, p->D * sizeof(double)));
+    CU(cudaMallocHost(&t.h_colfreq, p->D * sizeof(double)));
+    CU(cudaMalloc(&t.d_V, (size_t)p->q_capacity * nFormulas * sizeof(double)));
+    CU(cudaMalloc(&t.d_vdst, p->q_capacity * sizeof(int)));
+    // resident formula values of every slot (replay, shared-powers classification); cached directions of this template's
+    // groups are void now
+    CU(cudaMalloc(&t.d_Vres, (size_t)p->C * p->B * nFormulas * sizeof(double)));
+    if (p->d_ex_groups) {
+        for (int c = 0; c < (int)p->C; c++) {
+            const int g = (int)templateId * (int)p->C + c;
+            if (g < p->ex_G) {
+                CU(cudaMemset(static_cast<hb2::ExpmGroup *>(p->d_ex_groups) + g, 0, sizeof(hb2::ExpmGroup)));
+                p->ex_kind[g] = 0;
+            }
+        }
     }
-    CU(cudaMallocHost(&p->h_V, (size_t)p->q_capacity * nFormulas * sizeof(double)));
-    CU(cudaMallocHost(&p->h_vdst, p->q_capacity * sizeof(int)));
-    CU(cudaMemcpy(p->d_t_index, idx.data(), nnz * sizeof(int), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(p->d_t_formula, frm.data(), nnz * sizeof(int), cudaMemcpyHostToDevice));
-    p->t_has_colfreq = colFreq != nullptr;
-    if (colFreq) CU(cudaMemcpy(p->d_t_colfreq, colFreq, p->D * sizeof(double), cudaMemcpyHostToDevice));
-    p->t_nnz = nnz; p->t_nF = nFormulas; p->n_vpending = 0;
+    for (size_t k = 0; k < p->is_rate.size(); k++) if (p->is_rate[k] == 2 && p->res_tmpl[k] == templateId) p->is_rate[k] = 0;
+    CU(cudaMallocHost(&t.h_V, (size_t)p->q_capacity * nFormulas * sizeof(double)));
+    CU(cudaMallocHost(&t.h_vdst, p->q_capacity * sizeof(int)));
+    CU(cudaMemcpy(t.d_index, idx.data(), nnz * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(t.d_formula, frm.data(), nnz * sizeof(int), cudaMemcpyHostToDevice));
+    t.has_colfreq = colFreq != nullptr;
+    if (colFreq) CU(cudaMemcpy(t.d_colfreq, colFreq, p->D * sizeof(double), cudaMemcpyHostToDevice));
+    t.nnz = nnz; t.nF = nFormulas; t.n_pending = 0;
     return 0;
 }
 
-int hb2_set_matrices_compiled(hb2_partition *p, int64_t cat, int64_t n, const int64_t *nodeIds, const double *formulaValues) {
+int hb2_set_rate_template(hb2_partition *p, int64_t nnz, const int64_t *entryIndex, const int64_t *entryFormula,
+                          int64_t nFormulas, const double *colFreq) {
+    return hb2_set_rate_template_id(p, 0, nnz, entryIndex, entryFormula, nFormulas, colFreq);
+}
+
+int hb2_set_template_frequencies(hb2_partition *p, int64_t templateId, const double *colFreq) {
+    if (!p || !colFreq) return fail("null argument");
+    if (templateId < 0 || templateId >= (int64_t)p->tmpls.size() || p->tmpls[templateId].nnz == 0) return fail("template %lld has not been defined", (long long)templateId);
+    hb2_partition::Tmpl &t = p->tmpls[templateId];
+    if (!t.has_colfreq) return fail("template %lld was defined without column frequencies", (long long)templateId);
+    CU(cudaSetDevice(p->device));
+    if (flush_matrices(p)) return 1;          // matrices handed over so far were assembled with the old frequencies
+    if (wait_staging(p)) return 1;
+    memcpy(t.h_colfreq, colFreq, p->D * sizeof(double));
+    CU(cudaMemcpyAsync(t.d_colfreq, t.h_colfreq, p->D * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    CU(cudaEventRecord(p->ev_staging, p->stream));
+    p->staging_busy = true;
+    return 0;
+}
+
+int hb2_set_matrices_compiled_id(hb2_partition *p, int64_t templateId, int64_t cat, int64_t n, const int64_t *nodeIds, const double *formulaValues) {
     if (!p) return fail("null partition");
-    if (p->t_nnz == 0) return fail("hb2_set_rate_template has not been called");
+    if (templateId < 0 || templateId >= (int64_t)p->tmpls.size() || p->tmpls[templateId].nnz == 0) return fail("hb2_set_rate_template has not been called (template %lld)", (long long)templateId);
     if (n < 0 || (n > 0 && (!nodeIds || !formulaValues))) return fail("bad compiled matrix list");
     if (cat < 0) cat = 0;
     if (cat >= p->C) return fail("rate class %lld out of range (C=%lld)", (long long)cat, (long long)p->C);
+    hb2_partition::Tmpl &t = p->tmpls[templateId];
     const bool owned = cat >= p->own0 && cat < p->own0 + p->ownN;
     for (int64_t k = 0; k < n; k++) {
         if (nodeIds[k] < 0 || nodeIds[k] >= p->B) return fail("node id %lld has no branch", (long long)nodeIds[k]);
@@ -1272,19 +1316,24 @@ int hb2_set_matrices_compiled(hb2_partition *p, int64_t cat, int64_t n, const in
     }
     if (!owned) return 0;                                   // another class group's matrices
     if (wait_staging(p)) return 1;
-    const size_t row = (size_t)p->t_nF * sizeof(double);
+    const size_t row = (size_t)t.nF * sizeof(double);
     for (int64_t k = 0; k < n; k++) {
         const int64_t slot = cat * p->B + nodeIds[k];
-        int64_t at = claim_slot(p, slot, true);
+        int64_t at = claim_slot(p, slot, (int)templateId);
         if (at < 0) {
-            if (p->n_vpending == p->q_capacity) { cudaSetDevice(p->device); if (flush_compiled(p) || wait_staging(p)) return 1; }
-            at = p->n_vpending++;
+            if (t.n_pending == p->q_capacity) { cudaSetDevice(p->device); if (flush_compiled(p) || wait_staging(p)) return 1; }
+            at = t.n_pending++;
             p->pend_pos[slot] = (int)(-at - 2);
+            p->pend_tmpl[slot] = (signed char)templateId;
         }
-        memcpy(p->h_V + at * p->t_nF, formulaValues + k * p->t_nF, row);
-        p->h_vdst[at] = (int)slot;
+        memcpy(t.h_V + at * t.nF, formulaValues + k * t.nF, row);
+        t.h_vdst[at] = (int)slot;
     }
     return 0;
+}
+
+int hb2_set_matrices_compiled(hb2_partition *p, int64_t cat, int64_t n, const int64_t *nodeIds, const double *formulaValues) {
+    return hb2_set_matrices_compiled_id(p, 0, cat, n, nodeIds, formulaValues);
 }
 
 int hb2_evaluate(hb2_partition *p, int64_t cat, int64_t nUpdate, const int64_t *updateNodes, const double *rootFreqs,
@@ -1506,7 +1555,7 @@ int hb2_comm_class_groups(hb2_partition *p, int nGroups) {
     if (!p->comm) return fail("hb2_comm_class_groups needs hb2_comm_init first");
     if (nGroups < 1 || p->C % nGroups != 0 || p->n_ranks % nGroups != 0)
         return fail("class groups: %d must divide both the %lld rate classes and the %d ranks", nGroups, (long long)p->C, p->n_ranks);
-    if (p->n_pending || p->n_vpending) return fail("hb2_comm_class_groups must be called before matrices are set");
+    if (p->n_pending) return fail("hb2_comm_class_groups must be called before matrices are set");
     for (char h : p->have_matrix) if (h) return fail("hb2_comm_class_groups must be called before matrices are set");
     CU(cudaSetDevice(p->device));
     p->cg_G = nGroups; p->cg_g = p->rank % nGroups;
@@ -1547,14 +1596,13 @@ void hb2_destroy(hb2_partition *p) {
     if (p->comm) g_nccl.CommDestroy(p->comm);
     void *dev[] = {p->d_leaf, p->d_scal, p->d_rootE, p->d_child_start, p->d_child_ids, p->d_jobs, p->d_dst, p->d_flag,
                    p->d_mix_dst, p->d_mix_Q, p->d_ambig, p->d_freq, p->d_cond, p->d_PT, p->d_Q, p->d_pi, p->d_rootL, p->d_weights,
-                   p->d_partial, p->d_lnL, p->d_siteL, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_xsend, p->d_xrecv, p->d_xfreq, p->d_xpartial, p->d_bc_out, p->d_bc_outE, p->d_bc_sib, p->d_walk, p->d_t_index, p->d_t_formula, p->d_vdst, p->d_t_colfreq, p->d_V, p->d_forced, p->d_ex_int, p->d_ex_flag, p->d_ex_weight, p->d_ex_groups, p->d_ex_pow, p->d_ex_refvec, p->d_Vres, p->d_ex_flags};
+                   p->d_partial, p->d_lnL, p->d_siteL, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_xsend, p->d_xrecv, p->d_xfreq, p->d_xpartial, p->d_bc_out, p->d_bc_outE, p->d_bc_sib, p->d_walk, p->d_forced, p->d_ex_int, p->d_ex_flag, p->d_ex_weight, p->d_ex_groups, p->d_ex_pow, p->d_ex_refvec, p->d_ex_flags};
     for (void *d : dev) if (d) cudaFree(d);
     if (p->h_Q) cudaFreeHost(p->h_Q);
     if (p->h_small) cudaFreeHost(p->h_small);
     if (p->h_jobs) cudaFreeHost(p->h_jobs);
     if (p->h_dst) cudaFreeHost(p->h_dst);
-    if (p->h_V) cudaFreeHost(p->h_V);
-    if (p->h_vdst) cudaFreeHost(p->h_vdst);
+    for (auto &t : p->tmpls) free_template(t);
     if (p->h_walk) cudaFreeHost(p->h_walk);
     if (p->h_mix) cudaFreeHost(p->h_mix);
     if (p->h_forced) cudaFreeHost(p->h_forced);
@@ -1595,6 +1643,7 @@ int hb2_time_resident(hb2_partition *p, const double *weights, const double *roo
     for (int64_t k = (int64_t)p->own0 * p->B; k < (int64_t)(p->own0 + p->ownN) * p->B; k++) {
         if (!p->is_rate[k]) return fail("hb2_time_resident needs HB2_MATRIX_RATE matrices in every slot");
         if (res_kind && res_kind != p->is_rate[k]) return fail("hb2_time_resident: hand all matrices over the same way (dense or compiled) before timing");
+        if (p->is_rate[k] == 2 && p->res_tmpl[k] != 0) return fail("hb2_time_resident replays template 0 only");
         res_kind = p->is_rate[k];
         dst.push_back((int)k);
     }
@@ -1618,7 +1667,7 @@ int hb2_time_resident(hb2_partition *p, const double *weights, const double *roo
         CU(cudaEventRecord(p->ev[0], p->stream));
         const int64_t l0 = p->launches;
         if (res_kind == 2) {
-            if (launch_expm(p, p->d_Vres + (size_t)p->own0 * p->B * p->t_nF, p->d_dst, (int)dst.size(), 2, nullptr, true, nullptr, &sp)) return 1;
+            if (launch_expm(p, p->tmpls[0].d_Vres + (size_t)p->own0 * p->B * p->tmpls[0].nF, p->d_dst, (int)dst.size(), 2, nullptr, true, nullptr, &sp)) return 1;
         } else if (launch_expm(p, p->d_Qres + (size_t)p->own0 * p->B * p->D * p->D, p->d_dst, (int)dst.size(), 0, nullptr, true, nullptr, &sp)) return 1;
         const int64_t l1 = p->launches;
         CU(cudaEventRecord(p->ev[1], p->stream));

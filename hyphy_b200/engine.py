@@ -35,6 +35,9 @@ ABI = [
     ("hb2_set_matrices_packed", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _ip, _dp, C.c_int]),
     ("hb2_set_rate_template", C.c_int, [C.c_void_p, C.c_int64, _ip, _ip, C.c_int64, _dp]),
     ("hb2_set_matrices_compiled", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _ip, _dp]),
+    ("hb2_set_rate_template_id", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _ip, _ip, C.c_int64, _dp]),
+    ("hb2_set_matrices_compiled_id", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, _ip, _dp]),
+    ("hb2_set_template_frequencies", C.c_int, [C.c_void_p, C.c_int64, _dp]),
     ("hb2_set_mixture_matrices", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _ip, C.c_int64, _dp, _dp]),
     ("hb2_evaluate", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _ip, _dp, _dp, _dp, _ip]),
     ("hb2_evaluate_forced", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _ip, _dp, C.c_int64, _ip, _dp, _dp, _ip]),
@@ -165,11 +168,23 @@ class Partition:
         self.n_formulas = int(n_formulas)
         _check(self._lib.hb2_set_rate_template(self._h, len(ei), pei, pef, int(n_formulas), pcf))
 
-    def set_matrices_compiled(self, cat, node_ids, values):
+    def set_matrices_compiled(self, cat, node_ids, values, template=0):
         ids, pids = _i(node_ids)
         v, pv = _d(values)
-        assert v.shape == (len(ids), self.n_formulas)
-        _check(self._lib.hb2_set_matrices_compiled(self._h, int(cat), len(ids), pids, pv))
+        assert v.shape[0] == len(ids)
+        _check(self._lib.hb2_set_matrices_compiled_id(self._h, int(template), int(cat), len(ids), pids, pv))
+
+    def set_rate_template_id(self, template, entry_index, entry_formula, n_formulas, col_freq=None):
+        ei, pei = _i(entry_index)
+        ef, pef = _i(entry_formula)
+        pcf = None
+        if col_freq is not None:
+            cf, pcf = _d(col_freq)
+        _check(self._lib.hb2_set_rate_template_id(self._h, int(template), len(ei), pei, pef, int(n_formulas), pcf))
+
+    def set_template_frequencies(self, template, col_freq):
+        cf, pcf = _d(col_freq)
+        _check(self._lib.hb2_set_template_frequencies(self._h, int(template), pcf))
 
     def set_mixture_matrices(self, cat, node_ids, M, w):
         ids, pids = _i(node_ids)

@@ -82,6 +82,16 @@ int hb2_set_rate_template(hb2_partition *p, int64_t nnz, const int64_t *entryInd
                           int64_t nFormulas, const double *colFreq);
 int hb2_set_matrices_compiled(hb2_partition *p, int64_t cat, int64_t n, const int64_t *nodeIds,
                               const double *formulaValues);
+/* Several models on one tree (foreground / background branches of RELAX and BUSTED, per-branch models of aBSREL; every
+ * _CalcNode carries its own model index, calcnode.h): one template per model matrix, ids 0..HB2_MAX_TEMPLATES-1; the two
+ * calls above are the id-0 forms.  hb2_set_template_frequencies replaces colFreq when the model's equilibrium
+ * frequencies are themselves being estimated (cheap: D doubles, no reallocation). */
+#define HB2_MAX_TEMPLATES 16
+int hb2_set_rate_template_id(hb2_partition *p, int64_t templateId, int64_t nnz, const int64_t *entryIndex,
+                             const int64_t *entryFormula, int64_t nFormulas, const double *colFreq);
+int hb2_set_matrices_compiled_id(hb2_partition *p, int64_t templateId, int64_t cat, int64_t n, const int64_t *nodeIds,
+                                 const double *formulaValues);
+int hb2_set_template_frequencies(hb2_partition *p, int64_t templateId, const double *colFreq);
 
 /* Explicit-form mixtures P = sum_k w_k Exp(Q_k) per branch (BS-REL; tree.cpp:3047-3089):
  * K components for each listed node, M packed [n][K][D*D], w packed [n][K].  Asynchronous like the other hand-overs
