@@ -118,13 +118,21 @@ struct hb2_partition {
     bool mix_busy = false;
     // shared-powers expm (64 padded states, hb2_kernels_fp64.cuh "Shared powers"): group = rate class (plain batches) or
     // C + mixture component; per-entry arrays are indexed like the batch
-    int ex_G = 0, ex_stride = 0;              // groups, doubles per cached reference direction
-    int *d_ex_int = nullptr, *h_ex_int = nullptr, *d_ex_flag = nullptr;     // [group cap | ref cap | refs G]
-    double *d_ex_weight = nullptr, *d_ex_pow = nullptr, *d_ex_refvec = nullptr;
-    void *d_ex_groups = nullptr;
-    unsigned long long *d_ex_flags = nullptr, ex_gen = 0;   // generation flags of the coefficient matrices [G][EXPM_POW_TERMS]
-    std::vector<int> ex_kind;                 // host mirror: kind of the reference direction each group holds (0 none)
-    int64_t ex_cap = 0;
+    struct ExBuf {
+        int G = 0, stride = 0;                // groups, doubles per cached reference direction
+        int *d_int = nullptr, *h_int = nullptr, *d_flag = nullptr;     // [group cap | ref cap | refs G]
+        double *d_weight = nullptr, *d_pow = nullptr, *d_refvec = nullptr;
+        void *d_groups = nullptr;
+        unsigned long long *d_flags = nullptr, gen = 0;   // generation flags of the coefficient matrices [G][EXPM_POW_TERMS]
+        std::vector<int> kind;                // host mirror: kind of the reference direction each group holds (0 none)
+        int64_t cap = 0;
+    };
+    ExBuf ex;                                 // the partition's own hand-overs
+    ExBuf bex;                                // batched one-pattern likelihoods (hb2_batch_site_likelihoods): one group per set
+    int64_t b_cap = 0;                        // sets per chunk of the batch buffers below
+    double *d_bPT = nullptr, *d_bV = nullptr, *d_bcond = nullptr, *d_bout = nullptr;
+    int *d_bdst = nullptr, *d_bpat = nullptr, *d_bnodeex = nullptr, *h_bdst = nullptr;
+    int b_groups_per_set = 1;
     bool ex_enabled = true;                   // HB2_EXPM_SHARED=0 switches the path off (A/B testing)
     int64_t stage_launches[3] = {0, 0, 0};    // launches per evaluation of the last hb2_time_resident {expm, pruning, root}
     // compiled rate-matrix templates (hb2_set_rate_template*): static scatter map + own queue of per-evaluation formula
@@ -202,33 +210,37 @@ int wait_staging(hb2_partition *p) {
 struct SharedPlan {
     bool use = false;
     int kind = 0, n_refs = 0, tmpl = 0;
+    hb2_partition::ExBuf *x = nullptr;
 };
 constexpr int EX_MIN_GROUP = 24;
 
-int plan_shared(hb2_partition *p, const int *h_dst, int64_t n, int kind, const int *group_override, SharedPlan &sp, int tmpl = 0) {
+int plan_shared(hb2_partition *p, const int *h_dst, int64_t n, int kind, const int *group_override, SharedPlan &sp, int tmpl = 0,
+                hb2_partition::ExBuf *bx = nullptr, int min_group = EX_MIN_GROUP) {
     sp = SharedPlan();
-    if (p->Dp != 64 || p->expm_dfma || !p->ex_enabled || !p->d_ex_int || n <= 0 || n > p->ex_cap) return 0;
+    hb2_partition::ExBuf &x = bx ? *bx : p->ex;
+    sp.x = &x;
+    if (p->Dp != 64 || p->expm_dfma || !p->ex_enabled || !x.d_int || n <= 0 || n > x.cap) return 0;
     if (kind == 1 && !p->tmpls[tmpl].d_Vres) return 0;
     if (wait_staging(p)) return 1;            // an earlier plan's upload may still be reading the pinned arrays
-    int *grp = p->h_ex_int, *ref = p->h_ex_int + p->ex_cap, *refs = p->h_ex_int + 2 * p->ex_cap;
-    std::vector<int> count(p->ex_G, 0), first(p->ex_G, -1);
+    int *grp = x.h_int, *ref = x.h_int + x.cap, *refs = x.h_int + 2 * x.cap;
+    std::vector<int> count(x.G, 0), first(x.G, -1);
     for (int64_t k = 0; k < n; k++) {
         int g = -1;
         if (h_dst[k] >= 0) g = group_override ? group_override[k] : (int)(h_dst[k] / p->B) + tmpl * (int)p->C;   // (template, class)
-        if (g >= p->ex_G) g = -1;
+        if (g >= x.G) g = -1;
         grp[k] = g;
         if (g >= 0) { if (first[g] < 0) first[g] = (int)k; count[g]++; }
     }
     bool any = false;
     int nr = 0;
-    for (int g = 0; g < p->ex_G; g++) {
-        if (count[g] >= EX_MIN_GROUP) { refs[nr++] = first[g]; any = true; }
-        else { first[g] = -1; if (count[g] > 0 && p->ex_kind[g] == kind) any = true; }
+    for (int g = 0; g < x.G; g++) {
+        if (count[g] >= min_group) { refs[nr++] = first[g]; any = true; }
+        else { first[g] = -1; if (count[g] > 0 && x.kind[g] == kind) any = true; }
     }
     if (!any) return 0;
     for (int64_t k = 0; k < n; k++) ref[k] = grp[k] >= 0 ? first[grp[k]] : -1;
-    for (int r = 0; r < nr; r++) p->ex_kind[grp[refs[r]]] = kind;
-    CU(cudaMemcpyAsync(p->d_ex_int, p->h_ex_int, (size_t)(2 * p->ex_cap + p->ex_G) * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    for (int r = 0; r < nr; r++) x.kind[grp[refs[r]]] = kind;
+    CU(cudaMemcpyAsync(x.d_int, x.h_int, (size_t)(2 * x.cap + x.G) * sizeof(int), cudaMemcpyHostToDevice, p->stream));
     sp.use = true; sp.kind = kind; sp.n_refs = nr; sp.tmpl = tmpl;
     return 0;
 }
@@ -257,23 +269,24 @@ int launch_expm(hb2_partition *p, const double *dQ, const int *d_dst, int n, int
             } else {
                 const size_t smem = 3 * 64 * hb2::LD64 * sizeof(double);
                 if (sp && sp->use && is_trans != 1) {
+                    hb2_partition::ExBuf &x = *sp->x;
                     const int nV = sp->kind == 1 ? (int)p->tmpls[tmpl].nF : (int)(p->D * p->D);
-                    const hb2::ExpmGroup *groups = static_cast<const hb2::ExpmGroup *>(p->d_ex_groups);
+                    const hb2::ExpmGroup *groups = static_cast<const hb2::ExpmGroup *>(x.d_groups);
                     hb2::ExpmClassifyArgs ca{};
-                    ca.V = dQ; ca.nV = nV; ca.kind = sp->kind; ca.dst = d_dst; ca.group = p->d_ex_int + off;
-                    ca.ref = p->d_ex_int + p->ex_cap + off; ca.groups = groups; ca.refvec = p->d_ex_refvec; ca.refvec_stride = p->ex_stride;
-                    ca.weight = p->d_ex_weight + off; ca.flag = p->d_ex_flag + off;
-                    ca.res = sp->kind == 1 ? p->tmpls[tmpl].d_Vres : qres;
+                    ca.V = dQ; ca.nV = nV; ca.kind = sp->kind; ca.dst = d_dst; ca.group = x.d_int + off;
+                    ca.ref = x.d_int + x.cap + off; ca.groups = groups; ca.refvec = x.d_refvec; ca.refvec_stride = x.stride;
+                    ca.weight = x.d_weight + off; ca.flag = x.d_flag + off;
+                    ca.res = pt_override ? nullptr : (sp->kind == 1 ? p->tmpls[tmpl].d_Vres : qres);   // scratch targets keep no resident copy
                     // references index the whole batch: classification has to see it in one piece (off == 0 for compiled batches
                     // and for dense batches that consist of a single run; mixed dense batches fall back below)
                     hb2::expm_classify_kernel<<<n, 128, 0, p->stream>>>(ca);
-                    a.group = ca.group; a.flag = ca.flag; a.weight = ca.weight; a.groups = groups; a.pow = p->d_ex_pow;
+                    a.group = ca.group; a.flag = ca.flag; a.weight = ca.weight; a.groups = groups; a.pow = x.d_pow;
                     a.Qres = nullptr;                    // the classification stage keeps the resident copy
                     if (sp->n_refs > 0) {
                         hb2::ExpmPowersArgs pa{};
-                        pa.a = a; pa.refs = p->d_ex_int + 2 * p->ex_cap; pa.groups = static_cast<hb2::ExpmGroup *>(p->d_ex_groups);
-                        pa.pow = p->d_ex_pow; pa.refvec = p->d_ex_refvec; pa.refvec_stride = p->ex_stride; pa.nV = nV; pa.kind = sp->kind; pa.Vin = dQ;
-                        pa.flags = p->d_ex_flags; pa.gen = ++p->ex_gen; pa.err = p->d_err;
+                        pa.a = a; pa.refs = x.d_int + 2 * x.cap; pa.groups = static_cast<hb2::ExpmGroup *>(x.d_groups);
+                        pa.pow = x.d_pow; pa.refvec = x.d_refvec; pa.refvec_stride = x.stride; pa.nV = nV; pa.kind = sp->kind; pa.Vin = dQ;
+                        pa.flags = x.d_flags; pa.gen = ++x.gen; pa.err = p->d_err;
                         hb2::expm_powers_kernel<<<dim3(hb2::EXPM_POW_TERMS - 1, (unsigned)sp->n_refs), 256, smem, p->stream>>>(pa);
                         p->launches++;
                     }
@@ -1112,18 +1125,18 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
     if (Dp == 32) CUP(cudaFuncSetAttribute(hb2::expm_small_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hb2::expm_small_smem_bytes(32)));
     if (Dp == 64) {
         { const char *env = getenv("HB2_EXPM_SHARED"); p->ex_enabled = !(env && env[0] == '0'); }
-        p->ex_G = std::max((int)C + 8, HB2_MAX_TEMPLATES * (int)C); p->ex_cap = (int64_t)(C + 8) * p->B; p->ex_stride = 4096;
-        p->ex_kind.assign(p->ex_G, 0);
-        CUP(cudaMalloc(&p->d_ex_int, (size_t)(2 * p->ex_cap + p->ex_G) * sizeof(int)));
-        CUP(cudaMallocHost(&p->h_ex_int, (size_t)(2 * p->ex_cap + p->ex_G) * sizeof(int)));
-        CUP(cudaMalloc(&p->d_ex_flag, (size_t)p->ex_cap * sizeof(int)));
-        CUP(cudaMalloc(&p->d_ex_weight, (size_t)p->ex_cap * sizeof(double)));
-        CUP(cudaMalloc(&p->d_ex_groups, (size_t)p->ex_G * sizeof(hb2::ExpmGroup)));
-        CUP(cudaMemsetAsync(p->d_ex_groups, 0, (size_t)p->ex_G * sizeof(hb2::ExpmGroup), p->stream));
-        CUP(cudaMalloc(&p->d_ex_pow, (size_t)p->ex_G * hb2::EXPM_POW_TERMS * 4096 * sizeof(double)));
-        CUP(cudaMalloc(&p->d_ex_flags, (size_t)p->ex_G * hb2::EXPM_POW_TERMS * sizeof(unsigned long long)));
-        CUP(cudaMemsetAsync(p->d_ex_flags, 0, (size_t)p->ex_G * hb2::EXPM_POW_TERMS * sizeof(unsigned long long), p->stream));
-        CUP(cudaMalloc(&p->d_ex_refvec, (size_t)p->ex_G * p->ex_stride * sizeof(double)));
+        p->ex.G = std::max((int)C + 8, HB2_MAX_TEMPLATES * (int)C); p->ex.cap = (int64_t)(C + 8) * p->B; p->ex.stride = 4096;
+        p->ex.kind.assign(p->ex.G, 0);
+        CUP(cudaMalloc(&p->ex.d_int, (size_t)(2 * p->ex.cap + p->ex.G) * sizeof(int)));
+        CUP(cudaMallocHost(&p->ex.h_int, (size_t)(2 * p->ex.cap + p->ex.G) * sizeof(int)));
+        CUP(cudaMalloc(&p->ex.d_flag, (size_t)p->ex.cap * sizeof(int)));
+        CUP(cudaMalloc(&p->ex.d_weight, (size_t)p->ex.cap * sizeof(double)));
+        CUP(cudaMalloc(&p->ex.d_groups, (size_t)p->ex.G * sizeof(hb2::ExpmGroup)));
+        CUP(cudaMemsetAsync(p->ex.d_groups, 0, (size_t)p->ex.G * sizeof(hb2::ExpmGroup), p->stream));
+        CUP(cudaMalloc(&p->ex.d_pow, (size_t)p->ex.G * hb2::EXPM_POW_TERMS * 4096 * sizeof(double)));
+        CUP(cudaMalloc(&p->ex.d_flags, (size_t)p->ex.G * hb2::EXPM_POW_TERMS * sizeof(unsigned long long)));
+        CUP(cudaMemsetAsync(p->ex.d_flags, 0, (size_t)p->ex.G * hb2::EXPM_POW_TERMS * sizeof(unsigned long long), p->stream));
+        CUP(cudaMalloc(&p->ex.d_refvec, (size_t)p->ex.G * p->ex.stride * sizeof(double)));
         CUP(cudaFuncSetAttribute(hb2::expm_powers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * 64 * hb2::LD64 * sizeof(double))));
         CUP(cudaFuncSetAttribute(hb2::expm64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(5 * 64 * hb2::LD64 * sizeof(double))));
         CUP(cudaFuncSetAttribute(hb2::expm64_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * 64 * hb2::LD64 * sizeof(double))));
@@ -1261,12 +1274,12 @@ int hb2_set_rate_template_id(hb2_partition *p, int64_t templateId, int64_t nnz, 
     // resident formula values of every slot (replay, shared-powers classification); cached directions of this template's
     // groups are void now
     CU(cudaMalloc(&t.d_Vres, (size_t)p->C * p->B * nFormulas * sizeof(double)));
-    if (p->d_ex_groups) {
+    if (p->ex.d_groups) {
         for (int c = 0; c < (int)p->C; c++) {
             const int g = (int)templateId * (int)p->C + c;
-            if (g < p->ex_G) {
-                CU(cudaMemset(static_cast<hb2::ExpmGroup *>(p->d_ex_groups) + g, 0, sizeof(hb2::ExpmGroup)));
-                p->ex_kind[g] = 0;
+            if (g < p->ex.G) {
+                CU(cudaMemset(static_cast<hb2::ExpmGroup *>(p->ex.d_groups) + g, 0, sizeof(hb2::ExpmGroup)));
+                p->ex.kind[g] = 0;
             }
         }
     }
@@ -1358,6 +1371,98 @@ int hb2_evaluate_classes(hb2_partition *p, const double *weights, int64_t nUpdat
     if (!p) return fail("null partition");
     if (!weights) return fail("weights must not be null");
     return evaluate_impl(p, 0, (int)p->C, weights, nUpdate, updateNodes, rootFreqs, lnL, siteL, siteScale);
+}
+
+int hb2_batch_site_likelihoods(hb2_partition *p, int64_t templateId, int64_t nSets, const int64_t *patternOf,
+                               const double *formulaValues, const int64_t *branchGroup, const double *rootFreqs, double *siteLnL) {
+    if (!p || !patternOf || !formulaValues || !rootFreqs || !siteLnL) return fail("null argument");
+    if (nSets < 0) return fail("bad set count");
+    if (p->Dp != 64) return fail("hb2_batch_site_likelihoods supports 33..64-state (codon) partitions only");
+    if (templateId < 0 || templateId >= (int64_t)p->tmpls.size() || p->tmpls[templateId].nnz == 0) return fail("template %lld has not been defined", (long long)templateId);
+    if (p->cg_G > 1) return fail("hb2_batch_site_likelihoods is not available with class groups (shard the SETS across ranks instead)");
+    int gps = 1;                                // shared-powers groups per set: branches with the same branchGroup share a direction
+    if (branchGroup)
+        for (int64_t b = 0; b < p->B; b++) {
+            if (branchGroup[b] < 0 || branchGroup[b] >= 8) return fail("branchGroup[%lld]=%lld outside 0..7", (long long)b, (long long)branchGroup[b]);
+            gps = std::max(gps, (int)branchGroup[b] + 1);
+        }
+    for (int64_t s = 0; s < nSets; s++)
+        if (patternOf[s] < 0 || patternOf[s] >= p->S) return fail("patternOf[%lld]=%lld out of range", (long long)s, (long long)patternOf[s]);
+    if (nSets == 0) return 0;
+    CU(cudaSetDevice(p->device));
+    const hb2_partition::Tmpl &t = p->tmpls[templateId];
+    const int64_t B = p->B, nF = t.nF;
+    // chunk buffers: P matrices of `cap` sets (32 KB per branch) capped at ~8 GB
+    int64_t cap = std::min<int64_t>(nSets, std::max<int64_t>(1, (int64_t)(8.0e9 / ((double)B * 4096 * 8))));
+    cap = std::min<int64_t>(cap, 1024);
+    if (cap > p->b_cap || gps > p->b_groups_per_set) {
+        CU(cudaStreamSynchronize(p->stream));
+        hb2_partition::ExBuf &x = p->bex;
+        for (void *d : {(void *)x.d_int, (void *)x.d_flag, (void *)x.d_weight, (void *)x.d_groups, (void *)x.d_pow, (void *)x.d_refvec, (void *)x.d_flags,
+                        (void *)p->d_bPT, (void *)p->d_bV, (void *)p->d_bcond, (void *)p->d_bout, (void *)p->d_bdst, (void *)p->d_bpat, (void *)p->d_bnodeex}) if (d) cudaFree(d);
+        if (x.h_int) cudaFreeHost(x.h_int);
+        if (p->h_bdst) cudaFreeHost(p->h_bdst);
+        x = hb2_partition::ExBuf();
+        p->d_bPT = p->d_bV = p->d_bcond = p->d_bout = nullptr; p->d_bdst = p->d_bpat = p->d_bnodeex = nullptr; p->h_bdst = nullptr; p->b_cap = 0;
+        const int64_t ne = cap * B;
+        x.G = (int)(cap * gps); x.cap = ne; x.stride = 4096; x.kind.assign(x.G, 0);
+        CU(cudaMalloc(&x.d_int, (size_t)(2 * ne + x.G) * sizeof(int)));
+        CU(cudaMallocHost(&x.h_int, (size_t)(2 * ne + x.G) * sizeof(int)));
+        CU(cudaMalloc(&x.d_flag, (size_t)ne * sizeof(int)));
+        CU(cudaMalloc(&x.d_weight, (size_t)ne * sizeof(double)));
+        CU(cudaMalloc(&x.d_groups, (size_t)x.G * sizeof(hb2::ExpmGroup)));
+        CU(cudaMemset(x.d_groups, 0, (size_t)x.G * sizeof(hb2::ExpmGroup)));
+        CU(cudaMalloc(&x.d_pow, (size_t)x.G * hb2::EXPM_POW_TERMS * 4096 * sizeof(double)));
+        CU(cudaMalloc(&x.d_flags, (size_t)x.G * hb2::EXPM_POW_TERMS * sizeof(unsigned long long)));
+        CU(cudaMemset(x.d_flags, 0, (size_t)x.G * hb2::EXPM_POW_TERMS * sizeof(unsigned long long)));
+        CU(cudaMalloc(&x.d_refvec, (size_t)x.G * x.stride * sizeof(double)));
+        CU(cudaMalloc(&p->d_bPT, (size_t)ne * 4096 * sizeof(double)));
+        CU(cudaMalloc(&p->d_bV, (size_t)ne * nF * sizeof(double)));
+        CU(cudaMalloc(&p->d_bcond, (size_t)cap * p->I * 64 * sizeof(double)));
+        CU(cudaMalloc(&p->d_bnodeex, (size_t)cap * p->I * sizeof(int)));
+        CU(cudaMalloc(&p->d_bout, (size_t)cap * sizeof(double)));
+        CU(cudaMalloc(&p->d_bdst, (size_t)ne * sizeof(int)));
+        CU(cudaMalloc(&p->d_bpat, (size_t)cap * sizeof(int)));
+        CU(cudaMallocHost(&p->h_bdst, (size_t)(ne + cap) * sizeof(int)));
+        p->b_cap = cap; p->b_groups_per_set = gps;
+    }
+    double *hs = p->h_small;
+    CU(cudaStreamSynchronize(p->stream));
+    for (int k = 0; k < p->Dp; k++) hs[k] = k < p->D ? rootFreqs[k] : 0.0;
+    CU(cudaMemcpyAsync(p->d_pi, hs, p->Dp * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+    std::vector<int> grp;
+    for (int64_t s0 = 0; s0 < nSets; s0 += p->b_cap) {
+        const int64_t nb = std::min<int64_t>(p->b_cap, nSets - s0), ne = nb * B;
+        CU(cudaStreamSynchronize(p->stream));          // previous chunk done: buffers and pinned arrays are free again
+        for (int64_t e = 0; e < ne; e++) p->h_bdst[e] = (int)e;                      // slot in the chunk's P area: set-major
+        for (int64_t s = 0; s < nb; s++) p->h_bdst[ne + s] = (int)patternOf[s0 + s];
+        CU(cudaMemcpyAsync(p->d_bdst, p->h_bdst, (size_t)ne * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+        CU(cudaMemcpyAsync(p->d_bpat, p->h_bdst + ne, (size_t)nb * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+        CU(cudaMemcpyAsync(p->d_bV, formulaValues + (size_t)s0 * B * nF, (size_t)ne * nF * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+        grp.resize(ne);
+        for (int64_t s = 0; s < nb; s++)
+            for (int64_t b = 0; b < B; b++) grp[s * B + b] = (int)(s * p->b_groups_per_set + (branchGroup ? branchGroup[b] : 0));
+        SharedPlan sp;
+        std::fill(p->bex.kind.begin(), p->bex.kind.end(), 0);                     // every chunk rebuilds its tables
+        if (plan_shared(p, p->h_bdst, ne, 1, grp.data(), sp, (int)templateId, &p->bex, 4)) return 1;
+        CU(cudaEventRecord(p->ev_staging, p->stream));
+        p->staging_busy = true;
+        // classification writes its "resident copy" of the formula values in place (res = input) -- harmless
+        if (launch_expm(p, p->d_bV, p->d_bdst, (int)ne, 2, nullptr, false, p->d_bPT, &sp, 0, (int)templateId)) return 1;
+        hb2::BatchPruneArgs ba;
+        ba.PT = p->d_bPT; ba.cond = p->d_bcond; ba.node_ex = p->d_bnodeex; ba.pat = p->d_bpat; ba.leaf = p->d_leaf; ba.ambig = p->d_ambig; ba.pi = p->d_pi;
+        ba.tree.child_start = p->d_child_start; ba.tree.child_ids = p->d_child_ids; ba.out = p->d_bout;
+        ba.L = (int)p->L; ba.I = (int)p->I; ba.B = (int)B; ba.D = (int)p->D; ba.Sp = (int)p->Sp;
+        hb2::prune_batch_kernel<<<(unsigned)nb, 64, 0, p->stream>>>(ba);
+        p->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(siteLnL + s0, p->d_bout, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    }
+    int err = 0;
+    CU(cudaMemcpyAsync(&err, p->d_err, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    if (err) { cudaMemsetAsync(p->d_err, 0, sizeof(int), p->stream); return fail("a device-side wait timed out in the batched exponential (code %d)", err); }
+    return 0;
 }
 
 int hb2_read_conditionals(hb2_partition *p, int64_t cat, int64_t inode, double *cond, int32_t *exp2) {
@@ -1596,7 +1701,8 @@ void hb2_destroy(hb2_partition *p) {
     if (p->comm) g_nccl.CommDestroy(p->comm);
     void *dev[] = {p->d_leaf, p->d_scal, p->d_rootE, p->d_child_start, p->d_child_ids, p->d_jobs, p->d_dst, p->d_flag,
                    p->d_mix_dst, p->d_mix_Q, p->d_ambig, p->d_freq, p->d_cond, p->d_PT, p->d_Q, p->d_pi, p->d_rootL, p->d_weights,
-                   p->d_partial, p->d_lnL, p->d_siteL, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_xsend, p->d_xrecv, p->d_xfreq, p->d_xpartial, p->d_bc_out, p->d_bc_outE, p->d_bc_sib, p->d_walk, p->d_forced, p->d_ex_int, p->d_ex_flag, p->d_ex_weight, p->d_ex_groups, p->d_ex_pow, p->d_ex_refvec, p->d_ex_flags};
+                   p->d_partial, p->d_lnL, p->d_siteL, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_xsend, p->d_xrecv, p->d_xfreq, p->d_xpartial, p->d_bc_out, p->d_bc_outE, p->d_bc_sib, p->d_walk, p->d_forced, p->ex.d_int, p->ex.d_flag, p->ex.d_weight, p->ex.d_groups, p->ex.d_pow, p->ex.d_refvec, p->ex.d_flags, p->bex.d_int, p->bex.d_flag, p->bex.d_weight, p->bex.d_groups, p->bex.d_pow, p->bex.d_refvec, p->bex.d_flags,
+                   p->d_bPT, p->d_bV, p->d_bcond, p->d_bout, p->d_bdst, p->d_bpat, p->d_bnodeex};
     for (void *d : dev) if (d) cudaFree(d);
     if (p->h_Q) cudaFreeHost(p->h_Q);
     if (p->h_small) cudaFreeHost(p->h_small);
@@ -1606,7 +1712,9 @@ void hb2_destroy(hb2_partition *p) {
     if (p->h_walk) cudaFreeHost(p->h_walk);
     if (p->h_mix) cudaFreeHost(p->h_mix);
     if (p->h_forced) cudaFreeHost(p->h_forced);
-    if (p->h_ex_int) cudaFreeHost(p->h_ex_int);
+    if (p->ex.h_int) cudaFreeHost(p->ex.h_int);
+    if (p->bex.h_int) cudaFreeHost(p->bex.h_int);
+    if (p->h_bdst) cudaFreeHost(p->h_bdst);
     if (p->ev_mix) cudaEventDestroy(p->ev_mix);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
     if (p->ev_staging) cudaEventDestroy(p->ev_staging);

@@ -1423,6 +1423,90 @@ __global__ void __launch_bounds__(256) class_merge_kernel(const double *gath, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// Batched one-pattern likelihoods (the site phases of FEL / MEME fit thousands of one-pattern likelihood
+// functions on the same tree, FEL.bf:1180-1233, MEME.bf:699-746).  Set s prunes pattern pat[s] with ITS OWN transition
+// matrices PT[s][b] (64-padded, transposed, as the expm kernels write them).  One CTA of 64 threads per set: thread k owns
+// parent state k; a child's vector is broadcast from shared memory and column k of P is read from PT[.][j][k] -- 64
+// consecutive doubles per j, coalesced.  fp64 throughout; per-node power-of-two renormalisation like the main kernels.
+// Internal-node vectors live in global scratch cond[s][I][64] (L1/L2 resident: 512 bytes per node).
+// ------------------------------------------------------------------------------------------------
+struct BatchPruneArgs {
+    const double *PT;         // [nSets][B][4096]
+    double *cond;             // [nSets][I][64]
+    int *node_ex;             // [nSets][I] binary exponents of the node vectors
+    const int *pat;           // [nSets] pattern of the partition evaluated by each set
+    const int *leaf;          // [L][Sp]
+    const double *ambig;      // [nAmb][64]
+    const double *pi;         // [64]
+    TreeDev tree;
+    double *out;              // [nSets] log-likelihood of the pattern
+    int L, I, B, D, Sp;
+};
+
+__global__ void __launch_bounds__(64) prune_batch_kernel(BatchPruneArgs a) {
+    __shared__ double xs[64];
+    __shared__ double red[2];
+    const int s = blockIdx.x, k = threadIdx.x;
+    const int pattern = a.pat[s];
+    const double *PTs = a.PT + (size_t)s * a.B * 4096;
+    double *cs = a.cond + (size_t)s * a.I * 64;
+    int *node_ex = a.node_ex + (size_t)s * a.I;
+    for (int par = 0; par < a.I; par++) {
+        double v = k < a.D ? 1.0 : 0.0;
+        int ex = 0;
+        const int c_begin = a.tree.child_start[par], c_end = a.tree.child_start[par + 1];
+        for (int ci = c_begin; ci < c_end; ci++) {
+            const int child = a.tree.child_ids[ci];
+            const double *PT = PTs + (size_t)child * 4096;
+            double m = 0.0;
+            if (child < a.L) {
+                const int code = a.leaf[(size_t)child * a.Sp + pattern];
+                if (code >= 0) m = PT[code * 64 + k];
+                else {
+                    const double *amb = a.ambig + (size_t)(-code - 1) * 64;
+                    for (int j = 0; j < a.D; j++) { const double w = amb[j]; if (w != 0.0) m = fma(w, PT[j * 64 + k], m); }
+                }
+            } else {
+                const int cin = child - a.L;
+                __syncthreads();                 // xs free
+                xs[k] = cs[(size_t)cin * 64 + k];
+                __syncthreads();
+                for (int j = 0; j < a.D; j++) m = fma(xs[j], PT[j * 64 + k], m);
+                ex += node_ex[cin];
+            }
+            v *= m;
+        }
+        // renormalise: max over the 64 threads -> [0.5, 1)
+        double mx = v;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        __syncthreads();
+        if ((k & 31) == 0) red[k >> 5] = mx;
+        __syncthreads();
+        mx = fmax(red[0], red[1]);
+        if (mx > 0.0 && mx < INFINITY) {
+            const int e = ilogb(mx) + 1;
+            v = v * exp2i(-(e / 2)) * exp2i(-(e - e / 2));
+            ex += e;
+        }
+        cs[(size_t)par * 64 + k] = v;
+        if (k == 0) node_ex[par] = ex;
+        __syncthreads();                         // node_ex / cond of this node visible to the block before a parent reads them
+        if (par == a.I - 1) {
+            double r = v * a.pi[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+            if ((k & 31) == 0) red[k >> 5] = r;
+            __syncthreads();
+            if (k == 0) {
+                const double L = red[0] + red[1];
+                a.out[s] = L > 0.0 ? log(L) + (double)ex * 0.693147180559945309417232121458 : (L != L ? L : -INFINITY);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Peer exchange over NVLink (one process per GPU; every rank maps every other rank's exchange buffer through CUDA IPC).
 // Buffer of a rank:  data[2 parities][R source ranks][payload doubles]  followed by  flags[2][R] (uint64 generation).
 // A writer stores its payload into slot `rank` of EVERY rank's buffer (its own included), fences system-wide and then

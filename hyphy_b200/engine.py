@@ -42,6 +42,7 @@ ABI = [
     ("hb2_evaluate", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _ip, _dp, _dp, _dp, _ip]),
     ("hb2_evaluate_forced", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _ip, _dp, C.c_int64, _ip, _dp, _dp, _ip]),
     ("hb2_evaluate_classes", C.c_int, [C.c_void_p, _dp, C.c_int64, _ip, _dp, _dp, _dp, _ip]),
+    ("hb2_batch_site_likelihoods", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _ip, _dp, _ip, _dp, _dp]),
     ("hb2_read_conditionals", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _dp, _i32p]),
     ("hb2_read_transition", C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _dp]),
     ("hb2_comm_unique_id", C.c_int, [C.c_void_p]),
@@ -252,6 +253,21 @@ class Partition:
         _check(self._lib.hb2_branch_cache_evaluate(self._h, int(cat), pw, C.byref(lnl), sl.ctypes.data_as(_dp) if want_sites else None,
                                                    ss.ctypes.data_as(_ip) if want_sites else None))
         return (lnl.value, sl, ss) if want_sites else lnl.value
+
+    # -- batched one-pattern likelihoods (FEL / MEME site phases) -------------------------------------
+    def batch_site_likelihoods(self, pattern_of, formula_values, root_freqs, branch_group=None, template=0):
+        """formula_values: [nSets, B, nF]; returns the nSets log-likelihoods."""
+        po, ppo = _i(pattern_of)
+        v, pv = _d(formula_values)
+        assert v.ndim == 3 and v.shape[0] == len(po) and v.shape[1] == self.B
+        pi, ppi = _d(root_freqs)
+        pbg = None
+        if branch_group is not None:
+            bg, pbg = _i(branch_group)
+            assert bg.shape == (self.B,)
+        out = np.empty(len(po))
+        _check(self._lib.hb2_batch_site_likelihoods(self._h, int(template), len(po), ppo, pv, pbg, ppi, out.ctypes.data_as(_dp)))
+        return out
 
     # -- read-backs --------------------------------------------------------------------------------
     def read_conditionals(self, cat, inode):

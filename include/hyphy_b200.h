@@ -140,6 +140,20 @@ int hb2_branch_cache_build(hb2_partition *p, int64_t node, const double *rootFre
 int hb2_branch_cache_evaluate(hb2_partition *p, int64_t cat, const double *weights, double *lnL, double *siteL,
                               int64_t *siteScale);
 
+/* Batched one-pattern likelihoods on the partition's tree.  The site phases of FEL and MEME
+ * (res/TemplateBatchFiles/SelectionAnalyses/FEL.bf:1180-1233, MEME.bf:699-746) fit thousands of independent likelihood
+ * functions that all use ONE site pattern of the alignment, the same tree, and differ only in a few per-site parameters
+ * (alpha, beta, ...); the reference farms them out one by one (mpi.QueueJob).  Here `nSets` such problems are evaluated in
+ * one call: set s prunes pattern patternOf[s] of the partition with ITS OWN matrices for every branch, handed over in the
+ * compiled form of template `templateId`: formulaValues[s][b][nFormulas], b = 0..B-1 (one rate class per set).
+ * branchGroup (nullable, B entries in 0..7) tells the engine which branches of a set share one rate matrix up to a scalar
+ * (FEL: tested vs background branches); it is a hint for the shared-powers exponential, proportionality is still checked.
+ * siteLnL[s] = log-likelihood of the pattern under set s (NOT multiplied by the pattern's frequency).  fp64 throughout;
+ * the partition's resident caches are not touched.  33..64 states only. */
+int hb2_batch_site_likelihoods(hb2_partition *p, int64_t templateId, int64_t nSets, const int64_t *patternOf,
+                               const double *formulaValues, const int64_t *branchGroup, const double *rootFreqs,
+                               double *siteLnL);
+
 /* FillInConditionals-style read-back (tree.cpp:3335): conditionals of internal node `inode` (0..I-1), class cat,
  * as S*D doubles (original pattern order) and S binary exponents: true value = cond * 2^exp2. */
 int hb2_read_conditionals(hb2_partition *p, int64_t cat, int64_t inode, double *cond, int32_t *exp2);

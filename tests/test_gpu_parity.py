@@ -471,6 +471,54 @@ def test_forced_states_match_oracle(name, mode):
     np.testing.assert_allclose(tot, bl, rtol=max(10 * atol, 1e-9))
 
 
+def test_batched_site_likelihoods():
+    """SURVEY 8f row 3 (FEL / MEME site phases): many one-pattern likelihoods with per-set matrices in one call.
+    (a) every set = the model of the reference's fixture -> the reference's own per-site log-likelihoods;
+    (b) per-set parameters (alpha-, beta-like scalings, two branch classes) -> the oracle, set by set."""
+    w, g = gc.load("c2_mg94_50x1000_c1")
+    nb = w.tree.n_branches
+    lf = LF(w, "fp64")
+    lf.set_template()
+    vals = w.compiled_values()[0]                                  # [B, nF]
+    pats = np.arange(w.S)
+    got = lf.part.batch_site_likelihoods(pats, np.broadcast_to(vals, (w.S,) + vals.shape), w.pi)
+    assert np.abs(got[w.site_to_pattern] - g["site_lnL"]).max() <= 1e-9
+    assert abs((got * w.pattern_freq).sum() - g["lnL"]) <= 1e-10 * abs(g["lnL"])
+    # (b) sets with their own synonymous / non-synonymous scalings on two classes of branches
+    rng = np.random.default_rng(3)
+    ei, ef, nf, cf = w.compiled_template()
+    # which formulas are non-synonymous: the ones whose value moves with omega (the fixture's model has omega = 0.3)
+    wq = synth.Workload(w.name, w.tree, w.D, w.pi, [synth.mg94_rev_Q(0.6)], w.class_weights, w.leaf_states, w.ambig, w.pattern_freq,
+                        w.site_to_pattern, None, dict(w.meta, omegas=[0.6]))
+    keys_nonsyn = ~np.isclose(wq.compiled_values()[0][0], vals[0])
+    fg = np.zeros(nb, dtype=np.int64)
+    fg[rng.choice(nb, nb // 3, replace=False)] = 1                  # "tested" branches
+    n_sets = 40
+    sets = rng.choice(w.S, n_sets, replace=False)
+    alpha = rng.uniform(0.2, 3.0, n_sets)
+    beta_bg = rng.uniform(0.0, 4.0, n_sets)
+    beta_fg = rng.uniform(0.0, 12.0, n_sets)
+    beta_fg[:5] = beta_bg[:5]                                       # a few sets whose two classes coincide
+    V = np.empty((n_sets, nb, nf))
+    for i in range(n_sets):
+        for b in range(nb):
+            V[i, b] = vals[b] * np.where(keys_nonsyn, (beta_fg[i] if fg[b] else beta_bg[i]) / 0.3, alpha[i])
+    for bg in (fg, None):                                           # with the hint and without (same numbers either way)
+        got = lf.part.batch_site_likelihoods(sets, V, w.pi, branch_group=bg)
+        for i in range(n_sets):
+            Qt = np.zeros((1, nb, 61, 61))
+            for b in range(nb):
+                M = np.zeros((61, 61))
+                M.flat[ei] = V[i, b][ef]
+                M[np.diag_indices(61)] = -M.sum(axis=1)
+                Qt[0, b] = M
+            w1 = synth.Workload("one", w.tree, w.D, w.pi, w.Q_classes, w.class_weights, w.leaf_states[:, sets[i]:sets[i] + 1], w.ambig,
+                                np.array([1]), np.array([0]))
+            ref, _ = port.lnl(w1, Qt=Qt)
+            assert abs(got[i] - ref) <= 1e-10 * abs(ref) + 1e-12, (i, got[i], ref)
+    lf.close()
+
+
 def test_conditionals_readback_matches_oracle(mode):
     w, _ = gc.load("mg94_8x60_c1")
     lf = LF(w, mode)
