@@ -121,7 +121,7 @@ struct hb2_partition {
     struct ExBuf {
         int G = 0, stride = 0;                // groups, doubles per cached reference direction
         int *d_int = nullptr, *h_int = nullptr, *d_flag = nullptr;     // [group cap | ref cap | refs G]
-        double *d_weight = nullptr, *d_pow = nullptr, *d_refvec = nullptr;
+        double *d_weight = nullptr, *d_pow = nullptr, *d_refvec = nullptr, *d_colsum = nullptr;   // colsum [cap][16][64]
         void *d_groups = nullptr;
         unsigned long long *d_flags = nullptr, gen = 0;   // generation flags of the coefficient matrices [G][EXPM_POW_TERMS]
         std::vector<int> kind;                // host mirror: kind of the reference direction each group holds (0 none)
@@ -290,8 +290,12 @@ int launch_expm(hb2_partition *p, const double *dQ, const int *d_dst, int n, int
                         hb2::expm_powers_kernel<<<dim3(hb2::EXPM_POW_TERMS - 1, (unsigned)sp->n_refs), 256, smem, p->stream>>>(pa);
                         p->launches++;
                     }
-                    hb2::expm_poly_kernel<<<dim3(16, (unsigned)((n + hb2::EXPM_POLY_CHUNK - 1) / hb2::EXPM_POLY_CHUNK)), 256, 0, p->stream>>>(a, n);
-                    p->launches += 2;
+                    hb2::ExpmTcOut tcs{nullptr, nullptr};
+                    if (pack_tc) { tcs.PB = p->d_PB; tcs.PTf = p->d_PTf; }
+                    double *colsum = x.d_colsum + (size_t)off * 16 * 64;
+                    hb2::expm_poly_kernel<<<dim3(16, (unsigned)((n + hb2::EXPM_POLY_CHUNK - 1) / hb2::EXPM_POLY_CHUNK)), 256, 0, p->stream>>>(a, tcs, colsum, n);
+                    hb2::expm_diag_kernel<<<n, 64, 0, p->stream>>>(a, tcs, colsum);
+                    p->launches += 3;
                 }
                 hb2::ExpmTcOut tco{nullptr, nullptr};
                 if (pack_tc) { tco.PB = p->d_PB; tco.PTf = p->d_PTf; packed = true; }
@@ -1131,6 +1135,7 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
         CUP(cudaMallocHost(&p->ex.h_int, (size_t)(2 * p->ex.cap + p->ex.G) * sizeof(int)));
         CUP(cudaMalloc(&p->ex.d_flag, (size_t)p->ex.cap * sizeof(int)));
         CUP(cudaMalloc(&p->ex.d_weight, (size_t)p->ex.cap * sizeof(double)));
+        CUP(cudaMalloc(&p->ex.d_colsum, (size_t)p->ex.cap * 16 * 64 * sizeof(double)));
         CUP(cudaMalloc(&p->ex.d_groups, (size_t)p->ex.G * sizeof(hb2::ExpmGroup)));
         CUP(cudaMemsetAsync(p->ex.d_groups, 0, (size_t)p->ex.G * sizeof(hb2::ExpmGroup), p->stream));
         CUP(cudaMalloc(&p->ex.d_pow, (size_t)p->ex.G * hb2::EXPM_POW_TERMS * 4096 * sizeof(double)));
@@ -1393,12 +1398,12 @@ int hb2_batch_site_likelihoods(hb2_partition *p, int64_t templateId, int64_t nSe
     const hb2_partition::Tmpl &t = p->tmpls[templateId];
     const int64_t B = p->B, nF = t.nF;
     // chunk buffers: P matrices of `cap` sets (32 KB per branch) capped at ~8 GB
-    int64_t cap = std::min<int64_t>(nSets, std::max<int64_t>(1, (int64_t)(8.0e9 / ((double)B * 4096 * 8))));
+    int64_t cap = std::min<int64_t>(nSets, std::max<int64_t>(1, (int64_t)(8.0e9 / ((double)B * (4096 + 1024 + (double)nF) * 8))));
     cap = std::min<int64_t>(cap, 1024);
     if (cap > p->b_cap || gps > p->b_groups_per_set) {
         CU(cudaStreamSynchronize(p->stream));
         hb2_partition::ExBuf &x = p->bex;
-        for (void *d : {(void *)x.d_int, (void *)x.d_flag, (void *)x.d_weight, (void *)x.d_groups, (void *)x.d_pow, (void *)x.d_refvec, (void *)x.d_flags,
+        for (void *d : {(void *)x.d_int, (void *)x.d_flag, (void *)x.d_weight, (void *)x.d_groups, (void *)x.d_pow, (void *)x.d_refvec, (void *)x.d_flags, (void *)x.d_colsum,
                         (void *)p->d_bPT, (void *)p->d_bV, (void *)p->d_bcond, (void *)p->d_bout, (void *)p->d_bdst, (void *)p->d_bpat, (void *)p->d_bnodeex}) if (d) cudaFree(d);
         if (x.h_int) cudaFreeHost(x.h_int);
         if (p->h_bdst) cudaFreeHost(p->h_bdst);
@@ -1410,6 +1415,7 @@ int hb2_batch_site_likelihoods(hb2_partition *p, int64_t templateId, int64_t nSe
         CU(cudaMallocHost(&x.h_int, (size_t)(2 * ne + x.G) * sizeof(int)));
         CU(cudaMalloc(&x.d_flag, (size_t)ne * sizeof(int)));
         CU(cudaMalloc(&x.d_weight, (size_t)ne * sizeof(double)));
+        CU(cudaMalloc(&x.d_colsum, (size_t)ne * 16 * 64 * sizeof(double)));
         CU(cudaMalloc(&x.d_groups, (size_t)x.G * sizeof(hb2::ExpmGroup)));
         CU(cudaMemset(x.d_groups, 0, (size_t)x.G * sizeof(hb2::ExpmGroup)));
         CU(cudaMalloc(&x.d_pow, (size_t)x.G * hb2::EXPM_POW_TERMS * 4096 * sizeof(double)));
@@ -1701,7 +1707,7 @@ void hb2_destroy(hb2_partition *p) {
     if (p->comm) g_nccl.CommDestroy(p->comm);
     void *dev[] = {p->d_leaf, p->d_scal, p->d_rootE, p->d_child_start, p->d_child_ids, p->d_jobs, p->d_dst, p->d_flag,
                    p->d_mix_dst, p->d_mix_Q, p->d_ambig, p->d_freq, p->d_cond, p->d_PT, p->d_Q, p->d_pi, p->d_rootL, p->d_weights,
-                   p->d_partial, p->d_lnL, p->d_siteL, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_xsend, p->d_xrecv, p->d_xfreq, p->d_xpartial, p->d_bc_out, p->d_bc_outE, p->d_bc_sib, p->d_walk, p->d_forced, p->ex.d_int, p->ex.d_flag, p->ex.d_weight, p->ex.d_groups, p->ex.d_pow, p->ex.d_refvec, p->ex.d_flags, p->bex.d_int, p->bex.d_flag, p->bex.d_weight, p->bex.d_groups, p->bex.d_pow, p->bex.d_refvec, p->bex.d_flags,
+                   p->d_partial, p->d_lnL, p->d_siteL, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_xsend, p->d_xrecv, p->d_xfreq, p->d_xpartial, p->d_bc_out, p->d_bc_outE, p->d_bc_sib, p->d_walk, p->d_forced, p->ex.d_int, p->ex.d_flag, p->ex.d_weight, p->ex.d_groups, p->ex.d_pow, p->ex.d_refvec, p->ex.d_flags, p->ex.d_colsum, p->bex.d_colsum, p->bex.d_int, p->bex.d_flag, p->bex.d_weight, p->bex.d_groups, p->bex.d_pow, p->bex.d_refvec, p->bex.d_flags,
                    p->d_bPT, p->d_bV, p->d_bcond, p->d_bout, p->d_bdst, p->d_bpat, p->d_bnodeex};
     for (void *d : dev) if (d) cudaFree(d);
     if (p->h_Q) cudaFreeHost(p->h_Q);

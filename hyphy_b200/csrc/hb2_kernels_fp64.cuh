@@ -431,6 +431,7 @@ __global__ void __launch_bounds__(256, 2) expm64_dmma_kernel(ExpmArgs a, ExpmTcO
         const double rho = gi.nu * (a.weight[blockIdx.x] / gi.weight);
         int shift = 0;
         if (rho > EXPM_POLY_THETA) { int e = 0; frexp(rho / EXPM_POLY_THETA, &e); shift = max(e, 0); }
+        if (shift == 0 && rho == rho) return;    // finished by expm_poly_kernel + expm_diag_kernel
         if (!(rho == rho) || shift > 900) {
             for (int idx = tid; idx < 4096; idx += 256) out[idx] = __longlong_as_double(0x7ff8000000000000LL);
             if (tc.PB) {
@@ -694,17 +695,25 @@ __global__ void __launch_bounds__(256, 1) expm_powers_kernel(ExpmPowersArgs pa) 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Shared-powers path, stage 3: PT[slot] <- sum_m S_m x^m with x = rho / 2^shift <= EXPM_POLY_THETA for every flagged
-// entry.  grid = (16 element slices, chunks of EXPM_POLY_CHUNK entries); thread t of slice sl owns element
-// (row 4 sl + t/64, column t%64) of the PT layout and keeps that element's 24 coefficients in registers while it walks
-// its chunk (reloaded only when the group changes: batches are class-major).  The chunk's metadata is fetched up front
-// so that the loop carries no dependent global loads.  Writes are 2 KB contiguous per (entry, slice).
+// Shared-powers path, stage 3: P = sum_m S_m x^m with x = rho / 2^shift <= EXPM_POLY_THETA for every flagged entry, fused
+// with the epilogue for the (common) entries that need no squaring.
+// grid = (16 row slices, chunks of EXPM_POLY_CHUNK entries).  Thread t of slice sl owns element (row 4 sl + t%4,
+// column t/4) of the PT layout (row = child state, column = parent state) and keeps that element's 24 coefficients in
+// registers while it walks its chunk (reloaded only when the group changes: batches are class-major); the chunk's
+// metadata is fetched up front so that the loop carries no dependent global loads.
+//   shift == 0: the value is final up to the row repair.  It is clamped at 0, padding is zeroed, and PT (fp64), PTf (fp32
+//               table) and PB (tf32 hi/lo tiles; chunk sl of the canonical layout is exactly this slice, offset t) are
+//               written directly; the partial column sums of the slice (4 rows, diagonal excluded; 4 adjacent lanes) go to
+//               colsum[entry][sl][column] for expm_diag_kernel, which sets the diagonal to 1 - (sum of the rest of P's row).
+//   shift  > 0: the raw polynomial value goes to PT; expm64_dmma_kernel squares and finishes the entry.
 // ------------------------------------------------------------------------------------------------
 constexpr int EXPM_POLY_CHUNK = 8;
-__global__ void __launch_bounds__(256) expm_poly_kernel(ExpmArgs a, int n) {
-    const int tid = threadIdx.x;
-    const int e = blockIdx.x * 256 + tid;                             // element index in the 64x64 PT layout
-    const double unit = ((e >> 6) == (e & 63)) ? 1.0 : 0.0;
+__global__ void __launch_bounds__(256) expm_poly_kernel(ExpmArgs a, ExpmTcOut tc, double *__restrict__ colsum, int n) {
+    const int tid = threadIdx.x, sl = blockIdx.x;
+    const int row = 4 * sl + (tid & 3), col = tid >> 2;
+    const int e = row * 64 + col;                                     // element index in the 64x64 PT layout
+    const double unit = (row == col) ? 1.0 : 0.0;
+    const bool pad = row >= a.D || col >= a.D;
     const int k0 = blockIdx.y * EXPM_POLY_CHUNK;
     int slot[EXPM_POLY_CHUNK], grp[EXPM_POLY_CHUNK];
     double wgt[EXPM_POLY_CHUNK];
@@ -732,11 +741,12 @@ __global__ void __launch_bounds__(256) expm_poly_kernel(ExpmArgs a, int n) {
         }
         const double rho = nu * (wgt[i] / wref);
         double x = rho;
+        int shift = 0;
         if (rho > EXPM_POLY_THETA) {
-            int ex = 0;
-            frexp(rho / EXPM_POLY_THETA, &ex);
-            if (ex > 900) continue;                                   // the finishing kernel writes NaN for absurd rates
-            x = ldexp(rho, -max(ex, 0));
+            frexp(rho / EXPM_POLY_THETA, &shift);
+            if (shift > 900) continue;                                // the finishing kernel writes NaN for absurd rates
+            shift = max(shift, 0);
+            x = ldexp(rho, -shift);
         }
         // p(x) = 1 + x (c1 + c3 x^2 + .. + c23 x^22) + x^2 (c2 + c4 x^2 + .. + c24 x^22): two interleaved Horner chains in
         // x^2 halve the dependent-FMA depth
@@ -745,8 +755,49 @@ __global__ void __launch_bounds__(256) expm_poly_kernel(ExpmArgs a, int n) {
         double ve = c[24], vo = c[23];
 #pragma unroll
         for (int m = 22; m >= 2; m -= 2) { ve = fma(ve, x2, c[m]); vo = fma(vo, x2, c[m - 1]); }
-        const double v = fma(vo, x, fma(ve, x2, unit));
-        __stcg(a.PT + (size_t)slot[i] * 4096 + e, v);
+        double v = fma(vo, x, fma(ve, x2, unit));
+        const size_t sidx = (size_t)slot[i];
+        if (shift > 0) { __stcg(a.PT + sidx * 4096 + e, v); continue; }
+        v = (pad || v < 0.0) ? 0.0 : v;
+        // column sums over this slice's 4 rows (lanes t, t^1, t^2, t^3 share a column), diagonal element excluded
+        double part = (row == col) ? 0.0 : v;
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        if ((tid & 3) == 0) colsum[((size_t)(k0 + i) * 16 + sl) * 64 + col] = part;
+        if (row != col) {                                             // expm_diag_kernel owns the diagonal
+            __stcg(a.PT + sidx * 4096 + e, v);
+            if (tc.PB) {
+                tc.PTf[sidx * 4352 + row * 68 + col] = (float)v;
+                const float hi = tf32_rn_dev((float)v);
+                float *pb = tc.PB + sidx * 8192 + sl * 256 + tid;     // canonical tile: chunk = row/4 = sl, offset col*4 + row%4 = tid
+                pb[0] = hi;
+                pb[4096] = tf32_rn_dev((float)(v - (double)hi));
+            }
+        }
+    }
+}
+
+// Row repair of the entries expm_poly_kernel finished (flagged, no squaring): P[k][k] = max(1 - sum_{j != k} P[k][j], 0),
+// i.e. PT[k][k] from the column sums of PT, added up in slice order (deterministic).  One CTA of 64 threads per entry.
+__global__ void __launch_bounds__(64) expm_diag_kernel(ExpmArgs a, ExpmTcOut tc, const double *__restrict__ colsum) {
+    const int k = blockIdx.x, col = threadIdx.x;
+    const int slot = a.dst[k];
+    if (slot < 0 || !a.flag[k]) return;
+    const ExpmGroup gi = a.groups[a.group[k]];
+    const double rho = gi.nu * (a.weight[k] / gi.weight);
+    if (!(rho <= EXPM_POLY_THETA)) return;                            // squared and finished by expm64_dmma_kernel
+    double s = 0.0;
+#pragma unroll
+    for (int sl = 0; sl < 16; sl++) s += colsum[((size_t)k * 16 + sl) * 64 + col];
+    const double d = col < a.D ? fmax(1.0 - s, 0.0) : 0.0;
+    const size_t sidx = (size_t)slot;
+    a.PT[sidx * 4096 + col * 64 + col] = d;
+    if (tc.PB) {
+        tc.PTf[sidx * 4352 + col * 68 + col] = (float)d;
+        const float hi = tf32_rn_dev((float)d);
+        float *pb = tc.PB + sidx * 8192 + (col >> 2) * 256 + col * 4 + (col & 3);
+        pb[0] = hi;
+        pb[4096] = tf32_rn_dev((float)(d - (double)hi));
     }
 }
 
