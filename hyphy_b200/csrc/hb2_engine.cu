@@ -657,6 +657,7 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
     w.gen = p->d_walk + gen_off; w.NI = 2 * I; w.K = K; w.T = T; w.ncls = ncls; w.nslots = nslots;
     if (getenv("HB2_DEBUG")) fprintf(stderr, "[hb2] walk: jobs=%d steps=%d K=%d T=%d ncls=%d nslots=%d grid=%d resident=%d\n", total, ns, K, T, ncls, nslots, nslots * K, p->walk_max_resident);
     w.trace = nullptr; w.trace_cta = 0; w.trace_cta_times = nullptr;
+    { static const float thr = getenv("HB2_ANCHOR_THR") ? (float)atof(getenv("HB2_ANCHOR_THR")) : hb2::TC_ANCHOR_THR; w.anchor_thr = thr; }
     const char *trace_path = getenv("HB2_WALK_TRACE");
     long long *d_trace = nullptr;
     if (trace_path) {          // bring-up aid: per-step clock stamps of one CTA -> text file

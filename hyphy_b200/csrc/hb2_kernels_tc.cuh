@@ -453,6 +453,7 @@ struct WalkArgs {
     long long *trace;           // nullable debug buffer: 12 clock64 stamps per step of CTA `trace_cta` (HB2_WALK_TRACE)
     long long *trace_cta_times; // nullable: per CTA {smid, clock64 at entry, clock64 at exit, globaltimer at entry}
     int trace_cta;
+    float anchor_thr;           // entries >= this (rows are normalised to max in [0.5,1)) bypass the tensor core; default 2^-6
 };
 
 // Tagged hand-over between CTAs: relaxed gpu-scope accesses, every 32-bit word carries its own validity bit, so no
@@ -664,7 +665,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                         for (int k = 0; k < 64; k++) {
                             float x = v[k];
                             v[k] = 1.f;
-                            const bool big = x >= TC_ANCHOR_THR;
+                            const bool big = x >= w.anchor_thr;
                             if (big) { if (k < 16) am0 |= 1u << k; else if (k < 32) am1 |= 1u << (k - 16); else if (k < 48) am2 |= 1u << (k - 32); else am3 |= 1u << (k - 48); }
                             x = big ? 0.f : x;
                             const float h = tf32_rn(x);
@@ -688,7 +689,7 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                             for (int u = 0; u < 4; u++) {
                                 const int kq = 4 * q + u;
                                 const float xv = __uint_as_float(xs[u] & 0x7fffffffu);
-                                const bool big = xv >= TC_ANCHOR_THR;
+                                const bool big = xv >= w.anchor_thr;
                                 if (big) { if (kq < 16) am0 |= 1u << kq; else if (kq < 32) am1 |= 1u << (kq - 16); else if (kq < 48) am2 |= 1u << (kq - 32); else am3 |= 1u << (kq - 48); }
                                 const float x = big ? 0.f : xv;
                                 const float h = tf32_rn(x);
@@ -749,11 +750,18 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
                 __syncwarp();
                 // anchors on the CUDA cores while the tensor core works (rows of the P^T table in shared memory)
                 float acc[64];
-#pragma unroll
-                for (int k = 0; k < 64; k++) acc[k] = 0.f;
                 mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
+                {   // first anchor (nearly every row has one: its maximum is >= 0.5): a product, no zero-fill + FMA
+                    const float xv = ak[0] >= 0 ? fabsf(av[0]) : 0.f;
+                    const float4 *row = reinterpret_cast<const float4 *>(tab + max(ak[0], 0) * WALK_PT_ROW);
 #pragma unroll
-                for (int ai = 0; ai < WALK_FAST_ANCHORS; ai++) {
+                    for (int q = 0; q < 16; q++) {
+                        const float4 rr = row[q];
+                        acc[4 * q] = xv * rr.x; acc[4 * q + 1] = xv * rr.y; acc[4 * q + 2] = xv * rr.z; acc[4 * q + 3] = xv * rr.w;
+                    }
+                }
+#pragma unroll
+                for (int ai = 1; ai < WALK_FAST_ANCHORS; ai++) {
                     if (ak[ai] >= 0) {
                         const float xv = fabsf(av[ai]);
                         const float4 *row = reinterpret_cast<const float4 *>(tab + ak[ai] * WALK_PT_ROW);
