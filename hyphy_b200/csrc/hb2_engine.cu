@@ -155,6 +155,7 @@ struct hb2_partition {
     int forced_node = -1;
     // persistent walk kernel (one launch per evaluation): plan buffers, generation bits of the tagged hand-over, residency
     bool small_walk = true;                   // HB2_SMALL_WALK=0: per-level launches of prune_small_kernel (A/B testing)
+    bool fp64_walk = true;                    // HB2_FP64_WALK=0: per-level launches of prune64_kernel (A/B testing)
     bool expm_dfma = false;                   // HB2_EXPM_DFMA=1: previous FFMA-style fp64 expm kernel (A/B testing)
     bool use_walk = false;
     int walk_max_resident = 0;
@@ -724,8 +725,25 @@ int run_small_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::
     return 0;
 }
 
+// 33..64 states in fp64: one launch, CTA (tile, class) walks the dirty nodes in post-order (prune64_walk_kernel).
+int run_fp64_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector<int>> &levels) {
+    std::vector<int> jobs;
+    for (auto &lv : levels) jobs.insert(jobs.end(), lv.begin(), lv.end());
+    if (jobs.empty()) return 0;
+    std::sort(jobs.begin(), jobs.end());                 // internal indices ascending == post-order
+    std::copy(jobs.begin(), jobs.end(), p->h_jobs);      // (every evaluation ends with a stream synchronisation: the buffer is free)
+    CU(cudaMemcpyAsync(p->d_jobs, p->h_jobs, jobs.size() * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    hb2::PruneArgs a = prune_args(p, cat0);
+    dim3 grid((unsigned)(p->Sp / hb2::TILE_P), (unsigned)ncls);
+    hb2::prune64_walk_kernel<<<grid, 256, 2 * 64 * hb2::LD64 * sizeof(double), p->stream>>>(a, p->d_jobs, (int)jobs.size());
+    p->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int run_pruning(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector<int>> &levels) {
     if (p->use_tc && p->use_walk) return run_walk(p, cat0, ncls, levels);
+    if (!p->use_tc && p->Dp == 64 && p->fp64_walk) return run_fp64_walk(p, cat0, ncls, levels);
     if (p->Dp <= 32 && p->small_walk) return run_small_walk(p, cat0, ncls, levels);
     // upload all job lists in one copy
     int total = 0;
@@ -1151,9 +1169,11 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
     }
     {
         CUP(cudaFuncSetAttribute(hb2::prune64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 64 * hb2::LD64 * sizeof(double))));
+        CUP(cudaFuncSetAttribute(hb2::prune64_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 64 * hb2::LD64 * sizeof(double))));
     }
 #undef CUP
     { const char *env = getenv("HB2_SMALL_WALK"); p->small_walk = !(env && env[0] == '0'); }
+    { const char *env = getenv("HB2_FP64_WALK"); p->fp64_walk = !(env && env[0] == '0'); }
     p->have_matrix.assign(C * p->B, 0);
     p->is_rate.assign(C * p->B, 0);
     p->pend_pos.assign(C * p->B, -1);
@@ -1739,7 +1759,7 @@ int hb2_stage_launches(const hb2_partition *p, int64_t *out3) {
 const char *hb2_pruning_kernel(const hb2_partition *p) {
     if (!p) return "";
     if (p->use_tc) return p->use_walk ? "prune64_tc_walk_kernel" : "prune64_tc_kernel";
-    if (p->Dp == 64) return "prune64_kernel";
+    if (p->Dp == 64) return p->fp64_walk ? "prune64_walk_kernel" : "prune64_kernel";
     return p->small_walk ? "prune_small_walk_kernel" : "prune_small_kernel";
 }
 

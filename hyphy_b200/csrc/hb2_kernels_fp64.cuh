@@ -708,38 +708,43 @@ __global__ void __launch_bounds__(256, 1) expm_powers_kernel(ExpmPowersArgs pa) 
 //   shift  > 0: the raw polynomial value goes to PT; expm64_dmma_kernel squares and finishes the entry.
 // ------------------------------------------------------------------------------------------------
 constexpr int EXPM_POLY_CHUNK = 8;
-__global__ void __launch_bounds__(256) expm_poly_kernel(ExpmArgs a, ExpmTcOut tc, double *__restrict__ colsum, int n) {
+__global__ void __launch_bounds__(256, 3) expm_poly_kernel(ExpmArgs a, ExpmTcOut tc, double *__restrict__ colsum, int n) {
+    __shared__ int s_slot[EXPM_POLY_CHUNK], s_grp[EXPM_POLY_CHUNK];
+    __shared__ double s_wgt[EXPM_POLY_CHUNK];
     const int tid = threadIdx.x, sl = blockIdx.x;
     const int row = 4 * sl + (tid & 3), col = tid >> 2;
     const int e = row * 64 + col;                                     // element index in the 64x64 PT layout
     const double unit = (row == col) ? 1.0 : 0.0;
     const bool pad = row >= a.D || col >= a.D;
     const int k0 = blockIdx.y * EXPM_POLY_CHUNK;
-    int slot[EXPM_POLY_CHUNK], grp[EXPM_POLY_CHUNK];
-    double wgt[EXPM_POLY_CHUNK];
-#pragma unroll
-    for (int i = 0; i < EXPM_POLY_CHUNK; i++) {
-        const int k = k0 + i;
-        const bool live = k < n;
-        slot[i] = live ? a.dst[k] : -1;
-        if (live && slot[i] >= 0 && !a.flag[k]) slot[i] = -1;
-        grp[i] = live ? a.group[k] : -1;
-        wgt[i] = live ? a.weight[k] : 0.0;
+    if (tid < EXPM_POLY_CHUNK) {                                      // the chunk's metadata, once per CTA
+        const int k = k0 + tid;
+        int sv = -1, gv = -1;
+        double wv = 0.0;
+        if (k < n) {
+            sv = a.dst[k];
+            if (sv >= 0 && !a.flag[k]) sv = -1;
+            gv = a.group[k];
+            wv = a.weight[k];
+        }
+        s_slot[tid] = sv; s_grp[tid] = gv; s_wgt[tid] = wv;
     }
+    __syncthreads();
     double c[EXPM_POW_TERMS];
     int cur = -1;
     double nu = 0.0, wref = 1.0;
-#pragma unroll
+    const size_t out_pt = (size_t)e, out_ptf = (size_t)row * 68 + col, out_pb = (size_t)sl * 256 + tid;
     for (int i = 0; i < EXPM_POLY_CHUNK; i++) {
-        if (slot[i] < 0) continue;
-        if (grp[i] != cur) {
-            cur = grp[i];
+        const int slot = s_slot[i];
+        if (slot < 0) continue;
+        if (s_grp[i] != cur) {
+            cur = s_grp[i];
             const double *pw = a.pow + (size_t)cur * EXPM_POW_TERMS * 4096 + e;
 #pragma unroll
             for (int m = 1; m < EXPM_POW_TERMS; m++) c[m] = __ldcg(pw + (size_t)m * 4096);
             nu = a.groups[cur].nu; wref = a.groups[cur].weight;
         }
-        const double rho = nu * (wgt[i] / wref);
+        const double rho = nu * (s_wgt[i] / wref);
         double x = rho;
         int shift = 0;
         if (rho > EXPM_POLY_THETA) {
@@ -756,8 +761,8 @@ __global__ void __launch_bounds__(256) expm_poly_kernel(ExpmArgs a, ExpmTcOut tc
 #pragma unroll
         for (int m = 22; m >= 2; m -= 2) { ve = fma(ve, x2, c[m]); vo = fma(vo, x2, c[m - 1]); }
         double v = fma(vo, x, fma(ve, x2, unit));
-        const size_t sidx = (size_t)slot[i];
-        if (shift > 0) { __stcg(a.PT + sidx * 4096 + e, v); continue; }
+        const size_t sidx = (size_t)slot;
+        if (shift > 0) { __stcg(a.PT + sidx * 4096 + out_pt, v); continue; }
         v = (pad || v < 0.0) ? 0.0 : v;
         // column sums over this slice's 4 rows (lanes t, t^1, t^2, t^3 share a column), diagonal element excluded
         double part = (row == col) ? 0.0 : v;
@@ -765,11 +770,12 @@ __global__ void __launch_bounds__(256) expm_poly_kernel(ExpmArgs a, ExpmTcOut tc
         part += __shfl_xor_sync(0xffffffffu, part, 2);
         if ((tid & 3) == 0) colsum[((size_t)(k0 + i) * 16 + sl) * 64 + col] = part;
         if (row != col) {                                             // expm_diag_kernel owns the diagonal
-            __stcg(a.PT + sidx * 4096 + e, v);
+            __stcg(a.PT + sidx * 4096 + out_pt, v);
             if (tc.PB) {
-                tc.PTf[sidx * 4352 + row * 68 + col] = (float)v;
-                const float hi = tf32_rn_dev((float)v);
-                float *pb = tc.PB + sidx * 8192 + sl * 256 + tid;     // canonical tile: chunk = row/4 = sl, offset col*4 + row%4 = tid
+                const float vf = (float)v;
+                tc.PTf[sidx * 4352 + out_ptf] = vf;
+                const float hi = tf32_rn_dev(vf);
+                float *pb = tc.PB + sidx * 8192 + out_pb;             // canonical tile: chunk = row/4 = sl, offset col*4 + row%4 = tid
                 pb[0] = hi;
                 pb[4096] = tf32_rn_dev((float)(v - (double)hi));
             }
@@ -1000,6 +1006,126 @@ __global__ void __launch_bounds__(256, 2) prune64_kernel(PruneArgs a, const int 
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 33..64 states, fp64, WHOLE pruning pass in one launch: patterns are independent, so tile t of a node needs tile t of its
+// children only -- CTA (tile, class) walks the dirty internal nodes in post-order (jobs ascending) and every dependency is
+// CTA-local (a child's tile was written by this CTA earlier in the launch, or is resident from an earlier evaluation).  No
+// grid-wide synchronisation, no launch per tree level (the north-star tree has 48 levels: 54 launches per evaluation
+// before).  Same tile body as prune64_kernel.  grid = (Sp/64, classes).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2) prune64_walk_kernel(PruneArgs a, const int *__restrict__ jobs, int njobs) {
+    extern __shared__ __align__(16) double sm[];
+    double *Xs = sm;                    // [64][LD64] child conditionals (pattern-major)
+    double *Ps = sm + 64 * LD64;        // [64][LD64] PT of the child's branch
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int cat = a.cat0 + blockIdx.y;
+    const int s0 = blockIdx.x * TILE_P;
+    const size_t Sp = a.Sp;
+  for (int jb = 0; jb < njobs; jb++) {
+    const int par = __ldg(jobs + jb);
+    double v[4][4];
+    int ex[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        ex[i] = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[i][j] = 1.0;
+    }
+    const int c_begin = a.tree.child_start[par], c_end = a.tree.child_start[par + 1];
+    for (int ci = c_begin; ci < c_end; ci++) {
+        const int child = a.tree.child_ids[ci];
+        const double *PT = a.PT + ((size_t)cat * a.B + child) * 4096;
+        if (child < a.L) {
+            // leaf: column gather PT[state][k]; ambiguous: sum_j amb[j] PT[j][k]
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int code = (child == a.forced_node) ? a.forced[s0 + 4 * ty + i] : a.leaf[(size_t)child * Sp + s0 + 4 * ty + i];
+                double m0, m1, m2, m3;
+                if (code >= 0) {
+                    const double2 *p = reinterpret_cast<const double2 *>(PT + (size_t)code * 64 + 2 * tx);
+                    double2 q0 = __ldg(p), q1 = __ldg(p + 16);
+                    m0 = q0.x; m1 = q0.y; m2 = q1.x; m3 = q1.y;
+                } else {
+                    const double *amb = a.ambig + (size_t)(-code - 1) * 64;
+                    m0 = m1 = m2 = m3 = 0.0;
+                    for (int j = 0; j < a.D; j++) {
+                        const double w = __ldg(amb + j);
+                        if (w != 0.0) {
+                            const double2 *p = reinterpret_cast<const double2 *>(PT + (size_t)j * 64 + 2 * tx);
+                            double2 q0 = __ldg(p), q1 = __ldg(p + 16);
+                            m0 = fma(w, q0.x, m0); m1 = fma(w, q0.y, m1); m2 = fma(w, q1.x, m2); m3 = fma(w, q1.y, m3);
+                        }
+                    }
+                }
+                v[i][0] *= m0; v[i][1] *= m1; v[i][2] *= m2; v[i][3] *= m3;
+            }
+        } else {
+            const int cin = child - a.L;
+            const double *X = a.cond + (((size_t)cat * a.I + cin) * Sp + s0) * 64;
+            __syncthreads();            // previous child's tiles fully consumed
+            for (int idx = tid; idx < 2048; idx += 256) {       // 4096 doubles as double2, coalesced
+                const int r = idx >> 5, c2 = (idx & 31) * 2;
+                *reinterpret_cast<double2 *>(Xs + r * LD64 + c2) = *reinterpret_cast<const double2 *>(X + r * 64 + c2);
+                *reinterpret_cast<double2 *>(Ps + r * LD64 + c2) = __ldg(reinterpret_cast<const double2 *>(PT + r * 64 + c2));
+            }
+            __syncthreads();
+            double acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+            tile_mm64(Xs, Ps, tx, ty, acc);
+            const int *sc = a.scal + ((size_t)cat * a.I + cin) * Sp + s0 + 4 * ty;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                ex[i] += sc[i];
+#pragma unroll
+                for (int j = 0; j < 4; j++) v[i][j] *= acc[i][j];
+            }
+        }
+    }
+    if (a.L + par == a.forced_node) {            // pinned internal node: only the forced state survives
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int f = a.forced[s0 + 4 * ty + i];
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (col_of(tx, j) != f) v[i][j] = 0.0;
+        }
+    }
+    // per-pattern renormalisation: exact power of two so that max_k lands in [0.5, 1)
+    const bool is_root = (par == a.I - 1);
+    double *outp = a.cond + (((size_t)cat * a.I + par) * Sp + s0) * 64;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        double m = fmax(fmax(v[i][0], v[i][1]), fmax(v[i][2], v[i][3]));
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        int e = 0;
+        if (m > 0.0 && m < INFINITY) {
+            e = ilogb(m) + 1;
+            const double s1 = exp2i(-(e / 2)), s2 = exp2i(-(e - e / 2));   // two steps: |e| may exceed 1022
+#pragma unroll
+            for (int j = 0; j < 4; j++) v[i][j] = v[i][j] * s1 * s2;
+        }
+        ex[i] += e;
+        const int row = 4 * ty + i;
+        *reinterpret_cast<double2 *>(outp + (size_t)row * 64 + 2 * tx) = make_double2(v[i][0], v[i][1]);
+        *reinterpret_cast<double2 *>(outp + (size_t)row * 64 + 32 + 2 * tx) = make_double2(v[i][2], v[i][3]);
+        if (tx == 0) a.scal[((size_t)cat * a.I + par) * Sp + s0 + row] = ex[i];
+        if (is_root) {
+            double r = v[i][0] * a.pi[2 * tx] + v[i][1] * a.pi[2 * tx + 1] + v[i][2] * a.pi[32 + 2 * tx] + v[i][3] * a.pi[33 + 2 * tx];
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+            if (tx == 0) {
+                a.rootL[(size_t)cat * Sp + s0 + row] = r;
+                a.rootE[(size_t)cat * Sp + s0 + row] = ex[i];
+            }
+        }
+    }
+    __syncthreads();                 // this node's tile (global) is visible to the whole CTA before a parent reads it
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
