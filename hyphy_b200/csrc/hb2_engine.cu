@@ -156,6 +156,7 @@ struct hb2_partition {
     // persistent walk kernel (one launch per evaluation): plan buffers, generation bits of the tagged hand-over, residency
     bool small_walk = true;                   // HB2_SMALL_WALK=0: per-level launches of prune_small_kernel (A/B testing)
     bool fp64_walk = true;                    // HB2_FP64_WALK=0: per-level launches of prune64_kernel (A/B testing)
+    int sm_count = 148;
     bool expm_dfma = false;                   // HB2_EXPM_DFMA=1: previous FFMA-style fp64 expm kernel (A/B testing)
     bool use_walk = false;
     int walk_max_resident = 0;
@@ -743,7 +744,11 @@ int run_fp64_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::v
 
 int run_pruning(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector<int>> &levels) {
     if (p->use_tc && p->use_walk) return run_walk(p, cat0, ncls, levels);
-    if (!p->use_tc && p->Dp == 64 && p->fp64_walk) return run_fp64_walk(p, cat0, ncls, levels);
+    // one launch per evaluation pays only when (tiles x classes) fills the machine about twice over (c5: 316 CTAs); below
+    // that the per-level launches expose more parallelism (north-star shape: 128 CTAs walk 1.55 ms, 54 level launches take
+    // 1.38 ms; a single class of it -- the patched host's per-class ComputeBlock -- would leave 116 SMs idle)
+    if (!p->use_tc && p->Dp == 64 && p->fp64_walk && (int64_t)(p->Sp / hb2::TILE_P) * ncls >= 2 * p->sm_count)
+        return run_fp64_walk(p, cat0, ncls, levels);
     if (p->Dp <= 32 && p->small_walk) return run_small_walk(p, cat0, ncls, levels);
     // upload all job lists in one copy
     int total = 0;
@@ -1012,6 +1017,7 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
     CU(cudaSetDevice(device));
 
     hb2_partition *p = new hb2_partition();
+    cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, device);
     p->device = device; p->flags = flags; p->S = S; p->D = D; p->L = L; p->I = I; p->C = C; p->B = L + I - 1; p->nAmb = nAmb;
     p->Dp = Dp;
     p->use_tc = (Dp == 64) && !(flags & HB2_FLAG_FORCE_FP64);
@@ -1759,7 +1765,7 @@ int hb2_stage_launches(const hb2_partition *p, int64_t *out3) {
 const char *hb2_pruning_kernel(const hb2_partition *p) {
     if (!p) return "";
     if (p->use_tc) return p->use_walk ? "prune64_tc_walk_kernel" : "prune64_tc_kernel";
-    if (p->Dp == 64) return p->fp64_walk ? "prune64_walk_kernel" : "prune64_kernel";
+    if (p->Dp == 64) return (p->fp64_walk && (int64_t)(p->Sp / hb2::TILE_P) * p->ownN >= 2 * p->sm_count) ? "prune64_walk_kernel" : "prune64_kernel";
     return p->small_walk ? "prune_small_walk_kernel" : "prune_small_kernel";
 }
 

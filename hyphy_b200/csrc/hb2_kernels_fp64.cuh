@@ -1231,11 +1231,17 @@ __global__ void __launch_bounds__(128) prune_small_walk_kernel(PruneArgs a, cons
     // 16..32 states: the branch's P^T is staged in shared memory once per child (all threads of the CTA walk the same
     // job list in lockstep) and read as broadcasts; 4/8 states read the 16/64 doubles straight through L1.
     constexpr bool kStage = DP > 8;
+    // The node computed by the previous job is, in post-order, very often a child of the current one (every node follows
+    // its last child): its vector is handed over in registers instead of being re-read from L2 (the thread would wait a
+    // full L2 round trip for data it wrote a moment ago).  Register budget allows it up to 24 padded states.
+    constexpr bool kChain = DP <= 24;
     __shared__ double Ps[kStage ? DP * DP : 1];
     const int tid = threadIdx.x;
     const int cat = a.cat0 + blockIdx.y;
     const size_t Sp = a.Sp;
     const size_t s = (size_t)blockIdx.x * 128 + tid;
+    double pv[kChain ? DP : 1];
+    int prev = -1, pex = 0;
     for (int jb = 0; jb < njobs; jb++) {
         const int par = __ldg(jobs + jb);
         double v[DP];
@@ -1276,10 +1282,17 @@ __global__ void __launch_bounds__(128) prune_small_walk_kernel(PruneArgs a, cons
                 }
             } else {
                 const int cin = child - a.L;
-                const double2 *X = reinterpret_cast<const double2 *>(a.cond + (((size_t)cat * a.I + cin) * Sp + s) * DP);
                 double x[DP];
+                if (kChain && cin == prev) {
 #pragma unroll
-                for (int j = 0; j < DP; j += 2) { const double2 t = X[j / 2]; x[j] = t.x; x[j + 1] = t.y; }
+                    for (int j = 0; j < DP; j++) x[j] = pv[j];
+                    ex += pex;
+                } else {
+                    const double2 *X = reinterpret_cast<const double2 *>(a.cond + (((size_t)cat * a.I + cin) * Sp + s) * DP);
+#pragma unroll
+                    for (int j = 0; j < DP; j += 2) { const double2 t = X[j / 2]; x[j] = t.x; x[j + 1] = t.y; }
+                    ex += a.scal[((size_t)cat * a.I + cin) * Sp + s];
+                }
                 double acc[DP];
 #pragma unroll
                 for (int k = 0; k < DP; k++) acc[k] = 0.0;
@@ -1291,7 +1304,6 @@ __global__ void __launch_bounds__(128) prune_small_walk_kernel(PruneArgs a, cons
                 }
 #pragma unroll
                 for (int k = 0; k < DP; k++) v[k] *= acc[k];
-                ex += a.scal[((size_t)cat * a.I + cin) * Sp + s];
             }
         }
         if (a.L + par == a.forced_node) {
@@ -1313,6 +1325,11 @@ __global__ void __launch_bounds__(128) prune_small_walk_kernel(PruneArgs a, cons
 #pragma unroll
         for (int k = 0; k < DP; k += 2) outp[k / 2] = make_double2(v[k], v[k + 1]);
         a.scal[((size_t)cat * a.I + par) * Sp + s] = ex;
+        if (kChain) {
+#pragma unroll
+            for (int k = 0; k < DP; k++) pv[k] = v[k];
+            prev = par; pex = ex;
+        }
         if (par == a.I - 1) {
             double r = 0.0;
 #pragma unroll
