@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-host", action="store_true", help="skip the patched-HyPhy end-to-end leg")
     ap.add_argument("--no-c5", action="store_true", help="skip the extra 500 x 5000 x 4 line")
+    ap.add_argument("--no-small", action="store_true", help="skip the nucleotide / protein extra lines")
     ap.add_argument("--fp64", action="store_true", help="force the fp64 pruning kernels (HB2_FLAG_FORCE_FP64)")
     ap.add_argument("--class-groups", type=int, default=0, help="multi-GPU: force this many class groups (default: as many as divide both)")
     ap.add_argument("--no-class-groups", action="store_true", help="multi-GPU: shard patterns only (every rank exponentiates every class)")
@@ -352,6 +353,29 @@ def main():
               "layout": f"patterns/{lay5['shards']} x classes/{lay5['groups']}", "lnL": lnl5, "lnL_reference": golden5,
               "rel_err": abs(lnl5 - golden5) / abs(golden5)}
 
+    # ---- extra lines: the register kernels of the nucleotide (4 states) and protein (20 states) paths, HBM-bound by SURVEY §8d:
+    #      achieved algorithmic GB/s of the pruning pass against the measured copy bandwidth (same numbers as tools/bench_small.py)
+    small = None
+    if world == 1 and not args.no_small:
+        small = {}
+        for key, wk in (("nucleotide_d4_256x200000", lambda: synth.nucleotide_workload(256, 200000, mean_t=0.1)),
+                        ("protein_d20_128x20000_c4", lambda: synth.generic_workload(20, 128, 20000, 4, mean_t=0.1))):
+            ws = wk()
+            lfs = LikelihoodFunction(ws, device=local_rank)
+            lfs.set_template()
+            lfs.set_all_compiled()
+            lfs.compute()
+            lfs.part.time_resident(ws.class_weights, ws.pi, iters=3)
+            mss, sts, lnls = lfs.part.time_resident(ws.class_weights, ws.pi, iters=10)
+            kern = lfs.part.pruning_kernel
+            lfs.close()
+            Ls, Is, Ss, Cs = ws.tree.n_leaves, ws.tree.n_internal, ws.S, ws.C
+            Dps = 4 if ws.D <= 4 else (ws.D + 7) // 8 * 8
+            bys = Cs * ((2 * Is - 1) * Ss * Dps * 8 + (2 * Is - 1) * Ss * 4 + Ls * Ss * 4)
+            pk_, _k = peaks()
+            small[key] = {"kernel": kern, "patterns": Ss, "ms_per_eval": mss, "pruning_ms": float(sts[1]), "algorithmic_bytes": bys,
+                          "achieved_gbs": bys / (float(sts[1]) * 1e-3) / 1e9, "frac_of_hbm_peak": bys / (float(sts[1]) * 1e-3) / 1e9 / pk_["hbm_gbs"], "lnL": lnls}
+
     if rank == 0:
         pk, pk_kind = peaks()
         flops, byts, expm_flops = algorithmic_work(w, S, 4 if tc_mode else 8)
@@ -360,7 +384,8 @@ def main():
         prune_ms = stage[1]
         achieved_gbs = (byts / world) / (prune_ms * 1e-3) / 1e9
         single_launch = prune_launches == 1
-        kname = {"prune64_tc_walk_kernel": "prune64_tc_walk_kernel (tcgen05 3xTF32 fused pruning pass, whole tree in one launch)",
+        kname = {"prune64_tc_walk2_kernel": "prune64_tc_walk2_kernel (tcgen05 3xTF32 fused pruning pass, whole tree in one launch, two threads per pattern)",
+                 "prune64_tc_walk_kernel": "prune64_tc_walk_kernel (tcgen05 3xTF32 fused pruning pass, whole tree in one launch)",
                  "prune64_tc_kernel": "prune64_tc_kernel (tcgen05 3xTF32 fused pruning update, one launch per tree level)",
                  "prune64_kernel": "prune64_kernel (fp64 fused pruning update, one launch per tree level)"}.get(prune_kernel, prune_kernel)
         # DRAM traffic of that kernel from the committed `ncu --set full` capture of this same command (profiles/)
@@ -396,7 +421,7 @@ def main():
                 "e2e_dense": {"value": 1000.0 / e2e_dense_ms, "unit": "evals/s", "ms_per_step": e2e_dense_ms, "h2d_bytes_per_step": h2d_dense,
                               "d2h_bytes_per_step": 12, "api": "hb2_set_matrices_packed x C + hb2_evaluate_classes", "lnL": lnl_dense},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "lnL": lnl0, "lnL_resident": lnl_res,
-                "lnL_reference": -205416.12461664603, "root_exchange": root_path if world > 1 else None, "c5": c5}
+                "lnL_reference": -205416.12461664603, "root_exchange": root_path if world > 1 else None, "c5": c5, "small_states": small}
         # the same evaluation stream through the PATCHED HyPhy binary (host/_build/hyphy: the reference's HBL interpreter,
         # formula evaluation and DetermineNodesForUpdate on the host, everything below ComputeBlock on the engine):
         # wall-clock evaluations/s of `LFCompute` as a user of the reference would see them

@@ -159,6 +159,7 @@ struct hb2_partition {
     int sm_count = 148;
     bool expm_dfma = false;                   // HB2_EXPM_DFMA=1: previous FFMA-style fp64 expm kernel (A/B testing)
     bool use_walk = false;
+    bool walk_v2 = true;                      // two threads per pattern (prune64_tc_walk2_kernel); HB2_WALK_V2=0: the 128-thread kernel
     int walk_max_resident = 0;
     // single-branch shortcut (hb2_branch_cache_*): outside vectors of one branch, all owned classes
     double *d_bc_out = nullptr; int *d_bc_outE = nullptr, *d_bc_sib = nullptr; int64_t bc_node = -1;
@@ -671,7 +672,8 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
         w.trace = d_trace;
         w.trace_cta_times = d_trace + (size_t)(ns + 1) * 12;
     }
-    hb2::prune64_tc_walk_kernel<<<nslots * K, 128, hb2::WALK_SMEM_BYTES, p->stream>>>(w);
+    if (p->walk_v2) hb2::prune64_tc_walk2_kernel<<<nslots * K, 256, hb2::WALK2_SMEM_BYTES, p->stream>>>(w);
+    else hb2::prune64_tc_walk_kernel<<<nslots * K, 128, hb2::WALK_SMEM_BYTES, p->stream>>>(w);
     if (d_trace) {
         std::vector<long long> ht((size_t)(ns + 1) * 12 + (size_t)nslots * K * 4);
         CU(cudaStreamSynchronize(p->stream));
@@ -1065,26 +1067,34 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
         CUP(cudaMemsetAsync(p->d_PTf, 0, (size_t)C * p->B * hb2::TC_PTF_FLOATS * sizeof(float), p->stream));
         CUP(cudaFuncSetAttribute(hb2::prune64_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::TC_SMEM_BYTES));
         CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::WALK_SMEM_BYTES));
+        CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::WALK2_SMEM_BYTES));
+        CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        { const char *env = getenv("HB2_WALK_V2"); p->walk_v2 = !(env && env[0] == '0'); }
         {
             const char *env = getenv("HB2_TC_WALK");
             p->use_walk = !(env && env[0] == '0');
             int per_sm = 0, sms = 0;
             CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            CUP(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hb2::prune64_tc_walk_kernel, 128, hb2::WALK_SMEM_BYTES));
+            const void *wk = p->walk_v2 ? (const void *)hb2::prune64_tc_walk2_kernel : (const void *)hb2::prune64_tc_walk_kernel;
+            const int wk_threads = p->walk_v2 ? 256 : 128, wk_smem = p->walk_v2 ? hb2::WALK2_SMEM_BYTES : hb2::WALK_SMEM_BYTES;
+            CUP(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wk, wk_threads, wk_smem));
             if (getenv("HB2_DEBUG")) {
-                cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, hb2::prune64_tc_walk_kernel);
+                cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, wk);
                 cudaDeviceProp dp; cudaGetDeviceProperties(&dp, device);
                 fprintf(stderr, "[hb2] walk kernel occupancy: %d CTAs/SM (regs/thread %d, static smem %zu, dyn smem %d, regs/SM %d, smem/SM %zu, smem/block optin %zu, reserved/block %zu)\n",
-                        per_sm, fa.numRegs, fa.sharedSizeBytes, hb2::WALK_SMEM_BYTES, dp.regsPerMultiprocessor, dp.sharedMemPerMultiprocessor, dp.sharedMemPerBlockOptin, dp.reservedSharedMemPerBlock);
+                        per_sm, fa.numRegs, fa.sharedSizeBytes, wk_smem, dp.regsPerMultiprocessor, dp.sharedMemPerMultiprocessor, dp.sharedMemPerBlockOptin, dp.reservedSharedMemPerBlock);
             }
             CUP(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-            {   // the occupancy API reports 1 CTA/SM for this kernel on B200 although ncu (launch__occupancy_limit_* = 2) and a
-                // forced 2-per-SM run with cross-CTA dependencies (r01g) show two are co-resident; derive it from the resources
+            {   // The occupancy API reports 1 CTA/SM for these kernels on B200 although ncu (launch__occupancy_limit_* = 2) and
+                // the measured residence of 256-CTA grids show two are co-resident: the lane count is planned from the
+                // resources.  Correctness does not depend on it: blocks are dispatched in index order and a lane only waits
+                // for lanes of its own (class, tile) slot -- adjacent block indices -- with time-bounded waits, so fewer
+                // resident CTAs than planned only make the pass slower.
                 cudaFuncAttributes fa;
-                CUP(cudaFuncGetAttributes(&fa, hb2::prune64_tc_walk_kernel));
+                CUP(cudaFuncGetAttributes(&fa, wk));
                 cudaDeviceProp dp; CUP(cudaGetDeviceProperties(&dp, device));
-                const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * 128;
-                const size_t smem_per_cta = (size_t)hb2::WALK_SMEM_BYTES + fa.sharedSizeBytes + dp.reservedSharedMemPerBlock;
+                const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * wk_threads;
+                const size_t smem_per_cta = (size_t)wk_smem + fa.sharedSizeBytes + dp.reservedSharedMemPerBlock;
                 const int by_res = std::min(dp.regsPerMultiprocessor / std::max(regs_per_cta, 1), (int)(dp.sharedMemPerMultiprocessor / smem_per_cta));
                 per_sm = std::max(per_sm, std::min(by_res, 2));
             }
@@ -1558,7 +1568,7 @@ int hb2_branch_cache_build(hb2_partition *p, int64_t node, const double *rootFre
     if (!p->d_bc_out) {
         CU(cudaMalloc(&p->d_bc_out, (size_t)p->C * p->Sp * p->Dp * sizeof(double)));
         CU(cudaMalloc(&p->d_bc_outE, (size_t)p->C * p->Sp * sizeof(int)));
-        CU(cudaMalloc(&p->d_bc_sib, (size_t)(p->L + p->I) * sizeof(int)));
+        CU(cudaMalloc(&p->d_bc_sib, (size_t)(3 * (p->L + p->I) + 2) * sizeof(int)));
     }
     double *hs = p->h_small;
     for (int k = 0; k < p->Dp; k++) hs[k] = k < p->D ? rootFreqs[k] : 0.0;
@@ -1574,14 +1584,22 @@ int hb2_branch_cache_build(hb2_partition *p, int64_t node, const double *rootFre
         off[i + 1] = (int)sib.size();
         down[i] = (i + 1 < path.size()) ? on_path : -1;
     }
-    CU(cudaStreamSynchronize(p->stream));            // h_small / sibling upload below are synchronous with respect to earlier work
-    if (!sib.empty()) CU(cudaMemcpy(p->d_bc_sib, sib.data(), sib.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaStreamSynchronize(p->stream));            // h_small / path upload below are synchronous with respect to earlier work
+    // one launch for the whole path: [siblings | sibling offsets (npath+1) | path child below each path node (npath)]
+    std::vector<int> pk(sib);
+    const int o_off = (int)pk.size();
+    pk.insert(pk.end(), off.begin(), off.end());
+    const int o_down = (int)pk.size();
+    pk.insert(pk.end(), down.begin(), down.end());
+    if ((int64_t)pk.size() > 3 * (p->L + p->I) + 2) return fail("branch-cache path does not fit its buffer");
+    CU(cudaMemcpy(p->d_bc_sib, pk.data(), pk.size() * sizeof(int), cudaMemcpyHostToDevice));
     hb2::BranchCacheArgs a = bc_args(p, p->own0, p->ownN);
-    dim3 grid((unsigned)((p->S + 127) / 128), (unsigned)p->ownN);
-    for (size_t i = 0; i < path.size(); i++) {
-        hb2::bc_step_kernel<<<grid, 128, 0, p->stream>>>(a, p->d_bc_sib + off[i], off[i + 1] - off[i], down[i], i == 0 ? 1 : 0);
-        p->launches++;
-    }
+    hb2::BranchPathArgs bp;
+    bp.sib = p->d_bc_sib; bp.sib_off = p->d_bc_sib + o_off; bp.down = p->d_bc_sib + o_down; bp.npath = (int)path.size();
+    dim3 grid((unsigned)p->S, (unsigned)p->ownN);
+    if (p->Dp > 32) hb2::bc_path_kernel<64><<<grid, 64, 0, p->stream>>>(a, bp);
+    else hb2::bc_path_kernel<32><<<grid, 32, 0, p->stream>>>(a, bp);
+    p->launches++;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(p->stream));
     p->bc_node = node;
@@ -1764,7 +1782,7 @@ int hb2_stage_launches(const hb2_partition *p, int64_t *out3) {
 }
 const char *hb2_pruning_kernel(const hb2_partition *p) {
     if (!p) return "";
-    if (p->use_tc) return p->use_walk ? "prune64_tc_walk_kernel" : "prune64_tc_kernel";
+    if (p->use_tc) return p->use_walk ? (p->walk_v2 ? "prune64_tc_walk2_kernel" : "prune64_tc_walk_kernel") : "prune64_tc_kernel";
     if (p->Dp == 64) return (p->fp64_walk && (int64_t)(p->Sp / hb2::TILE_P) * p->ownN >= 2 * p->sm_count) ? "prune64_walk_kernel" : "prune64_kernel";
     return p->small_walk ? "prune_small_walk_kernel" : "prune_small_kernel";
 }

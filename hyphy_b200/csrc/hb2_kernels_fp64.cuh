@@ -1409,9 +1409,8 @@ __global__ void __launch_bounds__(256) combine_kernel(CombineArgs a) {
 // below_b = conditionals of b's subtree (already resident) and rest_b[s][a] = everything else, seen from state a at u:
 //   out_root[a] = pi_a ;  rest_v[a] = out_u[a] * prod_{siblings c of v at u} (P_c L_c)[a] ;  out_v[a'] = sum_a rest_v[a] P_v[a][a'].
 // (No reversibility is needed: the outside vectors are propagated with the transposed matrices instead of re-rooting.)
-// bc_step_kernel does one node of the root->u path; bc_eval_kernel then costs O(S*D^2) per probe of P_b.
-// One thread per (class, pattern), fp64 throughout, matrices read as broadcasts from PT (L1); built once per line search,
-// so simplicity wins over speed here.  CondView abstracts the two conditional layouts (fp64 [I][Sp][Dp]; the walk kernel's
+// bc_path_kernel walks the root->u path once; bc_eval_kernel then costs O(S*D^2) per probe of P_b.
+// fp64 throughout; the build runs one CTA per (class, pattern), the probe one thread per (class, pattern).  CondView abstracts the two conditional layouts (fp64 [I][Sp][Dp]; the walk kernel's
 // tile-wise fp32 with generation tags).
 // ------------------------------------------------------------------------------------------------
 struct CondView {
@@ -1482,35 +1481,81 @@ __device__ __forceinline__ void bc_renorm(double *v, int D, int &e) {
     }
 }
 
-// One path node u: rest = out_u * prod over `sib` (children of u except the path child); if `down` >= 0 (flat id of the
-// path child, which is not the target branch yet) out <- transpose-propagated through P_down, else out <- rest (= the cache).
-__global__ void __launch_bounds__(128) bc_step_kernel(BranchCacheArgs a, const int *sib, int nsib, int down, int first) {
-    const int s = blockIdx.x * 128 + threadIdx.x;
-    const int cat = a.cat0 + blockIdx.y;
-    if (s >= a.S) return;
-    double r[64], m[64];
+// The whole root -> parent(b) path in ONE launch: one CTA of Dp' = 64 (or 32) threads per (class, pattern), thread q owns
+// state q; vectors are exchanged through shared memory and a matrix column / row is read with consecutive threads on
+// consecutive addresses (the transposed table serves messages, its rows serve the outside propagation).  Replaces one
+// launch of bc_step_kernel per path node with a serial thread per pattern (17.7 ms at depth 48 on the north-star shape).
+//   path[i]      internal index of the i-th path node (root first), npath nodes
+//   sib_off[i]   range of its non-path children in sib[]
+//   down[i]      flat id of the path child below path[i] (the next path node), -1 for the last (whose child is the branch b)
+struct BranchPathArgs {
+    const int *sib, *sib_off, *down;
+    int npath;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(NT) bc_path_kernel(BranchCacheArgs a, BranchPathArgs bp) {
+    __shared__ double xs[64];
+    __shared__ double red[2];
+    const int s = blockIdx.x, cat = a.cat0 + blockIdx.y, q = threadIdx.x;
+    const bool live = q < a.D;
+    double r = live ? a.pi[q] : 0.0;             // out_root = pi
     int e = 0;
-    double *o = a.out + ((size_t)cat * a.Sp + s) * a.Dp;
-    if (first) { for (int q = 0; q < a.D; q++) r[q] = a.pi[q]; }
-    else { for (int q = 0; q < a.D; q++) r[q] = o[q]; e = a.outE[(size_t)cat * a.Sp + s]; }
-    for (int i = 0; i < nsib; i++) {
-        bc_message(a, cat, sib[i], s, m, e);
-        for (int q = 0; q < a.D; q++) r[q] *= m[q];
-        bc_renorm(r, a.D, e);
-    }
-    if (down >= 0) {
-        const double *PTd = a.PT + ((size_t)cat * a.B + down) * a.Dp * a.Dp;     // out'[a'] = sum_a r[a] * PT[a'][a]
-        for (int q = 0; q < a.D; q++) {
-            double acc = 0.0;
-            for (int k = 0; k < a.D; k++) acc = fma(r[k], __ldg(PTd + (size_t)q * a.Dp + k), acc);
-            m[q] = acc;
+    auto block_max = [&](double v) -> double {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (NT > 32) {
+            __syncthreads();
+            if ((q & 31) == 0) red[q >> 5] = v;
+            __syncthreads();
+            v = fmax(red[0], red[1]);
         }
-        bc_renorm(m, a.D, e);
-        for (int q = 0; q < a.D; q++) o[q] = m[q];
-    } else {
-        for (int q = 0; q < a.D; q++) o[q] = r[q];
+        return v;
+    };
+    auto renorm = [&](double &v) {
+        const double m = block_max(v);
+        if (m > 0.0 && m < INFINITY) {
+            int ex;
+            frexp(m, &ex);
+            if (ex != 0) { v *= exp2i(-(ex / 2)) * exp2i(-(ex - ex / 2)); e += ex; }
+        }
+    };
+    for (int i = 0; i < bp.npath; i++) {
+        for (int ci = bp.sib_off[i]; ci < bp.sib_off[i + 1]; ci++) {          // rest = out_u * prod over siblings (P_c L_c)
+            const int ch = bp.sib[ci];
+            const double *PTc = a.PT + ((size_t)cat * a.B + ch) * a.Dp * a.Dp;
+            double m = 0.0;
+            if (ch < a.L) {
+                const int code = a.leaf[(size_t)ch * a.Sp + s];
+                if (code >= 0) m = live ? PTc[(size_t)code * a.Dp + q] : 0.0;
+                else {
+                    const double *amb = a.ambig + (size_t)(-code - 1) * a.Dp;
+                    for (int k = 0; k < a.D; k++) if (amb[k] != 0.0 && live) m += PTc[(size_t)k * a.Dp + q];
+                }
+            } else {
+                const int cin = ch - a.L;
+                __syncthreads();
+                if (q < a.Dp) xs[q] = live ? cond_at(a.cv, cat, cin, s, q) : 0.0;
+                __syncthreads();
+                if (live) for (int k = 0; k < a.D; k++) m = fma(xs[k], PTc[(size_t)k * a.Dp + q], m);
+                e += exp_at(a.cv, cat, cin, s);
+            }
+            r *= m;
+            renorm(r);
+        }
+        if (bp.down[i] >= 0) {                                                  // out'[q] = sum_k rest[k] * P_down[k][q] = sum_k r[k] PT[q][k]
+            const double *PTd = a.PT + ((size_t)cat * a.B + bp.down[i]) * a.Dp * a.Dp;
+            __syncthreads();
+            if (q < a.Dp) xs[q] = r;
+            __syncthreads();
+            double acc = 0.0;
+            if (live) for (int k = 0; k < a.D; k++) acc = fma(xs[k], PTd[(size_t)q * a.Dp + k], acc);
+            r = acc;
+            renorm(r);
+        }
     }
-    a.outE[(size_t)cat * a.Sp + s] = e;
+    if (q < a.Dp) a.out[((size_t)cat * a.Sp + s) * a.Dp + q] = r;
+    if (q == 0) a.outE[(size_t)cat * a.Sp + s] = e;
 }
 
 // Probe: rootL/rootE <- sum_a rest[a] * (P_b * below)[a] with the CURRENT matrix of branch b.

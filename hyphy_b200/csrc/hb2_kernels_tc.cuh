@@ -837,4 +837,407 @@ __global__ void __launch_bounds__(128, 2) prune64_tc_walk_kernel(WalkArgs w) {
 }
 
 
+// ------------------------------------------------------------------------------------------------------------------
+// prune64_tc_walk2_kernel: the same pass with TWO threads per pattern (256-thread CTA).
+//
+// The 128-thread kernel above is bound by each warp's own instruction stream (~830 instructions per contraction step at
+// ~6 cycles each, two warps per scheduler: profiles/r2e_prune64_tc_walk_kernel.json) -- every thread carries all 64 states
+// of its pattern through the split, the anchor products and the read-back.  Here warp w (0..7) serves TMEM lane quarter
+// w % 4 (hardware rule for tcgen05.ld/st) and state half h = w / 4: thread (pattern t, half h) owns states 32h..32h+31 of
+// pattern t everywhere (conditional chunks 8h..8h+7, TMEM operand columns 32h.., accumulator columns 32h..), so the serial
+// stream per step halves while the tile, the MMAs, the staging ring and the plan stay exactly the same.
+//   * anchors: each thread publishes the anchor mask of ITS half in shared memory before barrier (2); afterwards both threads
+//     of a pattern enumerate the combined 64-bit mask (values re-read from the child's block in L2, as in the first kernel)
+//     and accumulate their own 32 parent states;
+//   * exponents: inside a job the two halves rescale independently (own guard, own exponent); when the job is complete
+//     (STEP_LAST) the halves exchange (maximum, exponent) through shared memory and bring the node to ONE power-of-two scale
+//     with max in [0.5,1), which is what is stored (tagged) and handed over in registers on a chain;
+//   * the root dot product is combined the same way.
+// Everything observable (layouts, tags, plan, results' meaning) is identical to prune64_tc_walk_kernel; the summation order
+// inside a row differs, so results agree to rounding, not bitwise (both are deterministic).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int WALK2_XBYTES = 2 * 128 * 4 /* anchor masks */ + 2 * 128 * 4 /* half maxima */ + 2 * 128 * 4 /* half exponents */ +
+                             2 * 128 * 8 /* root partials */;
+constexpr int WALK2_SMEM_BYTES = 2 * WALK_STAGE_FLOATS * 4 + WALK2_XBYTES + 64;
+
+__device__ __forceinline__ void renorm_half(float (&v)[32], int &ex) {     // guard inside a job: own half only, rarely taken
+    float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
+#pragma unroll
+    for (int k = 4; k < 32; k += 4) { m0 = fmaxf(m0, v[k]); m1 = fmaxf(m1, v[k + 1]); m2 = fmaxf(m2, v[k + 2]); m3 = fmaxf(m3, v[k + 3]); }
+    const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    if (m > 0.f && m < 2.3283064e-10f) {
+        const int e = max((int)((__float_as_uint(m) >> 23) & 0xffu) - 126, -125);
+        const float sc = __uint_as_float((uint32_t)(127 - e) << 23);
+#pragma unroll
+        for (int k = 0; k < 32; k++) v[k] *= sc;
+        ex += e;
+    }
+}
+
+__global__ void __launch_bounds__(256, 2) prune64_tc_walk2_kernel(WalkArgs w) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const PruneTcArgs &a = w.a;
+    float *stage_base = reinterpret_cast<float *>(smem);                           // 2 x [P^T table | Ph | Pl]
+    uint32_t *s_am = reinterpret_cast<uint32_t *>(smem + 2 * WALK_STAGE_FLOATS * 4);   // [2][128] anchor masks of the two halves
+    float *s_mx = reinterpret_cast<float *>(s_am + 2 * 128);                        // [2][128]
+    int *s_ex = reinterpret_cast<int *>(s_mx + 2 * 128);                            // [2][128]
+    double *s_rt = reinterpret_cast<double *>(s_ex + 2 * 128);                      // [2][128]
+    uint64_t *bar_full = reinterpret_cast<uint64_t *>(s_rt + 2 * 128);              // [2]
+    uint64_t *bar_mma = bar_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_mma + 1);
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int lq = warp & 3, h = warp >> 2, t = 32 * lq + (tid & 31);              // TMEM lane quarter, state half, pattern in tile
+    const size_t Sp = a.Sp;
+    float4 *cond4 = reinterpret_cast<float4 *>(a.cond);
+
+    if (tid == 0) {
+        mbar_init(bar_full, 1);
+        mbar_init(bar_full + 1, 1);
+        mbar_init(bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(lq * 32) << 16);
+    uint32_t n_step = 0, n_mma = 0;
+    bool bailed = false;
+
+    const int r = blockIdx.x % w.K;
+    const int i_begin = w.lane_start[r], i_end = w.lane_start[r + 1];
+    if (w.trace_cta_times && tid == 0) {
+        uint32_t smid; unsigned long long gt;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        long long *q = w.trace_cta_times + (size_t)blockIdx.x * 4;
+        q[0] = smid; q[1] = clock64(); q[3] = (long long)gt;
+    }
+
+    auto stage_step = [&](int cat, int tile, int2 st, uint32_t m) {
+        const int child = st.x & WALK_ID_MASK;
+        const bool internal = child >= a.L;
+        float *dst = stage_base + (m & 1u) * WALK_STAGE_FLOATS;
+        uint64_t *bar = bar_full + (m & 1u);
+        if (st.x & WALK_MUL) {
+            mbar_expect_tx(bar, 0u);
+            prefetch_l2_bulk(cond4 + cond_f4(cat, child - a.L, tile, 0, 0, w.NI, w.T), 32768u);
+            return;
+        }
+        const size_t slot = (size_t)cat * a.B + child;
+        mbar_expect_tx(bar, (uint32_t)(TC_PTF_FLOATS * 4) + (internal ? 32768u : 0u));
+        bulk_g2s(dst, a.PTf + slot * TC_PTF_FLOATS, (uint32_t)(TC_PTF_FLOATS * 4), bar);
+        if (internal) {
+            bulk_g2s(dst + 64 * WALK_PT_ROW, a.PB + slot * TC_PB_FLOATS, 32768u, bar);
+            if (!(st.x & WALK_CHAIN)) prefetch_l2_bulk(cond4 + cond_f4(cat, child - a.L, tile, 0, 0, w.NI, w.T), 32768u);
+        }
+    };
+
+    // this thread's 9 words of another node's tile: its 8 chunks (32 states) + the exponent word; `await` as in the first kernel
+    auto load_half_row = [&](const float4 *xrow, const int *scp, bool await, uint32_t want, uint4 (&x4)[8], uint32_t &sc) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) x4[q] = __ldcg(reinterpret_cast<const uint4 *>(xrow + (size_t)q * 128));
+        sc = (uint32_t)__ldcg(scp);
+        if (await) {
+            unsigned long long t0 = 0;
+            for (int it = 0; !bailed; it++) {
+                uint32_t bad = (sc << 31) ^ want;
+#pragma unroll
+                for (int q = 0; q < 8; q++) bad |= (x4[q].x ^ want) | (x4[q].y ^ want) | (x4[q].z ^ want) | (x4[q].w ^ want);
+                if (!(bad >> 31)) break;
+                if ((it & 255) == 255) {
+                    const unsigned long long now = globaltimer_ns();
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > HB2_WAIT_LIMIT_NS) { atomicExch(a.err, 2); bailed = true; }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; q++) x4[q] = ld_relaxed_u4(xrow + (size_t)q * 128);
+                sc = ld_relaxed_u32(scp);
+            }
+        }
+    };
+
+    for (int ct = blockIdx.x / w.K; ct < w.ncls * w.T; ct += w.nslots) {
+        const int cat = a.cat0 + ct / w.T;
+        const int tile = ct % w.T;
+        const size_t s = (size_t)tile * TC_TILE_P + t;
+        float v[32];
+        int ex = 0;
+        if (i_begin == i_end) continue;
+        int2 st = __ldg(w.steps + i_begin);
+        int2 nx = (i_begin + 1 < i_end) ? __ldg(w.steps + i_begin + 1) : make_int2(0, 0);
+        __syncthreads();
+        if (warp == 7 && elect_one()) stage_step(cat, tile, st, n_step);
+        auto step_aux = [&](int2 q) -> int {
+            const int ch = q.x & WALK_ID_MASK;
+            if (ch < a.L) return (ch == a.forced_node) ? __ldg(a.forced + s) : __ldg(a.leaf + (size_t)ch * Sp + s);
+            return (q.x & WALK_WAIT) ? __ldg(w.gen + (size_t)cat * w.NI + (ch - a.L)) : 0;
+        };
+        int next_code = step_aux(st);
+        for (int i = i_begin; i < i_end; i++) {
+            const int enc = st.x;
+            const int child = enc & WALK_ID_MASK;
+            const int par = st.y & WALK_ID_MASK;
+            const int flags = st.y;
+            const int code = next_code;
+            const uint32_t tagbit = (flags & STEP_LAST) ? ((uint32_t)__ldg(w.gen + (size_t)cat * w.NI + par) << 31) : 0u;
+            const bool has_next = (i + 1 < i_end);
+            const int2 nx2 = (i + 2 < i_end) ? __ldg(w.steps + i + 2) : make_int2(0, 0);
+            const bool tr = w.trace && tid == 0 && (int)blockIdx.x == w.trace_cta;
+            long long *trp = tr ? w.trace + (size_t)(i - i_begin) * 12 : nullptr;
+            if (tr) { trp[0] = ((long long)st.x << 32) | (unsigned)st.y; trp[1] = clock64(); }
+            __syncthreads();                  // (1) everyone is done with step i-1: ring slot (n_step+1)&1 and the exchange arrays are free
+            if (has_next) {
+                if (warp == 7 && elect_one()) stage_step(cat, tile, nx, n_step + 1);
+                next_code = step_aux(nx);
+            }
+            if ((flags & STEP_FIRST) && !(enc & WALK_CHAIN)) {
+#pragma unroll
+                for (int k = 0; k < 32; k++) v[k] = 1.f;
+                ex = 0;
+            }
+            const float *tab = stage_base + (n_step & 1u) * WALK_STAGE_FLOATS;
+            if (tr) trp[2] = clock64();
+            if (child < a.L) {
+                mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
+                if (tr) trp[3] = clock64();
+                if (code >= 0) {
+                    const float4 *row = reinterpret_cast<const float4 *>(tab + code * WALK_PT_ROW + 32 * h);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const float4 rr = row[q];
+                        v[4 * q] *= rr.x; v[4 * q + 1] *= rr.y; v[4 * q + 2] *= rr.z; v[4 * q + 3] *= rr.w;
+                    }
+                } else {
+                    float acc[32];
+#pragma unroll
+                    for (int k = 0; k < 32; k++) acc[k] = 0.f;
+                    const double *amb = a.ambig + (size_t)(-code - 1) * 64;
+                    for (int jj = 0; jj < a.D; jj++) {
+                        if (__ldg(amb + jj) != 0.0) {
+                            const float4 *row = reinterpret_cast<const float4 *>(tab + jj * WALK_PT_ROW + 32 * h);
+#pragma unroll
+                            for (int q = 0; q < 8; q++) {
+                                const float4 rr = row[q];
+                                acc[4 * q] += rr.x; acc[4 * q + 1] += rr.y; acc[4 * q + 2] += rr.z; acc[4 * q + 3] += rr.w;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 32; k++) v[k] *= acc[k];
+                }
+            } else if (enc & WALK_MUL) {
+                const int cin = child - a.L;
+                const bool await = (enc & WALK_WAIT) != 0;
+                uint4 x4[8];
+                uint32_t sc;
+                load_half_row(cond4 + cond_f4(cat, cin, tile, 8 * h, t, w.NI, w.T), a.scal + ((size_t)cat * w.NI + cin) * Sp + s, await,
+                              await ? ((uint32_t)code << 31) : 0u, x4, sc);
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    v[4 * q] *= __uint_as_float(x4[q].x & 0x7fffffffu); v[4 * q + 1] *= __uint_as_float(x4[q].y & 0x7fffffffu);
+                    v[4 * q + 2] *= __uint_as_float(x4[q].z & 0x7fffffffu); v[4 * q + 3] *= __uint_as_float(x4[q].w & 0x7fffffffu);
+                }
+                ex += (int)sc >> 1;
+                if (tr) trp[3] = clock64();
+            } else {
+                const int cin = child - a.L;
+                const float4 *xrow = cond4 + cond_f4(cat, cin, tile, 0, t, w.NI, w.T);      // chunk 0 of the pattern's row (all 64 states)
+                uint32_t am = 0;                                                         // anchors of this half (bit k <-> state 32h + k)
+                float xa[32];                                                            // this half's values (anchor values are taken from here)
+                if (enc & WALK_CHAIN) {
+#pragma unroll
+                    for (int k = 0; k < 32; k++) { xa[k] = v[k]; v[k] = 1.f; }
+                } else {
+                    const bool await = (enc & WALK_WAIT) != 0;
+                    const uint32_t want = await ? ((uint32_t)code << 31) : 0u;
+                    uint4 x4[8];
+                    uint32_t sc;
+                    load_half_row(xrow + (size_t)8 * h * 128, a.scal + ((size_t)cat * w.NI + cin) * Sp + s, await, want, x4, sc);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        xa[4 * q] = __uint_as_float(x4[q].x & 0x7fffffffu); xa[4 * q + 1] = __uint_as_float(x4[q].y & 0x7fffffffu);
+                        xa[4 * q + 2] = __uint_as_float(x4[q].z & 0x7fffffffu); xa[4 * q + 3] = __uint_as_float(x4[q].w & 0x7fffffffu);
+                    }
+                    ex += (int)sc >> 1;
+                }
+                // split in two 16-column pieces (registers): anchors out, tf32 hi / lo -> TMEM columns 64 + 32h.. / 128 + 32h..
+#pragma unroll
+                for (int o = 0; o < 32; o += 16) {
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int k = 0; k < 16; k++) {
+                        const float xv = xa[o + k];
+                        const bool big = xv >= w.anchor_thr;
+                        if (big) am |= 1u << (o + k);
+                        const float x = big ? 0.f : xv;
+                        const float hh = tf32_rn(x);
+                        hi[k] = __float_as_uint(hh);
+                        lo[k] = __float_as_uint(x - hh);
+                    }
+                    HB2_TMEM_ST16(lane_addr + 64 + 32 * h + o, hi, 0);
+                    HB2_TMEM_ST16(lane_addr + 128 + 32 * h + o, lo, 0);
+                }
+                if (tr) trp[8] = clock64();
+                s_am[h * 128 + t] = am;                                              // for both threads of the pattern
+                if (tr) trp[9] = clock64();
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                if (tr) { trp[10] = clock64(); trp[3] = trp[10]; }
+                tc_fence_before();
+                __syncthreads();             // (2) A operand complete in TMEM, anchor lists published; previous D consumed
+                if (tr) trp[4] = clock64();
+                if (warp == 0) {
+                    tc_fence_after();
+                    mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
+                    if (tr) trp[5] = clock64();
+                    const uint32_t baddr = __shfl_sync(0xffffffffu, smem_u32(tab + 64 * WALK_PT_ROW), 0);
+                    const uint64_t bdesc_hi = make_b_desc(baddr);
+                    const uint64_t bdesc_lo = make_b_desc(baddr + 4096 * 4);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kk = 0; kk < 8; kk++) tc_mma_tf32_ts(tmem_base, tmem_base + 128 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, kk > 0);
+#pragma unroll
+                        for (int kk = 0; kk < 8; kk++) tc_mma_tf32_ts(tmem_base, tmem_base + 64 + kk * 8, bdesc_lo + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u);
+#pragma unroll
+                        for (int kk = 0; kk < 8; kk++) tc_mma_tf32_ts(tmem_base, tmem_base + 64 + kk * 8, bdesc_hi + (uint64_t)(kk * 2 * 1024 >> 4), TC_IDESC, 1u);
+                        tc_commit(bar_mma);
+                    }
+                }
+                __syncwarp();
+                // anchors of BOTH halves on the CUDA cores while the tensor core works: this thread's 32 parent states.  Values
+                // are re-read from the child's block in L2 (loaded, or stored by the two threads of this pattern a moment ago --
+                // barrier (2) made those stores visible), a handful of loads in flight under the MMAs.
+                unsigned long long amask = (unsigned long long)s_am[t] | ((unsigned long long)s_am[128 + t] << 32);
+                const float *xrow_f = reinterpret_cast<const float *>(xrow);
+                int ak[WALK_FAST_ANCHORS];
+                float av[WALK_FAST_ANCHORS];
+#pragma unroll
+                for (int ai = 0; ai < WALK_FAST_ANCHORS; ai++) {
+                    ak[ai] = -1; av[ai] = 0.f;
+                    if (amask) {
+                        const int kk = __ffsll((long long)amask) - 1;
+                        amask &= amask - 1;
+                        ak[ai] = kk;
+                        av[ai] = __ldcg(xrow_f + ((size_t)(kk >> 2) * 128) * 4 + (kk & 3));
+                    }
+                }
+                float acc[32];
+                mbar_wait(bar_full + (n_step & 1u), (n_step >> 1) & 1u, a.err);
+                const float *tabh = tab + 32 * h;
+                {
+                    const float xv = ak[0] >= 0 ? fabsf(av[0]) : 0.f;
+                    const float4 *row = reinterpret_cast<const float4 *>(tabh + max(ak[0], 0) * WALK_PT_ROW);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const float4 rr = row[q];
+                        acc[4 * q] = xv * rr.x; acc[4 * q + 1] = xv * rr.y; acc[4 * q + 2] = xv * rr.z; acc[4 * q + 3] = xv * rr.w;
+                    }
+                }
+#pragma unroll
+                for (int ai = 1; ai < WALK_FAST_ANCHORS; ai++) {
+                    if (ak[ai] >= 0) {
+                        const float xv = fabsf(av[ai]);
+                        const float4 *row = reinterpret_cast<const float4 *>(tabh + ak[ai] * WALK_PT_ROW);
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            const float4 rr = row[q];
+                            acc[4 * q] = fmaf(xv, rr.x, acc[4 * q]); acc[4 * q + 1] = fmaf(xv, rr.y, acc[4 * q + 1]);
+                            acc[4 * q + 2] = fmaf(xv, rr.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(xv, rr.w, acc[4 * q + 3]);
+                        }
+                    }
+                }
+                while (amask) {                  // more than four entries above the threshold (diffuse vectors): rare
+                    const int kk = __ffsll((long long)amask) - 1;
+                    amask &= amask - 1;
+                    const float xv = fabsf(__ldcg(xrow_f + ((size_t)(kk >> 2) * 128) * 4 + (kk & 3)));
+                    const float4 *row = reinterpret_cast<const float4 *>(tabh + kk * WALK_PT_ROW);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const float4 rr = row[q];
+                        acc[4 * q] = fmaf(xv, rr.x, acc[4 * q]); acc[4 * q + 1] = fmaf(xv, rr.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(xv, rr.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(xv, rr.w, acc[4 * q + 3]);
+                    }
+                }
+                mbar_wait(bar_mma, n_mma & 1u, a.err);
+                if (tr) trp[6] = clock64();
+                tc_fence_after();
+#pragma unroll
+                for (int o = 0; o < 32; o += 16) {
+                    uint32_t d[16];
+                    HB2_TMEM_LD16(lane_addr + 32 * h + o, d, 0);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int k = 0; k < 16; k++) v[o + k] *= (__uint_as_float(d[k]) + acc[o + k]);
+                }
+                n_mma++;
+            }
+            n_step++;
+            if (!(flags & STEP_LAST)) {
+                renorm_half(v, ex);
+            } else {
+                if (a.L + par == a.forced_node) {                                      // pinned internal node
+                    const int f = __ldg(a.forced + s) - 32 * h;
+#pragma unroll
+                    for (int k = 0; k < 32; k++) if (k != f) v[k] = 0.f;
+                }
+                // the job is complete: ONE power-of-two scale for the whole row.  Exchange (half maximum, half exponent).
+                float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
+#pragma unroll
+                for (int k = 4; k < 32; k += 4) { m0 = fmaxf(m0, v[k]); m1 = fmaxf(m1, v[k + 1]); m2 = fmaxf(m2, v[k + 2]); m3 = fmaxf(m3, v[k + 3]); }
+                const float mh = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                s_mx[h * 128 + t] = mh;
+                s_ex[h * 128 + t] = ex;
+                __syncthreads();             // (3) once per job
+                const float mp = s_mx[(h ^ 1) * 128 + t];
+                const int exp_p = s_ex[(h ^ 1) * 128 + t];
+                // true exponent of each half's maximum (m = f * 2^e, f in [0.5,1)); a half that is all zero does not count
+                const bool okh = mh > 0.f && mh < INFINITY, okp = mp > 0.f && mp < INFINITY;
+                const int Eh = ex + max((int)((__float_as_uint(mh) >> 23) & 0xffu) - 126, -125);
+                const int Ep = exp_p + max((int)((__float_as_uint(mp) >> 23) & 0xffu) - 126, -125);
+                const int Et = (okh && okp) ? max(Eh, Ep) : okh ? Eh : okp ? Ep : ex;
+                if (okh || okp) {
+                    const int d = max(-127, min(ex - Et, 127));                         // this half's values are multiplied by 2^d
+                    if (d != 0) {
+                        const float sc = d < -126 ? 0.f : __uint_as_float((uint32_t)(127 + d) << 23);
+#pragma unroll
+                        for (int k = 0; k < 32; k++) v[k] *= sc;
+                    }
+                    ex = Et;
+                }
+                float4 *outp = cond4 + cond_f4(cat, par, tile, 8 * h, t, w.NI, w.T);
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    __stcg(reinterpret_cast<uint4 *>(outp + (size_t)q * 128),
+                           make_uint4(__float_as_uint(v[4 * q]) | tagbit, __float_as_uint(v[4 * q + 1]) | tagbit,
+                                      __float_as_uint(v[4 * q + 2]) | tagbit, __float_as_uint(v[4 * q + 3]) | tagbit));
+                if (h == 0) __stcg(a.scal + ((size_t)cat * w.NI + par) * Sp + s, (int)(((uint32_t)ex << 1) | (tagbit >> 31)));
+                if (par == a.I - 1) {
+                    double rr = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 32; k++) rr = fma((double)v[k], a.pi[32 * h + k], rr);
+                    s_rt[h * 128 + t] = rr;
+                    __syncthreads();
+                    if (h == 0) {
+                        a.rootL[(size_t)cat * Sp + s] = s_rt[t] + s_rt[128 + t];
+                        a.rootE[(size_t)cat * Sp + s] = ex;
+                    }
+                }
+            }
+            if (tr) trp[7] = clock64();
+            st = nx;
+            nx = nx2;
+        }
+    }
+    if (w.trace_cta_times && tid == 0) w.trace_cta_times[(size_t)blockIdx.x * 4 + 2] = clock64();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
 }  // namespace hb2
