@@ -7,6 +7,7 @@
 #include "../../include/hyphy_b200.h"
 #include "hb2_kernels_fp64.cuh"
 #include "hb2_kernels_tc.cuh"
+#include "hb2_kernels_lanes.cuh"
 
 #include <climits>
 #include <cstdarg>
@@ -155,11 +156,15 @@ struct hb2_partition {
     int forced_node = -1;
     // persistent walk kernel (one launch per evaluation): plan buffers, generation bits of the tagged hand-over, residency
     bool small_walk = true;                   // HB2_SMALL_WALK=0: per-level launches of prune_small_kernel (A/B testing)
-    bool fp64_walk = true;                    // HB2_FP64_WALK=0: per-level launches of prune64_kernel (A/B testing)
+    int fp64_mode = 2;                        // HB2_FP64_WALK: 2 (default) prune64_lanes_kernel, 1 prune64_walk_kernel when it fills the machine, 0 per-level launches
+    bool fp64_walk = true;                    // fp64_mode >= 1
+    double *d_cond_side = nullptr;            // fp64 lanes kernel: side products [C][I][Sp][64] (exponents: second half of d_scal)
+    int *d_lane_flags = nullptr;              // [C][2I][Sp/64] pass id of the last production
+    int lane_pass = 0, lanes_max_resident = 0;
     int sm_count = 148;
     bool expm_dfma = false;                   // HB2_EXPM_DFMA=1: previous FFMA-style fp64 expm kernel (A/B testing)
     bool use_walk = false;
-    bool walk_v2 = true;                      // two threads per pattern (prune64_tc_walk2_kernel); HB2_WALK_V2=0: the 128-thread kernel
+    bool walk_v2 = false;                     // HB2_WALK_V2=1: two threads per pattern (prune64_tc_walk2_kernel; correct, measured 20 % slower)
     int walk_max_resident = 0;
     // single-branch shortcut (hb2_branch_cache_*): outside vectors of one branch, all owned classes
     double *d_bc_out = nullptr; int *d_bc_outE = nullptr, *d_bc_sib = nullptr; int64_t bc_node = -1;
@@ -492,7 +497,12 @@ hb2::PruneArgs prune_args(hb2_partition *p, int cat0) {
 // (child encoding, job's node slot | flags); jdirty[2I] = jobs of the plan.  Returns the number of steps.  Exposed for
 // CPU tests through hb2_plan_walk.
 int plan_walk(const std::vector<std::vector<int>> &children, const std::vector<int> &height, int L, int I,
-              const std::vector<char> &dirty, int K, bool split_nodes, int *lane_start, int *steps, std::vector<char> &jdirty_out) {
+              const std::vector<char> &dirty, int K, bool split_nodes, int *lane_start, int *steps, std::vector<char> &jdirty_out,
+              bool canonical_multi = false) {
+    // canonical_multi (fp64 lanes kernel): a node with more than two children is neither split nor chained and its children
+    // are multiplied in tree order, so its product is associated the same way in every plan; with two children the product
+    // is exact-commutative and power-of-two rescalings are exact, hence conditionals do not depend on the plan at all (a
+    // partial re-evaluation reproduces the full one bit for bit, like the per-level kernel).
     // Jobs.  Job j < I is node j; job I + n is the SIDE PRODUCT of node n: a node with two or more internal children is
     // split into "contract the child with the deepest subtree" (+ multiply the side product in: no matrix, the cheapest
     // step after a leaf) and a side job that contracts all OTHER children.  Side jobs sit off the root path, so other
@@ -508,7 +518,7 @@ int plan_walk(const std::vector<std::vector<int>> &children, const std::vector<i
         jdirty[n] = 1;
         int heavy = -1, nint = 0;
         for (int ch : children[n]) if (ch >= L) { nint++; if (heavy < 0 || height[ch - L] > height[heavy - L]) heavy = ch; }
-        if (split_on && nint >= 2) {
+        if (split_on && nint >= 2 && !(canonical_multi && children[n].size() > 2)) {
             jch[n].push_back(heavy);
             jmul[n] = I + n;
             jdirty[I + n] = 1;
@@ -568,7 +578,7 @@ int plan_walk(const std::vector<std::vector<int>> &children, const std::vector<i
             const int j = best, r = best_r;
             double cost = base[j];
             for (int ch : jch[j])
-                if (ch >= L && dirty[ch - L] && lane_last[r] == job_of_child(ch)) { chain_child[j] = ch - L; cost -= C_INT - C_CHAIN; break; }
+                if (ch >= L && dirty[ch - L] && lane_last[r] == job_of_child(ch) && !(canonical_multi && jch[j].size() > 2)) { chain_child[j] = ch - L; cost -= C_INT - C_CHAIN; break; }
             finish[j] = best_start + cost;
             lane_time[r] = finish[j];
             lane_of[j] = r; lane_last[r] = j;
@@ -591,12 +601,16 @@ int plan_walk(const std::vector<std::vector<int>> &children, const std::vector<i
         for (int j : lanes[r]) {
             const int first = ns;
             auto push = [&](int enc) { steps[2 * ns] = enc; steps[2 * ns + 1] = j; ns++; };
+            if (canonical_multi && jch[j].size() > 2) {          // tree order, leaves and internal children interleaved
+                for (int ch : jch[j]) push(ch < L ? ch : (ch | ((dirty[ch - L] && lane_of[ch - L] != lane_of[j]) ? hb2::WALK_WAIT : 0)));
+            } else {
             if (chain_child[j] >= 0) push((chain_child[j] + L) | hb2::WALK_CHAIN);
             for (int ch : jch[j]) if (ch < L) push(ch);
             for (int ch : jch[j]) {
                 if (ch < L || ch - L == chain_child[j]) continue;
                 const int ci = ch - L;
                 push(ch | ((dirty[ci] && lane_of[ci] != lane_of[j]) ? hb2::WALK_WAIT : 0));
+            }
             }
             if (jmul[j] >= 0) push((L + jmul[j]) | hb2::WALK_MUL | (lane_of[jmul[j]] != lane_of[j] ? hb2::WALK_WAIT : 0));
             steps[2 * first + 1] |= hb2::STEP_FIRST;
@@ -744,11 +758,48 @@ int run_fp64_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::v
     return 0;
 }
 
+// 33..64 states in fp64, default: one launch, K in-order lanes per (class, 64-pattern tile) (prune64_lanes_kernel).  Same
+// planner and plan cache as the tensor walk; the step list travels without a generation table (hand-over by pass id).
+int run_fp64_lanes(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector<int>> &levels) {
+    const int I = (int)p->I, L = (int)p->L;
+    const int T = (int)(p->Sp / hb2::TILE_P);
+    const int CT = ncls * T;
+    int K = std::max(1, std::min(p->walk_lane_cap, p->lanes_max_resident / std::max(CT, 1)));
+    int total = 0;
+    for (auto &lv : levels) total += (int)lv.size();
+    if (total == 0) return 0;
+    K = std::min(K, total);
+    const int nslots = (K == 1) ? std::min(CT, p->lanes_max_resident) : CT;
+    std::vector<char> dirty(I, 0);
+    for (auto &lv : levels) for (int n : lv) dirty[n] = 1;
+    int *buf = p->h_walk;
+    int ns = p->plan_steps;
+    const bool reuse = p->plan_steps > 0 && p->plan_K == K && p->plan_dirty == dirty;
+    if (!reuse) {
+        ns = plan_walk(p->children, p->height, L, I, dirty, K, p->walk_split_nodes, buf, buf + 16, p->plan_jdirty, true);
+        p->plan_steps = ns; p->plan_K = K; p->plan_dirty = dirty;
+    }
+    CU(cudaMemcpyAsync(p->d_walk, p->h_walk, (size_t)(16 + 2 * ns) * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    hb2::LaneArgs w;
+    w.a = prune_args(p, cat0);
+    w.cond_side = p->d_cond_side;
+    w.scal_side = p->d_scal + (size_t)p->C * I * p->Sp;
+    w.lane_start = p->d_walk; w.steps = reinterpret_cast<const int2 *>(p->d_walk + 16);
+    w.flags = p->d_lane_flags; w.err = p->d_err;
+    w.K = K; w.T = T; w.ncls = ncls; w.nslots = nslots; w.pass = ++p->lane_pass;
+    if (getenv("HB2_DEBUG")) fprintf(stderr, "[hb2] fp64 lanes: jobs=%d steps=%d K=%d T=%d ncls=%d nslots=%d grid=%d resident=%d\n", total, ns, K, T, ncls, nslots, nslots * K, p->lanes_max_resident);
+    hb2::prune64_lanes_kernel<<<nslots * K, 256, hb2::LANES_SMEM_BYTES, p->stream>>>(w);
+    p->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int run_pruning(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector<int>> &levels) {
     if (p->use_tc && p->use_walk) return run_walk(p, cat0, ncls, levels);
     // one launch per evaluation pays only when (tiles x classes) fills the machine about twice over (c5: 316 CTAs); below
     // that the per-level launches expose more parallelism (north-star shape: 128 CTAs walk 1.55 ms, 54 level launches take
     // 1.38 ms; a single class of it -- the patched host's per-class ComputeBlock -- would leave 116 SMs idle)
+    if (!p->use_tc && p->Dp == 64 && p->fp64_mode == 2) return run_fp64_lanes(p, cat0, ncls, levels);
     if (!p->use_tc && p->Dp == 64 && p->fp64_walk && (int64_t)(p->Sp / hb2::TILE_P) * ncls >= 2 * p->sm_count)
         return run_fp64_walk(p, cat0, ncls, levels);
     if (p->Dp <= 32 && p->small_walk) return run_small_walk(p, cat0, ncls, levels);
@@ -1069,7 +1120,7 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
         CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::WALK_SMEM_BYTES));
         CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::WALK2_SMEM_BYTES));
         CUP(cudaFuncSetAttribute(hb2::prune64_tc_walk2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        { const char *env = getenv("HB2_WALK_V2"); p->walk_v2 = !(env && env[0] == '0'); }
+        { const char *env = getenv("HB2_WALK_V2"); p->walk_v2 = env && env[0] == '1'; }
         {
             const char *env = getenv("HB2_TC_WALK");
             p->use_walk = !(env && env[0] == '0');
@@ -1112,6 +1163,28 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
     } else {
         CUP(cudaMalloc(&p->d_cond, (size_t)C * I * Sp * Dp * sizeof(double)));
         CUP(cudaMemsetAsync(p->d_cond, 0, (size_t)C * I * Sp * Dp * sizeof(double), p->stream));
+        { const char *env = getenv("HB2_FP64_WALK"); p->fp64_mode = (env && env[0] >= '0' && env[0] <= '2') ? env[0] - '0' : 2; }
+        if (Dp == 64 && p->fp64_mode == 2) {
+            // lanes kernel: side products, hand-over flags, the step list, and how many CTAs can be co-resident
+            const size_t T = Sp / hb2::TILE_P;
+            CUP(cudaMalloc(&p->d_cond_side, (size_t)C * I * Sp * 64 * sizeof(double)));
+            CUP(cudaMemsetAsync(p->d_cond_side, 0, (size_t)C * I * Sp * 64 * sizeof(double), p->stream));
+            CUP(cudaMalloc(&p->d_lane_flags, (size_t)C * 2 * I * T * sizeof(int)));
+            CUP(cudaMemsetAsync(p->d_lane_flags, 0, (size_t)C * 2 * I * T * sizeof(int), p->stream));
+            const size_t walk_ints = 16 + 2 * (size_t)(L + 2 * I);
+            CUP(cudaMalloc(&p->d_walk, walk_ints * sizeof(int)));
+            CUP(cudaMallocHost(&p->h_walk, walk_ints * sizeof(int)));
+            { const char *ev = getenv("HB2_WALK_SPLIT_NODES"); p->walk_split_nodes = !(ev && ev[0] == '0'); }
+            if (const char *ov = getenv("HB2_WALK_LANES")) p->walk_lane_cap = std::max(1, std::min(atoi(ov), 15));
+            CUP(cudaFuncSetAttribute(hb2::prune64_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::LANES_SMEM_BYTES));
+            CUP(cudaFuncSetAttribute(hb2::prune64_lanes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            int per_sm = 0, sms = 0;
+            CUP(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hb2::prune64_lanes_kernel, 256, hb2::LANES_SMEM_BYTES));
+            CUP(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+            if (const char *ov = getenv("HB2_WALK_CTAS_PER_SM")) per_sm = atoi(ov);
+            if (getenv("HB2_DEBUG")) fprintf(stderr, "[hb2] fp64 lanes kernel occupancy: %d CTAs/SM on %d SMs\n", per_sm, sms);
+            p->lanes_max_resident = std::max(per_sm, 1) * sms;
+        }
     }
     CUP(cudaMalloc(&p->d_err, sizeof(int)));
     CUP(cudaMemsetAsync(p->d_err, 0, sizeof(int), p->stream));
@@ -1189,7 +1262,7 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
     }
 #undef CUP
     { const char *env = getenv("HB2_SMALL_WALK"); p->small_walk = !(env && env[0] == '0'); }
-    { const char *env = getenv("HB2_FP64_WALK"); p->fp64_walk = !(env && env[0] == '0'); }
+    p->fp64_walk = p->fp64_mode >= 1;
     p->have_matrix.assign(C * p->B, 0);
     p->is_rate.assign(C * p->B, 0);
     p->pend_pos.assign(C * p->B, -1);
@@ -1752,7 +1825,7 @@ void hb2_destroy(hb2_partition *p) {
     if (p->comm) g_nccl.CommDestroy(p->comm);
     void *dev[] = {p->d_leaf, p->d_scal, p->d_rootE, p->d_child_start, p->d_child_ids, p->d_jobs, p->d_dst, p->d_flag,
                    p->d_mix_dst, p->d_mix_Q, p->d_ambig, p->d_freq, p->d_cond, p->d_PT, p->d_Q, p->d_pi, p->d_rootL, p->d_weights,
-                   p->d_partial, p->d_lnL, p->d_siteL, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_xsend, p->d_xrecv, p->d_xfreq, p->d_xpartial, p->d_bc_out, p->d_bc_outE, p->d_bc_sib, p->d_walk, p->d_forced, p->ex.d_int, p->ex.d_flag, p->ex.d_weight, p->ex.d_groups, p->ex.d_pow, p->ex.d_refvec, p->ex.d_flags, p->ex.d_colsum, p->bex.d_colsum, p->bex.d_int, p->bex.d_flag, p->bex.d_weight, p->bex.d_groups, p->bex.d_pow, p->bex.d_refvec, p->bex.d_flags,
+                   p->d_partial, p->d_lnL, p->d_siteL, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_xsend, p->d_xrecv, p->d_xfreq, p->d_xpartial, p->d_bc_out, p->d_bc_outE, p->d_bc_sib, p->d_walk, p->d_forced, p->d_cond_side, p->d_lane_flags, p->ex.d_int, p->ex.d_flag, p->ex.d_weight, p->ex.d_groups, p->ex.d_pow, p->ex.d_refvec, p->ex.d_flags, p->ex.d_colsum, p->bex.d_colsum, p->bex.d_int, p->bex.d_flag, p->bex.d_weight, p->bex.d_groups, p->bex.d_pow, p->bex.d_refvec, p->bex.d_flags,
                    p->d_bPT, p->d_bV, p->d_bcond, p->d_bout, p->d_bdst, p->d_bpat, p->d_bnodeex};
     for (void *d : dev) if (d) cudaFree(d);
     if (p->h_Q) cudaFreeHost(p->h_Q);
@@ -1783,6 +1856,7 @@ int hb2_stage_launches(const hb2_partition *p, int64_t *out3) {
 const char *hb2_pruning_kernel(const hb2_partition *p) {
     if (!p) return "";
     if (p->use_tc) return p->use_walk ? (p->walk_v2 ? "prune64_tc_walk2_kernel" : "prune64_tc_walk_kernel") : "prune64_tc_kernel";
+    if (p->Dp == 64 && p->fp64_mode == 2) return "prune64_lanes_kernel";
     if (p->Dp == 64) return (p->fp64_walk && (int64_t)(p->Sp / hb2::TILE_P) * p->ownN >= 2 * p->sm_count) ? "prune64_walk_kernel" : "prune64_kernel";
     return p->small_walk ? "prune_small_walk_kernel" : "prune_small_kernel";
 }
