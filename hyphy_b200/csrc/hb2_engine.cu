@@ -160,7 +160,7 @@ struct hb2_partition {
     bool fp64_walk = true;                    // fp64_mode >= 1
     double *d_cond_side = nullptr;            // fp64 lanes kernel: side products [C][I][Sp][64] (exponents: second half of d_scal)
     int *d_lane_flags = nullptr;              // [C][2I][Sp/64] pass id of the last production
-    int lane_pass = 0, lanes_max_resident = 0;
+    int lane_pass = 0, lanes_resident[2] = {0, 0}, lanes_force_nw = 0;   // co-resident CTAs of the 4- and 8-warp shapes; HB2_LANES_WARPS
     int sm_count = 148;
     bool expm_dfma = false;                   // HB2_EXPM_DFMA=1: previous FFMA-style fp64 expm kernel (A/B testing)
     bool use_walk = false;
@@ -762,14 +762,16 @@ int run_fp64_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::v
 // planner and plan cache as the tensor walk; the step list travels without a generation table (hand-over by pass id).
 int run_fp64_lanes(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector<int>> &levels) {
     const int I = (int)p->I, L = (int)p->L;
-    const int T = (int)(p->Sp / hb2::TILE_P);
-    const int CT = ncls * T;
-    int K = std::max(1, std::min(p->walk_lane_cap, p->lanes_max_resident / std::max(CT, 1)));
     int total = 0;
     for (auto &lv : levels) total += (int)lv.size();
     if (total == 0) return 0;
-    K = std::min(K, total);
-    const int nslots = (K == 1) ? std::min(CT, p->lanes_max_resident) : CT;
+    // CTA shape: 4 warps x 8 patterns, 4 CTAs per SM.  The 8-warp shape (64 patterns, 3 per SM) gives the north-star shape a
+    // third lane and c5 a single round, and is slower on both (1.28 vs 0.98 ms, 7.6 vs 5.6 ms: profiles/r2s_*): it stays
+    // behind HB2_LANES_WARPS=8 for A/B runs.
+    const int nw = p->lanes_force_nw == 8 ? 8 : 4;
+    const int T = (int)(p->Sp / (8 * nw)), CT = ncls * T, resident = p->lanes_resident[nw == 8];
+    const int K = std::max(1, std::min(std::min(p->walk_lane_cap, total), resident / std::max(CT, 1)));
+    const int nslots = (K == 1) ? std::min(CT, resident) : CT;
     std::vector<char> dirty(I, 0);
     for (auto &lv : levels) for (int n : lv) dirty[n] = 1;
     int *buf = p->h_walk;
@@ -778,17 +780,62 @@ int run_fp64_lanes(hb2_partition *p, int cat0, int ncls, const std::vector<std::
     if (!reuse) {
         ns = plan_walk(p->children, p->height, L, I, dirty, K, p->walk_split_nodes, buf, buf + 16, p->plan_jdirty, true);
         p->plan_steps = ns; p->plan_K = K; p->plan_dirty = dirty;
+        // the kernel's descriptors: (child, job, branch id of the lane's next contraction, -) behind the planner's pairs
+        int *d4 = buf + ((16 + 2 * ns + 3) & ~3);
+        std::vector<char> awaited(2 * I, 0);                 // jobs some other lane waits for: only those publish a flag
+        for (int i = 0; i < ns; i++)
+            if (buf[16 + 2 * i] & hb2::WALK_WAIT) awaited[(buf[16 + 2 * i] & hb2::WALK_ID_MASK) - L] = 1;
+        for (int r = 0; r < K; r++) {
+            int nextb = -1;
+            for (int i = buf[r + 1] - 1; i >= buf[r]; i--) {
+                const int enc = buf[16 + 2 * i], child = enc & hb2::WALK_ID_MASK;
+                const int fl = buf[16 + 2 * i + 1];
+                d4[4 * i] = enc; d4[4 * i + 1] = fl; d4[4 * i + 2] = nextb;
+                d4[4 * i + 3] = ((fl & hb2::STEP_LAST) && awaited[fl & hb2::WALK_ID_MASK]) ? 1 : 0;
+                if (child >= L && !(enc & hb2::WALK_MUL)) nextb = child;
+            }
+        }
     }
-    CU(cudaMemcpyAsync(p->d_walk, p->h_walk, (size_t)(16 + 2 * ns) * sizeof(int), cudaMemcpyHostToDevice, p->stream));
+    const int o4 = (16 + 2 * ns + 3) & ~3;
+    CU(cudaMemcpyAsync(p->d_walk, p->h_walk, (size_t)(o4 + 4 * ns) * sizeof(int), cudaMemcpyHostToDevice, p->stream));
     hb2::LaneArgs w;
     w.a = prune_args(p, cat0);
     w.cond_side = p->d_cond_side;
     w.scal_side = p->d_scal + (size_t)p->C * I * p->Sp;
-    w.lane_start = p->d_walk; w.steps = reinterpret_cast<const int2 *>(p->d_walk + 16);
+    w.lane_start = p->d_walk; w.steps = reinterpret_cast<const int4 *>(p->d_walk + o4);
     w.flags = p->d_lane_flags; w.err = p->d_err;
     w.K = K; w.T = T; w.ncls = ncls; w.nslots = nslots; w.pass = ++p->lane_pass;
-    if (getenv("HB2_DEBUG")) fprintf(stderr, "[hb2] fp64 lanes: jobs=%d steps=%d K=%d T=%d ncls=%d nslots=%d grid=%d resident=%d\n", total, ns, K, T, ncls, nslots, nslots * K, p->lanes_max_resident);
-    hb2::prune64_lanes_kernel<<<nslots * K, 256, hb2::LANES_SMEM_BYTES, p->stream>>>(w);
+    if (getenv("HB2_DEBUG")) fprintf(stderr, "[hb2] fp64 lanes: jobs=%d steps=%d K=%d T=%d ncls=%d nslots=%d grid=%d warps=%d resident=%d\n", total, ns, K, T, ncls, nslots, nslots * K, nw, resident);
+    w.trace = nullptr; w.trace_cta = 0;
+    const char *trace_path = getenv("HB2_WALK_TRACE");
+    long long *d_trace = nullptr;
+    if (trace_path) {          // bring-up aid: per-step clock stamps of one CTA -> text file
+        const char *tc = getenv("HB2_WALK_TRACE_CTA");
+        w.trace_cta = tc ? atoi(tc) : 0;
+        CU(cudaMalloc(&d_trace, (size_t)(ns + 1) * 12 * sizeof(long long)));
+        CU(cudaMemsetAsync(d_trace, 0, (size_t)(ns + 1) * 12 * sizeof(long long), p->stream));
+        w.trace = d_trace;
+    }
+    if (nw == 4) hb2::prune64_lanes_kernel<4><<<nslots * K, 128, hb2::lanes_smem_bytes(4), p->stream>>>(w);
+    else hb2::prune64_lanes_kernel<8><<<nslots * K, 256, hb2::lanes_smem_bytes(8), p->stream>>>(w);
+    if (d_trace) {
+        std::vector<long long> ht((size_t)(ns + 1) * 12);
+        CU(cudaStreamSynchronize(p->stream));
+        CU(cudaMemcpy(ht.data(), d_trace, ht.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(d_trace);
+        if (FILE *f = fopen(trace_path, "w")) {
+            const int r = w.trace_cta % K;
+            fprintf(f, "# fp64 lanes kernel, cta %d lane %d steps %d..%d ; columns: child_enc job_flags begin staged landed barrier product barrier2 body_end stored barrier3 published (cycles rel. to first)\n", w.trace_cta, r, buf[r], buf[r + 1]);
+            const long long t00 = ht[1];
+            for (int i = 0; i < buf[r + 1] - buf[r]; i++) {
+                const long long *q = ht.data() + (size_t)i * 12;
+                fprintf(f, "%d 0x%x 0x%x", i, (unsigned)(q[0] >> 32), (unsigned)(q[0] & 0xffffffff));
+                for (int c = 1; c < 12; c++) fprintf(f, " %lld", q[c] ? q[c] - t00 : -1LL);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
     p->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -1166,24 +1213,38 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
         { const char *env = getenv("HB2_FP64_WALK"); p->fp64_mode = (env && env[0] >= '0' && env[0] <= '2') ? env[0] - '0' : 2; }
         if (Dp == 64 && p->fp64_mode == 2) {
             // lanes kernel: side products, hand-over flags, the step list, and how many CTAs can be co-resident
-            const size_t T = Sp / hb2::TILE_P;
+            const size_t T = Sp / 32;                                        // flags are sized for the smaller tile
             CUP(cudaMalloc(&p->d_cond_side, (size_t)C * I * Sp * 64 * sizeof(double)));
             CUP(cudaMemsetAsync(p->d_cond_side, 0, (size_t)C * I * Sp * 64 * sizeof(double), p->stream));
             CUP(cudaMalloc(&p->d_lane_flags, (size_t)C * 2 * I * T * sizeof(int)));
             CUP(cudaMemsetAsync(p->d_lane_flags, 0, (size_t)C * 2 * I * T * sizeof(int), p->stream));
-            const size_t walk_ints = 16 + 2 * (size_t)(L + 2 * I);
+            const size_t walk_ints = 16 + 6 * (size_t)(L + 2 * I) + 4;       // planner's pairs + the kernel's int4 descriptors
             CUP(cudaMalloc(&p->d_walk, walk_ints * sizeof(int)));
             CUP(cudaMallocHost(&p->h_walk, walk_ints * sizeof(int)));
             { const char *ev = getenv("HB2_WALK_SPLIT_NODES"); p->walk_split_nodes = !(ev && ev[0] == '0'); }
             if (const char *ov = getenv("HB2_WALK_LANES")) p->walk_lane_cap = std::max(1, std::min(atoi(ov), 15));
-            CUP(cudaFuncSetAttribute(hb2::prune64_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, hb2::LANES_SMEM_BYTES));
-            CUP(cudaFuncSetAttribute(hb2::prune64_lanes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            int per_sm = 0, sms = 0;
-            CUP(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hb2::prune64_lanes_kernel, 256, hb2::LANES_SMEM_BYTES));
+            if (const char *ov = getenv("HB2_LANES_WARPS")) p->lanes_force_nw = atoi(ov) == 8 ? 8 : atoi(ov) == 4 ? 4 : 0;
+            int sms = 0;
             CUP(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-            if (const char *ov = getenv("HB2_WALK_CTAS_PER_SM")) per_sm = atoi(ov);
-            if (getenv("HB2_DEBUG")) fprintf(stderr, "[hb2] fp64 lanes kernel occupancy: %d CTAs/SM on %d SMs\n", per_sm, sms);
-            p->lanes_max_resident = std::max(per_sm, 1) * sms;
+            cudaDeviceProp dp; CUP(cudaGetDeviceProperties(&dp, device));
+            for (int v = 0; v < 2; v++) {
+                const void *fn = v ? (const void *)hb2::prune64_lanes_kernel<8> : (const void *)hb2::prune64_lanes_kernel<4>;
+                const int threads = v ? 256 : 128, smem = hb2::lanes_smem_bytes(v ? 8 : 4), cap = v ? 3 : 4;
+                CUP(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                CUP(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                int per_sm = 0;
+                CUP(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
+                // same resource arithmetic as for the tensor walk kernel (the occupancy API under-reports there)
+                cudaFuncAttributes fa;
+                CUP(cudaFuncGetAttributes(&fa, fn));
+                const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * threads;
+                const size_t smem_per_cta = (size_t)smem + fa.sharedSizeBytes + dp.reservedSharedMemPerBlock;
+                const int by_res = std::min(dp.regsPerMultiprocessor / std::max(regs_per_cta, 1), (int)(dp.sharedMemPerMultiprocessor / smem_per_cta));
+                if (getenv("HB2_DEBUG")) fprintf(stderr, "[hb2] fp64 lanes kernel <%d warps>: occupancy API %d, by resources %d (regs %d)\n", v ? 8 : 4, per_sm, by_res, fa.numRegs);
+                per_sm = std::max(per_sm, std::min(by_res, cap));
+                if (const char *ov = getenv("HB2_WALK_CTAS_PER_SM")) per_sm = atoi(ov);
+                p->lanes_resident[v] = std::max(per_sm, 1) * sms;
+            }
         }
     }
     CUP(cudaMalloc(&p->d_err, sizeof(int)));

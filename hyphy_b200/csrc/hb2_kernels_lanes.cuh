@@ -2,19 +2,30 @@
 //
 // Replaces, for the double-precision path, both the per-level launches of prune64_kernel (54 launches on the north-star
 // tree, each bound by launch + load latency) and prune64_walk_kernel (one CTA per (class, tile) walking ALL dirty nodes
-// serially: 120 CTAs x 198 nodes).  Same decomposition as the tensor walk kernel (hb2_kernels_tc.cuh): the host planner
-// (hb2_engine.cu plan_walk) list-schedules the dirty jobs -- nodes and side products of nodes with two internal children
-// -- on K lanes; CTA (class c, 64-pattern tile t, lane r) executes its lane's steps back to back.  Reference semantics:
+// serially).  Same decomposition as the tensor walk kernel (hb2_kernels_tc.cuh): the host planner (hb2_engine.cu
+// plan_walk) list-schedules the dirty jobs -- nodes and side products of nodes with two internal children -- on K lanes;
+// CTA (class c, 32-pattern tile t, lane r) executes its lane's steps back to back.  Reference semantics:
 // ComputeTreeBlockByBranch (tree_evaluator.cpp:3556-4171) restricted to the nodes DetermineNodesForUpdate marked.
+//   * CTA = 4 warps x 8 patterns; the contraction C[pattern][parent] = sum_j X[pattern][j] * PT[j][parent] runs on the FP64
+//     tensor pipe (mma.sync.m8n8k4.f64): warp tile 8 x 64, 128 DMMA + 144 shared-memory loads per warp and contraction.
+//     History (profiles/r2p_, r2q_, r2r_lanes_trace_cta0.txt): the register-blocked DFMA product took 7.4 k cycles per
+//     contraction, this one 6.0 k (a warp issues one DMMA every ~45 cycles whatever its dependencies); splitting the
+//     parent states over two warps per 8 patterns (8 warps per CTA) brought the product to 4.0 k but cost more than that
+//     in the cross-warp row maximum and in barrier time (1.15 vs 0.99 ms per evaluation): not kept;
+//   * a thread owns ONE pattern (row 8*warp + lane/4) and 16 of its states (8j + 2*(lane%4) + {0,1}): renormalisation and
+//     the root dot product reduce over 4 lanes (two shuffles);
+//   * one P buffer + one X buffer = 53 KB, 128 threads: four CTAs per SM, so that the load / renormalise / publish
+//     phases of one CTA run under the products of the others;
 //   * hand-over between lanes: a flag per (class, job, tile) holding the id of the pass that produced the tile
 //     (st.release.gpu by the producer after its stores, ld.acquire.gpu poll by the consumer, time-bounded);
 //   * a child produced by THIS CTA in its previous job goes straight from registers to the shared-memory operand;
-//   * the transition matrix of the NEXT contraction is staged with cp.async while the current one is multiplied
-//     (two P buffers + one X buffer = 99 KB: two CTAs per SM);
-//   * tile product: tile_mm64 (4x4 register blocks, DFMA at the FP64 pipe's rate; hb2_kernels_fp64.cuh).
-// Per element the products are those of prune64_kernel; the children of a node are multiplied in plan order (chain child,
-// leaves, other internal children, side product), so results agree with the per-level kernel to rounding (parity bound
-// 1e-10 relative on lnL, observed 1e-15), and are deterministic for a given plan.
+//   * the transition matrix of the NEXT contraction (its branch id travels in the step descriptor) is staged with
+//     cp.async as soon as the current product has released the buffer, i.e. under the epilogue and the leaf steps in
+//     between; step descriptors run two steps ahead, leaf state codes one.
+// The children of a node are multiplied in plan order; with two children the product is exact-commutative and
+// power-of-two rescalings are exact, and nodes with more children are planned in tree order (plan_walk,
+// canonical_multi), so conditionals do not depend on the plan: a partial re-evaluation reproduces the full one bit for
+// bit.  Against prune64_kernel results agree to rounding (different summation tree inside a product).
 #pragma once
 #include "hb2_kernels_fp64.cuh"
 #include "hb2_kernels_tc.cuh"      // step encoding (WALK_*, STEP_*), globaltimer_ns, HB2_WAIT_LIMIT_NS
@@ -26,13 +37,20 @@ struct LaneArgs {
     double *cond_side;          // [C][I][Sp][64] side products (job I + n)
     int *scal_side;             // [C][I][Sp]
     const int *lane_start;      // [K+1]
-    const int2 *steps;
+    const int4 *steps;          // x: child | WALK_*, y: job | STEP_*, z: branch id of the next contraction of the lane (-1: none),
+                                // w: 1 if another lane waits for this job (STEP_LAST publishes its flag)
     int *flags;                 // [C][2I][T] id of the pass that last produced (class, job, tile)
     int *err;
     int K, T, ncls, nslots, pass;
+    long long *trace;           // nullable bring-up aid (HB2_WALK_TRACE): 12 clock64 stamps per step of CTA `trace_cta`
+    int trace_cta;
 };
 
-constexpr int LANES_SMEM_BYTES = 3 * 64 * LD64 * (int)sizeof(double);
+// Two CTA shapes, NW warps x 8 patterns: NW = 4 (32 patterns, 128 threads, four CTAs per SM; the default) and NW = 8 (64
+// patterns, 256 threads, three CTAs per SM; HB2_LANES_WARPS=8, measured slower).
+constexpr int LANES_LDX = 68;                    // leading dimensions (doubles): both fragment loads are 2 wavefronts, the
+constexpr int LANES_LDP = 72;                    // minimum for 256 bytes per warp
+constexpr int lanes_smem_bytes(int nw) { return (8 * nw * LANES_LDX + 64 * LANES_LDP) * (int)sizeof(double); }
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -40,30 +58,45 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(256, 2) prune64_lanes_kernel(LaneArgs w) {
+// warp tile 8 patterns x 64 parent states, K = 64: acc[j] = C[row][8j + 2*q4 + {0,1}]
+__device__ __forceinline__ void lanes_mm(const double *__restrict__ Xs, const double *__restrict__ Ps, int row, int g, int q4,
+                                         double (&acc)[8][2]) {
+    const double *a0 = Xs + row * LANES_LDX + q4;
+    const double *b0 = Ps + q4 * LANES_LDP + g;
+#pragma unroll 4
+    for (int k0 = 0; k0 < 64; k0 += 4) {
+        const double x = a0[k0];
+#pragma unroll
+        for (int j = 0; j < 8; j++) dmma884(acc[j], x, b0[k0 * LANES_LDP + 8 * j]);
+    }
+}
+
+template <int NW>
+__global__ void __launch_bounds__(32 * NW, NW == 4 ? 4 : 3) prune64_lanes_kernel(LaneArgs w) {
+    constexpr int LANES_TILE_P = 8 * NW, LANES_THREADS = 32 * NW;
     extern __shared__ __align__(16) double sm[];
-    double *Xs = sm;                              // [64][LD64] child conditionals (pattern-major)
-    double *Pb = sm + 64 * LD64;                  // 2 x [64][LD64] transition matrices (transposed), ring
+    double *Xs = sm;                              // [8 NW][LDX] child conditionals (pattern-major)
+    double *Ps = sm + LANES_TILE_P * LANES_LDX;   // [64][LDP] transition matrix (transposed) of the current / next contraction
     const PruneArgs &a = w.a;
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tid = threadIdx.x, warp = tid >> 5, g = (tid & 31) >> 2, q4 = tid & 3;
+    const int row = 8 * warp + g;                 // this thread's pattern within the tile
+    const int c0s = 2 * q4;                       // this thread's states: c0s + 8j + {0,1}, j = 0..7
     const size_t Sp = a.Sp;
     const int r = blockIdx.x % w.K;
     const int i_begin = w.lane_start[r], i_end = w.lane_start[r + 1];
     if (i_begin == i_end) return;
 
-    auto is_contraction = [&](int enc) { return (enc & WALK_ID_MASK) >= a.L && !(enc & WALK_MUL); };
-    auto next_contraction = [&](int from) {
-        int j = from;
-        while (j < i_end && !is_contraction(__ldg(&w.steps[j].x))) j++;
-        return j;
-    };
-    // 64 x 64 doubles, contiguous in global memory -> padded rows in shared memory, 8 x 16 bytes per thread
-    auto stage_tile = [&](double *dst, const double *src) {
-#pragma unroll
-        for (int m = 0; m < 8; m++) {
-            const int idx = tid + 256 * m, rr = idx >> 5, c2 = (idx & 31) * 2;
-            cp_async16(dst + rr * LD64 + c2, src + rr * 64 + c2);
+    // ROWS x 64 doubles, contiguous in global memory -> padded rows in shared memory, 16 bytes per copy
+    auto stage_rows = [&](double *dst, const int ld, const double *src, const int rows) {
+#pragma unroll 8
+        for (int idx = tid; idx < rows * 32; idx += LANES_THREADS) {
+            const int rr = idx >> 5, c2 = (idx & 31) * 2;
+            cp_async16(dst + rr * ld + c2, src + rr * 64 + c2);
         }
+    };
+    auto stage_P = [&](int cat, int branch) {
+        stage_rows(Ps, LANES_LDP, a.PT + ((size_t)cat * a.B + branch) * 4096, 64);
+        cp_async_commit();
     };
     // wait until (class, job, tile) has been produced by this pass.  Uniform call (contains a barrier).
     auto wait_flag = [&](int cat, int job, int tile) {
@@ -87,161 +120,183 @@ __global__ void __launch_bounds__(256, 2) prune64_lanes_kernel(LaneArgs w) {
     for (int ct = blockIdx.x / w.K; ct < w.ncls * w.T; ct += w.nslots) {
         const int cat = a.cat0 + ct / w.T;
         const int tile = ct % w.T;
-        const int s0 = tile * TILE_P;
-        double v[4][4];
-        int ex[4];
-        int cur = 0;
+        const int s0 = tile * LANES_TILE_P;
+        const size_t s = (size_t)s0 + row;        // this thread's pattern
+        double v[8][2];
+        int ex = 0;
         __syncthreads();                          // previous (class, tile): the buffers are free
-        {
-            const int j0 = next_contraction(i_begin);
-            if (j0 < i_end) {
-                stage_tile(Pb, a.PT + ((size_t)cat * a.B + (__ldg(&w.steps[j0].x) & WALK_ID_MASK)) * 4096);
-                cp_async_commit();
-            }
+        int4 st_a = __ldg(w.steps + i_begin);
+        int4 st_b = (i_begin + 1 < i_end) ? __ldg(w.steps + i_begin + 1) : make_int4(0, 0, -1, 0);
+        {   // the lane's first contraction
+            const int c0 = st_a.x & WALK_ID_MASK;
+            const int b0 = (c0 >= a.L && !(st_a.x & WALK_MUL)) ? c0 : st_a.z;
+            if (b0 >= 0) stage_P(cat, b0);
         }
+        auto leaf_code = [&](int4 q) -> int {
+            const int ch = q.x & WALK_ID_MASK;
+            if (ch >= a.L) return 0;
+            return (ch == a.forced_node) ? __ldg(a.forced + s) : __ldg(a.leaf + (size_t)ch * Sp + s);
+        };
+        int code_next = leaf_code(st_a);
         for (int i = i_begin; i < i_end; i++) {
-            const int2 st = __ldg(w.steps + i);
+            const int4 st = st_a;
+            const int code = code_next;
+            st_a = st_b;
+            if (i + 2 < i_end) st_b = __ldg(w.steps + i + 2);       // descriptors two steps ahead ...
+            if (i + 1 < i_end) code_next = leaf_code(st_a);          // ... so that this address is ready: codes one step ahead
             const int enc = st.x, flags = st.y;
             const int child = enc & WALK_ID_MASK;
             const int job = flags & WALK_ID_MASK;            // node (< I) or side product (I + node)
+            const bool tr = w.trace && tid == 0 && (int)blockIdx.x == w.trace_cta;
+            long long *trp = tr ? w.trace + (size_t)(i - i_begin) * 12 : nullptr;
+            if (tr) { trp[0] = ((long long)st.x << 32) | (unsigned)st.y; trp[1] = clock64(); }
             if ((flags & STEP_FIRST) && !(enc & WALK_CHAIN)) {
+                ex = 0;
 #pragma unroll
-                for (int ii = 0; ii < 4; ii++) {
-                    ex[ii] = 0;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) v[ii][j] = 1.0;
-                }
+                for (int j = 0; j < 8; j++) { v[j][0] = 1.0; v[j][1] = 1.0; }
             }
             if (child < a.L) {
                 // leaf: column gather PT[state][k]; ambiguous: sum_j amb[j] PT[j][k]
-                const double *PT = a.PT + ((size_t)cat * a.B + child) * 4096;
+                const double *PT = a.PT + ((size_t)cat * a.B + child) * 4096 + c0s;
+                if (code >= 0) {
+                    const double2 *p = reinterpret_cast<const double2 *>(PT + (size_t)code * 64);
+                    double2 m[8];
 #pragma unroll
-                for (int ii = 0; ii < 4; ii++) {
-                    const int code = (child == a.forced_node) ? a.forced[s0 + 4 * ty + ii] : __ldg(a.leaf + (size_t)child * Sp + s0 + 4 * ty + ii);
-                    double m0, m1, m2, m3;
-                    if (code >= 0) {
-                        const double2 *p = reinterpret_cast<const double2 *>(PT + (size_t)code * 64 + 2 * tx);
-                        const double2 q0 = __ldg(p), q1 = __ldg(p + 16);
-                        m0 = q0.x; m1 = q0.y; m2 = q1.x; m3 = q1.y;
-                    } else {
-                        const double *amb = a.ambig + (size_t)(-code - 1) * 64;
-                        m0 = m1 = m2 = m3 = 0.0;
-                        for (int j = 0; j < a.D; j++) {
-                            const double wj = __ldg(amb + j);
-                            if (wj != 0.0) {
-                                const double2 *p = reinterpret_cast<const double2 *>(PT + (size_t)j * 64 + 2 * tx);
-                                const double2 q0 = __ldg(p), q1 = __ldg(p + 16);
-                                m0 = fma(wj, q0.x, m0); m1 = fma(wj, q0.y, m1); m2 = fma(wj, q1.x, m2); m3 = fma(wj, q1.y, m3);
+                    for (int j = 0; j < 8; j++) m[j] = __ldg(p + 4 * j);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) { v[j][0] *= m[j].x; v[j][1] *= m[j].y; }
+                } else {
+                    const double *amb = a.ambig + (size_t)(-code - 1) * 64;
+                    double2 m[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) m[j] = make_double2(0.0, 0.0);
+                    for (int jj = 0; jj < a.D; jj++) {
+                        const double wj = __ldg(amb + jj);
+                        if (wj != 0.0) {
+                            const double2 *p = reinterpret_cast<const double2 *>(PT + (size_t)jj * 64);
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const double2 q = __ldg(p + 4 * j);
+                                m[j].x = fma(wj, q.x, m[j].x); m[j].y = fma(wj, q.y, m[j].y);
                             }
                         }
                     }
-                    v[ii][0] *= m0; v[ii][1] *= m1; v[ii][2] *= m2; v[ii][3] *= m3;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) { v[j][0] *= m[j].x; v[j][1] *= m[j].y; }
                 }
             } else if (enc & WALK_MUL) {
                 // side product of this node (its other children, contracted by another lane or earlier in this one)
                 const int n = child - a.L - a.I;
                 if (enc & WALK_WAIT) wait_flag(cat, child - a.L, tile);
-                const double *X = w.cond_side + (((size_t)cat * a.I + n) * Sp + s0) * 64;
-                const int *sc = w.scal_side + ((size_t)cat * a.I + n) * Sp + s0 + 4 * ty;
+                const double2 *X = reinterpret_cast<const double2 *>(w.cond_side + (((size_t)cat * a.I + n) * Sp + s) * 64 + c0s);
+                double2 m[8];
 #pragma unroll
-                for (int ii = 0; ii < 4; ii++) {
-                    const double2 q0 = __ldcg(reinterpret_cast<const double2 *>(X + (size_t)(4 * ty + ii) * 64 + 2 * tx));
-                    const double2 q1 = __ldcg(reinterpret_cast<const double2 *>(X + (size_t)(4 * ty + ii) * 64 + 32 + 2 * tx));
-                    v[ii][0] *= q0.x; v[ii][1] *= q0.y; v[ii][2] *= q1.x; v[ii][3] *= q1.y;
-                    ex[ii] += __ldcg(sc + ii);
-                }
+                for (int j = 0; j < 8; j++) m[j] = __ldcg(X + 4 * j);
+                ex += __ldcg(w.scal_side + ((size_t)cat * a.I + n) * Sp + s);
+#pragma unroll
+                for (int j = 0; j < 8; j++) { v[j][0] *= m[j].x; v[j][1] *= m[j].y; }
             } else {
                 const int cin = child - a.L;
-                __syncthreads();                  // (A) every thread is past the previous product: Xs and Pb[cur^1] are free
-                int sc4[4] = {0, 0, 0, 0};
+                int sc = 0;
                 if (enc & WALK_CHAIN) {
-                    // the child is this lane's previous job: its renormalised values are still in v, its exponents in ex
+                    // the child is this lane's previous job: its renormalised values are still in v, its exponent in ex
+                    // (Xs is free: every product ends with a barrier)
 #pragma unroll
-                    for (int ii = 0; ii < 4; ii++) {
-                        *reinterpret_cast<double2 *>(Xs + (4 * ty + ii) * LD64 + 2 * tx) = make_double2(v[ii][0], v[ii][1]);
-                        *reinterpret_cast<double2 *>(Xs + (4 * ty + ii) * LD64 + 32 + 2 * tx) = make_double2(v[ii][2], v[ii][3]);
-#pragma unroll
-                        for (int j = 0; j < 4; j++) v[ii][j] = 1.0;
+                    for (int j = 0; j < 8; j++) {
+                        *reinterpret_cast<double2 *>(Xs + row * LANES_LDX + c0s + 8 * j) = make_double2(v[j][0], v[j][1]);
+                        v[j][0] = 1.0; v[j][1] = 1.0;
                     }
                 } else {
                     if (enc & WALK_WAIT) wait_flag(cat, cin, tile);
-                    stage_tile(Xs, a.cond + (((size_t)cat * a.I + cin) * Sp + s0) * 64);
-                    const int *sc = a.scal + ((size_t)cat * a.I + cin) * Sp + s0 + 4 * ty;
-#pragma unroll
-                    for (int ii = 0; ii < 4; ii++) sc4[ii] = __ldcg(sc + ii);
-                }
-                cp_async_commit();                // group of X (empty on a chain)
-                const int jn = next_contraction(i + 1);
-                if (jn < i_end) {                 // stage the next contraction's matrix behind this step's product
-                    stage_tile(Pb + (cur ^ 1) * 64 * LD64, a.PT + ((size_t)cat * a.B + (__ldg(&w.steps[jn].x) & WALK_ID_MASK)) * 4096);
+                    stage_rows(Xs, LANES_LDX, a.cond + (((size_t)cat * a.I + cin) * Sp + s0) * 64, LANES_TILE_P);
                     cp_async_commit();
-                    cp_async_wait<1>();           // everything but the newest group: this step's P and X have landed
-                } else {
-                    cp_async_wait<0>();
+                    sc = __ldcg(a.scal + ((size_t)cat * a.I + cin) * Sp + s);
                 }
+                if (tr) trp[2] = clock64();
+                cp_async_wait<0>();               // this step's P (staged after the previous product) and X have landed
+                if (tr) trp[3] = clock64();
                 __syncthreads();
-                double acc[4][4];
+                if (tr) trp[4] = clock64();
+                double acc[8][2];
 #pragma unroll
-                for (int ii = 0; ii < 4; ii++)
+                for (int j = 0; j < 8; j++) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
+                lanes_mm(Xs, Ps, row, g, q4, acc);
+                if (tr) trp[5] = clock64();
+                __syncthreads();                  // every thread is done with Xs and Ps
+                if (tr) trp[6] = clock64();
+                if (st.z >= 0) stage_P(cat, st.z);    // lands under the epilogue, the leaf steps and the next X load
+                ex += sc;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) acc[ii][j] = 0.0;
-                tile_mm64(Xs, Pb + cur * 64 * LD64, tx, ty, acc);
-                cur ^= 1;
-#pragma unroll
-                for (int ii = 0; ii < 4; ii++) {
-                    ex[ii] += sc4[ii];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) v[ii][j] *= acc[ii][j];
-                }
+                for (int j = 0; j < 8; j++) { v[j][0] *= acc[j][0]; v[j][1] *= acc[j][1]; }
             }
+            if (tr) trp[7] = clock64();
             if (flags & STEP_LAST) {
                 const bool side = job >= a.I;
                 const int node = side ? job - a.I : job;
                 if (!side && a.L + node == a.forced_node) {            // pinned internal node: only the forced state survives
+                    const int f = __ldg(a.forced + s);
 #pragma unroll
-                    for (int ii = 0; ii < 4; ii++) {
-                        const int f = a.forced[s0 + 4 * ty + ii];
-#pragma unroll
-                        for (int j = 0; j < 4; j++) if (col_of(tx, j) != f) v[ii][j] = 0.0;
+                    for (int j = 0; j < 8; j++) {
+                        if (c0s + 8 * j != f) v[j][0] = 0.0;
+                        if (c0s + 8 * j + 1 != f) v[j][1] = 0.0;
                     }
                 }
-                // per-pattern renormalisation: exact power of two so that max_k lands in [0.5, 1)
-                const bool is_root = !side && node == a.I - 1;
-                double *outp = (side ? w.cond_side : a.cond) + (((size_t)cat * a.I + node) * Sp + s0) * 64;
-                int *outs = (side ? w.scal_side : a.scal) + ((size_t)cat * a.I + node) * Sp + s0;
+                // per-pattern renormalisation: exact power of two so that max_k lands in [0.5, 1).  The values are
+                // non-negative, so the row maximum is the maximum of the bit patterns; its exponent needs the high words only.
+                int mh = 0;
 #pragma unroll
-                for (int ii = 0; ii < 4; ii++) {
-                    double m = fmax(fmax(v[ii][0], v[ii][1]), fmax(v[ii][2], v[ii][3]));
+                for (int j = 0; j < 8; j++) mh = max(mh, max(__double2hiint(v[j][0]), __double2hiint(v[j][1])));
+                mh = max(mh, __shfl_xor_sync(0xffffffffu, mh, 1));
+                mh = max(mh, __shfl_xor_sync(0xffffffffu, mh, 2));
+                int e = 0;
+                if (mh >= 0x00100000 && mh < 0x7ff00000) {             // normal, finite, positive maximum
+                    e = (mh >> 20) - 1022;                             // m = f * 2^e, f in [0.5, 1); |e| <= 1022: one exact step
+                    if (e != 0) {
+                        const double sc1 = exp2i(-e);
 #pragma unroll
-                    for (int o = 1; o < 16; o <<= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-                    int e = 0;
-                    if (m > 0.0 && m < INFINITY) {
+                        for (int j = 0; j < 8; j++) { v[j][0] *= sc1; v[j][1] *= sc1; }
+                    }
+                } else if (mh < 0x7ff00000) {
+                    // zero or subnormal high word (uniform over the four lanes of the pattern): the slow exact path
+                    const unsigned gmask = 0xFu << (tid & 28);          // the four lanes of this pattern take this branch together
+                    double m = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) m = fmax(m, fmax(v[j][0], v[j][1]));
+                    m = fmax(m, __shfl_xor_sync(gmask, m, 1));
+                    m = fmax(m, __shfl_xor_sync(gmask, m, 2));
+                    if (m > 0.0) {
                         e = ilogb(m) + 1;
-                        const double s1 = exp2i(-(e / 2)), s2 = exp2i(-(e - e / 2));   // two steps: |e| may exceed 1022
+                        const double s1 = exp2i(-(e / 2)), s2 = exp2i(-(e - e / 2));
 #pragma unroll
-                        for (int j = 0; j < 4; j++) v[ii][j] = v[ii][j] * s1 * s2;
+                        for (int j = 0; j < 8; j++) { v[j][0] = v[j][0] * s1 * s2; v[j][1] = v[j][1] * s1 * s2; }
                     }
-                    ex[ii] += e;
-                    const int row = 4 * ty + ii;
-                    __stcg(reinterpret_cast<double2 *>(outp + (size_t)row * 64 + 2 * tx), make_double2(v[ii][0], v[ii][1]));
-                    __stcg(reinterpret_cast<double2 *>(outp + (size_t)row * 64 + 32 + 2 * tx), make_double2(v[ii][2], v[ii][3]));
-                    if (tx == 0) __stcg(outs + row, ex[ii]);
-                    if (is_root) {
-                        double rr = v[ii][0] * a.pi[2 * tx] + v[ii][1] * a.pi[2 * tx + 1] + v[ii][2] * a.pi[32 + 2 * tx] + v[ii][3] * a.pi[33 + 2 * tx];
+                }                                                     // inf / NaN: left alone, like prune64_kernel
+                ex += e;
+                const bool is_root = !side && node == a.I - 1;
+                double2 *outp = reinterpret_cast<double2 *>((side ? w.cond_side : a.cond) + (((size_t)cat * a.I + node) * Sp + s) * 64 + c0s);
 #pragma unroll
-                        for (int o = 1; o < 16; o <<= 1) rr += __shfl_xor_sync(0xffffffffu, rr, o);
-                        if (tx == 0) {
-                            a.rootL[(size_t)cat * Sp + s0 + row] = rr;
-                            a.rootE[(size_t)cat * Sp + s0 + row] = ex[ii];
-                        }
+                for (int j = 0; j < 8; j++) __stcg(outp + 4 * j, make_double2(v[j][0], v[j][1]));
+                if (q4 == 0) __stcg((side ? w.scal_side : a.scal) + ((size_t)cat * a.I + node) * Sp + s, ex);
+                if (is_root) {
+                    double rr = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) rr += v[j][0] * a.pi[c0s + 8 * j] + v[j][1] * a.pi[c0s + 8 * j + 1];
+                    rr += __shfl_xor_sync(0xffffffffu, rr, 1);
+                    rr += __shfl_xor_sync(0xffffffffu, rr, 2);
+                    if (q4 == 0) {
+                        a.rootL[(size_t)cat * Sp + s] = rr;
+                        a.rootE[(size_t)cat * Sp + s] = ex;
                     }
                 }
+                if (tr) trp[8] = clock64();
                 __syncthreads();                  // the whole tile is written (and visible to this CTA's later reads)
-                if (tid == 0) {                   // publish: other lanes of this (class, tile) may consume it now
-                    __threadfence();
+                if (tr) trp[9] = clock64();
+                if (tid == 0 && st.w) {           // publish: another lane of this (class, tile) waits for this job.  The release
+                    // is cumulative over the stores this thread observed through the barrier.
                     int *f = w.flags + ((size_t)cat * 2 * a.I + job) * w.T + tile;
                     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(w.pass) : "memory");
                 }
+                if (tr) trp[10] = clock64();
             }
         }
     }

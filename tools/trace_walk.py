@@ -10,7 +10,8 @@ os.environ["HB2_WALK_TRACE_CTA"] = cta
 from hyphy_b200 import synth, LikelihoodFunction  # noqa: E402
 
 w = synth.codon_workload(200, 2000, 4)
-lf = LikelihoodFunction(w)
+from hyphy_b200.engine import FLAG_DEFAULT, FLAG_FORCE_FP64  # noqa: E402
+lf = LikelihoodFunction(w, flags=FLAG_FORCE_FP64 if os.environ.get("HB2_TRACE_FP64") == "1" else FLAG_DEFAULT)    # HB2_TRACE_FP64=1: the fp64 lanes kernel
 lf.set_template()
 for k in range(3):
     lf.set_all_compiled(w.compiled_values(perturb=1e-4 * k))
