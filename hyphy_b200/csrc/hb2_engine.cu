@@ -156,6 +156,7 @@ struct hb2_partition {
     int forced_node = -1;
     // persistent walk kernel (one launch per evaluation): plan buffers, generation bits of the tagged hand-over, residency
     bool small_walk = true;                   // HB2_SMALL_WALK=0: per-level launches of prune_small_kernel (A/B testing)
+    bool small_dmma = true;                   // HB2_SMALL_DMMA=0: one thread per pattern (prune_small_walk_kernel) also for 16..32 states
     int fp64_mode = 2;                        // HB2_FP64_WALK: 2 (default) prune64_lanes_kernel, 1 prune64_walk_kernel when it fills the machine, 0 per-level launches
     bool fp64_walk = true;                    // fp64_mode >= 1
     double *d_cond_side = nullptr;            // fp64 lanes kernel: side products [C][I][Sp][64] (exponents: second half of d_scal)
@@ -729,6 +730,18 @@ int run_small_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::
     hb2::PruneArgs a = prune_args(p, cat0);
     dim3 grid((unsigned)(p->Sp / 128), (unsigned)ncls);
     const int n = (int)jobs.size();
+    if (p->Dp >= 16 && p->small_dmma) {          // 16 / 24 / 32 padded states: FP64 tensor pipe, 8 patterns per warp
+        dim3 g64((unsigned)(p->Sp / 64), (unsigned)ncls);
+        switch (p->Dp) {
+            case 16: hb2::prune_small_dmma_kernel<16><<<g64, 256, 0, p->stream>>>(a, p->d_jobs, n); break;
+            case 24: hb2::prune_small_dmma_kernel<24><<<g64, 256, 0, p->stream>>>(a, p->d_jobs, n); break;
+            case 32: hb2::prune_small_dmma_kernel<32><<<g64, 256, 0, p->stream>>>(a, p->d_jobs, n); break;
+            default: return fail("unsupported padded state count %d", p->Dp);
+        }
+        p->launches++;
+        CU(cudaGetLastError());
+        return 0;
+    }
     switch (p->Dp) {
         case 4: hb2::prune_small_walk_kernel<4><<<grid, 128, 0, p->stream>>>(a, p->d_jobs, n); break;
         case 8: hb2::prune_small_walk_kernel<8><<<grid, 128, 0, p->stream>>>(a, p->d_jobs, n); break;
@@ -1323,6 +1336,7 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
     }
 #undef CUP
     { const char *env = getenv("HB2_SMALL_WALK"); p->small_walk = !(env && env[0] == '0'); }
+    { const char *env = getenv("HB2_SMALL_DMMA"); p->small_dmma = !(env && env[0] == '0'); }
     p->fp64_walk = p->fp64_mode >= 1;
     p->have_matrix.assign(C * p->B, 0);
     p->is_rate.assign(C * p->B, 0);
@@ -1919,6 +1933,7 @@ const char *hb2_pruning_kernel(const hb2_partition *p) {
     if (p->use_tc) return p->use_walk ? (p->walk_v2 ? "prune64_tc_walk2_kernel" : "prune64_tc_walk_kernel") : "prune64_tc_kernel";
     if (p->Dp == 64 && p->fp64_mode == 2) return "prune64_lanes_kernel";
     if (p->Dp == 64) return (p->fp64_walk && (int64_t)(p->Sp / hb2::TILE_P) * p->ownN >= 2 * p->sm_count) ? "prune64_walk_kernel" : "prune64_kernel";
+    if (p->small_walk && p->small_dmma && p->Dp >= 16) return "prune_small_dmma_kernel";
     return p->small_walk ? "prune_small_walk_kernel" : "prune_small_kernel";
 }
 

@@ -303,3 +303,174 @@ __global__ void __launch_bounds__(32 * NW, NW == 4 ? 4 : 3) prune64_lanes_kernel
 }
 
 }  // namespace hb2
+
+namespace hb2 {
+
+// ------------------------------------------------------------------------------------------------------------------
+// prune_small_dmma_kernel<DP>: 16 / 24 / 32 padded states (proteins: 20 -> 24) on the FP64 tensor pipe, whole pass in one
+// launch.  CTA = 8 warps x 8 patterns; every CTA walks the dirty nodes in post-order (jobs ascending), so all dependencies
+// are thread-local, like prune_small_walk_kernel -- but a warp contracts 8 patterns with DP/4 x DP/8 DMMA (m8n8k4) instead
+// of DP*DP DFMA per thread, a thread carries 2*DP/8 values of ONE pattern instead of four DP-vectors (the one-thread-per-
+// pattern kernel needs ~230 registers at DP = 24: two CTAs per SM, 12.5 -> 20 % of the HBM roofline), and
+//   * the child's vector is read from global memory directly in A-fragment order (lanes q4 = 0..3 of a pattern read 32
+//     contiguous bytes per k-step: whole sectors, no shared-memory round trip);
+//   * P^T of the NEXT child is staged with cp.async under the current product (two buffers, one barrier per child);
+//   * a child that is the previous job's node is rebuilt from the accumulator fragments with shuffles.
+// Layouts, scaling convention and results' meaning are those of prune_small_walk_kernel (reference
+// tree_evaluator.cpp:3556-4171, generic-D branch :3704-4043); summation order inside a product differs (rounding).
+// ------------------------------------------------------------------------------------------------------------------
+template <int DP>
+__global__ void __launch_bounds__(256, DP == 32 ? 3 : 4) prune_small_dmma_kernel(PruneArgs a, const int *__restrict__ jobs, int njobs) {
+    constexpr int NT = DP / 8, KS = DP / 4;
+    constexpr int LD = (DP == 24) ? 24 : DP + 8;          // 2*LD mod 32 == 16: the 4 rows of a B fragment hit disjoint banks
+    __shared__ __align__(16) double Pbuf[2][DP * LD];
+    const int tid = threadIdx.x, warp = tid >> 5, g = (tid & 31) >> 2, q4 = tid & 3;
+    const int cat = a.cat0 + blockIdx.y;
+    const size_t Sp = a.Sp;
+    const size_t s = (size_t)blockIdx.x * 64 + 8 * warp + g;         // this thread's pattern
+    if (njobs <= 0) return;
+
+    auto stage_P = [&](int child, int buf) {
+        const double *src = a.PT + ((size_t)cat * a.B + child) * DP * DP;
+        for (int idx = tid; idx < DP * DP / 2; idx += 256) {
+            const int rr = idx / (DP / 2), c2 = (idx % (DP / 2)) * 2;
+            cp_async16(&Pbuf[buf][rr * LD + c2], src + rr * DP + c2);
+        }
+        cp_async_commit();
+    };
+    double pv[NT][2];                    // previous job's node (accumulator-fragment order) for the register hand-over
+    int prev = -1, pex = 0;
+    int step = 0;                        // children processed so far: buffer = step & 1
+    stage_P(__ldg(a.tree.child_ids + __ldg(a.tree.child_start + __ldg(jobs))), 0);
+    for (int jb = 0; jb < njobs; jb++) {
+        const int par = __ldg(jobs + jb);
+        double v[NT][2];
+#pragma unroll
+        for (int t = 0; t < NT; t++) { v[t][0] = 1.0; v[t][1] = 1.0; }
+        int ex = 0;
+        const int c_begin = __ldg(a.tree.child_start + par), c_end = __ldg(a.tree.child_start + par + 1);
+        for (int ci = c_begin; ci < c_end; ci++, step++) {
+            const int child = __ldg(a.tree.child_ids + ci);
+            // the child after this one (next child of this node, or the first child of the next job)
+            int nchild = -1;
+            if (ci + 1 < c_end) nchild = __ldg(a.tree.child_ids + ci + 1);
+            else if (jb + 1 < njobs) nchild = __ldg(a.tree.child_ids + __ldg(a.tree.child_start + __ldg(jobs + jb + 1)));
+            // operands of an internal child: issued before the barrier, consumed after it
+            double x[KS];
+            int sc = 0;
+            const bool internal = child >= a.L;
+            const bool chained = internal && (child - a.L == prev);
+            int code = 0;
+            if (!internal) {
+                code = (child == a.forced_node) ? __ldg(a.forced + s) : __ldg(a.leaf + (size_t)child * Sp + s);
+            } else if (!chained) {
+                const double *X = a.cond + (((size_t)cat * a.I + (child - a.L)) * Sp + s) * DP + q4;
+#pragma unroll
+                for (int ks = 0; ks < KS; ks++) x[ks] = __ldcg(X + 4 * ks);
+                sc = __ldcg(a.scal + ((size_t)cat * a.I + (child - a.L)) * Sp + s);
+            } else {
+                // rebuild the A fragments from the previous node's accumulator fragments: k = 4 ks + q4 lives in n-tile
+                // ks/2, column (ks odd ? 4 : 0) + q4 -> lane (ks odd ? 2 : 0) + q4/2 of this pattern, element q4 & 1
+                const int base = (tid & 31) & ~3;
+#pragma unroll
+                for (int ks = 0; ks < KS; ks++) {
+                    const int src = base + ((ks & 1) ? 2 : 0) + (q4 >> 1);
+                    const double t0 = __shfl_sync(0xffffffffu, pv[ks >> 1][0], src);
+                    const double t1 = __shfl_sync(0xffffffffu, pv[ks >> 1][1], src);
+                    x[ks] = (q4 & 1) ? t1 : t0;
+                }
+                sc = pex;
+            }
+            cp_async_wait<0>();              // this child's P has landed (this thread's copies) ...
+            __syncthreads();                 // ... everyone's; and every warp is past the previous product: the other buffer is free
+            if (nchild >= 0) stage_P(nchild, (step + 1) & 1);
+            const double *Ps = Pbuf[step & 1];
+            if (!internal) {
+                if (code >= 0) {
+                    const double *row = Ps + code * LD + 2 * q4;
+#pragma unroll
+                    for (int t = 0; t < NT; t++) { const double2 r = *reinterpret_cast<const double2 *>(row + 8 * t); v[t][0] *= r.x; v[t][1] *= r.y; }
+                } else {
+                    const double *amb = a.ambig + (size_t)(-code - 1) * DP;
+                    double acc[NT][2];
+#pragma unroll
+                    for (int t = 0; t < NT; t++) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+                    for (int j = 0; j < a.D; j++) {
+                        const double wgt = __ldg(amb + j);
+                        if (wgt != 0.0) {
+                            const double *row = Ps + j * LD + 2 * q4;
+#pragma unroll
+                            for (int t = 0; t < NT; t++) { const double2 r = *reinterpret_cast<const double2 *>(row + 8 * t); acc[t][0] = fma(wgt, r.x, acc[t][0]); acc[t][1] = fma(wgt, r.y, acc[t][1]); }
+                        }
+                    }
+#pragma unroll
+                    for (int t = 0; t < NT; t++) { v[t][0] *= acc[t][0]; v[t][1] *= acc[t][1]; }
+                }
+            } else {
+                double acc[NT][2];
+#pragma unroll
+                for (int t = 0; t < NT; t++) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+                const double *b0 = Ps + q4 * LD + g;
+#pragma unroll
+                for (int ks = 0; ks < KS; ks++)
+#pragma unroll
+                    for (int t = 0; t < NT; t++) dmma884(acc[t], x[ks], b0[4 * ks * LD + 8 * t]);
+                ex += sc;
+#pragma unroll
+                for (int t = 0; t < NT; t++) { v[t][0] *= acc[t][0]; v[t][1] *= acc[t][1]; }
+            }
+        }
+        if (a.L + par == a.forced_node) {
+            const int f = __ldg(a.forced + s);
+#pragma unroll
+            for (int t = 0; t < NT; t++) {
+                if (8 * t + 2 * q4 != f) v[t][0] = 0.0;
+                if (8 * t + 2 * q4 + 1 != f) v[t][1] = 0.0;
+            }
+        }
+        // per-pattern renormalisation (max in [0.5, 1)): own values, then the 4 lanes of the pattern
+        double m = 0.0;
+#pragma unroll
+        for (int t = 0; t < NT; t++) m = fmax(m, fmax(v[t][0], v[t][1]));
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        if (m > 0.0 && m < INFINITY) {
+            const int mh = __double2hiint(m);
+            int e;
+            if (mh >= 0x00100000) {
+                e = (mh >> 20) - 1022;
+                if (e != 0) {
+                    const double sc1 = exp2i(-e);
+#pragma unroll
+                    for (int t = 0; t < NT; t++) { v[t][0] *= sc1; v[t][1] *= sc1; }
+                }
+            } else {
+                e = ilogb(m) + 1;
+                const double s1 = exp2i(-(e / 2)), s2 = exp2i(-(e - e / 2));
+#pragma unroll
+                for (int t = 0; t < NT; t++) { v[t][0] = v[t][0] * s1 * s2; v[t][1] = v[t][1] * s1 * s2; }
+            }
+            ex += e;
+        }
+        double *outp = a.cond + (((size_t)cat * a.I + par) * Sp + s) * DP + 2 * q4;
+#pragma unroll
+        for (int t = 0; t < NT; t++) *reinterpret_cast<double2 *>(outp + 8 * t) = make_double2(v[t][0], v[t][1]);
+        if (q4 == 0) a.scal[((size_t)cat * a.I + par) * Sp + s] = ex;
+#pragma unroll
+        for (int t = 0; t < NT; t++) { pv[t][0] = v[t][0]; pv[t][1] = v[t][1]; }
+        prev = par; pex = ex;
+        if (par == a.I - 1) {
+            double r = 0.0;
+#pragma unroll
+            for (int t = 0; t < NT; t++) r += v[t][0] * a.pi[8 * t + 2 * q4] + v[t][1] * a.pi[8 * t + 2 * q4 + 1];
+            r += __shfl_xor_sync(0xffffffffu, r, 1);
+            r += __shfl_xor_sync(0xffffffffu, r, 2);
+            if (q4 == 0) {
+                a.rootL[(size_t)cat * Sp + s] = r;
+                a.rootE[(size_t)cat * Sp + s] = ex;
+            }
+        }
+    }
+}
+
+}  // namespace hb2

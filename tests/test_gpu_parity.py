@@ -424,6 +424,63 @@ def test_other_state_counts(D, taxa, sites, C, mode):
     assert abs(got - ref) <= tol(w, mode)[0] * abs(ref)
 
 
+@pytest.mark.parametrize("D,taxa,sites,C", [(20, 24, 400, 2), (16, 11, 130, 1), (29, 10, 90, 2)])
+def test_protein_sized_states_ambiguity_partial_forced_readback(D, taxa, sites, C):
+    """16 / 24 / 32 padded states run on the FP64 tensor pipe (prune_small_dmma_kernel): ambiguous leaves, partial updates
+    (bit-identical to a full recomputation), a pinned node against the oracle, and the conditionals' read-back."""
+    w = synth.generic_workload(D, taxa, sites, C, seed=77)
+    rng = np.random.default_rng(5)
+    # make some leaf observations ambiguous: 7 random 0/1 vectors (the reference's resolution vectors, likefunc.cpp:4299)
+    amb = (rng.random((7, D)) < 0.3).astype(float)
+    amb[np.arange(7), rng.integers(0, D, 7)] = 1.0
+    w.ambig = amb
+    ls = w.leaf_states.copy()
+    hit = rng.random(ls.shape) < 0.04
+    ls[hit] = -(rng.integers(0, 7, size=hit.sum()) + 1)
+    w.leaf_states = ls
+    lf = LF(w, "fp64")
+    assert lf.part.pruning_kernel() == "prune_small_dmma_kernel"
+    lf.set_all_matrices()
+    got = lf.compute()
+    ref, _ = port.lnl(w, sparse_storage=False)
+    assert abs(got - ref) <= 1e-10 * abs(ref)
+    L, I = w.tree.n_leaves, w.tree.n_internal
+    # conditionals of every internal node, class 0
+    P0 = np.stack([port.expm(w.Q_classes[0] * w.tree.t[b], False) for b in range(w.tree.n_branches)])
+    _, _, ocond = port.prune(w, P0, want_cond=True)
+    for inode in range(I):
+        cond, e = lf.part.read_conditionals(0, inode)
+        rowmax = ocond[inode].max(axis=1, keepdims=True)
+        assert np.all(np.abs(cond * np.exp2(e)[:, None] - ocond[inode]) <= 1e-12 * rowmax + 1e-9 * ocond[inode])
+        assert np.all(cond.max(axis=1) >= 0.5) and np.all(cond.max(axis=1) <= 1.0)
+    # partial updates
+    for node in [1, L + 1, w.tree.n_branches - 1]:
+        w.tree.t[node] *= 1.4
+        Qt = w.Qt()
+        for c in range(w.C):
+            lf.part.set_matrices(c, [node], Qt[c, node:node + 1])
+        part = lf.compute(update_nodes=[node])
+        ref, _ = port.lnl(w, sparse_storage=False)
+        assert abs(part - ref) <= 1e-10 * abs(ref)
+        assert lf.compute(update_nodes=None) == part
+    # a pinned node: leaf, internal, root
+    c = w.C - 1
+    Qt = w.Qt()
+    Pc = np.stack([port.expm(q, False) for q in Qt[c]])
+    base, bl, bs = lf.compute_block(c, want_sites=True)
+    children = w.tree.children()
+    for node in (0, L + I // 2, L + I - 1):
+        fs = rng.integers(0, D, size=w.S)
+        oL, oS = port.prune_forced(w, Pc, node, fs)
+        lnl, sl, ss = lf.part.evaluate_forced(c, w.pi, node, fs, update_nodes=[node] if node < L else children[node - L])
+        ok = oL > 0
+        assert np.array_equal(sl > 0, ok)
+        assert np.abs(_site_lnl(np.maximum(sl, 1e-300), ss)[ok] - _site_lnl(np.maximum(oL, 1e-300), oS)[ok]).max() <= 1e-9
+        again, al, as_ = lf.compute_block(c, update_nodes=[node] if node < L else children[node - L], want_sites=True)
+        assert again == base and np.array_equal(al, bl) and np.array_equal(as_, bs)
+    lf.close()
+
+
 @pytest.mark.parametrize("name", ["mg94_8x60_c4_ambig", "mg94_200x64_c4_scaling", "c1_hky85_8x500"])
 def test_forced_states_match_oracle(name, mode):
     """ComputeBlock(..., branchIndex, branchValues) -- one node pinned to a per-pattern state (tree_evaluator.cpp:3624,
