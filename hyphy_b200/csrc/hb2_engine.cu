@@ -1822,7 +1822,7 @@ int hb2_plan_walk(int64_t L, int64_t I, const int64_t *flatParents, int64_t nUpd
     if (stepCapacity < L + 2 * I) return fail("steps needs room for %lld entries", (long long)(L + 2 * I));
     std::vector<int> ls(K + 1), st(2 * (size_t)(L + 2 * I));
     std::vector<char> jdirty;
-    const int ns = plan_walk(children, height, (int)L, (int)I, dirty, K, splitNodes != 0, ls.data(), st.data(), jdirty);
+    const int ns = plan_walk(children, height, (int)L, (int)I, dirty, K, (splitNodes & 1) != 0, ls.data(), st.data(), jdirty, (splitNodes & 2) != 0);
     for (int r = 0; r <= lanes; r++) laneStart[r] = ls[std::min(r, K)];
     for (int i = 0; i < 2 * ns; i++) steps[i] = st[i];
     *nSteps = ns;

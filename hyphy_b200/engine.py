@@ -87,7 +87,7 @@ STEP_WAIT, STEP_CHAIN, STEP_MUL, STEP_ID_MASK = 1 << 30, 1 << 29, 1 << 28, (1 <<
 STEP_FIRST, STEP_LAST = 1 << 28, 1 << 29
 
 
-def plan_walk(flat_parents, n_leaves, update_nodes=None, lanes=4, split_nodes=True):
+def plan_walk(flat_parents, n_leaves, update_nodes=None, lanes=4, split_nodes=True, canonical_multi=False):
     """The walk kernel's plan for a tree and a dirty set (host code only: works without a GPU).
     Returns (lane_start[lanes+1], steps[n, 2])."""
     fp, pfp = _i(flat_parents)
@@ -101,7 +101,7 @@ def plan_walk(flat_parents, n_leaves, update_nodes=None, lanes=4, split_nodes=Tr
     else:
         u, pu = _i(update_nodes)
         nu = len(u)
-    _check(load_library().hb2_plan_walk(L, I, pfp, nu, pu, int(lanes), int(bool(split_nodes)), ls.ctypes.data_as(_i32p),
+    _check(load_library().hb2_plan_walk(L, I, pfp, nu, pu, int(lanes), int(bool(split_nodes)) | (2 if canonical_multi else 0), ls.ctypes.data_as(_i32p),
                                         st.ctypes.data_as(_i32p), len(st) // 2, C.byref(n)))
     return ls, st[:2 * n.value].reshape(-1, 2).copy()
 

@@ -190,7 +190,8 @@ void hb2_destroy(hb2_partition *p);
  * 2 ints per step -- child id | HB2_STEP_WAIT (1<<30: produced by another lane) | HB2_STEP_CHAIN (1<<29: produced by
  * the lane's previous job, taken from registers) | HB2_STEP_MUL (1<<28: side product, multiply without a matrix); job's
  * node slot (>= I: side product of node slot-I) | HB2_STEP_FIRST (1<<28) | HB2_STEP_LAST (1<<29).  `steps` must hold
- * 2*(L+2I) ints. */
+ * 2*(L+2I) ints.  splitNodes: bit 0 = side products on; bit 1 = the fp64 lanes kernel's rule for nodes with more than
+ * two children (never split or chained, children in tree order), which makes conditionals independent of the plan. */
 int hb2_plan_walk(int64_t L, int64_t I, const int64_t *flatParents, int64_t nUpdate, const int64_t *updateNodes, int lanes,
                   int splitNodes, int32_t *laneStart, int32_t *steps, int64_t stepCapacity, int64_t *nSteps);
 

@@ -50,9 +50,9 @@ def trees():
 TREES = trees()
 
 
-def check_plan(par, L, update, lanes, split):
+def check_plan(par, L, update, lanes, split, canonical=False):
     I = len(par) - L
-    ls, st = engine.plan_walk(par, L, update, lanes, split)
+    ls, st = engine.plan_walk(par, L, update, lanes, split, canonical)
     children = [[] for _ in range(I)]
     for n in range(L + I - 1):
         children[par[n]].append(n)
@@ -176,6 +176,26 @@ def test_spine_keeps_registers_and_side_products_leave_it():
     _, st_plain, jobs_plain = check_plan(par, L, None, 8, False)
     assert any(s >= len(par) - L for s in jobs_split) and not any(s >= len(par) - L for s in jobs_plain)
     assert len(st_split) == len(st_plain) + sum(1 for s in jobs_split if s >= len(par) - L)   # one MUL step per side product
+
+
+@pytest.mark.parametrize("name,par,L", TREES, ids=[t[0] for t in TREES])
+@pytest.mark.parametrize("lanes", [1, 3, 8])
+def test_canonical_rule_for_multifurcations(name, par, L, lanes):
+    """fp64 lanes kernel: a node with more than two children is never split or chained and its children come in tree order
+    (one association of the product in every plan); all other invariants hold; binary nodes may still split / chain."""
+    I = len(par) - L
+    children = [[] for _ in range(I)]
+    for n in range(L + I - 1):
+        children[par[n]].append(n)
+    rng = np.random.default_rng(3)
+    for update in (None, [int(x) for x in rng.integers(0, L + I - 1, size=3)]):
+        ls, st, jobs = check_plan(par, L, update, lanes, True, canonical=True)
+        for slot, (r, order, items) in jobs.items():
+            n = slot if slot < I else slot - I
+            if len(children[n]) > 2:
+                assert slot < I and (I + n) not in jobs
+                assert [c for c, f in items] == children[n]
+                assert not any(f & (STEP_CHAIN | STEP_MUL) for c, f in items)
 
 
 def test_planner_rejects_bad_input():
