@@ -10,6 +10,7 @@
 #include "hb2_kernels_lanes.cuh"
 
 #include <climits>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -731,12 +732,25 @@ int run_small_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::
     dim3 grid((unsigned)(p->Sp / 128), (unsigned)ncls);
     const int n = (int)jobs.size();
     if (p->Dp >= 16 && p->small_dmma) {          // 16 / 24 / 32 padded states: FP64 tensor pipe, 8 patterns per warp
-        dim3 g64((unsigned)(p->Sp / 64), (unsigned)ncls);
-        switch (p->Dp) {
-            case 16: hb2::prune_small_dmma_kernel<16><<<g64, 256, 0, p->stream>>>(a, p->d_jobs, n); break;
-            case 24: hb2::prune_small_dmma_kernel<24><<<g64, 256, 0, p->stream>>>(a, p->d_jobs, n); break;
-            case 32: hb2::prune_small_dmma_kernel<32><<<g64, 256, 0, p->stream>>>(a, p->d_jobs, n); break;
-            default: return fail("unsupported padded state count %d", p->Dp);
+        // every CTA walks the whole tree: the launch is a few long waves.  Shape with the smaller last-wave loss: 8 warps
+        // (4 CTAs per SM; 3 at 32 states) or, up to 24 states, 4 warps (9 per SM).
+        const double warps = (double)(p->Sp / 8) * ncls;
+        const int cap8 = (p->Dp == 32 ? 3 : 4) * 8 * p->sm_count, cap4 = 9 * 4 * p->sm_count;
+        auto cost = [&](int cap) { const double wv = warps / cap; return std::ceil(wv - 1e-9) / wv; };      // 1 = no tail loss
+        int nw = 8;
+        if (p->Dp <= 24 && cost(cap4) < cost(cap8) - 0.05) nw = 4;
+        if (const char *ov = getenv("HB2_SMALL_WARPS")) nw = (atoi(ov) == 4 && p->Dp <= 24) ? 4 : 8;
+        dim3 g((unsigned)(p->Sp / (8 * nw)), (unsigned)ncls);
+        if (nw == 8) {
+            switch (p->Dp) {
+                case 16: hb2::prune_small_dmma_kernel<16, 8><<<g, 256, 0, p->stream>>>(a, p->d_jobs, n); break;
+                case 24: hb2::prune_small_dmma_kernel<24, 8><<<g, 256, 0, p->stream>>>(a, p->d_jobs, n); break;
+                case 32: hb2::prune_small_dmma_kernel<32, 8><<<g, 256, 0, p->stream>>>(a, p->d_jobs, n); break;
+                default: return fail("unsupported padded state count %d", p->Dp);
+            }
+        } else {
+            if (p->Dp == 16) hb2::prune_small_dmma_kernel<16, 4><<<g, 128, 0, p->stream>>>(a, p->d_jobs, n);
+            else hb2::prune_small_dmma_kernel<24, 4><<<g, 128, 0, p->stream>>>(a, p->d_jobs, n);
         }
         p->launches++;
         CU(cudaGetLastError());

@@ -319,20 +319,22 @@ namespace hb2 {
 // Layouts, scaling convention and results' meaning are those of prune_small_walk_kernel (reference
 // tree_evaluator.cpp:3556-4171, generic-D branch :3704-4043); summation order inside a product differs (rounding).
 // ------------------------------------------------------------------------------------------------------------------
-template <int DP>
-__global__ void __launch_bounds__(256, DP == 32 ? 3 : 4) prune_small_dmma_kernel(PruneArgs a, const int *__restrict__ jobs, int njobs) {
+// NW warps per CTA.  Every CTA walks the whole tree, so the launch is a few long waves; the host picks the shape (8 warps at
+// 4 CTAs per SM, or 4 warps at 9 per SM for DP <= 24) whose resident capacity leaves the smaller tail wave.
+template <int DP, int NW>
+__global__ void __launch_bounds__(32 * NW, NW == 4 ? 9 : (DP == 32 ? 3 : 4)) prune_small_dmma_kernel(PruneArgs a, const int *__restrict__ jobs, int njobs) {
     constexpr int NT = DP / 8, KS = DP / 4;
     constexpr int LD = (DP == 24) ? 24 : DP + 8;          // 2*LD mod 32 == 16: the 4 rows of a B fragment hit disjoint banks
     __shared__ __align__(16) double Pbuf[2][DP * LD];
     const int tid = threadIdx.x, warp = tid >> 5, g = (tid & 31) >> 2, q4 = tid & 3;
     const int cat = a.cat0 + blockIdx.y;
     const size_t Sp = a.Sp;
-    const size_t s = (size_t)blockIdx.x * 64 + 8 * warp + g;         // this thread's pattern
+    const size_t s = (size_t)blockIdx.x * (8 * NW) + 8 * warp + g;   // this thread's pattern
     if (njobs <= 0) return;
 
     auto stage_P = [&](int child, int buf) {
         const double *src = a.PT + ((size_t)cat * a.B + child) * DP * DP;
-        for (int idx = tid; idx < DP * DP / 2; idx += 256) {
+        for (int idx = tid; idx < DP * DP / 2; idx += 32 * NW) {
             const int rr = idx / (DP / 2), c2 = (idx % (DP / 2)) * 2;
             cp_async16(&Pbuf[buf][rr * LD + c2], src + rr * DP + c2);
         }
