@@ -157,6 +157,7 @@ struct hb2_partition {
     int forced_node = -1;
     // persistent walk kernel (one launch per evaluation): plan buffers, generation bits of the tagged hand-over, residency
     bool small_walk = true;                   // HB2_SMALL_WALK=0: per-level launches of prune_small_kernel (A/B testing)
+    int small_ilp = 0, small_resident[2] = {1, 1};   // HB2_SMALL_ILP=1/2 forces one / two patterns per thread (4 states); co-resident CTAs of both
     bool small_dmma = true;                   // HB2_SMALL_DMMA=0: one thread per pattern (prune_small_walk_kernel) also for 16..32 states
     int fp64_mode = 2;                        // HB2_FP64_WALK: 2 (default) prune64_lanes_kernel, 1 prune64_walk_kernel when it fills the machine, 0 per-level launches
     bool fp64_walk = true;                    // fp64_mode >= 1
@@ -756,6 +757,19 @@ int run_small_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::
         CU(cudaGetLastError());
         return 0;
     }
+    if (p->Dp == 4 && p->small_ilp != 1) {
+        // one or two patterns per thread: (passes over the resident capacity) x (measured cost of a pass: 0.63 vs 0.98 ms
+        // at 256 taxa, profiles/r2x_small*.json)
+        const long ct1 = (long)(p->Sp / 128) * ncls, ct2 = (long)((p->Sp + 255) / 256) * ncls;
+        const double c1 = std::ceil((double)ct1 / p->small_resident[0]), c2 = 1.55 * std::ceil((double)ct2 / p->small_resident[1]);
+        if (p->small_ilp == 2 || c2 < c1) {
+            dim3 g2((unsigned)((p->Sp + 255) / 256), (unsigned)ncls);
+            hb2::prune_small_walk_ilp_kernel<4, 2><<<g2, 128, 0, p->stream>>>(a, p->d_jobs, n);
+            p->launches++;
+            CU(cudaGetLastError());
+            return 0;
+        }
+    }
     switch (p->Dp) {
         case 4: hb2::prune_small_walk_kernel<4><<<grid, 128, 0, p->stream>>>(a, p->d_jobs, n); break;
         case 8: hb2::prune_small_walk_kernel<8><<<grid, 128, 0, p->stream>>>(a, p->d_jobs, n); break;
@@ -1351,6 +1365,14 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
 #undef CUP
     { const char *env = getenv("HB2_SMALL_WALK"); p->small_walk = !(env && env[0] == '0'); }
     { const char *env = getenv("HB2_SMALL_DMMA"); p->small_dmma = !(env && env[0] == '0'); }
+    if (Dp == 4) {
+        if (const char *env = getenv("HB2_SMALL_ILP")) p->small_ilp = atoi(env);
+        int b1 = 0, b2 = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, hb2::prune_small_walk_kernel<4>, 128, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b2, hb2::prune_small_walk_ilp_kernel<4, 2>, 128, 0);
+        p->small_resident[0] = std::max(b1, 1) * p->sm_count;
+        p->small_resident[1] = std::max(b2, 1) * p->sm_count;
+    }
     p->fp64_walk = p->fp64_mode >= 1;
     p->have_matrix.assign(C * p->B, 0);
     p->is_rate.assign(C * p->B, 0);

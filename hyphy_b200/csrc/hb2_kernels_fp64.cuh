@@ -1341,6 +1341,149 @@ __global__ void __launch_bounds__(128) prune_small_walk_kernel(PruneArgs a, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// 4 / 8 padded states, PP patterns per thread: the one-pattern kernel above is bound by the latency of each thread's serial
+// node chain, and -- every CTA walking the whole tree -- by wave quantisation (256 x 200 k nucleotides: 1563 CTAs on 1332
+// resident = 1.17 waves, i.e. two passes).  With two patterns per thread the loads and the arithmetic of both are in flight
+// together (the pass gets 1.55x longer, not 2x) and half as many CTAs cover the alignment; the host picks the variant
+// with the cheaper (passes x pass cost).  Thread t of CTA b owns patterns (b*PP + u)*128 + t: coalesced for every u.
+// ------------------------------------------------------------------------------------------------
+template <int DP, int PP>
+__global__ void __launch_bounds__(128, 6) prune_small_walk_ilp_kernel(PruneArgs a, const int *__restrict__ jobs, int njobs) {
+    const int tid = threadIdx.x;
+    const int cat = a.cat0 + blockIdx.y;
+    const size_t Sp = a.Sp;
+    size_t s[PP];
+    bool live[PP];
+#pragma unroll
+    for (int u = 0; u < PP; u++) {
+        s[u] = ((size_t)blockIdx.x * PP + u) * 128 + tid;
+        live[u] = s[u] < Sp;
+        if (!live[u]) s[u] = Sp - 1;          // loads stay in range; nothing is stored for a dead slot
+    }
+    double pv[PP][DP];
+    int prev = -1, pex[PP];
+#pragma unroll
+    for (int u = 0; u < PP; u++) pex[u] = 0;
+    for (int jb = 0; jb < njobs; jb++) {
+        const int par = __ldg(jobs + jb);
+        double v[PP][DP];
+        int ex[PP];
+#pragma unroll
+        for (int u = 0; u < PP; u++) {
+            ex[u] = 0;
+#pragma unroll
+            for (int k = 0; k < DP; k++) v[u][k] = 1.0;
+        }
+        const int c_begin = __ldg(a.tree.child_start + par), c_end = __ldg(a.tree.child_start + par + 1);
+        for (int ci = c_begin; ci < c_end; ci++) {
+            const int child = __ldg(a.tree.child_ids + ci);
+            const double *PT = a.PT + ((size_t)cat * a.B + child) * DP * DP;
+            if (child < a.L) {
+                int code[PP];
+#pragma unroll
+                for (int u = 0; u < PP; u++) code[u] = (child == a.forced_node) ? __ldg(a.forced + s[u]) : __ldg(a.leaf + (size_t)child * Sp + s[u]);
+#pragma unroll
+                for (int u = 0; u < PP; u++) {
+                    if (code[u] >= 0) {
+                        const double2 *row = reinterpret_cast<const double2 *>(PT + (size_t)code[u] * DP);
+#pragma unroll
+                        for (int k = 0; k < DP; k += 2) { const double2 r = __ldg(row + k / 2); v[u][k] *= r.x; v[u][k + 1] *= r.y; }
+                    } else {
+                        const double *amb = a.ambig + (size_t)(-code[u] - 1) * DP;
+                        double acc[DP];
+#pragma unroll
+                        for (int k = 0; k < DP; k++) acc[k] = 0.0;
+                        for (int j = 0; j < a.D; j++) {
+                            const double wgt = __ldg(amb + j);
+                            const double2 *row = reinterpret_cast<const double2 *>(PT + (size_t)j * DP);
+#pragma unroll
+                            for (int k = 0; k < DP; k += 2) { const double2 r = __ldg(row + k / 2); acc[k] = fma(wgt, r.x, acc[k]); acc[k + 1] = fma(wgt, r.y, acc[k + 1]); }
+                        }
+#pragma unroll
+                        for (int k = 0; k < DP; k++) v[u][k] *= acc[k];
+                    }
+                }
+            } else {
+                const int cin = child - a.L;
+                double x[PP][DP];
+                if (cin == prev) {
+#pragma unroll
+                    for (int u = 0; u < PP; u++) {
+#pragma unroll
+                        for (int j = 0; j < DP; j++) x[u][j] = pv[u][j];
+                        ex[u] += pex[u];
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < PP; u++) {
+                        const double2 *X = reinterpret_cast<const double2 *>(a.cond + (((size_t)cat * a.I + cin) * Sp + s[u]) * DP);
+#pragma unroll
+                        for (int j = 0; j < DP; j += 2) { const double2 t = X[j / 2]; x[u][j] = t.x; x[u][j + 1] = t.y; }
+                    }
+#pragma unroll
+                    for (int u = 0; u < PP; u++) ex[u] += a.scal[((size_t)cat * a.I + cin) * Sp + s[u]];
+                }
+                double acc[PP][DP];
+#pragma unroll
+                for (int u = 0; u < PP; u++)
+#pragma unroll
+                    for (int k = 0; k < DP; k++) acc[u][k] = 0.0;
+#pragma unroll
+                for (int j = 0; j < DP; j++) {
+                    const double2 *row = reinterpret_cast<const double2 *>(PT + (size_t)j * DP);
+#pragma unroll
+                    for (int k = 0; k < DP; k += 2) {
+                        const double2 r = __ldg(row + k / 2);           // one load serves all PP patterns
+#pragma unroll
+                        for (int u = 0; u < PP; u++) { acc[u][k] = fma(x[u][j], r.x, acc[u][k]); acc[u][k + 1] = fma(x[u][j], r.y, acc[u][k + 1]); }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < PP; u++)
+#pragma unroll
+                    for (int k = 0; k < DP; k++) v[u][k] *= acc[u][k];
+            }
+        }
+        const bool pinned = a.L + par == a.forced_node;
+#pragma unroll
+        for (int u = 0; u < PP; u++) {
+            if (pinned) {
+                const int f = __ldg(a.forced + s[u]);
+#pragma unroll
+                for (int k = 0; k < DP; k++) if (k != f) v[u][k] = 0.0;
+            }
+            double m = 0.0;
+#pragma unroll
+            for (int k = 0; k < DP; k++) m = fmax(m, v[u][k]);
+            if (m > 0.0 && m < INFINITY) {
+                const int e = ilogb(m) + 1;
+                const double s1 = exp2i(-(e / 2)), s2 = exp2i(-(e - e / 2));
+#pragma unroll
+                for (int k = 0; k < DP; k++) v[u][k] = v[u][k] * s1 * s2;
+                ex[u] += e;
+            }
+            if (live[u]) {
+                double2 *outp = reinterpret_cast<double2 *>(a.cond + (((size_t)cat * a.I + par) * Sp + s[u]) * DP);
+#pragma unroll
+                for (int k = 0; k < DP; k += 2) outp[k / 2] = make_double2(v[u][k], v[u][k + 1]);
+                a.scal[((size_t)cat * a.I + par) * Sp + s[u]] = ex[u];
+                if (par == a.I - 1) {
+                    double r = 0.0;
+#pragma unroll
+                    for (int k = 0; k < DP; k++) r = fma(v[u][k], a.pi[k], r);
+                    a.rootL[(size_t)cat * Sp + s[u]] = r;
+                    a.rootE[(size_t)cat * Sp + s[u]] = ex[u];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < DP; k++) pv[u][k] = v[u][k];
+            pex[u] = ex[u];
+        }
+        prev = par;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Root reduction: rate-class mixture + log + pattern frequency + block partial sums.
 //   L_s = sum_c w_c * rootL[c][s] * 2^(rootE[c][s]);  lnL_s = log(sum_c w_c rootL 2^(e_c-emax)) + emax ln2
 // Optional per-pattern outputs in the reference's convention: siteL * 2^(-64*siteScale).

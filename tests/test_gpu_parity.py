@@ -77,6 +77,34 @@ def test_lnl_matches_reference_golden(name, mode):
     assert np.all(sl > 0) and np.all(sl <= 1.0)
 
 
+@pytest.mark.parametrize("name", ["c1_hky85_8x500", "nuc_300x200_scaling"])
+def test_nucleotide_one_and_two_patterns_per_thread_agree_bitwise(name, monkeypatch):
+    """4 states: prune_small_walk_kernel (one pattern per thread) and prune_small_walk_ilp_kernel (two) do the same arithmetic
+    per pattern -- identical per-pattern values, both equal to the reference's; partial updates and pinned nodes included."""
+    w, g = gc.load(name)
+    L, I = w.tree.n_leaves, w.tree.n_internal
+    rng = np.random.default_rng(11)
+    fs = rng.integers(0, w.D, size=w.S)
+    out = {}
+    for ilp in ("1", "2"):
+        monkeypatch.setenv("HB2_SMALL_ILP", ilp)
+        lf = LF(w, "fp64")
+        lf.set_all_matrices()
+        lnl, sl, ss = lf.compute(want_sites=True)
+        part = lf.compute(update_nodes=[2, L + 1])
+        forced = lf.part.evaluate_forced(w.C - 1, w.pi, L + I // 2, fs)
+        after = lf.compute(update_nodes=None)
+        lf.close()
+        out[ilp] = (lnl, sl, ss, part, forced, after)
+        site = _site_lnl(sl, ss)
+        assert abs(lnl - g["lnL"]) <= 1e-10 * abs(g["lnL"])
+        assert float(np.abs(site[w.site_to_pattern] - g["site_lnL"]).max()) <= 1e-8
+        assert part == lnl and after == lnl
+    a, b = out["1"], out["2"]
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert a[4][0] == b[4][0] and np.array_equal(a[4][1], b[4][1]) and np.array_equal(a[4][2], b[4][2])
+
+
 def test_reference_own_golden_smallcodon(mode):
     """The reference's own golden vector: tests/hbltests/SimpleOptimizations/SmallCodon.bf:37 (-3189.516375 +- 0.002),
     evaluated at the parameters the reference binary fitted."""
