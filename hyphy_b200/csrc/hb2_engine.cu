@@ -721,6 +721,15 @@ int run_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector
     return 0;
 }
 
+// 4 states: one or two patterns per thread -- (passes over the resident capacity) x (measured cost of a pass: 0.63 vs 0.98 ms
+// at 256 taxa, profiles/r2x_small*.json)
+static bool small_two_patterns(const hb2_partition *p, int ncls) {
+    if (p->Dp != 4 || p->small_ilp == 1) return false;
+    if (p->small_ilp == 2) return true;
+    const long ct1 = (long)(p->Sp / 128) * ncls, ct2 = (long)((p->Sp + 255) / 256) * ncls;
+    return 1.55 * std::ceil((double)ct2 / p->small_resident[1]) < std::ceil((double)ct1 / p->small_resident[0]);
+}
+
 // Small state spaces: one launch, one thread per pattern walking the dirty nodes in post-order.
 int run_small_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::vector<int>> &levels) {
     std::vector<int> jobs;
@@ -757,18 +766,12 @@ int run_small_walk(hb2_partition *p, int cat0, int ncls, const std::vector<std::
         CU(cudaGetLastError());
         return 0;
     }
-    if (p->Dp == 4 && p->small_ilp != 1) {
-        // one or two patterns per thread: (passes over the resident capacity) x (measured cost of a pass: 0.63 vs 0.98 ms
-        // at 256 taxa, profiles/r2x_small*.json)
-        const long ct1 = (long)(p->Sp / 128) * ncls, ct2 = (long)((p->Sp + 255) / 256) * ncls;
-        const double c1 = std::ceil((double)ct1 / p->small_resident[0]), c2 = 1.55 * std::ceil((double)ct2 / p->small_resident[1]);
-        if (p->small_ilp == 2 || c2 < c1) {
-            dim3 g2((unsigned)((p->Sp + 255) / 256), (unsigned)ncls);
-            hb2::prune_small_walk_ilp_kernel<4, 2><<<g2, 128, 0, p->stream>>>(a, p->d_jobs, n);
-            p->launches++;
-            CU(cudaGetLastError());
-            return 0;
-        }
+    if (small_two_patterns(p, ncls)) {
+        dim3 g2((unsigned)((p->Sp + 255) / 256), (unsigned)ncls);
+        hb2::prune_small_walk_ilp_kernel<4, 2><<<g2, 128, 0, p->stream>>>(a, p->d_jobs, n);
+        p->launches++;
+        CU(cudaGetLastError());
+        return 0;
     }
     switch (p->Dp) {
         case 4: hb2::prune_small_walk_kernel<4><<<grid, 128, 0, p->stream>>>(a, p->d_jobs, n); break;
@@ -1970,6 +1973,7 @@ const char *hb2_pruning_kernel(const hb2_partition *p) {
     if (p->Dp == 64 && p->fp64_mode == 2) return "prune64_lanes_kernel";
     if (p->Dp == 64) return (p->fp64_walk && (int64_t)(p->Sp / hb2::TILE_P) * p->ownN >= 2 * p->sm_count) ? "prune64_walk_kernel" : "prune64_kernel";
     if (p->small_walk && p->small_dmma && p->Dp >= 16) return "prune_small_dmma_kernel";
+    if (p->small_walk && small_two_patterns(p, p->ownN)) return "prune_small_walk_ilp_kernel";
     return p->small_walk ? "prune_small_walk_kernel" : "prune_small_kernel";
 }
 

@@ -10,7 +10,7 @@ run() {   # name, extra flags
 import json
 try:
     d=[json.loads(l) for l in open('gpurun_out/${TAG}_bench_n${N}_$1.json') if l.startswith('{')][-1]
-    print('$1', d['config']['sharding'], round(d['value'],1), 'evals/s e2e', round(d['e2e']['value'],1), {k:round(v,4) for k,v in d['roofline']['stage_ms'].items()}, 'lnL', repr(d['lnL']), 'resident', repr(d['lnL_resident']))
+    print('$1', d.get('layout'), round(d['value'],1), 'evals/s e2e', round(d['e2e']['value'],1), 'lnL', repr(d.get('lnL')), 'c5', (d.get('c5') or {}).get('value'))
 except Exception as e:
     print('$1 ERR', e)
 PY
