@@ -1,5 +1,10 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
-timeout 600 python -m pytest tests/test_multigpu.py -m gpu -q -x > gpurun_out/r2y_pytest_multigpu.log 2>&1; echo pytest_multi_rc=$?; tail -4 gpurun_out/r2y_pytest_multigpu.log | cut -c1-250
-bash tools/gpu_multi.sh 2 r2y
-NCCL_DEBUG=WARN timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29602 bench.py --gpus 2 --steps 20 --warmup 3 --fp64 > gpurun_out/r2y_bench_n2_fp64.json 2> gpurun_out/r2y_bench_n2_fp64.err; echo fp64_n2_rc=$?; cut -c1-300 gpurun_out/r2y_bench_n2_fp64.json
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x > gpurun_out/r2z2_pytest.log 2>&1; echo pytest_rc=$?; tail -3 gpurun_out/r2z2_pytest.log | cut -c1-220
+timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-host --no-small > gpurun_out/r2z2_bench.json 2> gpurun_out/r2z2_bench.err; echo bench_rc=$?
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2z2_bench.json').readline())
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline'].get('stage_ms'), d.get('c5',{}).get('value'))
+PY
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file gpurun_out/r2z2_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-host --no-c5 --no-small > /dev/null 2>&1; python tools/ncu_summary.py launches gpurun_out/r2z2_launches.csv gpurun_out/r2z2_launches.md; cat gpurun_out/r2z2_launches.md | tail -10
 echo done
