@@ -290,7 +290,9 @@ int launch_expm(hb2_partition *p, const double *dQ, const int *d_dst, int n, int
                     ca.res = pt_override ? nullptr : (sp->kind == 1 ? p->tmpls[tmpl].d_Vres : qres);   // scratch targets keep no resident copy
                     // references index the whole batch: classification has to see it in one piece (off == 0 for compiled batches
                     // and for dense batches that consist of a single run; mixed dense batches fall back below)
-                    hb2::expm_classify_kernel<<<n, 128, 0, p->stream>>>(ca);
+                    static const bool warp_classify = !(getenv("HB2_CLASSIFY_WARP") && getenv("HB2_CLASSIFY_WARP")[0] == '0');
+                    if (nV <= 256 && warp_classify) hb2::expm_classify_warp_kernel<<<(n + 7) / 8, 256, 0, p->stream>>>(ca, n);
+                    else hb2::expm_classify_kernel<<<n, 128, 0, p->stream>>>(ca);
                     a.group = ca.group; a.flag = ca.flag; a.weight = ca.weight; a.groups = groups; a.pow = x.d_pow;
                     a.Qres = nullptr;                    // the classification stage keeps the resident copy
                     if (sp->n_refs > 0) {

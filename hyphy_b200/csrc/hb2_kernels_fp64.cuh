@@ -405,6 +405,42 @@ __global__ void __launch_bounds__(128) expm_classify_kernel(ExpmClassifyArgs a) 
     }
 }
 
+// The same classification with one WARP per entry, eight entries per CTA, for short inputs (compiled hand-overs: ~50 formula
+// values): 1588 CTAs of 128 threads that each touch 47 doubles cost 17 us of launch and drain; n/8 CTAs are one wave.
+// (Sums are taken lane-strided, then by xor-shuffle: a fixed order, different from the 128-thread kernel's.)
+__global__ void __launch_bounds__(256) expm_classify_warp_kernel(ExpmClassifyArgs a, int n) {
+    const int lane = threadIdx.x & 31, k = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (k >= n) return;
+    const int slot = a.dst[k];
+    if (slot < 0) { if (lane == 0) { a.flag[k] = 0; a.weight[k] = 0.0; } return; }
+    const double *v = a.V + (size_t)k * a.nV;
+    const int g = a.group[k], r = a.ref[k];
+    const double *vr = nullptr;
+    double wr_cached = -1.0;
+    if (g >= 0) {
+        if (r >= 0) vr = a.V + (size_t)r * a.nV;
+        else if (a.groups[g].kind == a.kind) { vr = a.refvec + (size_t)g * a.refvec_stride; wr_cached = a.groups[g].weight; }
+    }
+    double wk = 0.0, wr = 0.0;
+    for (int f = lane; f < a.nV; f += 32) {
+        const double x = v[f];
+        wk += fabs(x);
+        if (vr) wr += fabs(vr[f]);
+        if (a.res) a.res[(size_t)slot * a.nV + f] = x;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { wk += __shfl_xor_sync(0xffffffffu, wk, o); wr += __shfl_xor_sync(0xffffffffu, wr, o); }
+    if (wr_cached >= 0.0) wr = wr_cached;
+    int ok = (vr != nullptr) && (wr > 0.0) && (wk >= 0.0) && (wk < INFINITY) && (wr < INFINITY);   // NaN fails every comparison
+    if (ok) {
+        const double tol = 1e-13 * wk * wr;
+        for (int f = lane; f < a.nV; f += 32)
+            if (!(fabs(v[f] * wr - vr[f] * wk) <= tol)) ok = 0;
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) { a.flag[k] = ok; a.weight[k] = wk; }
+}
+
 __global__ void __launch_bounds__(256, 2) expm64_dmma_kernel(ExpmArgs a, ExpmTcOut tc) {
     // Three shared 64x64 fp64 buffers (101 KB) so that TWO CTAs share an SM and one CTA's load/norm/epilogue phases
     // overlap the other's DMMA products:  X0 = A -> later R,  X1 = A^2,  X2 = A^3.  The polynomial blocks need A at the
