@@ -153,6 +153,7 @@ struct hb2_partition {
     bool use_tc = false;
     float *d_condf = nullptr, *d_PB = nullptr, *d_PTf = nullptr;
     int *d_err = nullptr;
+    unsigned *d_root_counter = nullptr;       // ticket counter of the fused root reduction (combine_kernel's last block)
     int *d_forced = nullptr, *h_forced = nullptr;   // forced states of the current evaluation (hb2_evaluate_forced)
     int forced_node = -1;
     // persistent walk kernel (one launch per evaluation): plan buffers, generation bits of the tagged hand-over, residency
@@ -307,8 +308,11 @@ int launch_expm(hb2_partition *p, const double *dQ, const int *d_dst, int n, int
                     if (pack_tc) { tcs.PB = p->d_PB; tcs.PTf = p->d_PTf; }
                     double *colsum = x.d_colsum + (size_t)off * 16 * 64;
                     hb2::expm_poly_kernel<<<dim3(16, (unsigned)((n + hb2::EXPM_POLY_CHUNK - 1) / hb2::EXPM_POLY_CHUNK)), 256, 0, p->stream>>>(a, tcs, colsum, n);
-                    hb2::expm_diag_kernel<<<n, 64, 0, p->stream>>>(a, tcs, colsum);
-                    p->launches += 3;
+                    // the row repair of the entries the polynomial kernel finished rides in the finishing kernel below (same
+                    // arithmetic as expm_diag_kernel, one launch less); needs the tensor-path outputs to be the same set
+                    static const bool fuse_diag = !(getenv("HB2_EXPM_FUSE_DIAG") && getenv("HB2_EXPM_FUSE_DIAG")[0] == '0');
+                    if (fuse_diag) { a.colsum = colsum; p->launches += 2; }
+                    else { hb2::expm_diag_kernel<<<n, 64, 0, p->stream>>>(a, tcs, colsum); p->launches += 3; }
                 }
                 hb2::ExpmTcOut tco{nullptr, nullptr};
                 if (pack_tc) { tco.PB = p->d_PB; tco.PTf = p->d_PTf; packed = true; }
@@ -997,8 +1001,11 @@ hb2::PeerBuf peer_buf(hb2_partition *p) {
 }
 
 int run_root(hb2_partition *p, int c0, int nc, bool use_weights, bool want_sites) {
-    CU(cudaMemsetAsync(p->d_flag, 0, sizeof(int), p->stream));
+    static const bool fuse_root = !(getenv("HB2_ROOT_FUSED") && getenv("HB2_ROOT_FUSED")[0] == '0');
+    const bool plain = p->cg_G <= 1;           // single GPU or pattern shards: combine + sum in one kernel (its last block)
+    if (!(plain && fuse_root)) CU(cudaMemsetAsync(p->d_flag, 0, sizeof(int), p->stream));
     hb2::CombineArgs c;
+    c.counter = nullptr; c.out = nullptr;
     c.rootL = p->d_rootL; c.rootE = p->d_rootE; c.weights = use_weights ? p->d_weights : nullptr; c.freq = p->d_freq;
     c.partial = p->d_partial; c.flag = p->d_flag; c.siteL = want_sites ? p->d_siteL : nullptr;
     c.siteScale = want_sites ? p->d_siteScale : nullptr;
@@ -1032,9 +1039,15 @@ int run_root(hb2_partition *p, int c0, int nc, bool use_weights, bool want_sites
         CU(cudaGetLastError());
         return 0;
     }
-    hb2::combine_kernel<<<p->n_partial_blocks, 256, 0, p->stream>>>(c);
-    hb2::final_sum_kernel<<<1, 256, 0, p->stream>>>(p->d_partial, p->n_partial_blocks, p->d_flag, p->d_lnL);
-    p->launches += 2;
+    if (fuse_root) {
+        c.counter = p->d_root_counter; c.out = p->d_lnL;
+        hb2::combine_kernel<<<p->n_partial_blocks, 256, 0, p->stream>>>(c);
+        p->launches += 1;
+    } else {
+        hb2::combine_kernel<<<p->n_partial_blocks, 256, 0, p->stream>>>(c);
+        hb2::final_sum_kernel<<<1, 256, 0, p->stream>>>(p->d_partial, p->n_partial_blocks, p->d_flag, p->d_lnL);
+        p->launches += 2;
+    }
     CU(cudaGetLastError());
     if (p->comm && p->px_ok) {                // pattern shards: R partial lnL over peer memory, summed in rank order
         hb2::peer_sum_kernel<<<1, 64, 0, p->stream>>>(peer_buf(p), p->d_lnL);
@@ -1309,6 +1322,9 @@ int hb2_create(hb2_partition **out, int64_t S, int64_t D, int64_t L, int64_t I, 
     CUP(cudaMalloc(&p->d_partial, p->n_partial_blocks * sizeof(double)));
     CUP(cudaMalloc(&p->d_lnL, sizeof(double)));
     CUP(cudaMalloc(&p->d_flag, sizeof(int)));
+    CUP(cudaMemsetAsync(p->d_flag, 0, sizeof(int), p->stream));
+    CUP(cudaMalloc(&p->d_root_counter, sizeof(unsigned)));
+    CUP(cudaMemsetAsync(p->d_root_counter, 0, sizeof(unsigned), p->stream));
     CUP(cudaMalloc(&p->d_siteL, Sp * sizeof(double)));
     CUP(cudaMalloc(&p->d_siteScale, Sp * sizeof(long long)));
     CUP(cudaMalloc(&p->d_jobs, I * sizeof(int)));
@@ -1941,7 +1957,7 @@ void hb2_destroy(hb2_partition *p) {
     if (p->comm) g_nccl.CommDestroy(p->comm);
     void *dev[] = {p->d_leaf, p->d_scal, p->d_rootE, p->d_child_start, p->d_child_ids, p->d_jobs, p->d_dst, p->d_flag,
                    p->d_mix_dst, p->d_mix_Q, p->d_ambig, p->d_freq, p->d_cond, p->d_PT, p->d_Q, p->d_pi, p->d_rootL, p->d_weights,
-                   p->d_partial, p->d_lnL, p->d_siteL, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_xsend, p->d_xrecv, p->d_xfreq, p->d_xpartial, p->d_bc_out, p->d_bc_outE, p->d_bc_sib, p->d_walk, p->d_forced, p->d_cond_side, p->d_lane_flags, p->ex.d_int, p->ex.d_flag, p->ex.d_weight, p->ex.d_groups, p->ex.d_pow, p->ex.d_refvec, p->ex.d_flags, p->ex.d_colsum, p->bex.d_colsum, p->bex.d_int, p->bex.d_flag, p->bex.d_weight, p->bex.d_groups, p->bex.d_pow, p->bex.d_refvec, p->bex.d_flags,
+                   p->d_partial, p->d_lnL, p->d_siteL, p->d_siteScale, p->d_Qres, p->d_condf, p->d_PB, p->d_PTf, p->d_err, p->d_mix_scratch, p->d_xsend, p->d_xrecv, p->d_xfreq, p->d_xpartial, p->d_bc_out, p->d_bc_outE, p->d_bc_sib, p->d_walk, p->d_forced, p->d_cond_side, p->d_lane_flags, p->d_root_counter, p->ex.d_int, p->ex.d_flag, p->ex.d_weight, p->ex.d_groups, p->ex.d_pow, p->ex.d_refvec, p->ex.d_flags, p->ex.d_colsum, p->bex.d_colsum, p->bex.d_int, p->bex.d_flag, p->bex.d_weight, p->bex.d_groups, p->bex.d_pow, p->bex.d_refvec, p->bex.d_flags,
                    p->d_bPT, p->d_bV, p->d_bcond, p->d_bout, p->d_bdst, p->d_bpat, p->d_bnodeex};
     for (void *d : dev) if (d) cudaFree(d);
     if (p->h_Q) cudaFreeHost(p->h_Q);

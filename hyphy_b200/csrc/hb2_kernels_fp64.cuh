@@ -101,6 +101,8 @@ struct ExpmArgs {
     const double *Q;        // [n][D*D]
     const int *dst;         // [n] destination slot; < 0: retired entry (the slot was handed over again), skipped
     double *PT;
+    const double *colsum;   // nullable [n][16][64]: column-sum partials of expm_poly_kernel; non-null = expm64_dmma_kernel also
+                            // does the row repair of the entries that kernel finished (no separate expm_diag_kernel launch)
     double *Qres;           // nullable [slots][D*D]: resident copy of the rate matrices, written while loading
     int D;
     int is_trans;           // 1: input already a transition matrix -> just transpose/pad
@@ -467,7 +469,24 @@ __global__ void __launch_bounds__(256, 2) expm64_dmma_kernel(ExpmArgs a, ExpmTcO
         const double rho = gi.nu * (a.weight[blockIdx.x] / gi.weight);
         int shift = 0;
         if (rho > EXPM_POLY_THETA) { int e = 0; frexp(rho / EXPM_POLY_THETA, &e); shift = max(e, 0); }
-        if (shift == 0 && rho == rho) return;    // finished by expm_poly_kernel + expm_diag_kernel
+        if (shift == 0 && rho == rho) {          // finished by expm_poly_kernel up to the row repair (expm_diag_kernel's arithmetic)
+            if (a.colsum && tid < 64) {
+                const int col = tid;
+                double s = 0.0;
+#pragma unroll
+                for (int sl = 0; sl < 16; sl++) s += a.colsum[((size_t)blockIdx.x * 16 + sl) * 64 + col];
+                const double d = col < a.D ? fmax(1.0 - s, 0.0) : 0.0;
+                out[col * 64 + col] = d;
+                if (tc.PB) {
+                    tc.PTf[slot * 4352 + col * 68 + col] = (float)d;
+                    const float hi = tf32_rn_dev((float)d);
+                    float *pb = tc.PB + slot * 8192 + (col >> 2) * 256 + col * 4 + (col & 3);
+                    pb[0] = hi;
+                    pb[4096] = tf32_rn_dev((float)(d - (double)hi));
+                }
+            }
+            return;
+        }
         if (!(rho == rho) || shift > 900) {
             for (int idx = tid; idx < 4096; idx += 256) out[idx] = __longlong_as_double(0x7ff8000000000000LL);
             if (tc.PB) {
@@ -1530,6 +1549,8 @@ struct CombineArgs {
     const double *rootL; const int *rootE; const double *weights; const double *freq;
     double *partial; int *flag; double *siteL; long long *siteScale;
     int Sp, S, c0, nc;
+    unsigned *counter;      // nullable: with `out`, the LAST block to finish adds up the partials (final_sum_kernel's arithmetic,
+    double *out;            // same order) and re-arms counter and flag -- one launch and one memset less per evaluation
 };
 
 __global__ void __launch_bounds__(256) combine_kernel(CombineArgs a) {
@@ -1580,6 +1601,29 @@ __global__ void __launch_bounds__(256) combine_kernel(CombineArgs a) {
         __syncthreads();
     }
     if (threadIdx.x == 0) a.partial[blockIdx.x] = red[0];
+    if (a.counter) {
+        __shared__ int s_last;
+        if (threadIdx.x == 0) {
+            __threadfence();                                   // partial[] (and flag) before the ticket
+            s_last = atomicAdd(a.counter, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        double s = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += 256) s += __ldcg(a.partial + i);
+        red[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            a.out[0] = __ldcg(a.flag) ? -INFINITY : red[0];
+            *a.flag = 0;
+            *a.counter = 0u;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
