@@ -1911,6 +1911,49 @@ int hb2_comm_init(hb2_partition *p, int nRanks, int rank, const void *uniqueId12
     return peer_setup(p, 2);
 }
 
+int hb2_comm_gather_sites(hb2_partition *p, const double *siteL, const int64_t *siteScale, double *allSiteL, int64_t *allSiteScale,
+                          int64_t capacity, int64_t *total) {
+    if (!p || !siteL || !siteScale || !allSiteL || !allSiteScale || !total) return fail("null argument");
+    if (!p->comm) return fail("hb2_comm_gather_sites needs hb2_comm_init first");
+    CU(cudaSetDevice(p->device));
+    const int R = p->n_ranks, G = std::max(p->cg_G, 1);
+    // 1. every rank's pattern count
+    long long mine = (long long)p->S, *d_cnt = nullptr;
+    std::vector<long long> cnt(R);
+    CU(cudaMalloc(&d_cnt, (size_t)(R + 1) * sizeof(long long)));
+    CU(cudaMemcpyAsync(d_cnt + R, &mine, sizeof(long long), cudaMemcpyHostToDevice, p->stream));
+    ncclResult_t nr = g_nccl.AllGather(d_cnt + R, d_cnt, sizeof(long long), ncclChar, p->comm, p->stream);
+    if (nr != ncclSuccess) { cudaFree(d_cnt); return fail("ncclAllGather (pattern counts): %s", g_nccl.GetErrorString(nr)); }
+    CU(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)R * sizeof(long long), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    cudaFree(d_cnt);
+    long long mx = 0, tot = 0;
+    for (int r = 0; r < R; r++) { mx = std::max(mx, cnt[r]); if (r % G == 0) tot += cnt[r]; }    // ranks of one shard hold the same patterns
+    *total = (int64_t)tot;
+    if (tot > capacity) return fail("hb2_comm_gather_sites: %lld patterns in all shards, room for %lld", tot, (long long)capacity);
+    // 2. (likelihood, scaler count) pairs, padded to the largest shard
+    const size_t rec = (size_t)mx * 16;
+    std::vector<unsigned char> send(rec, 0), all(rec * R);
+    for (long long s = 0; s < mine; s++) { memcpy(&send[(size_t)s * 16], siteL + s, 8); memcpy(&send[(size_t)s * 16 + 8], siteScale + s, 8); }
+    unsigned char *d_send = nullptr, *d_all = nullptr;
+    CU(cudaMalloc(&d_send, std::max<size_t>(rec, 16)));
+    CU(cudaMalloc(&d_all, std::max<size_t>(rec * R, 16)));
+    CU(cudaMemcpyAsync(d_send, send.data(), rec, cudaMemcpyHostToDevice, p->stream));
+    nr = g_nccl.AllGather(d_send, d_all, rec, ncclChar, p->comm, p->stream);
+    if (nr != ncclSuccess) { cudaFree(d_send); cudaFree(d_all); return fail("ncclAllGather (per-pattern outputs): %s", g_nccl.GetErrorString(nr)); }
+    CU(cudaMemcpyAsync(all.data(), d_all, rec * R, cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    cudaFree(d_send); cudaFree(d_all);
+    // 3. shard order = rank order of the first rank of every shard
+    int64_t at = 0;
+    for (int r = 0; r < R; r += G)
+        for (long long s = 0; s < cnt[r]; s++, at++) {
+            memcpy(allSiteL + at, &all[(size_t)r * rec + (size_t)s * 16], 8);
+            memcpy(allSiteScale + at, &all[(size_t)r * rec + (size_t)s * 16 + 8], 8);
+        }
+    return 0;
+}
+
 int hb2_comm_class_groups(hb2_partition *p, int nGroups) {
     if (!p) return fail("null partition");
     if (!p->comm) return fail("hb2_comm_class_groups needs hb2_comm_init first");

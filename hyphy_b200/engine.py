@@ -51,6 +51,7 @@ ABI = [
     ("hb2_plan_walk", C.c_int, [C.c_int64, C.c_int64, _ip, C.c_int64, _ip, C.c_int, C.c_int, _i32p, _i32p, C.c_int64, _ip]),
     ("hb2_comm_init", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     ("hb2_comm_class_groups", C.c_int, [C.c_void_p, C.c_int]),
+    ("hb2_comm_gather_sites", C.c_int, [C.c_void_p, _dp, _ip, _dp, _ip, C.c_int64, C.POINTER(C.c_int64)]),
     ("hb2_destroy", None, [C.c_void_p]),
     ("hb2_launch_count", C.c_int64, [C.c_void_p]),
     ("hb2_precision_mode", C.c_int, [C.c_void_p]),
@@ -296,6 +297,17 @@ class Partition:
     def comm_class_groups(self, n_groups: int):
         """Second sharding axis (rate classes); see hb2_comm_class_groups in include/hyphy_b200.h."""
         _check(self._lib.hb2_comm_class_groups(self._h, int(n_groups)))
+
+    def comm_gather_sites(self, site_l, site_scale, capacity: int):
+        """All shards' per-pattern outputs on every rank (hb2_comm_gather_sites); returns (siteL, siteScale) of the whole alignment."""
+        sl = np.ascontiguousarray(site_l, dtype=np.float64)
+        ss = np.ascontiguousarray(site_scale, dtype=np.int64)
+        out_l = np.empty(int(capacity))
+        out_s = np.empty(int(capacity), dtype=np.int64)
+        tot = C.c_int64()
+        _check(self._lib.hb2_comm_gather_sites(self._h, sl.ctypes.data_as(_dp), ss.ctypes.data_as(_ip), out_l.ctypes.data_as(_dp),
+                                               out_s.ctypes.data_as(_ip), int(capacity), C.byref(tot)))
+        return out_l[:tot.value], out_s[:tot.value]
 
     # -- introspection -----------------------------------------------------------------------------
     @property

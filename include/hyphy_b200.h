@@ -180,6 +180,13 @@ int hb2_comm_init(hb2_partition *p, int nRanks, int rank, const void *uniqueId12
  * Requires C % nGroups == 0 and nRanks % nGroups == 0; hb2_evaluate (single class) is refused in this mode.  Call after
  * hb2_comm_init, before the first matrix is set. */
 int hb2_comm_class_groups(hb2_partition *p, int nGroups);
+/* Per-pattern outputs of ALL pattern shards on every rank ("per-pattern outputs, when requested, are gathered";
+ * what the host needs for ConstructCategoryMatrix / SITE_LOG_LIKELIHOODS on a sharded partition, likefunc.cpp:1791).
+ * siteL / siteScale: this rank's S values as returned by the last hb2_evaluate*; allSiteL / allSiteScale: room for
+ * `capacity` patterns, filled in shard order (= pattern order of the unsharded partition when shards are contiguous
+ * slices); *total = patterns over all shards.  Collective over the partition's communicator (two ncclAllGather). */
+int hb2_comm_gather_sites(hb2_partition *p, const double *siteL, const int64_t *siteScale, double *allSiteL,
+                          int64_t *allSiteScale, int64_t capacity, int64_t *total);
 
 /* Pair of SetupLFCaches in DeleteCaches (likefunc.cpp:10556-10601). */
 void hb2_destroy(hb2_partition *p);
