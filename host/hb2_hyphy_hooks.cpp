@@ -96,6 +96,9 @@ void create(void *&state, unsigned long n_trees, unsigned long index, _TheTree *
     if (!st) { st = new State(); state = st; }
     if (st->parts.size() < n_trees) st->parts.resize(n_trees, nullptr);
     if (st->parts[index]) { hb2_destroy(st->parts[index]->h); delete st->parts[index]; st->parts[index] = nullptr; }
+    // two-sequence analyses have no internal-node cache and never reach the pruning branch of ComputeBlock
+    // (likefunc.cpp:4216, :11260-11281: ComputeTwoSequenceLikelihood): nothing to take over, the host's own code runs
+    if (tree->GetLeafCount() < 2 || tree->GetINodeCount() < 1) return;
     if (hb2_device_count() <= 0) fatal("no CUDA device is visible (set HYPHY_B200=0 to run the CPU path)");
 
     Part *p = new Part();

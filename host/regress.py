@@ -33,6 +33,7 @@ TESTS = [
     "SimpleOptimizations/IntermediateProtein.bf",   # 20 states
     "SimpleOptimizations/LargeNuc.bf",
     "SimpleOptimizations/multi-part-codon.bf",      # several partitions in one likelihood function
+    "SimpleOptimizations/TwoSequenceTest.bf",       # two-sequence special case (likefunc.cpp:11260): stays on the host's own path
     "REL/GTR_G_I.bf",                               # category variables: per-class ComputeBlock + host combination
     "REL/NY.bf",
     "REL/ModelMixture.bf",
