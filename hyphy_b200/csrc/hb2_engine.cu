@@ -19,6 +19,8 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <mutex>
+#include <unordered_map>
 
 #include <nccl.h>
 
@@ -41,6 +43,70 @@ int fail(const char *fmt, ...) {
         cudaError_t e_ = (x);                                                                         \
         if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
+
+// ---- Block pool for device and pinned-host memory ----------------------------------------------------------------------
+// The site phases of FEL / MEME create and destroy one small likelihood function per site: through the
+// patched host that is one hb2_create / hb2_destroy pair each, i.e. ~60 cudaMalloc / cudaMallocHost and as many frees (each
+// cudaFree synchronises the device).  Blocks up to 32 MB are rounded up to a power of two and recycled through a
+// process-wide free list per device (caps: 1 GB device, 256 MB pinned); larger blocks go straight to the runtime.
+// Recycled memory is NOT zero: every buffer whose initial contents matter is cleared explicitly at hb2_create, as it
+// always had to be (cudaMalloc gives no such guarantee either).  HB2_POOL=0 switches the pool off.
+struct BlockPool {
+    struct Info { size_t cls; int dev; bool host; };
+    std::mutex mu;
+    std::unordered_map<void *, Info> live;
+    std::unordered_map<unsigned long long, std::vector<void *>> free_blocks;      // key = (host, device, class)
+    size_t pooled_dev = 0, pooled_host = 0;
+    static constexpr size_t kMaxClass = (size_t)32 << 20, kDevCap = (size_t)1 << 30, kHostCap = (size_t)256 << 20;
+    bool enabled() { static const bool on = !(getenv("HB2_POOL") && getenv("HB2_POOL")[0] == '0'); return on; }
+    static size_t size_class(size_t n) { size_t c = 256; while (c < n) c <<= 1; return c; }
+    static unsigned long long key(bool host, int dev, size_t cls) { return ((unsigned long long)host << 63) | ((unsigned long long)(dev & 0xff) << 52) | (unsigned long long)cls; }
+    cudaError_t alloc(void **p, size_t n, bool host) {
+        if (!enabled() || n > kMaxClass) return host ? (cudaMallocHost)(p, n) : (cudaMalloc)(p, n);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const size_t cls = size_class(n);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            auto it = free_blocks.find(key(host, host ? 0 : dev, cls));
+            if (it != free_blocks.end() && !it->second.empty()) {
+                *p = it->second.back();
+                it->second.pop_back();
+                (host ? pooled_host : pooled_dev) -= cls;
+                live[*p] = Info{cls, dev, host};
+                return cudaSuccess;
+            }
+        }
+        const cudaError_t e = host ? (cudaMallocHost)(p, cls) : (cudaMalloc)(p, cls);
+        if (e == cudaSuccess) { std::lock_guard<std::mutex> lk(mu); live[*p] = Info{cls, dev, host}; }
+        return e;
+    }
+    cudaError_t release(void *p, bool host) {
+        if (!p) return cudaSuccess;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            auto it = live.find(p);
+            if (it != live.end()) {
+                const Info in = it->second;
+                live.erase(it);
+                size_t &pooled = in.host ? pooled_host : pooled_dev;
+                if (pooled + in.cls <= (in.host ? kHostCap : kDevCap)) {
+                    free_blocks[key(in.host, in.host ? 0 : in.dev, in.cls)].push_back(p);
+                    pooled += in.cls;
+                    return cudaSuccess;
+                }
+            }
+        }
+        return host ? (cudaFreeHost)(p) : (cudaFree)(p);
+    }
+};
+BlockPool g_pool;
+// every allocation of this file goes through the pool (buffers that are exported through CUDA IPC opt out with the
+// parenthesised runtime name)
+#define cudaMalloc(p, n) g_pool.alloc((void **)(p), (n), false)
+#define cudaMallocHost(p, n) g_pool.alloc((void **)(p), (n), true)
+#define cudaFree(p) g_pool.release((void *)(p), false)
+#define cudaFreeHost(p) g_pool.release((void *)(p), true)
 
 // ---- NCCL through dlopen: single-GPU users never need the library -------------------------------
 struct NcclApi {
@@ -923,7 +989,7 @@ void peer_teardown(hb2_partition *p) {
     for (size_t r = 0; r < p->px_peer.size(); r++)
         if ((int)r != p->rank && p->px_peer[r]) cudaIpcCloseMemHandle(p->px_peer[r]);
     p->px_peer.clear();
-    if (p->px_local) cudaFree(p->px_local);
+    if (p->px_local) (cudaFree)(p->px_local);                 // IPC-exported: never pooled
     if (p->d_px_peer) cudaFree(p->d_px_peer);
     if (p->d_px_counter) cudaFree(p->d_px_counter);
     p->px_local = nullptr; p->d_px_peer = nullptr; p->d_px_counter = nullptr; p->px_ok = false;
@@ -938,7 +1004,7 @@ int peer_setup(hb2_partition *p, int payload) {
     int ok = p->px_enabled ? 1 : 0;
     cudaIpcMemHandle_t mine;
     memset(&mine, 0, sizeof mine);
-    if (ok && cudaMalloc(&p->px_local, doubles * sizeof(double)) != cudaSuccess) { cudaGetLastError(); p->px_local = nullptr; ok = 0; }
+    if (ok && (cudaMalloc)((void **)&p->px_local, doubles * sizeof(double)) != cudaSuccess) { cudaGetLastError(); p->px_local = nullptr; ok = 0; }
     if (ok) {
         CU(cudaMemsetAsync(p->px_local, 0, doubles * sizeof(double), p->stream));
         if (cudaIpcGetMemHandle(&mine, p->px_local) != cudaSuccess) { cudaGetLastError(); ok = 0; }
