@@ -53,6 +53,13 @@ HOOKS = [
     ("core/likefunc.cpp", "  delete_array_elements_and_self(conditionalInternalNodeLikelihoodCaches,", "before",
      "  hb2_hooks::destroy_all(hb2_state);   // hyphy_b200: pair of SetupLFCaches\n",
      "DeleteCaches (likefunc.cpp:10594)"),
+    # ---- likefunc2.cpp: ancestral reconstruction reads matrices and conditionals on the host -----------------------------
+    ("core/likefunc2.cpp", '#include "likefunc.h"', "after", INCLUDE, "include"),
+    ("core/likefunc2.cpp", "    _List *expandedMap = dsf->ComputePatternToSiteMap(), *thisSet;", "before",
+     "    // hyphy_b200: joint reconstruction / sampling read P and the internal-node conditionals on the host\n"
+     "    hb2_hooks::materialize(hb2_hooks::partition(hb2_state, partIndex), tree, dsf, conditionalInternalNodeLikelihoodCaches[partIndex],\n"
+     "                           (_SimpleList *)optimalOrders.list_data[partIndex]);\n",
+     "ReconstructAncestors (likefunc2.cpp:411): device -> host copies"),
     # ---- calcnode.cpp: SetCompExp is where every matrix of the queue ends up -------------------------------------------
     ("core/calcnode.cpp", '#include "calcnode.h"', "after", INCLUDE, "include"),
     ("core/calcnode.cpp", "void _CalcNode::SetCompExp(_Matrix *m, long catID, bool do_exponentiation) {", "after",

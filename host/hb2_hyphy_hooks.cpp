@@ -298,4 +298,33 @@ double compute_block(void *part, _TheTree *tree, long catID, _SimpleList const &
     return lnl;
 }
 
+void materialize(void *part, _TheTree *tree, _DataSetFilter const *filter, double *inode_cache, _SimpleList const *site_ordering) {
+    Part *p = static_cast<Part *>(part);
+    if (!p) return;
+    long const S = p->S, D = p->D, L = p->L, I = p->I, C = p->C;
+    std::vector<double> buf((size_t)std::max(S * D, D * D));
+    std::vector<int32_t> ex((size_t)S);
+    for (long cat = 0; cat < C; cat++) {
+        // transition matrices: every branch (all nodes but the root), into the matrix the node keeps for this class
+        for (long n = 0; n < L + I - 1; n++) {
+            _CalcNode *node = n < L ? (_CalcNode *)tree->flatCLeaves.GetItem(n) : (_CalcNode *)tree->flatTree.GetItem(n - L);
+            _Matrix *m = node->GetCompExp(C > 1 ? cat : -1);
+            if (!m || m->GetHDim() != D || m->GetVDim() != D || !m->theData) continue;      // nothing the host could read either
+            if (hb2_read_transition(p->h, cat, n, buf.data())) fatal("hb2_read_transition failed");
+            memcpy(m->theData, buf.data(), (size_t)D * D * sizeof(double));
+        }
+        // conditionals of the internal nodes, in the host's cache order (position s holds pattern site_ordering[s])
+        if (inode_cache)
+            for (long i = 0; i < I; i++) {
+                if (hb2_read_conditionals(p->h, cat, i, buf.data(), ex.data())) fatal("hb2_read_conditionals failed");
+                double *dst = inode_cache + ((size_t)cat * I + i) * S * D;
+                for (long s = 0; s < S; s++) {
+                    long const pat = site_ordering ? site_ordering->list_data[s] : s;
+                    memcpy(dst + (size_t)s * D, buf.data() + (size_t)pat * D, (size_t)D * sizeof(double));
+                }
+            }
+    }
+    (void)filter;
+}
+
 }  // namespace hb2_hooks

@@ -15,6 +15,8 @@
 //   _CalcNode::RecomputeMatrix           (calcnode.cpp:526)   -> hb2_hooks::compiled    formula VALUES go to the GPU instead
 //                                                                                       of a numeric rate matrix
 //   _LikelihoodFunction::DeleteCaches    (likefunc.cpp:10556) -> hb2_hooks::destroy_all
+//   _LikelihoodFunction::ReconstructAncestors (likefunc2.cpp:308) -> hb2_hooks::materialize  device -> host copies for the
+//                                                                                       ancestral-state readers
 //
 // Environment: HYPHY_B200=0 disables the engine (the unmodified CPU path runs); HYPHY_B200_TC=1 selects the tcgen05
 // pruning path for 33..64-state partitions (error-compensated 3xTF32: every evaluation is within 1e-6*|lnL| of the
@@ -73,5 +75,12 @@ class Bypass {
 // ComputeBlock after DetermineNodesForUpdate + ExponentiateMatrices: pruning, root reduction, scaling correction.
 double compute_block(void *part, _TheTree *tree, long catID, _SimpleList const &branches, double *siteRes, long *scc,
                      long branchIndex, _SimpleList *branchValues);
+
+// ReconstructAncestors (likefunc2.cpp:308): joint reconstruction and ancestral sampling read the nodes' transition matrices
+// (tree.cpp:4273, :4110) and the internal-node conditionals (tree.cpp:4107, FillInConditionals :3335) on the HOST.  With the
+// engine those live on the device: this copies them back once -- P of every branch and class into the matrices the nodes
+// keep (the NaN placeholders), the conditionals (normalised per node and pattern: both readers are scale-invariant there)
+// into conditionalInternalNodeLikelihoodCaches in the host's cache order.
+void materialize(void *part, _TheTree *tree, _DataSetFilter const *filter, double *inode_cache, _SimpleList const *site_ordering);
 
 }  // namespace hb2_hooks

@@ -38,7 +38,7 @@ def _fmt(x: float) -> str:
 
 
 def write_hbl(w: synth.Workload, path_bf: str, path_fas: str, n_evals: int = 0, threads: int = 0,
-              per_site: bool = True, n_warm: int = 0) -> None:
+              per_site: bool = True, n_warm: int = 0, ancestors: bool = False) -> None:
     """Emit FASTA + HBL for workload `w`.  n_evals>0 appends the timed full-evaluation loop (one global
     parameter perturbed by 1e-4 relative each time); threads>0 enables OpenMP inside LFCompute
     the only way the unmodified reference allows (NUMBER_THREADS + an Optimize call, likefunc.cpp:223-227)."""
@@ -144,13 +144,19 @@ def write_hbl(w: synth.Workload, path_bf: str, path_fas: str, n_evals: int = 0, 
     if per_site:
         o.append("ConstructCategoryMatrix (sl, lf, SITE_LOG_LIKELIHOODS);")
         o.append('for (k = 0; k < Columns (sl); k += 1) { fprintf (stdout, "SITE ", k, " ", Format (sl[k], 30, 16), "\\n"); }')
+    if ancestors:
+        # joint ML ancestral reconstruction (likefunc2.cpp:308 -> tree.cpp:4209), printed the way the reference's own
+        # Ancestors/NucAncestors.bf reads it back
+        o.append("DataSet anc = ReconstructAncestors (lf);")
+        o.append("DataSetFilter ancf = CreateFilter (anc,1);")
+        o.append('for (k = 0; k < ancf.species; k += 1) { GetDataInfo (aSeq, ancf, k); fprintf (stdout, "ANC ", k, " ", aSeq, "\n"); }')
     with open(path_bf, "w") as f:
         f.write("\n".join(o) + "\n")
 
 
 def run_reference(w: synth.Workload, n_evals: int = 0, threads: int = 0, per_site: bool = True,
                   timeout: float = 3600.0, workdir: str | None = None, n_warm: int = 0, binary: str | None = None,
-                  env_extra: dict | None = None) -> dict:
+                  env_extra: dict | None = None, ancestors: bool = False) -> dict:
     """Run the reference binary on `w`.  Returns {"lnL", "site_lnL" (np array, alignment order) or None,
     "loop_seconds" (wall time between LOOP_BEGIN and LOOP_END, measured on this side of the pipe), "wall"}.
     binary: another HyPhy executable fed the same script -- the PATCHED host (host/_build/hyphy) in tests/test_host_binding.py."""
@@ -158,7 +164,7 @@ def run_reference(w: synth.Workload, n_evals: int = 0, threads: int = 0, per_sit
         raise RuntimeError(f"reference binary missing: {REF_BIN} (build with make -f oracle/Makefile.ref)")
     tmp = workdir or tempfile.mkdtemp(prefix="hb2ref_")
     bf, fas = os.path.join(tmp, "job.bf"), os.path.join(tmp, "job.fas")
-    write_hbl(w, bf, fas, n_evals, threads, per_site, n_warm)
+    write_hbl(w, bf, fas, n_evals, threads, per_site, n_warm, ancestors)
     env = dict(os.environ)
     env.update(env_extra or {})
     if threads > 0:
@@ -167,6 +173,7 @@ def run_reference(w: synth.Workload, n_evals: int = 0, threads: int = 0, per_sit
     proc = subprocess.Popen([binary or REF_BIN, f"CPU={max(threads, 1)}", bf], cwd=tmp, stdin=subprocess.DEVNULL,
                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
     lnL, sites, t_begin, t_end, loop_lnl, tail, engine_lines = None, {}, None, None, None, [], []
+    anc = {}
     try:
         for line in proc.stdout:
             tail.append(line)
@@ -183,6 +190,9 @@ def run_reference(w: synth.Workload, n_evals: int = 0, threads: int = 0, per_sit
             elif line.startswith("SITE "):
                 _, k, v = line.split()
                 sites[int(k)] = float(v)
+            elif line.startswith("ANC "):
+                _, k, v = line.split()
+                anc[int(k)] = v
             if time.time() - t0 > timeout:
                 proc.kill()
                 raise TimeoutError("reference run exceeded timeout")
@@ -196,4 +206,5 @@ def run_reference(w: synth.Workload, n_evals: int = 0, threads: int = 0, per_sit
     if sites:
         site_arr = np.array([sites[k] for k in range(len(sites))])
     return {"lnL": lnL, "site_lnL": site_arr, "loop_lnL": loop_lnl, "engine": engine_lines,
+            "ancestors": [anc[k] for k in range(len(anc))],
             "loop_seconds": (t_end - t_begin) if (t_begin and t_end) else None, "wall": time.time() - t0}

@@ -57,6 +57,37 @@ def test_patched_host_evaluation_stream_and_partial_updates():
     assert abs(b["lnL"] - g["lnL"]) <= 1e-7 * abs(g["lnL"])
 
 
+@pytest.mark.parametrize("name", ["mg94_8x60_c1", "mg94_8x60_c4_ambig", "c1_hky85_8x500", "mg94_30x100_c4_ambig"])
+def test_patched_host_ancestral_reconstruction_matches_reference(name):
+    """ReconstructAncestors (joint ML, likefunc2.cpp:308 -> tree.cpp:4209) reads the nodes' transition matrices -- and, for
+    rate variation, the class assignments -- on the HOST; with the engine they are copied back from the device first
+    (hb2_hooks::materialize).  Same ancestral sequences as the unmodified binary, in both precisions."""
+    w, g = gc.load(name)
+    ref = rh.run_reference(w, ancestors=True, per_site=False)
+    assert ref["ancestors"] and all(len(a) == len(ref["ancestors"][0]) for a in ref["ancestors"])
+    for mode in MODES:
+        r = rh.run_reference(w, ancestors=True, per_site=False, binary=HOST_BIN, env_extra=dict(MODES[mode][0], HYPHY_B200_VERBOSE="1"))
+        assert any("partition 0 on device" in l for l in r["engine"])
+        assert abs(r["lnL"] - g["lnL"]) <= _tol(w, mode)[0] * abs(g["lnL"])
+        if mode == "fp64":
+            assert r["ancestors"] == ref["ancestors"]
+        else:       # fp32 conditionals never enter the joint reconstruction (it recomputes from the matrices), but P's last bits can flip a tie
+            diff = sum(a != b for x, y in zip(r["ancestors"], ref["ancestors"]) for a, b in zip(x, y))
+            assert len(r["ancestors"]) == len(ref["ancestors"]) and diff <= 2, diff
+
+
+def test_patched_host_reference_ancestor_batch_file():
+    """The reference's own Ancestors/NucAncestors.bf compares the joint ML reconstruction with sequences stored in the file
+    ([OK: ML SEQUENCE RECONSTRUCTION]); its later sections fail with the unmodified binary as well and are not judged."""
+    import tempfile
+    test = os.path.join(ROOT, "host", "_build", "hbltests", "Ancestors", "NucAncestors.bf")
+    tmp = tempfile.mkdtemp(prefix="hb2anc_")
+    pr = subprocess.run([HOST_BIN, f"LIBPATH={os.path.join(ROOT, 'host', '_build', 'res')}", test], cwd=tmp, stdin=subprocess.DEVNULL,
+                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=dict(os.environ, HYPHY_B200_VERBOSE="1"), timeout=600)
+    assert "partition 0 on device" in pr.stdout
+    assert "[OK: ML SEQUENCE RECONSTRUCTION]" in pr.stdout and "MISMATCHED" not in pr.stdout, pr.stdout[-1500:]
+
+
 def test_patched_host_runs_reference_regression_batch_files():
     """The reference's own regression batch files (tests/hbltests: optimisations, category variables, HMM, explicit-form
     mixtures, ancestral reconstruction, per-site likelihoods) through the patched binary, UNMODIFIED: same verdict and the
