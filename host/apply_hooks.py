@@ -60,6 +60,11 @@ HOOKS = [
      "    hb2_hooks::materialize(hb2_hooks::partition(hb2_state, partIndex), tree, dsf, conditionalInternalNodeLikelihoodCaches[partIndex],\n"
      "                           (_SimpleList *)optimalOrders.list_data[partIndex]);\n",
      "ReconstructAncestors (likefunc2.cpp:411): device -> host copies"),
+    # ---- tree.cpp: the node-support reader behind ConstructCategoryMatrix (tree) ---------------------------------------------------
+    ("core/tree.cpp", '#include "tree.h"', "after", INCLUDE, "include"),
+    ("core/tree.cpp", "  IntPopulateLeaves(dsf, site_index);", "before",
+     "  if (site_index == 0L) hb2_hooks::materialize_tree(this);   // hyphy_b200: the loop below reads GetCompExp()->theData (tree.cpp:2589)\n",
+     "RecoverNodeSupportStates (tree.cpp:2533): device -> host copy of the transition matrices"),
     # ---- calcnode.cpp: SetCompExp is where every matrix of the queue ends up -------------------------------------------
     ("core/calcnode.cpp", '#include "calcnode.h"', "after", INCLUDE, "include"),
     ("core/calcnode.cpp", "void _CalcNode::SetCompExp(_Matrix *m, long catID, bool do_exponentiation) {", "after",

@@ -68,6 +68,8 @@ struct State {
 };
 
 Part *g_current = nullptr;          // ComputeBlock is entered from the single interpreter thread
+std::unordered_map<_TheTree const *, Part *> g_tree_part;      // for readers that only know the tree (materialize_tree)
+std::mutex g_tree_mu;
 int g_bypass = 0;
 
 bool env_true(char const *name) {
@@ -95,7 +97,10 @@ void create(void *&state, unsigned long n_trees, unsigned long index, _TheTree *
     State *st = static_cast<State *>(state);
     if (!st) { st = new State(); state = st; }
     if (st->parts.size() < n_trees) st->parts.resize(n_trees, nullptr);
-    if (st->parts[index]) { hb2_destroy(st->parts[index]->h); delete st->parts[index]; st->parts[index] = nullptr; }
+    if (st->parts[index]) {
+        { std::lock_guard<std::mutex> lk(g_tree_mu); auto it = g_tree_part.find(st->parts[index]->tree); if (it != g_tree_part.end() && it->second == st->parts[index]) g_tree_part.erase(it); }
+        hb2_destroy(st->parts[index]->h); delete st->parts[index]; st->parts[index] = nullptr;
+    }
     // two-sequence analyses have no internal-node cache and never reach the pruning branch of ComputeBlock
     // (likefunc.cpp:4216, :11260-11281: ComputeTwoSequenceLikelihood): nothing to take over, the host's own code runs
     if (tree->GetLeafCount() < 2 || tree->GetINodeCount() < 1) return;
@@ -126,6 +131,7 @@ void create(void *&state, unsigned long n_trees, unsigned long index, _TheTree *
         fatal("hb2_create failed");
     }
     st->parts[index] = p;
+    { std::lock_guard<std::mutex> lk(g_tree_mu); g_tree_part[tree] = p; }
     p->t_created = std::chrono::steady_clock::now();
     if (env_true("HYPHY_B200_VERBOSE"))
         fprintf(stderr, "[hyphy_b200] partition %lu on device %d: %ld patterns x %ld states, %ld leaves, %ld internal nodes, %ld rate classes, %s pruning\n",
@@ -147,6 +153,7 @@ void destroy_all(void *&state) {
                             "%lu of them handed over as formula values through %zu template(s); lifetime %.3f s of which %.3f s in matrix hand-over and %.3f s in hb2_evaluate (rest = HyPhy host code)\n",
                     p->n_eval, p->n_rate, p->n_trans, (long long)hb2_launch_count(p->h), p->n_compiled, p->templates.size(), seconds_since(p->t_created), p->t_handover, p->t_evaluate);
         if (g_current == p) g_current = nullptr;
+        { std::lock_guard<std::mutex> lk(g_tree_mu); auto it = g_tree_part.find(p->tree); if (it != g_tree_part.end() && it->second == p) g_tree_part.erase(it); }
         hb2_destroy(p->h);
         delete p;
     }
@@ -325,6 +332,12 @@ void materialize(void *part, _TheTree *tree, _DataSetFilter const *filter, doubl
             }
     }
     (void)filter;
+}
+
+void materialize_tree(_TheTree *tree) {
+    Part *p = nullptr;
+    { std::lock_guard<std::mutex> lk(g_tree_mu); auto it = g_tree_part.find(tree); if (it != g_tree_part.end()) p = it->second; }
+    if (p) materialize(p, tree, nullptr, nullptr, nullptr);
 }
 
 }  // namespace hb2_hooks

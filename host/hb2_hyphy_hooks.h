@@ -82,5 +82,9 @@ double compute_block(void *part, _TheTree *tree, long catID, _SimpleList const &
 // keep (the NaN placeholders), the conditionals (normalised per node and pattern: both readers are scale-invariant there)
 // into conditionalInternalNodeLikelihoodCaches in the host's cache order.
 void materialize(void *part, _TheTree *tree, _DataSetFilter const *filter, double *inode_cache, _SimpleList const *site_ordering);
+// _TheTree::RecoverNodeSupportStates (tree.cpp:2515; ConstructCategoryMatrix on a tree linked to a likelihood function,
+// batchlanruntime.cpp:1198) reads the transition matrices knowing only the tree: same copy-back, matrices only.  (Untested:
+// that HBL path segfaults in the unmodified reference at this commit.)
+void materialize_tree(_TheTree *tree);
 
 }  // namespace hb2_hooks

@@ -149,7 +149,7 @@ def write_hbl(w: synth.Workload, path_bf: str, path_fas: str, n_evals: int = 0, 
         # Ancestors/NucAncestors.bf reads it back
         o.append("DataSet anc = ReconstructAncestors (lf);")
         o.append("DataSetFilter ancf = CreateFilter (anc,1);")
-        o.append('for (k = 0; k < ancf.species; k += 1) { GetDataInfo (aSeq, ancf, k); fprintf (stdout, "ANC ", k, " ", aSeq, "\n"); }')
+        o.append('for (k = 0; k < ancf.species; k += 1) { GetDataInfo (aSeq, ancf, k); fprintf (stdout, "ANC ", k, " ", aSeq, "\\n"); }')
     with open(path_bf, "w") as f:
         f.write("\n".join(o) + "\n")
 
